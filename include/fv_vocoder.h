@@ -1,0 +1,156 @@
+/*
+ * fv_vocoder.h - C ABI of libfv_b200.so: B200 (sm_100a) kernels for the fish-vocoder generator forward.
+ *
+ * The reference (fishaudio/vocoder) has NO native/FFI layer of its own: its boundary is the
+ * nn.Module contract `Generator.forward(mel[, template]) -> wav`.  This header is the
+ * thin C boundary underneath our Python mirror of that contract; every entry point names the
+ * reference call it replaces (paths relative to the reference repo root).
+ *
+ * Conventions
+ *  - All data pointers are CUDA device pointers, caller-owned, never retained past the call.
+ *  - `stream` is a cudaStream_t passed as void*; every call is stream-ordered, no hidden sync.
+ *  - Activations are channels-last inside the path:  [B][L][pitch]  (pitch = channel count rounded
+ *    up to a multiple of 8; padded channels hold zeros).  "a16" tensors are IEEE fp16 tensor-core
+ *    operands, "x32" tensors are fp32 (residual stream / accumulators).
+ *  - Return value: 0 ok; <0 argument/shape error (FV_E_*); >0 a cudaError_t.  fv_last_error() returns a
+ *    thread-local human readable message for the last non-zero return.
+ *  - Only mel-in and wav-out are channels-first, as in the reference ([B, n_mels, T] / [B, 1, T*hop]).
+ */
+#ifndef FV_VOCODER_H_
+#define FV_VOCODER_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FV_ABI_VERSION 1
+
+/* error codes (negative) */
+#define FV_E_BADARG (-1)
+#define FV_E_ALIGN (-2)
+#define FV_E_UNSUPPORTED (-3)
+#define FV_E_DRIVER (-4)
+
+/* fused epilogue activations */
+enum fv_act {
+  FV_ACT_NONE = 0,  /* y = o                                                                      */
+  FV_ACT_SILU = 1,  /* F.silu: hifigan.py:103,105,230,245                                          */
+  FV_ACT_LEAKY = 2, /* F.leaky_relu(o, act_param): refinegan.py:89,91,302,313,319                  */
+  FV_ACT_GELU = 3,  /* nn.GELU() exact erf: encoders/convnext.py:115                               */
+  FV_ACT_TANH = 4,  /* torch.tanh: hifigan.py:247                                                  */
+  FV_ACT_POLAR = 5  /* column pairs (2k,2k+1) = (log-mag, phase) -> (min(exp(m),100)cos p, ..sin p):
+                       generators/vocos.py:57-67                                                  */
+};
+
+/* which kernel family executes fv_conv1d */
+enum fv_engine {
+  FV_ENGINE_TC = 0,  /* tcgen05.mma + TMA implicit GEMM (product path)                             */
+  FV_ENGINE_SIMT = 1 /* plain CUDA-core kernel with identical semantics (bring-up / cross-check)   */
+};
+
+#define FV_MAX_TAPS 64 /* n_phase * n_taps <= FV_MAX_TAPS */
+
+/*
+ * One (dilated | transposed-polyphase | pointwise) convolution = one implicit GEMM with a fused epilogue.
+ *
+ *   acc[b, q, o] = sum_{tap} sum_{c} a[b, q + tap_off[phase][tap], c] * w[phase][tap][o][c]      (fp16 x fp16 -> fp32)
+ *   row  = q * n_phase + phase                     (n_phase == 1: plain conv;  == stride u: ConvTranspose1d)
+ *   v    = acc + bias[o];  if gamma: v *= gamma[o];  if residual: v += residual[b, row, o]
+ *   o32  = v * out_scale (+ out32[b,row,o] if accumulate)          -> out32 (fp32), optional
+ *   o16  = fp16(act(o32))                                           -> out16 (fp16), optional
+ *   rows of `a` outside [0, L_in) read as zero ("same" zero padding of the reference convs).
+ *
+ * Replaces: nn.Conv1d in ResBlock1/AMPBlock (hifigan.py:29-98, bigvgan.py:149-218), conv_pre/conv_post
+ * (hifigan.py:158-166), nn.ConvTranspose1d ups (hifigan.py:177-187, polyphase form SURVEY B3),
+ * nn.Linear pwconv1/2 and 1x1 convs (encoders/convnext.py:112-116,172-177), ISTFTHead.out (vocos.py:41,55)
+ * and the inverse-DFT basis GEMM that stands in for torch.fft.irfft.
+ */
+typedef struct fv_conv_desc {
+  /* A operand: fp16 [B][L_in][a_pitch] */
+  const void* a;
+  int32_t B, L_in, a_pitch;
+  /* weights: fp16 [n_phase][n_taps][C_out_pad][w_pitch]; rows >= C_out and cols >= C_in are zero */
+  const void* w;
+  int32_t n_phase, n_taps, C_out, C_out_pad, w_pitch;
+  const int32_t* tap_off; /* HOST pointer, n_phase * n_taps input-row offsets */
+  /* output rows per batch element (L_out = L_in for a conv, L_in*u (+1) for ConvTranspose1d) */
+  int32_t L_out;
+  /* epilogue */
+  const float* bias;     /* [C_out] or NULL */
+  const float* gamma;    /* [C_out] or NULL: ConvNeXt layer scale (convnext.py:137-138) */
+  const float* residual; /* fp32 [B][L_out][res_pitch] or NULL */
+  int32_t res_pitch;
+  float* out32; /* fp32 [B][L_out][out32_pitch] or NULL */
+  int32_t out32_pitch;
+  int32_t accumulate; /* 1: out32 += ... (MRF mean over resblocks, hifigan.py:132-133) */
+  float out_scale;
+  void* out16; /* fp16 [B][L_out][out16_pitch] or NULL */
+  int32_t out16_pitch;
+  int32_t act; /* enum fv_act applied to the value written to out16 */
+  float act_param;
+} fv_conv_desc;
+
+const char* fv_last_error(void);
+int fv_abi_version(void);
+/* number of kernels launched by this library since load / since the last reset (bench.py "gpu_launches") */
+int64_t fv_launch_count(void);
+void fv_reset_launch_count(void);
+
+int fv_conv1d(const fv_conv_desc* d, int engine, void* stream);
+/* tuning overrides for the tcgen05 engine (0 = built-in heuristic): N tile in {16,32,64,128,256}, 128-row
+ * accumulators per CTA in {1,2}.  Process-global; meant for benchmarking sweeps. */
+void fv_set_tc_tuning(int block_n, int m_sub);
+
+/* mel [B][C][T] fp32 channels-first -> fp16 channels-last [B][T][pitch] (zero padded channels).
+ * Entry of the path: the tensor handed to Generator.forward (hifigan.py:226, convnext.py:206). */
+int fv_pack_input(const float* x, void* out16, int B, int C, int T, int pitch, void* stream);
+
+/* fp32 channels-last [B][L][pitch] -> fp32 channels-first [B][C][L]  (leaving the path; debugging) */
+int fv_unpack_output(const float* x32, float* out, int B, int C, int L, int pitch, void* stream);
+
+/* conv_post + tanh (hifigan.py:214-222,246-247): a16 [B][L][pitch] (already activated) * w32 [k][C] + bias
+ * -> wav fp32 [B][L] (== [B,1,L]).  C_out == 1, so this is a CUDA-core dot product with a warp-shuffle
+ * reduction along the channel axis. */
+int fv_conv_post_tanh(const void* a16, const float* w32, const float* bias, float* wav, int B, int L, int C,
+                      int pitch, int k, int apply_tanh, void* stream);
+
+/* Anti-aliased Snake / SnakeBeta = alias_free_torch.Activation1d(SnakeBeta) (bigvgan.py:226-233,335-337;
+ * SURVEY B4): 2x Kaiser-sinc up (12 taps, replicate edges) -> x + sin^2(a x)/(b+1e-9) -> 2x down, ONE kernel.
+ * x32 [B][L][pitch] fp32 -> out16 [B][L][pitch] fp16.  alpha/beta are the raw (log-scale) parameters [C];
+ * beta == NULL selects Snake (beta := alpha).  filt_up / filt_down = HOST pointers to the 12 fp32 taps (the
+ * module's `upsample.filter` / `downsample.lowpass.filter` buffers; passed by value to the kernel). */
+int fv_snake_aa(const float* x32, void* out16, const float* alpha, const float* beta, const float* filt_up,
+                const float* filt_down, int logscale, int B, int L, int C, int pitch, void* stream);
+
+/* ConvNeXt block front half (convnext.py:127-129): depthwise conv k (zero pad) + LayerNorm over C (eps) -> fp16.
+ * x32 [B][T][pitch] -> out16 [B][T][pitch].  dw_w [C][k], dw_b [C], ln_w/ln_b [C]. k <= 0 means "no conv"
+ * (plain LayerNorm over C: convnext.py:64-74).  out32 (optional) receives the fp32 result as well. */
+int fv_dwconv_layernorm(const float* x32, void* out16, float* out32, const float* dw_w, const float* dw_b,
+                        const float* ln_w, const float* ln_b, float eps, int B, int T, int C, int pitch, int k,
+                        void* stream);
+
+/* ISTFT("same") tail (vocos==0.0.2 spectral_ops.ISTFT): windowed frames [B][T][n_fft] fp32 (window
+ * already folded into the inverse-DFT basis) -> overlap-add, trim (win-hop)/2, divide by the hann^2 envelope.
+ * wav [B][T*hop]. */
+int fv_istft_ola(const float* frames, const float* window, float* wav, int B, int T, int n_fft, int hop,
+                 int frame_pitch, void* stream);
+
+/* template path (hifigan.py:191-204,233-234): noise_convs[i](template) as fp32 [B][L_i][pitch]; C_in == 1.
+ * template [B][L_audio], w [C][k], bias [C]; out row t = sum_j w[c][j] * template[t*stride - pad + j]. */
+int fv_noise_conv(const float* tpl, const float* w, const float* bias, float* out32, int B, int L_audio, int L_out,
+                  int C, int pitch, int k, int stride, int pad, void* stream);
+
+/* RefineGAN helpers (refinegan.py:124-127,222,252,302-313): elementwise/linear-resample glue, channels-last.
+ * fv_act_cast: out16 = fp16(act(x32 [+ noise*noise_w[c]]))   (AdaIN when noise != NULL, plain leaky otherwise)
+ * fv_resample_linear: F.interpolate(mode="linear", align_corners=False) along L; scale = 1/scale_factor. */
+int fv_act_cast(const float* x32, const float* noise, const float* noise_w, void* out16, float* out32, int act,
+                float act_param, int B, int L, int C, int in_pitch, int out_pitch, int out_coff, void* stream);
+int fv_resample_linear(const float* x32, float* out32, void* out16, int act, float act_param, int B, int L_in,
+                       int L_out, int C, int in_pitch, int out_pitch, int out_coff, float scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FV_VOCODER_H_ */

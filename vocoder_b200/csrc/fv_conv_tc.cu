@@ -1,0 +1,434 @@
+// fv_conv_tc.cu - the hot op of the generator forward: (dilated | polyphase-transposed | pointwise) Conv1d as an
+// implicit GEMM on the 5th-gen tensor cores (tcgen05.mma, fp16 operands, fp32 accumulators in TMEM), operands
+// staged by TMA into 128B-swizzled shared memory, fused bias / layer-scale / residual / MRF-mean / activation
+// epilogue.  One persistent CTA per SM, warp-specialised:
+//     warp 0    : TMA producer  (one elected lane)
+//     warp 1    : tcgen05.mma issuer (one elected lane) + TMEM allocator
+//     warps 2-5 : epilogue (TMEM -> registers -> global), one TMEM lane quarter each
+//
+// GEMM view (time on M, C_out on N, K = taps x C_in):
+//     D[q, o] = sum_tap sum_c A[b, q + off[phase][tap], c] * W[phase][tap][o][c]
+// A is the channels-last fp16 activation [B][L][pitch]: a tap / dilation shift is a different TMA box origin along
+// L, and rows outside [0, L) are zero-filled by TMA = the reference's "same" zero padding for free.
+//
+// Replaces the cuDNN/cuBLAS calls behind nn.Conv1d / nn.ConvTranspose1d / nn.Linear in
+// fish_vocoder/modules/generators/hifigan.py:29-98,158-187,214-222, bigvgan.py:149-218,
+// encoders/convnext.py:104-116,160-177 and generators/vocos.py:41,55.
+#include <mutex>
+
+#include "fv_common.cuh"
+
+namespace fv {
+
+constexpr int kTcThreads = 192;
+constexpr int kSmemLimit = 232448;  // 227 KB opt-in maximum per CTA on sm_100
+
+struct ConvTcParams {
+  CUtensorMap tmA;  // 3D {pitch, L_in, B} fp16, box {BLOCK_K, rows, 1}
+  CUtensorMap tmW;  // 2D {w_pitch, n_phase*n_taps*C_out_pad} fp16, box {BLOCK_K, BLOCK_N}
+  int B, n_phase, n_taps, k_chunks, C_out, C_out_r8, C_out_pad, q_rows, L_out;
+  int m_tiles, n_tiles, total_tiles;
+  const float* bias;
+  const float* gamma;
+  const float* residual;
+  float* out32;
+  __half* out16;
+  int res_pitch, out32_pitch, out16_pitch, accumulate, act;
+  float out_scale, act_param;
+  int16_t tap_off[FV_MAX_TAPS];
+};
+
+template <int BLOCK_N, int M_SUB, int BLOCK_K>
+struct TcCfg {
+  static constexpr int ROW_BYTES = BLOCK_K * 2;
+  static constexpr int A_SUB_BYTES = 128 * ROW_BYTES;
+  static constexpr int A_STAGE = M_SUB * A_SUB_BYTES;
+  static constexpr int A_BOX_ROWS = (M_SUB * 128 <= 256) ? M_SUB * 128 : 256;
+  static constexpr int N_A_BOX = M_SUB * 128 / A_BOX_ROWS;
+  static constexpr int B_STAGE = BLOCK_N * ROW_BYTES;
+  static constexpr int STAGE = A_STAGE + B_STAGE;
+  static constexpr int ACC_COLS = M_SUB * BLOCK_N;
+  static constexpr int ACC_BUFS = (2 * ACC_COLS <= 512) ? 2 : 1;
+  static constexpr int TMEM_COLS_RAW = ACC_BUFS * ACC_COLS;
+  static constexpr int TMEM_COLS = TMEM_COLS_RAW <= 32 ? 32 : TMEM_COLS_RAW <= 64 ? 64 : TMEM_COLS_RAW <= 128 ? 128
+                                   : TMEM_COLS_RAW <= 256 ? 256 : 512;
+  static constexpr int TAIL_BYTES = 512 + 2 * BLOCK_N * 4;  // barriers + tmem ptr + bias/gamma staging
+  static constexpr int STAGES_RAW = (kSmemLimit - 1024 - TAIL_BYTES) / STAGE;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE + TAIL_BYTES;
+  static constexpr int CH = BLOCK_N < 32 ? BLOCK_N : 32;  // epilogue column chunk
+  static_assert(STAGES >= 2, "pipeline needs at least two stages");
+  static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 16 && BLOCK_N <= 256, "invalid UMMA N");
+  static_assert(TMEM_COLS_RAW <= 512, "accumulators exceed TMEM");
+};
+
+template <int BLOCK_N, int M_SUB, int BLOCK_K>
+__global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
+  using Cfg = TcCfg<BLOCK_N, M_SUB, BLOCK_K>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE);
+  uint64_t* empty_bar = full_bar + Cfg::STAGES;
+  uint64_t* tfull_bar = empty_bar + Cfg::STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* s_bias = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE + 512);
+  float* s_gamma = s_bias + BLOCK_N;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmW);
+    for (int i = 0; i < Cfg::STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 128);
+    }
+    fence_barrier_init();
+  } else if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int k_steps = p.n_taps * p.k_chunks;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int r = tile;
+        const int n_t = r % p.n_tiles; r /= p.n_tiles;
+        const int m_t = r % p.m_tiles; r /= p.m_tiles;
+        const int b = r % p.B;
+        const int phase = r / p.B;
+        const int q0 = m_t * (M_SUB * 128);
+        const int n0 = n_t * BLOCK_N;
+        for (int tap = 0; tap < p.n_taps; ++tap) {
+          const int row0 = q0 + p.tap_off[phase * p.n_taps + tap];
+          const int wrow = (phase * p.n_taps + tap) * p.C_out_pad + n0;
+          for (int kc = 0; kc < p.k_chunks; ++kc, ++it) {
+            const int s = it % Cfg::STAGES;
+            mbar_wait(&empty_bar[s], ((it / Cfg::STAGES) & 1) ^ 1);
+            mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE);
+            uint8_t* sa = smem + s * Cfg::STAGE;
+#pragma unroll
+            for (int bx = 0; bx < Cfg::N_A_BOX; ++bx)
+              tma_load_3d(sa + bx * Cfg::A_BOX_ROWS * Cfg::ROW_BYTES, &p.tmA, &full_bar[s], kc * BLOCK_K,
+                          row0 + bx * Cfg::A_BOX_ROWS, b);
+            tma_load_2d(sa + Cfg::A_STAGE, &p.tmW, &full_bar[s], kc * BLOCK_K, wrow);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(128, BLOCK_N);
+      uint32_t it = 0, tile_i = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tile_i) {
+        const uint32_t buf = tile_i % Cfg::ACC_BUFS;
+        mbar_wait(&tempty_bar[buf], ((tile_i / Cfg::ACC_BUFS) & 1) ^ 1);
+        tc_fence_after();
+        for (int st = 0; st < k_steps; ++st, ++it) {
+          const int s = it % Cfg::STAGES;
+          mbar_wait(&full_bar[s], (it / Cfg::STAGES) & 1);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(smem + s * Cfg::STAGE);
+          const uint32_t b_base = a_base + Cfg::A_STAGE;
+#pragma unroll
+          for (int sub = 0; sub < M_SUB; ++sub) {
+#pragma unroll
+            for (int kk = 0; kk < BLOCK_K / 16; ++kk) {
+              const uint64_t da = make_kmajor_desc(a_base + sub * Cfg::A_SUB_BYTES + kk * 32, Cfg::ROW_BYTES);
+              const uint64_t db = make_kmajor_desc(b_base + kk * 32, Cfg::ROW_BYTES);
+              umma_f16_ss(tmem_base + (buf * M_SUB + sub) * BLOCK_N, da, db, idesc, (st > 0 || kk > 0) ? 1u : 0u);
+            }
+          }
+          umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
+        }
+        umma_commit(&tfull_bar[buf]);  // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps
+    const int quarter = warp & 3;            // TMEM lane quarter this warp may access
+    const int tid_e = threadIdx.x - 64;      // 0..127
+    uint32_t tile_i = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tile_i) {
+      int r = tile;
+      const int n_t = r % p.n_tiles; r /= p.n_tiles;
+      const int m_t = r % p.m_tiles; r /= p.m_tiles;
+      const int b = r % p.B;
+      const int phase = r / p.B;
+      const int q0 = m_t * (M_SUB * 128);
+      const int n0 = n_t * BLOCK_N;
+      const uint32_t buf = tile_i % Cfg::ACC_BUFS;
+
+      named_bar_sync(1, 128);  // previous tile's readers of s_bias/s_gamma are done
+      for (int i = tid_e; i < BLOCK_N; i += 128) {
+        const int col = n0 + i;
+        s_bias[i] = (p.bias != nullptr && col < p.C_out) ? p.bias[col] : 0.f;
+        s_gamma[i] = (p.gamma != nullptr && col < p.C_out) ? p.gamma[col] : 1.f;
+      }
+      named_bar_sync(1, 128);
+
+      mbar_wait(&tfull_bar[buf], (tile_i / Cfg::ACC_BUFS) & 1);
+      tc_fence_after();
+
+#pragma unroll 1
+      for (int sub = 0; sub < M_SUB; ++sub) {
+        const int q = q0 + sub * 128 + quarter * 32 + lane;
+        const int orow = q * p.n_phase + phase;
+        const bool row_ok = (q < p.q_rows) && (orow < p.L_out);
+        const size_t grow = static_cast<size_t>(b) * p.L_out + orow;
+#pragma unroll 1
+        for (int ch = 0; ch < BLOCK_N / Cfg::CH; ++ch) {
+          const int cbase = n0 + ch * Cfg::CH;
+          uint32_t acc[32];
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                                 (buf * M_SUB + sub) * BLOCK_N + ch * Cfg::CH;
+          if constexpr (Cfg::CH == 32) tmem_ld_32x32b_x32(taddr, acc);
+          else tmem_ld_32x32b_x16(taddr, acc);
+
+          // issue the global reads this chunk needs while the TMEM load is in flight
+          float4 res[Cfg::CH / 4];
+          float4 old[Cfg::CH / 4];
+#pragma unroll
+          for (int g = 0; g < Cfg::CH / 4; ++g) {
+            res[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+            old[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int col = cbase + 4 * g;
+            if (row_ok && col < p.C_out_r8) {
+              if (p.residual != nullptr)
+                res[g] = *reinterpret_cast<const float4*>(p.residual + grow * p.res_pitch + col);
+              if (p.accumulate && p.out32 != nullptr)
+                old[g] = *reinterpret_cast<const float4*>(p.out32 + grow * p.out32_pitch + col);
+            }
+          }
+          tmem_ld_wait();
+          if (sub == M_SUB - 1 && ch == BLOCK_N / Cfg::CH - 1) {
+            // every TMEM read of this accumulator buffer is complete: hand it back to the MMA warp
+            tc_fence_before();
+            mbar_arrive(&tempty_bar[buf]);
+          }
+
+          float o[Cfg::CH];
+#pragma unroll
+          for (int g = 0; g < Cfg::CH / 4; ++g) {
+            const float rr[4] = {res[g].x, res[g].y, res[g].z, res[g].w};
+            const float oo[4] = {old[g].x, old[g].y, old[g].z, old[g].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int i = 4 * g + e;
+              float v = __uint_as_float(acc[i]) + s_bias[ch * Cfg::CH + i];
+              v = v * s_gamma[ch * Cfg::CH + i] + rr[e];
+              o[i] = v * p.out_scale + oo[e];
+            }
+          }
+          if (p.out32 != nullptr && row_ok) {
+#pragma unroll
+            for (int g = 0; g < Cfg::CH / 4; ++g) {
+              const int col = cbase + 4 * g;
+              if (col < p.C_out_r8)
+                *reinterpret_cast<float4*>(p.out32 + grow * p.out32_pitch + col) =
+                    make_float4(o[4 * g], o[4 * g + 1], o[4 * g + 2], o[4 * g + 3]);
+            }
+          }
+          if (p.out16 != nullptr && row_ok) {
+            if (p.act == FV_ACT_POLAR) {
+#pragma unroll
+              for (int i = 0; i < Cfg::CH; i += 2) {
+                const float m = fminf(expf(o[i]), 100.f);
+                float sn, cs;
+                sincosf(o[i + 1], &sn, &cs);
+                o[i] = m * cs;
+                o[i + 1] = m * sn;
+              }
+            } else if (p.act != FV_ACT_NONE) {
+#pragma unroll
+              for (int i = 0; i < Cfg::CH; ++i) o[i] = act_apply(o[i], p.act, p.act_param);
+            }
+#pragma unroll
+            for (int g = 0; g < Cfg::CH / 8; ++g) {
+              const int col = cbase + 8 * g;
+              if (col < p.C_out_r8) {
+                uint4 pk;
+                pk.x = pack_half2_sat(o[8 * g + 0], o[8 * g + 1]);
+                pk.y = pack_half2_sat(o[8 * g + 2], o[8 * g + 3]);
+                pk.z = pack_half2_sat(o[8 * g + 4], o[8 * g + 5]);
+                pk.w = pack_half2_sat(o[8 * g + 6], o[8 * g + 7]);
+                *reinterpret_cast<uint4*>(p.out16 + grow * p.out16_pitch + col) = pk;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side: tensor maps + dispatch
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  });
+  return fn;
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+static CUtensorMapSwizzle swizzle_for(int row_bytes) {
+  return row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+template <int BLOCK_N, int M_SUB, int BLOCK_K>
+static int launch_tc(const fv_conv_desc* d, ConvTcParams& p, cudaStream_t stream) {
+  using Cfg = TcCfg<BLOCK_N, M_SUB, BLOCK_K>;
+  EncodeTiledFn enc = get_encode_fn();
+  FV_REQUIRE(enc != nullptr, FV_E_DRIVER, "cuTensorMapEncodeTiled not available from the driver");
+
+  {  // activations: {pitch, L_in, B}
+    cuuint64_t dims[3] = {(cuuint64_t)d->a_pitch, (cuuint64_t)d->L_in, (cuuint64_t)d->B};
+    cuuint64_t strides[2] = {(cuuint64_t)d->a_pitch * 2, (cuuint64_t)d->a_pitch * 2 * (cuuint64_t)d->L_in};
+    cuuint32_t box[3] = {(cuuint32_t)BLOCK_K, (cuuint32_t)Cfg::A_BOX_ROWS, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&p.tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(d->a), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(Cfg::ROW_BYTES), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    FV_REQUIRE(r == CUDA_SUCCESS, FV_E_DRIVER, "cuTensorMapEncodeTiled(A) failed: %d", (int)r);
+  }
+  {  // weights: {w_pitch, n_phase*n_taps*C_out_pad}
+    cuuint64_t dims[2] = {(cuuint64_t)d->w_pitch, (cuuint64_t)d->n_phase * d->n_taps * d->C_out_pad};
+    cuuint64_t strides[1] = {(cuuint64_t)d->w_pitch * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)BLOCK_N};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&p.tmW, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(d->w), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(Cfg::ROW_BYTES), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    FV_REQUIRE(r == CUDA_SUCCESS, FV_E_DRIVER, "cuTensorMapEncodeTiled(W) failed: %d", (int)r);
+  }
+  p.k_chunks = ceil_div(d->a_pitch, BLOCK_K);
+  p.m_tiles = ceil_div(p.q_rows, M_SUB * 128);
+  p.n_tiles = ceil_div(d->C_out, BLOCK_N);
+  FV_REQUIRE(p.n_tiles * BLOCK_N <= d->C_out_pad, FV_E_BADARG, "C_out_pad %d too small for %d tiles of %d",
+             d->C_out_pad, p.n_tiles, BLOCK_N);
+  const long long total = (long long)p.m_tiles * p.n_tiles * d->B * d->n_phase;
+  FV_REQUIRE(total > 0 && total < (1ll << 30), FV_E_BADARG, "bad tile count %lld", total);
+  p.total_tiles = (int)total;
+
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, M_SUB, BLOCK_K>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+  });
+  int rc = check_cuda(attr_err, "cudaFuncSetAttribute(conv_tc_kernel)");
+  if (rc) return rc;
+  const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  conv_tc_kernel<BLOCK_N, M_SUB, BLOCK_K><<<grid, kTcThreads, Cfg::SMEM_BYTES, stream>>>(p);
+  FV_CHECK_LAUNCH("conv_tc_kernel");
+  return 0;
+}
+
+template <int BLOCK_N, int M_SUB>
+static int dispatch_k(const fv_conv_desc* d, ConvTcParams& p, cudaStream_t s) {
+  if (d->a_pitch > 32) return launch_tc<BLOCK_N, M_SUB, 64>(d, p, s);
+  if constexpr (M_SUB == 2) {
+    if (d->a_pitch > 16) return launch_tc<BLOCK_N, 2, 32>(d, p, s);
+    return launch_tc<BLOCK_N, 2, 16>(d, p, s);
+  } else {
+    return launch_tc<BLOCK_N, M_SUB, 64>(d, p, s);  // small-K variants only exist for M_SUB == 2
+  }
+}
+
+template <int BLOCK_N>
+static int dispatch_m(const fv_conv_desc* d, ConvTcParams& p, cudaStream_t s, int m_sub) {
+  if (m_sub == 1) return dispatch_k<BLOCK_N, 1>(d, p, s);
+  return dispatch_k<BLOCK_N, 2>(d, p, s);
+}
+
+int pick_block_n(int C_out) {
+  if (C_out <= 16) return 16;
+  if (C_out <= 32) return 32;
+  if (C_out <= 64) return 64;
+  if (C_out <= 128) return 128;
+  const int pad128 = round_up(C_out, 128), pad256 = round_up(C_out, 256);
+  return pad256 <= pad128 ? 256 : 128;
+}
+
+// Called by fv_conv1d (fv_api.cu) after argument validation.  m_sub_override / block_n_override: 0 = heuristic.
+int conv1d_tc(const fv_conv_desc* d, cudaStream_t stream, int block_n_override, int m_sub_override) {
+  ConvTcParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = d->B;
+  p.n_phase = d->n_phase;
+  p.n_taps = d->n_taps;
+  p.C_out = d->C_out;
+  p.C_out_r8 = round_up(d->C_out, 8);
+  p.C_out_pad = d->C_out_pad;
+  p.L_out = d->L_out;
+  p.q_rows = ceil_div(d->L_out, d->n_phase);
+  p.bias = d->bias;
+  p.gamma = d->gamma;
+  p.residual = d->residual;
+  p.out32 = d->out32;
+  p.out16 = reinterpret_cast<__half*>(d->out16);
+  p.res_pitch = d->res_pitch;
+  p.out32_pitch = d->out32_pitch;
+  p.out16_pitch = d->out16_pitch;
+  p.accumulate = d->accumulate;
+  p.act = d->act;
+  p.out_scale = d->out_scale;
+  p.act_param = d->act_param;
+  for (int i = 0; i < d->n_phase * d->n_taps; ++i) p.tap_off[i] = (int16_t)d->tap_off[i];
+
+  const int bn = block_n_override ? block_n_override : pick_block_n(d->C_out);
+  // two 128-row accumulators per CTA share every weight tile; a single one when the sequence is short
+  int m_sub = m_sub_override ? m_sub_override : (p.q_rows > 128 ? 2 : 1);
+  if (d->a_pitch <= 32) m_sub = 2;
+  switch (bn) {
+    case 16: return dispatch_m<16>(d, p, stream, m_sub);
+    case 32: return dispatch_m<32>(d, p, stream, m_sub);
+    case 64: return dispatch_m<64>(d, p, stream, m_sub);
+    case 128: return dispatch_m<128>(d, p, stream, m_sub);
+    case 256: return dispatch_m<256>(d, p, stream, m_sub);
+    default: return set_error(FV_E_BADARG, "unsupported BLOCK_N %d", bn);
+  }
+}
+
+}  // namespace fv

@@ -1,0 +1,559 @@
+// fv_simt.cu - CUDA-core kernels of the generator forward: layout entry/exit, conv_post(+tanh), the fused
+// anti-aliased Snake, depthwise-conv + LayerNorm, ISTFT overlap-add, the template (noise_convs) path, RefineGAN
+// glue, and a CUDA-core implementation of fv_conv1d with semantics identical to the tcgen05 kernel (bring-up /
+// cross-check engine).  All HBM-bound: coalesced along the channel axis of the channels-last layout, 16-byte
+// vector accesses where the layout allows, grids sized from the problem (>= several waves of 148 SMs at the
+// BASELINE shapes).
+#include "fv_common.cuh"
+
+namespace fv {
+
+// ------------------------------------------------------------------------------------------------
+// fv_conv1d, CUDA-core engine (one thread = one output row x one column pair)
+// ------------------------------------------------------------------------------------------------
+struct ConvSimtParams {
+  const __half* a;
+  const __half* w;
+  int B, L_in, a_pitch, n_phase, n_taps, C_out, C_out_r8, C_out_pad, w_pitch, L_out;
+  const float* bias;
+  const float* gamma;
+  const float* residual;
+  float* out32;
+  __half* out16;
+  int res_pitch, out32_pitch, out16_pitch, accumulate, act;
+  float out_scale, act_param;
+  int16_t tap_off[FV_MAX_TAPS];
+};
+
+__global__ void conv_simt_kernel(const __grid_constant__ ConvSimtParams p) {
+  const int half_cols = p.C_out_r8 / 2;
+  const long long total = (long long)p.B * p.L_out * half_cols;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int col = (int)(idx % half_cols) * 2;
+    const long long grow = idx / half_cols;
+    const int b = (int)(grow / p.L_out);
+    const int orow = (int)(grow % p.L_out);
+    const int phase = orow % p.n_phase;
+    const int q = orow / p.n_phase;
+    float acc[2] = {0.f, 0.f};
+    const int kmax = p.a_pitch < p.w_pitch ? p.a_pitch : p.w_pitch;
+    for (int tap = 0; tap < p.n_taps; ++tap) {
+      const int r = q + p.tap_off[phase * p.n_taps + tap];
+      if (r < 0 || r >= p.L_in) continue;
+      const __half* arow = p.a + ((size_t)b * p.L_in + r) * p.a_pitch;
+      for (int e = 0; e < 2; ++e) {
+        if (col + e >= p.C_out) continue;
+        const __half* wrow = p.w + ((size_t)(phase * p.n_taps + tap) * p.C_out_pad + col + e) * p.w_pitch;
+        float s = 0.f;
+        for (int c = 0; c < kmax; ++c) s = fmaf(__half2float(arow[c]), __half2float(wrow[c]), s);
+        acc[e] += s;
+      }
+    }
+    float o[2];
+    for (int e = 0; e < 2; ++e) {
+      const int c = col + e;
+      float v = acc[e] + ((p.bias && c < p.C_out) ? p.bias[c] : 0.f);
+      v *= (p.gamma && c < p.C_out) ? p.gamma[c] : 1.f;
+      if (p.residual) v += p.residual[grow * p.res_pitch + c];
+      v *= p.out_scale;
+      if (p.accumulate && p.out32) v += p.out32[grow * p.out32_pitch + c];
+      o[e] = v;
+    }
+    if (p.out32) {
+      p.out32[grow * p.out32_pitch + col] = o[0];
+      p.out32[grow * p.out32_pitch + col + 1] = o[1];
+    }
+    if (p.out16) {
+      if (p.act == FV_ACT_POLAR) {
+        const float m = fminf(expf(o[0]), 100.f);
+        float sn, cs;
+        sincosf(o[1], &sn, &cs);
+        o[0] = m * cs;
+        o[1] = m * sn;
+      } else {
+        o[0] = act_apply(o[0], p.act, p.act_param);
+        o[1] = act_apply(o[1], p.act, p.act_param);
+      }
+      p.out16[grow * p.out16_pitch + col] = to_half_sat(o[0]);
+      p.out16[grow * p.out16_pitch + col + 1] = to_half_sat(o[1]);
+    }
+  }
+}
+
+int conv1d_simt(const fv_conv_desc* d, cudaStream_t stream) {
+  ConvSimtParams p;
+  memset(&p, 0, sizeof(p));
+  p.a = reinterpret_cast<const __half*>(d->a);
+  p.w = reinterpret_cast<const __half*>(d->w);
+  p.B = d->B; p.L_in = d->L_in; p.a_pitch = d->a_pitch; p.n_phase = d->n_phase; p.n_taps = d->n_taps;
+  p.C_out = d->C_out; p.C_out_r8 = round_up(d->C_out, 8); p.C_out_pad = d->C_out_pad; p.w_pitch = d->w_pitch;
+  p.L_out = d->L_out; p.bias = d->bias; p.gamma = d->gamma; p.residual = d->residual; p.out32 = d->out32;
+  p.out16 = reinterpret_cast<__half*>(d->out16); p.res_pitch = d->res_pitch; p.out32_pitch = d->out32_pitch;
+  p.out16_pitch = d->out16_pitch; p.accumulate = d->accumulate; p.act = d->act; p.out_scale = d->out_scale;
+  p.act_param = d->act_param;
+  for (int i = 0; i < d->n_phase * d->n_taps; ++i) p.tap_off[i] = (int16_t)d->tap_off[i];
+  const long long total = (long long)p.B * p.L_out * (p.C_out_r8 / 2);
+  const int threads = 128;
+  long long blocks = (total + threads - 1) / threads;
+  if (blocks > 148 * 64) blocks = 148 * 64;
+  conv_simt_kernel<<<(int)blocks, threads, 0, stream>>>(p);
+  FV_CHECK_LAUNCH("conv_simt_kernel");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// layout entry / exit: [B][C][T] fp32 <-> channels-last
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_input_kernel(const float* __restrict__ x, __half* __restrict__ out, int C, int T, int pitch) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {  // read: t fastest
+    const int c = c0 + i, t = t0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && t < T) ? x[((size_t)b * C + c) * T + t] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {  // write: c fastest
+    const int t = t0 + i, c = c0 + threadIdx.x;
+    if (t < T && c < pitch) out[((size_t)b * T + t) * pitch + c] = __float2half_rn(tile[threadIdx.x][i]);
+  }
+}
+
+__global__ void unpack_output_kernel(const float* __restrict__ x, float* __restrict__ out, int C, int L, int pitch) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {  // read: c fastest
+    const int t = t0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (t < L && c < C) ? x[((size_t)b * L + t) * pitch + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {  // write: t fastest
+    const int c = c0 + i, t = t0 + threadIdx.x;
+    if (c < C && t < L) out[((size_t)b * C + c) * L + t] = tile[threadIdx.x][i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// conv_post (+tanh): C_out == 1.  G lanes cooperate on one output sample (channel axis split across lanes,
+// 16-byte fp16 loads), partial dot products combined with warp shuffles.
+// ------------------------------------------------------------------------------------------------
+template <int G>
+__global__ void conv_post_kernel(const __half* __restrict__ a, const float* __restrict__ w, const float* bias,
+                                 float* __restrict__ wav, int B, int L, int C, int pitch, int k, int apply_tanh) {
+  extern __shared__ float s_w[];  // [k][pitch]
+  for (int i = threadIdx.x; i < k * pitch; i += blockDim.x) {
+    const int j = i / pitch, c = i % pitch;
+    s_w[i] = c < C ? w[j * C + c] : 0.f;
+  }
+  __syncthreads();
+  const int g = threadIdx.x % G;
+  const int half_k = (k - 1) / 2;
+  const int chunks = pitch / 8;
+  const long long total = (long long)B * L;
+  const int groups = blockDim.x / G;
+  const long long per_iter = (long long)gridDim.x * groups;
+  const long long n_iter = (total + per_iter - 1) / per_iter;
+  for (long long it = 0; it < n_iter; ++it) {  // uniform trip count: every lane reaches the shuffles
+    const long long s = (it * gridDim.x + blockIdx.x) * groups + threadIdx.x / G;
+    const bool live = s < total;
+    float acc = 0.f;
+    if (live) {
+      const int b = (int)(s / L), t = (int)(s % L);
+      for (int j = 0; j < k; ++j) {
+        const int r = t + j - half_k;
+        if (r < 0 || r >= L) continue;
+        const __half* row = a + ((size_t)b * L + r) * pitch;
+        for (int ci = g; ci < chunks; ci += G) {
+          const uint4 pk = *reinterpret_cast<const uint4*>(row + ci * 8);
+          const __half2* h2 = reinterpret_cast<const __half2*>(&pk);
+          const float* wj = s_w + j * pitch + ci * 8;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = __half22float2(h2[e]);
+            acc = fmaf(f.x, wj[2 * e], acc);
+            acc = fmaf(f.y, wj[2 * e + 1], acc);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int off = G / 2; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (live && g == 0) {
+      const float v = acc + (bias ? bias[0] : 0.f);
+      wav[s] = apply_tanh ? tanhf(v) : v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// anti-aliased Snake: up 2x (polyphase 6+6 taps) -> x + sin^2(a x)/(b+1e-9) -> down 2x (12 taps), one pass.
+// One thread = one channel x SN_T consecutive time steps; the activated 2x signal lives only in registers.
+// ------------------------------------------------------------------------------------------------
+constexpr int SN_T = 16;
+struct SnakeFilt {
+  float up[12];
+  float dn[12];
+};
+
+__device__ __forceinline__ float snake_fn(float u, float a, float inv_b) {
+  const float s = sinf(u * a);
+  return fmaf(inv_b * s, s, u);
+}
+
+__global__ void __launch_bounds__(256) snake_aa_kernel(const float* __restrict__ x, __half* __restrict__ out,
+                                                       const float* __restrict__ alpha, const float* __restrict__ beta,
+                                                       const SnakeFilt f, int logscale, int B, int L, int C, int pitch,
+                                                       int n_chunks) {
+  const long long total = (long long)B * n_chunks * pitch;
+  const long long item = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (item >= total) return;
+  const int c = (int)(item % pitch);
+  const int chunk = (int)((item / pitch) % n_chunks);
+  const int b = (int)(item / ((long long)pitch * n_chunks));
+  const int t0 = chunk * SN_T;
+  __half* orow = out + ((size_t)b * L) * pitch + c;
+  if (c >= C) {  // padded channels stay zero
+    for (int tt = 0; tt < SN_T && t0 + tt < L; ++tt) orow[(size_t)(t0 + tt) * pitch] = __float2half_rn(0.f);
+    return;
+  }
+  float a = alpha[c];
+  float bb = beta ? beta[c] : a;
+  if (logscale) {
+    a = expf(a);
+    bb = expf(bb);
+  }
+  const float inv_b = 1.0f / (bb + 1e-9f);
+  const float* xc = x + ((size_t)b * L) * pitch + c;
+
+  float xs[SN_T + 10];
+#pragma unroll
+  for (int i = 0; i < SN_T + 10; ++i) {
+    int t = t0 - 5 + i;
+    t = t < 0 ? 0 : (t > L - 1 ? L - 1 : t);  // replicate edge of the INPUT (first filter)
+    xs[i] = xc[(size_t)t * pitch];
+  }
+  // v[i] = act(up[n]), n = 2*t0 - 5 + i
+  float v[2 * SN_T + 10];
+#pragma unroll
+  for (int i = 0; i < 2 * SN_T + 10; ++i) {
+    float u = 0.f;
+    if ((i & 1) == 0) {  // n odd: up[2s+1] = 2 * sum_q f[2q] * x[s+3-q],  xs index i/2 + 5 - q
+#pragma unroll
+      for (int q = 0; q < 6; ++q) u = fmaf(f.up[2 * q], xs[i / 2 + 5 - q], u);
+    } else {             // n even: up[2s] = 2 * sum_q f[2q+1] * x[s+2-q],  xs index (i+9)/2 - q
+#pragma unroll
+      for (int q = 0; q < 6; ++q) u = fmaf(f.up[2 * q + 1], xs[(i + 9) / 2 - q], u);
+    }
+    v[i] = snake_fn(2.0f * u, a, inv_b);
+  }
+  // replicate edges of the ACTIVATED 2x signal (second filter pads its own input)
+  if (t0 == 0) {
+#pragma unroll
+    for (int i = 0; i < 5; ++i) v[i] = v[5];  // n < 0 -> v[n = 0]
+  }
+  const int n_last = 2 * L - 1;
+  if (2 * t0 - 5 + (2 * SN_T + 9) > n_last) {
+    // v[n = 2L-1] = act(2 * sum_q f[2q] * x~[L+2-q])
+    float u = 0.f;
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+      int t = L + 2 - q;
+      t = t > L - 1 ? L - 1 : (t < 0 ? 0 : t);
+      u = fmaf(f.up[2 * q], xc[(size_t)t * pitch], u);
+    }
+    const float vl = snake_fn(2.0f * u, a, inv_b);
+#pragma unroll
+    for (int i = 0; i < 2 * SN_T + 10; ++i)
+      if (2 * t0 - 5 + i > n_last) v[i] = vl;
+  }
+#pragma unroll
+  for (int tt = 0; tt < SN_T; ++tt) {
+    if (t0 + tt < L) {
+      float o = 0.f;
+#pragma unroll
+      for (int j = 0; j < 12; ++j) o = fmaf(f.dn[j], v[2 * tt + j], o);
+      orow[(size_t)(t0 + tt) * pitch] = to_half_sat(o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// depthwise conv (k taps, zero pad) + LayerNorm over C, one warp per (b, t) row.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) dwconv_ln_kernel(const float* __restrict__ x, __half* __restrict__ out16,
+                                                        float* __restrict__ out32, const float* __restrict__ dw_w,
+                                                        const float* __restrict__ dw_b, const float* __restrict__ ln_w,
+                                                        const float* __restrict__ ln_b, float eps, int B, int T, int C,
+                                                        int pitch, int k) {
+  extern __shared__ float s_h[];  // [warps][pitch]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + warp;
+  if (row >= (long long)B * T) return;
+  const int b = (int)(row / T), t = (int)(row % T);
+  float* h = s_h + warp * pitch;
+  const float* xb = x + (size_t)b * T * pitch;
+  const int half_k = (k - 1) / 2;
+  float sum = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    float acc;
+    if (k > 0) {
+      acc = dw_b[c];
+      for (int j = 0; j < k; ++j) {
+        const int r = t + j - half_k;
+        if (r >= 0 && r < T) acc = fmaf(dw_w[c * k + j], xb[(size_t)r * pitch + c], acc);
+      }
+    } else {
+      acc = xb[(size_t)t * pitch + c];
+    }
+    h[c] = acc;
+    sum += acc;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+  const float mean = sum / C;
+  float var = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    const float dlt = h[c] - mean;
+    var = fmaf(dlt, dlt, var);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) var += __shfl_xor_sync(0xffffffffu, var, off);
+  const float rstd = 1.0f / sqrtf(var / C + eps);
+  for (int c = lane; c < pitch; c += 32) {
+    const float y = c < C ? fmaf((h[c] - mean) * rstd, ln_w[c], ln_b[c]) : 0.f;
+    if (out16) out16[(size_t)row * pitch + c] = to_half_sat(y);
+    if (out32) out32[(size_t)row * pitch + c] = y;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// ISTFT("same") overlap-add + envelope normalisation
+// ------------------------------------------------------------------------------------------------
+__global__ void istft_ola_kernel(const float* __restrict__ frames, const float* __restrict__ window,
+                                 float* __restrict__ wav, int B, int T, int n_fft, int hop, int frame_pitch) {
+  const long long total = (long long)B * T * hop;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int Lw = T * hop;
+  const int b = (int)(idx / Lw), s = (int)(idx % Lw);
+  const int pad = (n_fft - hop) / 2;
+  const int pos = s + pad;
+  int f_hi = pos / hop;
+  if (f_hi > T - 1) f_hi = T - 1;
+  int f_lo = (pos - n_fft + hop) / hop;  // ceil((pos - n_fft + 1) / hop) for pos - n_fft + 1 > 0
+  if (pos - n_fft + 1 <= 0) f_lo = 0;
+  float acc = 0.f, env = 0.f;
+  for (int f = f_lo; f <= f_hi; ++f) {
+    const int i = pos - f * hop;
+    if (i < 0 || i >= n_fft) continue;
+    acc += frames[((size_t)b * T + f) * frame_pitch + i];
+    const float wv = window[i];
+    env = fmaf(wv, wv, env);
+  }
+  wav[idx] = acc / env;
+}
+
+// ------------------------------------------------------------------------------------------------
+// template path: noise_convs[i](template), C_in == 1
+// ------------------------------------------------------------------------------------------------
+__global__ void noise_conv_kernel(const float* __restrict__ tpl, const float* __restrict__ w,
+                                  const float* __restrict__ bias, float* __restrict__ out, int B, int L_audio, int L_out,
+                                  int C, int pitch, int k, int stride, int pad) {
+  const long long total = (long long)B * L_out * pitch;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = (int)(idx % pitch);
+  const long long grow = idx / pitch;
+  const int b = (int)(grow / L_out), t = (int)(grow % L_out);
+  float acc = 0.f;
+  if (c < C) {
+    acc = bias[c];
+    const float* tb = tpl + (size_t)b * L_audio;
+    for (int j = 0; j < k; ++j) {
+      const int r = t * stride - pad + j;
+      if (r >= 0 && r < L_audio) acc = fmaf(w[c * k + j], tb[r], acc);
+    }
+  }
+  out[idx] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// RefineGAN glue
+// ------------------------------------------------------------------------------------------------
+__global__ void act_cast_kernel(const float* __restrict__ x, const float* __restrict__ noise,
+                                const float* __restrict__ noise_w, __half* __restrict__ out16,
+                                float* __restrict__ out32, int act, float param, long long rows, int C, int in_pitch,
+                                int out_pitch, int out_coff) {
+  const long long total = rows * C;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = (int)(idx % C);
+  const long long r = idx / C;
+  float v = x[r * in_pitch + c];
+  if (noise) v = fmaf(noise[r * in_pitch + c], noise_w[c], v);
+  v = act_apply(v, act, param);
+  if (out16) out16[r * out_pitch + out_coff + c] = to_half_sat(v);
+  if (out32) out32[r * out_pitch + out_coff + c] = v;
+}
+
+__global__ void resample_linear_kernel(const float* __restrict__ x, float* __restrict__ out32,
+                                       __half* __restrict__ out16, int act, float param, int B, int L_in, int L_out,
+                                       int C, int in_pitch, int out_pitch, int out_coff, float scale) {
+  const long long total = (long long)B * L_out * C;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = (int)(idx % C);
+  const long long grow = idx / C;
+  const int b = (int)(grow / L_out), t = (int)(grow % L_out);
+  float src = (t + 0.5f) * scale - 0.5f;  // align_corners=False
+  if (src < 0.f) src = 0.f;
+  int i0 = (int)src;
+  if (i0 > L_in - 1) i0 = L_in - 1;
+  const int i1 = i0 + 1 < L_in ? i0 + 1 : L_in - 1;
+  const float lam = src - (float)i0;
+  const float* xb = x + (size_t)b * L_in * in_pitch + c;
+  float v = (1.0f - lam) * xb[(size_t)i0 * in_pitch] + lam * xb[(size_t)i1 * in_pitch];
+  v = act_apply(v, act, param);
+  if (out32) out32[grow * out_pitch + out_coff + c] = v;
+  if (out16) out16[grow * out_pitch + out_coff + c] = to_half_sat(v);
+}
+
+}  // namespace fv
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+using namespace fv;
+
+static inline int grid1d(long long total, int threads) { return (int)((total + threads - 1) / threads); }
+
+extern "C" int fv_pack_input(const float* x, void* out16, int B, int C, int T, int pitch, void* stream) {
+  FV_REQUIRE(x && out16 && B > 0 && C > 0 && T > 0 && pitch >= C && pitch % 8 == 0, FV_E_BADARG,
+             "fv_pack_input: bad arguments (B=%d C=%d T=%d pitch=%d)", B, C, T, pitch);
+  dim3 grid(ceil_div(T, 32), ceil_div(pitch, 32), B), block(32, 8);
+  pack_input_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(x, (__half*)out16, C, T, pitch);
+  FV_CHECK_LAUNCH("pack_input_kernel");
+  return 0;
+}
+
+extern "C" int fv_unpack_output(const float* x32, float* out, int B, int C, int L, int pitch, void* stream) {
+  FV_REQUIRE(x32 && out && B > 0 && C > 0 && L > 0 && pitch >= C, FV_E_BADARG, "fv_unpack_output: bad arguments");
+  dim3 grid(ceil_div(L, 32), ceil_div(C, 32), B), block(32, 8);
+  unpack_output_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(x32, out, C, L, pitch);
+  FV_CHECK_LAUNCH("unpack_output_kernel");
+  return 0;
+}
+
+extern "C" int fv_conv_post_tanh(const void* a16, const float* w32, const float* bias, float* wav, int B, int L, int C,
+                                 int pitch, int k, int apply_tanh, void* stream) {
+  FV_REQUIRE(a16 && w32 && wav && B > 0 && L > 0 && C > 0 && pitch >= C && pitch % 8 == 0 && k > 0 && (k & 1),
+             FV_E_BADARG, "fv_conv_post_tanh: bad arguments (C=%d pitch=%d k=%d)", C, pitch, k);
+  const int smem = k * pitch * (int)sizeof(float);
+  FV_REQUIRE(smem <= 48 * 1024, FV_E_UNSUPPORTED, "fv_conv_post_tanh: k*pitch too large (%d bytes)", smem);
+  const int chunks = pitch / 8;
+  const int threads = 256;
+  const long long total = (long long)B * L;
+#define FV_POST(G)                                                                                          \
+  {                                                                                                         \
+    long long blocks = (total + (threads / G) - 1) / (threads / G);                                         \
+    if (blocks > 148 * 16) blocks = 148 * 16;                                                               \
+    conv_post_kernel<G><<<(int)blocks, threads, smem, (cudaStream_t)stream>>>(                              \
+        (const __half*)a16, w32, bias, wav, B, L, C, pitch, k, apply_tanh);                                 \
+  }
+  if (chunks <= 1) FV_POST(1)
+  else if (chunks <= 2) FV_POST(2)
+  else if (chunks <= 4) FV_POST(4)
+  else if (chunks <= 8) FV_POST(8)
+  else if (chunks <= 16) FV_POST(16)
+  else FV_POST(32)
+#undef FV_POST
+  FV_CHECK_LAUNCH("conv_post_kernel");
+  return 0;
+}
+
+extern "C" int fv_snake_aa(const float* x32, void* out16, const float* alpha, const float* beta, const float* filt_up,
+                           const float* filt_down, int logscale, int B, int L, int C, int pitch, void* stream) {
+  FV_REQUIRE(x32 && out16 && alpha && filt_up && filt_down && B > 0 && L > 0 && C > 0 && pitch >= C, FV_E_BADARG,
+             "fv_snake_aa: bad arguments");
+  SnakeFilt f;
+  // the 12 taps are tiny, deterministic buffers of the module; fetch them once per call (async, stream ordered
+  // copies would need a staging buffer - the module passes HOST copies of the taps instead, see python side)
+  for (int i = 0; i < 12; ++i) {
+    f.up[i] = filt_up[i];
+    f.dn[i] = filt_down[i];
+  }
+  const int n_chunks = ceil_div(L, SN_T);
+  const long long total = (long long)B * n_chunks * pitch;
+  snake_aa_kernel<<<grid1d(total, 256), 256, 0, (cudaStream_t)stream>>>(x32, (__half*)out16, alpha, beta, f, logscale,
+                                                                       B, L, C, pitch, n_chunks);
+  FV_CHECK_LAUNCH("snake_aa_kernel");
+  return 0;
+}
+
+extern "C" int fv_dwconv_layernorm(const float* x32, void* out16, float* out32, const float* dw_w, const float* dw_b,
+                                   const float* ln_w, const float* ln_b, float eps, int B, int T, int C, int pitch,
+                                   int k, void* stream) {
+  FV_REQUIRE(x32 && (out16 || out32) && ln_w && ln_b && B > 0 && T > 0 && C > 0 && pitch >= C, FV_E_BADARG,
+             "fv_dwconv_layernorm: bad arguments");
+  FV_REQUIRE(k <= 0 || (dw_w && dw_b && (k & 1)), FV_E_BADARG, "fv_dwconv_layernorm: bad depthwise kernel");
+  const int warps = 4;
+  const int smem = warps * pitch * (int)sizeof(float);
+  FV_REQUIRE(smem <= 48 * 1024, FV_E_UNSUPPORTED, "fv_dwconv_layernorm: C too large (%d)", C);
+  const long long rows = (long long)B * T;
+  dwconv_ln_kernel<<<(int)((rows + warps - 1) / warps), warps * 32, smem, (cudaStream_t)stream>>>(
+      x32, (__half*)out16, out32, dw_w, dw_b, ln_w, ln_b, eps, B, T, C, pitch, k);
+  FV_CHECK_LAUNCH("dwconv_ln_kernel");
+  return 0;
+}
+
+extern "C" int fv_istft_ola(const float* frames, const float* window, float* wav, int B, int T, int n_fft, int hop,
+                            int frame_pitch, void* stream) {
+  FV_REQUIRE(frames && window && wav && B > 0 && T > 0 && n_fft > 0 && hop > 0 && hop <= n_fft &&
+                 frame_pitch >= n_fft && (n_fft - hop) % 2 == 0,
+             FV_E_BADARG, "fv_istft_ola: bad arguments");
+  const long long total = (long long)B * T * hop;
+  istft_ola_kernel<<<grid1d(total, 256), 256, 0, (cudaStream_t)stream>>>(frames, window, wav, B, T, n_fft, hop,
+                                                                        frame_pitch);
+  FV_CHECK_LAUNCH("istft_ola_kernel");
+  return 0;
+}
+
+extern "C" int fv_noise_conv(const float* tpl, const float* w, const float* bias, float* out32, int B, int L_audio,
+                             int L_out, int C, int pitch, int k, int stride, int pad, void* stream) {
+  FV_REQUIRE(tpl && w && bias && out32 && B > 0 && L_audio > 0 && L_out > 0 && C > 0 && pitch >= C && k > 0 &&
+                 stride > 0,
+             FV_E_BADARG, "fv_noise_conv: bad arguments");
+  const long long total = (long long)B * L_out * pitch;
+  noise_conv_kernel<<<grid1d(total, 256), 256, 0, (cudaStream_t)stream>>>(tpl, w, bias, out32, B, L_audio, L_out, C,
+                                                                         pitch, k, stride, pad);
+  FV_CHECK_LAUNCH("noise_conv_kernel");
+  return 0;
+}
+
+extern "C" int fv_act_cast(const float* x32, const float* noise, const float* noise_w, void* out16, float* out32,
+                           int act, float act_param, int B, int L, int C, int in_pitch, int out_pitch, int out_coff,
+                           void* stream) {
+  FV_REQUIRE(x32 && (out16 || out32) && B > 0 && L > 0 && C > 0 && in_pitch >= C && out_pitch >= out_coff + C &&
+                 (noise == nullptr || noise_w != nullptr),
+             FV_E_BADARG, "fv_act_cast: bad arguments");
+  const long long rows = (long long)B * L;
+  act_cast_kernel<<<grid1d(rows * C, 256), 256, 0, (cudaStream_t)stream>>>(
+      x32, noise, noise_w, (__half*)out16, out32, act, act_param, rows, C, in_pitch, out_pitch, out_coff);
+  FV_CHECK_LAUNCH("act_cast_kernel");
+  return 0;
+}
+
+extern "C" int fv_resample_linear(const float* x32, float* out32, void* out16, int act, float act_param, int B,
+                                  int L_in, int L_out, int C, int in_pitch, int out_pitch, int out_coff, float scale,
+                                  void* stream) {
+  FV_REQUIRE(x32 && (out16 || out32) && B > 0 && L_in > 0 && L_out > 0 && C > 0 && in_pitch >= C &&
+                 out_pitch >= out_coff + C && scale > 0.f,
+             FV_E_BADARG, "fv_resample_linear: bad arguments");
+  const long long total = (long long)B * L_out * C;
+  resample_linear_kernel<<<grid1d(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      x32, out32, (__half*)out16, act, act_param, B, L_in, L_out, C, in_pitch, out_pitch, out_coff, scale);
+  FV_CHECK_LAUNCH("resample_linear_kernel");
+  return 0;
+}
