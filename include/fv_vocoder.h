@@ -27,6 +27,12 @@ extern "C" {
 
 #define FV_ABI_VERSION 1
 
+#if defined(__GNUC__)
+#define FV_API __attribute__((visibility("default")))
+#else
+#define FV_API
+#endif
+
 /* error codes (negative) */
 #define FV_E_BADARG (-1)
 #define FV_E_ALIGN (-2)
@@ -92,28 +98,28 @@ typedef struct fv_conv_desc {
   float act_param;
 } fv_conv_desc;
 
-const char* fv_last_error(void);
-int fv_abi_version(void);
+FV_API const char* fv_last_error(void);
+FV_API int fv_abi_version(void);
 /* number of kernels launched by this library since load / since the last reset (bench.py "gpu_launches") */
-int64_t fv_launch_count(void);
-void fv_reset_launch_count(void);
+FV_API int64_t fv_launch_count(void);
+FV_API void fv_reset_launch_count(void);
 
-int fv_conv1d(const fv_conv_desc* d, int engine, void* stream);
+FV_API int fv_conv1d(const fv_conv_desc* d, int engine, void* stream);
 /* tuning overrides for the tcgen05 engine (0 = built-in heuristic): N tile in {16,32,64,128,256}, 128-row
  * accumulators per CTA in {1,2}.  Process-global; meant for benchmarking sweeps. */
-void fv_set_tc_tuning(int block_n, int m_sub);
+FV_API void fv_set_tc_tuning(int block_n, int m_sub);
 
 /* mel [B][C][T] fp32 channels-first -> fp16 channels-last [B][T][pitch] (zero padded channels).
  * Entry of the path: the tensor handed to Generator.forward (hifigan.py:226, convnext.py:206). */
-int fv_pack_input(const float* x, void* out16, int B, int C, int T, int pitch, void* stream);
+FV_API int fv_pack_input(const float* x, void* out16, int B, int C, int T, int pitch, void* stream);
 
 /* fp32 channels-last [B][L][pitch] -> fp32 channels-first [B][C][L]  (leaving the path; debugging) */
-int fv_unpack_output(const float* x32, float* out, int B, int C, int L, int pitch, void* stream);
+FV_API int fv_unpack_output(const float* x32, float* out, int B, int C, int L, int pitch, void* stream);
 
 /* conv_post + tanh (hifigan.py:214-222,246-247): a16 [B][L][pitch] (already activated) * w32 [k][C] + bias
  * -> wav fp32 [B][L] (== [B,1,L]).  C_out == 1, so this is a CUDA-core dot product with a warp-shuffle
  * reduction along the channel axis. */
-int fv_conv_post_tanh(const void* a16, const float* w32, const float* bias, float* wav, int B, int L, int C,
+FV_API int fv_conv_post_tanh(const void* a16, const float* w32, const float* bias, float* wav, int B, int L, int C,
                       int pitch, int k, int apply_tanh, void* stream);
 
 /* Anti-aliased Snake / SnakeBeta = alias_free_torch.Activation1d(SnakeBeta) (bigvgan.py:226-233,335-337;
@@ -121,33 +127,33 @@ int fv_conv_post_tanh(const void* a16, const float* w32, const float* bias, floa
  * x32 [B][L][pitch] fp32 -> out16 [B][L][pitch] fp16.  alpha/beta are the raw (log-scale) parameters [C];
  * beta == NULL selects Snake (beta := alpha).  filt_up / filt_down = HOST pointers to the 12 fp32 taps (the
  * module's `upsample.filter` / `downsample.lowpass.filter` buffers; passed by value to the kernel). */
-int fv_snake_aa(const float* x32, void* out16, const float* alpha, const float* beta, const float* filt_up,
+FV_API int fv_snake_aa(const float* x32, void* out16, const float* alpha, const float* beta, const float* filt_up,
                 const float* filt_down, int logscale, int B, int L, int C, int pitch, void* stream);
 
 /* ConvNeXt block front half (convnext.py:127-129): depthwise conv k (zero pad) + LayerNorm over C (eps) -> fp16.
  * x32 [B][T][pitch] -> out16 [B][T][pitch].  dw_w [C][k], dw_b [C], ln_w/ln_b [C]. k <= 0 means "no conv"
  * (plain LayerNorm over C: convnext.py:64-74).  out32 (optional) receives the fp32 result as well. */
-int fv_dwconv_layernorm(const float* x32, void* out16, float* out32, const float* dw_w, const float* dw_b,
+FV_API int fv_dwconv_layernorm(const float* x32, void* out16, float* out32, const float* dw_w, const float* dw_b,
                         const float* ln_w, const float* ln_b, float eps, int B, int T, int C, int pitch, int k,
                         void* stream);
 
 /* ISTFT("same") tail (vocos==0.0.2 spectral_ops.ISTFT): windowed frames [B][T][n_fft] fp32 (window
  * already folded into the inverse-DFT basis) -> overlap-add, trim (win-hop)/2, divide by the hann^2 envelope.
  * wav [B][T*hop]. */
-int fv_istft_ola(const float* frames, const float* window, float* wav, int B, int T, int n_fft, int hop,
+FV_API int fv_istft_ola(const float* frames, const float* window, float* wav, int B, int T, int n_fft, int hop,
                  int frame_pitch, void* stream);
 
 /* template path (hifigan.py:191-204,233-234): noise_convs[i](template) as fp32 [B][L_i][pitch]; C_in == 1.
  * template [B][L_audio], w [C][k], bias [C]; out row t = sum_j w[c][j] * template[t*stride - pad + j]. */
-int fv_noise_conv(const float* tpl, const float* w, const float* bias, float* out32, int B, int L_audio, int L_out,
+FV_API int fv_noise_conv(const float* tpl, const float* w, const float* bias, float* out32, int B, int L_audio, int L_out,
                   int C, int pitch, int k, int stride, int pad, void* stream);
 
 /* RefineGAN helpers (refinegan.py:124-127,222,252,302-313): elementwise/linear-resample glue, channels-last.
  * fv_act_cast: out16 = fp16(act(x32 [+ noise*noise_w[c]]))   (AdaIN when noise != NULL, plain leaky otherwise)
  * fv_resample_linear: F.interpolate(mode="linear", align_corners=False) along L; scale = 1/scale_factor. */
-int fv_act_cast(const float* x32, const float* noise, const float* noise_w, void* out16, float* out32, int act,
+FV_API int fv_act_cast(const float* x32, const float* noise, const float* noise_w, void* out16, float* out32, int act,
                 float act_param, int B, int L, int C, int in_pitch, int out_pitch, int out_coff, void* stream);
-int fv_resample_linear(const float* x32, float* out32, void* out16, int act, float act_param, int B, int L_in,
+FV_API int fv_resample_linear(const float* x32, float* out32, void* out16, int act, float act_param, int B, int L_in,
                        int L_out, int C, int in_pitch, int out_pitch, int out_coff, float scale, void* stream);
 
 #ifdef __cplusplus

@@ -1,0 +1,337 @@
+"""ctypes binding of ``libfv_b200.so`` (C ABI declared in ``include/fv_vocoder.h``).
+
+PyTorch is used for device memory and streams only: every function here passes raw device pointers
+(``tensor.data_ptr()``) and the current CUDA stream to the library.  There is NO CPU fallback: if the
+shared library is missing or a tensor is not on a CUDA device the call raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfv_b200.so")
+
+ACT_NONE, ACT_SILU, ACT_LEAKY, ACT_GELU, ACT_TANH, ACT_POLAR = range(6)
+ENGINE_TC, ENGINE_SIMT = 0, 1
+MAX_TAPS = 64
+
+# every symbol include/fv_vocoder.h declares (tests check the library exports exactly these)
+EXPORTS = [
+    "fv_last_error", "fv_abi_version", "fv_launch_count", "fv_reset_launch_count", "fv_conv1d",
+    "fv_set_tc_tuning", "fv_pack_input", "fv_unpack_output", "fv_conv_post_tanh", "fv_snake_aa",
+    "fv_dwconv_layernorm", "fv_istft_ola", "fv_noise_conv", "fv_act_cast", "fv_resample_linear",
+]
+
+
+class FvError(RuntimeError):
+    pass
+
+
+class ConvDesc(ctypes.Structure):
+    """Mirror of ``struct fv_conv_desc``."""
+    _fields_ = [
+        ("a", ctypes.c_void_p), ("B", ctypes.c_int32), ("L_in", ctypes.c_int32), ("a_pitch", ctypes.c_int32),
+        ("w", ctypes.c_void_p), ("n_phase", ctypes.c_int32), ("n_taps", ctypes.c_int32),
+        ("C_out", ctypes.c_int32), ("C_out_pad", ctypes.c_int32), ("w_pitch", ctypes.c_int32),
+        ("tap_off", ctypes.POINTER(ctypes.c_int32)),
+        ("L_out", ctypes.c_int32),
+        ("bias", ctypes.c_void_p), ("gamma", ctypes.c_void_p), ("residual", ctypes.c_void_p),
+        ("res_pitch", ctypes.c_int32),
+        ("out32", ctypes.c_void_p), ("out32_pitch", ctypes.c_int32), ("accumulate", ctypes.c_int32),
+        ("out_scale", ctypes.c_float),
+        ("out16", ctypes.c_void_p), ("out16_pitch", ctypes.c_int32), ("act", ctypes.c_int32),
+        ("act_param", ctypes.c_float),
+    ]
+
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    """Load the CUDA extension; fail loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FvError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(vocoder_b200/csrc/build.sh). There is no CPU fallback for the generator forward.")
+    L = ctypes.CDLL(LIB_PATH)
+    L.fv_last_error.restype = ctypes.c_char_p
+    L.fv_abi_version.restype = ctypes.c_int
+    L.fv_launch_count.restype = ctypes.c_int64
+    L.fv_reset_launch_count.restype = None
+    L.fv_set_tc_tuning.restype = None
+    L.fv_set_tc_tuning.argtypes = [ctypes.c_int, ctypes.c_int]
+    vp, ci, cf = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+    L.fv_conv1d.argtypes = [ctypes.POINTER(ConvDesc), ci, vp]
+    L.fv_pack_input.argtypes = [vp, vp, ci, ci, ci, ci, vp]
+    L.fv_unpack_output.argtypes = [vp, vp, ci, ci, ci, ci, vp]
+    L.fv_conv_post_tanh.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, vp]
+    L.fv_snake_aa.argtypes = [vp, vp, vp, vp, ctypes.POINTER(cf), ctypes.POINTER(cf), ci, ci, ci, ci, ci, vp]
+    L.fv_dwconv_layernorm.argtypes = [vp, vp, vp, vp, vp, vp, vp, cf, ci, ci, ci, ci, ci, vp]
+    L.fv_istft_ola.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, vp]
+    L.fv_noise_conv.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, vp]
+    L.fv_act_cast.argtypes = [vp, vp, vp, vp, vp, ci, cf, ci, ci, ci, ci, ci, ci, vp]
+    L.fv_resample_linear.argtypes = [vp, vp, vp, ci, cf, ci, ci, ci, ci, ci, ci, ci, cf, vp]
+    for name in EXPORTS:
+        fn = getattr(L, name)
+        if name not in ("fv_last_error", "fv_launch_count", "fv_reset_launch_count", "fv_set_tc_tuning"):
+            fn.restype = ctypes.c_int
+    if L.fv_abi_version() != 1:
+        raise FvError("libfv_b200.so ABI version mismatch")
+    _lib = L
+    return L
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise FvError(f"{what} failed (rc={rc}): {lib().fv_last_error().decode()}")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor], dtype=None) -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise FvError("vocoder_b200 kernels need CUDA tensors (no CPU fallback)")
+    if not t.is_contiguous():
+        raise FvError("tensor must be contiguous")
+    if dtype is not None and t.dtype != dtype:
+        raise FvError(f"expected dtype {dtype}, got {t.dtype}")
+    return t.data_ptr()
+
+
+def round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+def pitch_of(channels: int) -> int:
+    """Channel pitch of a channels-last activation buffer."""
+    return round_up(channels, 8)
+
+
+def c_out_pad_of(c_out: int) -> int:
+    """Weight rows per tap: a multiple of every N tile the kernel may pick for this C_out."""
+    if c_out <= 128:
+        p = 16
+        while p < c_out:
+            p *= 2
+        return p
+    return round_up(c_out, 256)
+
+
+# ----------------------------------------------------------------------------------------------
+# packed weights
+# ----------------------------------------------------------------------------------------------
+@dataclass
+class PackedConv:
+    """Weights of one fv_conv1d call, laid out [n_phase][n_taps][C_out_pad][w_pitch] fp16."""
+    w: torch.Tensor
+    bias: Optional[torch.Tensor]
+    tap_off: Sequence[int]
+    n_phase: int
+    n_taps: int
+    c_in: int
+    c_out: int
+    c_out_pad: int
+    w_pitch: int
+
+    def __post_init__(self):
+        assert self.n_phase * self.n_taps <= MAX_TAPS, "too many taps for one call"
+        self._tap_arr = (ctypes.c_int32 * len(self.tap_off))(*[int(v) for v in self.tap_off])
+
+    def to(self, device) -> "PackedConv":
+        return PackedConv(self.w.to(device), None if self.bias is None else self.bias.to(device),
+                          list(self.tap_off), self.n_phase, self.n_taps, self.c_in, self.c_out,
+                          self.c_out_pad, self.w_pitch)
+
+
+def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], dilation: int = 1) -> PackedConv:
+    """nn.Conv1d weight [C_out, C_in, k] with "same" padding (k*d-d)//2 (hifigan.py:21-22)."""
+    c_out, c_in, k = weight.shape
+    assert k % 2 == 1, "same-padded convs on this path have odd kernels"
+    cp, wp = c_out_pad_of(c_out), pitch_of(c_in)
+    w = torch.zeros(1, k, cp, wp, dtype=torch.float16, device=weight.device)
+    w[0, :, :c_out, :c_in] = weight.detach().float().permute(2, 0, 1).to(torch.float16)
+    offs = [(j - (k - 1) // 2) * dilation for j in range(k)]
+    b = None if bias is None else bias.detach().float().contiguous()
+    return PackedConv(w.contiguous(), b, offs, 1, k, c_in, c_out, cp, wp)
+
+
+def pack_linear(weight: torch.Tensor, bias: Optional[torch.Tensor]) -> PackedConv:
+    """nn.Linear / 1x1 conv weight [C_out, C_in]."""
+    return pack_conv(weight.reshape(weight.shape[0], weight.shape[1], 1), bias)
+
+
+def pack_conv_transpose(weight: torch.Tensor, bias: Optional[torch.Tensor], stride: int) -> PackedConv:
+    """nn.ConvTranspose1d weight [C_in, C_out, k], padding (k-u)//2, as u polyphase convs:
+    y[q*u + r] = sum_m x[q - m] * w[:, :, m*u + r + p]  over m with 0 <= m*u + r + p < k."""
+    c_in, c_out, k = weight.shape
+    u = stride
+    p = (k - u) // 2
+    phases = []
+    for r in range(u):
+        taps = []
+        m = -((r + p) // u)
+        while m * u + r + p < k:
+            j = m * u + r + p
+            if j >= 0:
+                taps.append((-m, j))
+            m += 1
+        phases.append(taps)
+    n_taps = max(1, max(len(t) for t in phases))
+    cp, wp = c_out_pad_of(c_out), pitch_of(c_in)
+    w = torch.zeros(u, n_taps, cp, wp, dtype=torch.float16, device=weight.device)
+    offs = []
+    wf = weight.detach().float()
+    for r, taps in enumerate(phases):
+        for i in range(n_taps):
+            if i < len(taps):
+                off, j = taps[i]
+                w[r, i, :c_out, :c_in] = wf[:, :, j].t().to(torch.float16)
+                offs.append(off)
+            else:
+                offs.append(0)
+    b = None if bias is None else bias.detach().float().contiguous()
+    return PackedConv(w.contiguous(), b, offs, u, n_taps, c_in, c_out, cp, wp)
+
+
+def conv_transpose_out_len(L: int, k: int, u: int) -> int:
+    return (L - 1) * u - 2 * ((k - u) // 2) + k
+
+
+# ----------------------------------------------------------------------------------------------
+# op wrappers
+# ----------------------------------------------------------------------------------------------
+def conv1d(a16: torch.Tensor, pc: PackedConv, L_out: Optional[int] = None, *, gamma=None, residual=None,
+           out32=None, accumulate=False, out_scale=1.0, out16=None, act=ACT_NONE, act_param=0.0,
+           engine=ENGINE_TC, use_bias=True) -> None:
+    """a16 [B, L_in, a_pitch] fp16 -> out32 [B, L_out, >=C_out] fp32 and/or out16 fp16 (see fv_conv_desc)."""
+    B, L_in, a_pitch = a16.shape
+    if L_out is None:
+        L_out = L_in
+    d = ConvDesc()
+    d.a, d.B, d.L_in, d.a_pitch = _ptr(a16, torch.float16), B, L_in, a_pitch
+    d.w, d.n_phase, d.n_taps = _ptr(pc.w, torch.float16), pc.n_phase, pc.n_taps
+    d.C_out, d.C_out_pad, d.w_pitch = pc.c_out, pc.c_out_pad, pc.w_pitch
+    d.tap_off = pc._tap_arr
+    d.L_out = L_out
+    d.bias = _ptr(pc.bias, torch.float32) if (use_bias and pc.bias is not None) else None
+    d.gamma = _ptr(gamma, torch.float32)
+    for name, t in (("residual", residual), ("out32", out32), ("out16", out16)):
+        if t is not None and (t.shape[0] != B or t.shape[1] != L_out):
+            raise FvError(f"{name} has shape {tuple(t.shape)}, expected [{B}, {L_out}, pitch]")
+    d.residual, d.res_pitch = _ptr(residual, torch.float32), (0 if residual is None else residual.shape[2])
+    d.out32, d.out32_pitch = _ptr(out32, torch.float32), (0 if out32 is None else out32.shape[2])
+    d.accumulate, d.out_scale = int(bool(accumulate)), float(out_scale)
+    d.out16, d.out16_pitch = _ptr(out16, torch.float16), (0 if out16 is None else out16.shape[2])
+    d.act, d.act_param = int(act), float(act_param)
+    _check(lib().fv_conv1d(ctypes.byref(d), int(engine), _stream()), "fv_conv1d")
+
+
+def pack_input(x: torch.Tensor, pitch: Optional[int] = None) -> torch.Tensor:
+    """[B, C, T] fp32 channels-first -> [B, T, pitch] fp16 channels-last."""
+    B, C, T = x.shape
+    pitch = pitch or pitch_of(C)
+    out = torch.empty(B, T, pitch, dtype=torch.float16, device=x.device)
+    _check(lib().fv_pack_input(_ptr(x, torch.float32), _ptr(out), B, C, T, pitch, _stream()), "fv_pack_input")
+    return out
+
+
+def unpack_output(x32: torch.Tensor, C: int) -> torch.Tensor:
+    B, L, pitch = x32.shape
+    out = torch.empty(B, C, L, dtype=torch.float32, device=x32.device)
+    _check(lib().fv_unpack_output(_ptr(x32, torch.float32), _ptr(out), B, C, L, pitch, _stream()),
+           "fv_unpack_output")
+    return out
+
+
+def conv_post_tanh(a16: torch.Tensor, w32: torch.Tensor, bias: Optional[torch.Tensor], C: int,
+                   apply_tanh: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """a16 [B, L, pitch] fp16, w32 [k, C] fp32 -> wav [B, 1, L] fp32."""
+    B, L, pitch = a16.shape
+    k = w32.shape[0]
+    if out is None:
+        out = torch.empty(B, 1, L, dtype=torch.float32, device=a16.device)
+    _check(lib().fv_conv_post_tanh(_ptr(a16, torch.float16), _ptr(w32, torch.float32), _ptr(bias, torch.float32),
+                                   _ptr(out, torch.float32), B, L, C, pitch, k, int(apply_tanh), _stream()),
+           "fv_conv_post_tanh")
+    return out
+
+
+def snake_aa(x32: torch.Tensor, out16: torch.Tensor, alpha: torch.Tensor, beta: Optional[torch.Tensor],
+             filt_up: Sequence[float], filt_down: Sequence[float], C: int, logscale: bool = True) -> None:
+    B, L, pitch = x32.shape
+    fu = (ctypes.c_float * 12)(*[float(v) for v in filt_up])
+    fd = (ctypes.c_float * 12)(*[float(v) for v in filt_down])
+    _check(lib().fv_snake_aa(_ptr(x32, torch.float32), _ptr(out16, torch.float16), _ptr(alpha, torch.float32),
+                             _ptr(beta, torch.float32), fu, fd, int(logscale), B, L, C, pitch, _stream()),
+           "fv_snake_aa")
+
+
+def dwconv_layernorm(x32: torch.Tensor, C: int, dw_w, dw_b, ln_w, ln_b, eps: float, k: int,
+                     out16: Optional[torch.Tensor] = None, out32: Optional[torch.Tensor] = None) -> None:
+    B, T, pitch = x32.shape
+    _check(lib().fv_dwconv_layernorm(_ptr(x32, torch.float32), _ptr(out16, torch.float16),
+                                     _ptr(out32, torch.float32), _ptr(dw_w, torch.float32),
+                                     _ptr(dw_b, torch.float32), _ptr(ln_w, torch.float32),
+                                     _ptr(ln_b, torch.float32), float(eps), B, T, C, pitch, int(k), _stream()),
+           "fv_dwconv_layernorm")
+
+
+def istft_ola(frames: torch.Tensor, window: torch.Tensor, n_fft: int, hop: int,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    B, T, fp = frames.shape
+    if out is None:
+        out = torch.empty(B, T * hop, dtype=torch.float32, device=frames.device)
+    _check(lib().fv_istft_ola(_ptr(frames, torch.float32), _ptr(window, torch.float32), _ptr(out), B, T, n_fft,
+                              hop, fp, _stream()), "fv_istft_ola")
+    return out
+
+
+def noise_conv(tpl: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, out32: torch.Tensor, C: int, k: int,
+               stride: int, pad: int) -> None:
+    B, L_out, pitch = out32.shape
+    L_audio = tpl.shape[-1]
+    _check(lib().fv_noise_conv(_ptr(tpl, torch.float32), _ptr(w, torch.float32), _ptr(bias, torch.float32),
+                               _ptr(out32, torch.float32), B, L_audio, L_out, C, pitch, k, stride, pad, _stream()),
+           "fv_noise_conv")
+
+
+def act_cast(x32: torch.Tensor, C: int, act: int, act_param: float = 0.0, *, noise=None, noise_w=None,
+             out16=None, out32=None, out_coff: int = 0) -> None:
+    B, L, in_pitch = x32.shape
+    o = out16 if out16 is not None else out32
+    _check(lib().fv_act_cast(_ptr(x32, torch.float32), _ptr(noise, torch.float32), _ptr(noise_w, torch.float32),
+                             _ptr(out16, torch.float16), _ptr(out32, torch.float32), int(act), float(act_param),
+                             B, L, C, in_pitch, o.shape[2], out_coff, _stream()), "fv_act_cast")
+
+
+def resample_linear(x32: torch.Tensor, C: int, L_out: int, scale: float, *, act=ACT_NONE, act_param=0.0,
+                    out16=None, out32=None, out_coff: int = 0) -> None:
+    B, L_in, in_pitch = x32.shape
+    o = out16 if out16 is not None else out32
+    _check(lib().fv_resample_linear(_ptr(x32, torch.float32), _ptr(out32, torch.float32),
+                                    _ptr(out16, torch.float16), int(act), float(act_param), B, L_in, L_out, C,
+                                    in_pitch, o.shape[2], out_coff, float(scale), _stream()), "fv_resample_linear")
+
+
+def launch_count() -> int:
+    return int(lib().fv_launch_count())
+
+
+def reset_launch_count() -> None:
+    lib().fv_reset_launch_count()
+
+
+def set_tc_tuning(block_n: int = 0, m_sub: int = 0) -> None:
+    lib().fv_set_tc_tuning(int(block_n), int(m_sub))
