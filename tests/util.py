@@ -43,3 +43,17 @@ def oracle_forward(name, kwargs, sd, ins, extra=None):
 
 ALL_GOLDEN = ["hifigan_small_ref", "hifigan_small_stress", "hifigan_template_stress", "bigvgan_small_ref",
               "bigvgan_small_stress", "vocos_small_ref", "vocos_small_stress", "refinegan_small_stress"]
+
+
+def channels_last_noise(seed):
+    """AdaIN noise for the RefineGAN parity test: the same numpy stream the golden was generated with
+    (drawn channels-first [B, C, L] like torch.randn_like in refinegan.py:125), handed over channels-last."""
+    rs = np.random.RandomState(int(seed))
+
+    def fn(B, L, C, pitch, device):
+        z = torch.from_numpy(rs.standard_normal((B, C, L)).astype(np.float32))
+        out = torch.zeros(B, L, pitch)
+        out[..., :C] = z.permute(0, 2, 1)
+        return out.to(device)
+
+    return fn

@@ -1,0 +1,239 @@
+"""Shared host-side driver for the two MRF ("multi-receptive-field") generators, HiFiGAN and BigVGAN.
+
+conv_pre -> N x [ConvTranspose1d upsample -> mean of num_kernels residual blocks] -> activation -> conv_post -> tanh
+(reference: fish_vocoder/modules/generators/hifigan.py:226-249 and bigvgan.py:352-371).  This file only sequences
+kernel launches of libfv_b200.so over channels-last workspace buffers; all arithmetic happens in the kernels.
+
+HBM layout of one stage (B utterances, L time steps, C channels; pitch = C rounded up to 8):
+    x0   fp32 [B][L][pitch]  stage input (ups output)        - residual for the first pair of each block
+    xr   fp32 [B][L][pitch]  running residual stream of the block being evaluated
+    xa   fp16 [B][L][pitch]  act(x): tensor-core operand of convs1
+    ta   fp16 [B][L][pitch]  act(convs1 out): operand of convs2   (BigVGAN: + t32 fp32 pre-activation)
+    acc  fp32 [B][L][pitch]  sum_j block_j(x0) / num_kernels (MRF mean, accumulated by the last epilogue)
+    h16  fp16 [B][L][pitch]  activated stage output: operand of the next ups / conv_post
+"""
+from __future__ import annotations
+
+from math import prod
+from typing import List, Optional
+
+import torch
+from torch import nn
+from torch.nn.utils.parametrizations import weight_norm
+from torch.nn.utils.parametrize import remove_parametrizations as _torch_remove_parametrizations
+
+from .. import cabi
+from ..runtime import GraphedForward, Workspace, params_key, require_cuda
+
+
+def same_padding(kernel_size: int, dilation: int = 1) -> int:
+    return (kernel_size * dilation - dilation) // 2
+
+
+def wn_conv(c_in: int, c_out: int, k: int, dilation: int = 1) -> nn.Module:
+    """weight-normed "same" Conv1d parameter holder (state_dict: bias, parametrizations.weight.original{0,1})."""
+    conv = nn.Conv1d(c_in, c_out, k, 1, dilation=dilation, padding=same_padding(k, dilation))
+    return weight_norm(conv)
+
+
+def init_normal(module: nn.Module, std: float = 0.01) -> None:
+    """N(0, std) on every conv weight below `module` (the reference's init_weights, hifigan.py:15-18)."""
+    for m in module.modules():
+        if isinstance(m, (nn.Conv1d, nn.ConvTranspose1d)):
+            m.weight.data.normal_(0.0, std)
+
+
+def strip_weight_norm(module: nn.Module) -> None:
+    for m in module.modules():
+        if hasattr(m, "parametrizations") and "weight" in getattr(m, "parametrizations", {}):
+            _torch_remove_parametrizations(m, "weight")
+
+
+_ACT_OF_MODULE = {nn.SiLU: (cabi.ACT_SILU, 0.0), nn.Identity: (cabi.ACT_NONE, 0.0), nn.Tanh: (cabi.ACT_TANH, 0.0),
+                  nn.GELU: (cabi.ACT_GELU, 0.0)}
+
+
+def act_of_module(m: nn.Module):
+    if isinstance(m, nn.LeakyReLU):
+        return cabi.ACT_LEAKY, float(m.negative_slope)
+    for cls, v in _ACT_OF_MODULE.items():
+        if type(m) is cls:
+            return v
+    raise NotImplementedError(f"post activation {type(m).__name__} has no fused kernel epilogue")
+
+
+class MRFGeneratorBase(nn.Module):
+    """Common constructor pieces + launch sequence.  Subclasses provide the residual blocks."""
+
+    snake_blocks = False  # BigVGAN: anti-aliased Snake between convs instead of SiLU epilogues
+
+    def _build_trunk(self, *, hop_length, upsample_rates, upsample_kernel_sizes, num_mels,
+                     upsample_initial_channel, use_template, pre_conv_kernel_size, post_conv_kernel_size):
+        assert prod(upsample_rates) == hop_length, f"hop_length must be {prod(upsample_rates)}"
+        self.hop_length = hop_length
+        self.upsample_rates = tuple(int(u) for u in upsample_rates)
+        self.upsample_kernel_sizes = tuple(int(k) for k in upsample_kernel_sizes)
+        self.num_mels = num_mels
+        self.num_upsamples = len(upsample_rates)
+        self.use_template = use_template
+        ch0 = upsample_initial_channel
+        self.conv_pre = wn_conv(num_mels, ch0, pre_conv_kernel_size)
+        self.noise_convs = nn.ModuleList()
+        self.ups = nn.ModuleList()
+        self.stage_channels: List[int] = []
+        for i, (u, k) in enumerate(zip(self.upsample_rates, self.upsample_kernel_sizes)):
+            c_in, c_out = ch0 // (2 ** i), ch0 // (2 ** (i + 1))
+            self.stage_channels.append(c_out)
+            self.ups.append(weight_norm(nn.ConvTranspose1d(c_in, c_out, k, u, padding=(k - u) // 2)))
+            if use_template:
+                if i + 1 < len(self.upsample_rates):
+                    s = int(prod(self.upsample_rates[i + 1:]))
+                    self.noise_convs.append(nn.Conv1d(1, c_out, kernel_size=s * 2, stride=s, padding=s // 2))
+                else:
+                    self.noise_convs.append(nn.Conv1d(1, c_out, kernel_size=1))
+        self._post_k = post_conv_kernel_size
+        self._ws = Workspace()
+        self._packed = None
+        self._packed_key = None
+        self._graphed: Optional[GraphedForward] = None
+        self.use_cuda_graph = False
+        self.engine = cabi.ENGINE_TC
+
+    def _finish_trunk(self):
+        self.conv_post = wn_conv(self.stage_channels[-1], 1, self._post_k)
+        init_normal(self.ups)
+        init_normal(self.conv_post)
+
+    # ---- reference surface -------------------------------------------------------------------
+    def remove_parametrizations(self):
+        """Fold weight-norm into plain weights (hifigan.py:251-257).  The kernels always consume folded,
+        pre-packed weights, so this only changes the state_dict layout, exactly as in the reference."""
+        strip_weight_norm(self)
+        self._packed = None
+
+    def forward(self, x: torch.Tensor, template: Optional[torch.Tensor] = None) -> torch.Tensor:
+        require_cuda(x, type(self).__name__)
+        if self.use_template and template is None:
+            raise ValueError("use_template=True requires a template [B, 1, T*hop]")
+        x = x.contiguous().float()
+        tpl = None
+        if self.use_template:
+            tpl = template.contiguous().float()
+        if self.use_cuda_graph and not torch.is_grad_enabled():
+            self._ensure_packed(x.device)
+            if self._graphed is None:
+                self._graphed = GraphedForward(self._forward_eager)
+            return self._graphed(x, tpl).clone()
+        return self._forward_eager(x, tpl)
+
+    def _forward_eager(self, x, tpl):
+        a0 = cabi.pack_input(x)
+        return self._forward_cl(a0, tpl)
+
+    # ---- weight packing ------------------------------------------------------------------------
+    def _block_modules(self, stage: int):  # -> list of blocks, each with .convs1/.convs2 (+ .activations)
+        raise NotImplementedError
+
+    def _ensure_packed(self, device):
+        key = params_key(list(self.parameters()) + list(self.buffers()))
+        if self._packed is not None and self._packed_key == key:
+            return self._packed
+        with torch.no_grad():
+            P = {"pre": cabi.pack_conv(self.conv_pre.weight, self.conv_pre.bias), "ups": [], "blocks": [],
+                 "noise": []}
+            for i, up in enumerate(self.ups):
+                P["ups"].append(cabi.pack_conv_transpose(up.weight, up.bias, self.upsample_rates[i]))
+                blocks = []
+                for blk in self._block_modules(i):
+                    c1 = [cabi.pack_conv(c.weight, c.bias, c.dilation[0]) for c in blk.convs1]
+                    c2 = [cabi.pack_conv(c.weight, c.bias, c.dilation[0]) for c in blk.convs2]
+                    blocks.append((c1, c2, blk))
+                P["blocks"].append(blocks)
+            for nc in self.noise_convs:
+                P["noise"].append((nc.weight.detach().float().reshape(nc.out_channels, -1).contiguous(),
+                                   nc.bias.detach().float().contiguous(), nc.kernel_size[0], nc.stride[0],
+                                   nc.padding[0]))
+            wp = self.conv_post.weight.detach().float()  # [1, C, k]
+            P["post_w"] = wp[0].t().contiguous()          # [k, C]
+            P["post_b"] = self.conv_post.bias.detach().float().contiguous()
+        self._packed, self._packed_key = P, key
+        if self._graphed is not None:
+            self._graphed.invalidate()
+        return P
+
+    # ---- hooks for the activation flavour -------------------------------------------------------
+    def _pre_act(self):        # activation fused into conv_pre's epilogue (what ups[0] consumes)
+        raise NotImplementedError
+
+    def _stage_out_act(self, last_stage: bool):   # activation fused into the stage's final epilogue
+        raise NotImplementedError
+
+    def _final_activation(self, acc, h16, C):     # un-fusable activation_post (BigVGAN AA-Snake) else no-op
+        return None
+
+    # ---- the launch sequence ----------------------------------------------------------------------
+    def _forward_cl(self, a0: torch.Tensor, tpl: Optional[torch.Tensor]) -> torch.Tensor:
+        """a0: fp16 [B, T, pitch(num_mels)] channels-last.  Returns wav fp32 [B, 1, T*hop]."""
+        P = self._ensure_packed(a0.device)
+        ws, dev, eng = self._ws, a0.device, self.engine
+        B, T, _ = a0.shape
+        pre = P["pre"]
+        act_pre, act_pre_p = self._pre_act()
+        h16 = ws.f16("h_pre", B, T, pre.c_out, dev)
+        cabi.conv1d(a0, pre, out16=h16, act=act_pre, act_param=act_pre_p, engine=eng)
+        L = T
+        n_stage = self.num_upsamples
+        for i in range(n_stage):
+            up = P["ups"][i]
+            C = up.c_out
+            Lo = cabi.conv_transpose_out_len(L, self.upsample_kernel_sizes[i], self.upsample_rates[i])
+            x0 = ws.f32(f"x0_{i}", B, Lo, C, dev)
+            nz = None
+            if self.use_template:
+                w, b, k, s, p = P["noise"][i]
+                nz = ws.f32(f"nz_{i}", B, Lo, C, dev)
+                cabi.noise_conv(tpl.reshape(B, -1), w, b, nz, C, k, s, p)
+            last_stage = i == n_stage - 1
+            if self.snake_blocks:
+                cabi.conv1d(h16, up, Lo, residual=nz, out32=x0, engine=eng)
+                xa0 = None
+            else:
+                xa0 = ws.f16(f"xa0_{i}", B, Lo, C, dev)
+                cabi.conv1d(h16, up, Lo, residual=nz, out32=x0, out16=xa0, act=cabi.ACT_SILU, engine=eng)
+            acc = ws.f32(f"acc_{i}", B, Lo, C, dev)
+            h_next = ws.f16(f"h_{i}", B, Lo, C, dev)
+            xr_w = ws.f32(f"xr_{i}", B, Lo, C, dev)
+            xa_w = ws.f16(f"xa_{i}", B, Lo, C, dev)
+            ta = ws.f16(f"ta_{i}", B, Lo, C, dev)
+            t32 = ws.f32(f"t32_{i}", B, Lo, C, dev) if self.snake_blocks else None
+            blocks = P["blocks"][i]
+            nk = len(blocks)
+            out_act, out_act_p = self._stage_out_act(last_stage)
+            for j, (c1s, c2s, blk) in enumerate(blocks):
+                xr, xa = x0, xa0
+                n_pairs = len(c1s)
+                for p_i in range(n_pairs):
+                    last_pair = p_i == n_pairs - 1
+                    if self.snake_blocks:
+                        self._snake(blk.activations[2 * p_i], xr, xa_w, C)
+                        cabi.conv1d(xa_w, c1s[p_i], out32=t32, engine=eng)
+                        self._snake(blk.activations[2 * p_i + 1], t32, ta, C)
+                    else:
+                        cabi.conv1d(xa, c1s[p_i], out16=ta, act=cabi.ACT_SILU, engine=eng)
+                    if not last_pair:
+                        cabi.conv1d(ta, c2s[p_i], residual=xr, out32=xr_w,
+                                    out16=None if self.snake_blocks else xa_w, act=cabi.ACT_SILU, engine=eng)
+                        xr, xa = xr_w, xa_w
+                    else:
+                        want16 = (j == nk - 1) and out_act is not None
+                        cabi.conv1d(ta, c2s[p_i], residual=xr, out32=acc, accumulate=j > 0, out_scale=1.0 / nk,
+                                    out16=h_next if want16 else None, act=out_act if want16 else cabi.ACT_NONE,
+                                    act_param=out_act_p, engine=eng)
+            if last_stage:
+                self._final_activation(acc, h_next, C)
+            h16, L = h_next, Lo
+        wav = cabi.conv_post_tanh(h16, P["post_w"], P["post_b"], self.stage_channels[-1], apply_tanh=True)
+        return wav
+
+    def _snake(self, act_module, x32, out16, C):
+        raise NotImplementedError
