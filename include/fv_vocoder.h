@@ -156,6 +156,10 @@ FV_API int fv_act_cast(const float* x32, const float* noise, const float* noise_
 FV_API int fv_resample_linear(const float* x32, float* out32, void* out16, int act, float act_param, int B, int L_in,
                        int L_out, int C, int in_pitch, int out_pitch, int out_coff, float scale, void* stream);
 
+/* bring-up probe (not on the product path): 12 row shifts x {base_offset 0, base_offset r&7} of a 128x64x64 UMMA whose
+ * A descriptor starts r rows into a TMA-written 144x64 fp16 slab.  a16 [144][64], w16 [64][64], out [12][2][128][64]. */
+FV_API int fv_debug_rowshift_probe(const void* a16, const void* w16, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

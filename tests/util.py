@@ -57,3 +57,36 @@ def channels_last_noise(seed):
         return out.to(device)
 
     return fn
+
+
+class emulate_f16_operands:
+    """Context manager: run the CPU oracle with the operands of every dense conv / conv-transpose / linear rounded
+    to fp16 (round-to-nearest), fp32 accumulation - the arithmetic of the default "f16" tensor-core mode
+    (depthwise convs, anti-alias filters, LayerNorm, activations and residual adds stay fp32, as in the kernels)."""
+
+    def __enter__(self):
+        import torch.nn.functional as F
+        self.F = F
+        self.saved = (F.conv1d, F.conv_transpose1d, F.linear)
+        c1, ct, li = self.saved
+        r = lambda t: t.half().float()
+
+        def conv1d(x, w, b=None, stride=1, padding=0, dilation=1, groups=1):
+            if groups == 1:
+                x, w = r(x), r(w)
+            return c1(x, w, b, stride, padding, dilation, groups)
+
+        def conv_transpose1d(x, w, b=None, stride=1, padding=0, output_padding=0, groups=1, dilation=1):
+            if groups == 1:
+                x, w = r(x), r(w)
+            return ct(x, w, b, stride, padding, output_padding, groups, dilation)
+
+        def linear(x, w, b=None):
+            return li(r(x), r(w), b)
+
+        F.conv1d, F.conv_transpose1d, F.linear = conv1d, conv_transpose1d, linear
+        return self
+
+    def __exit__(self, *exc):
+        self.F.conv1d, self.F.conv_transpose1d, self.F.linear = self.saved
+        return False

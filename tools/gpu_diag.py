@@ -299,7 +299,24 @@ def group_simt():
     return res
 
 
-GROUPS = {"simt": group_simt, "conv_small": group_conv_small, "convT": group_convT, "gemm": group_gemm,
+def group_probe():
+    """row-shifted UMMA descriptor probe (see csrc/fv_debug.cu)"""
+    g = torch.Generator().manual_seed(0)
+    a = torch.randn(144, 64, generator=g).half()
+    w = torch.randn(64, 64, generator=g).half()
+    out = torch.full((12, 2, 128, 64), float("nan"), device="cuda")
+    rc = cabi.lib().fv_debug_rowshift_probe(a.cuda().data_ptr(), w.cuda().data_ptr(), out.data_ptr(), None)
+    torch.cuda.synchronize()
+    res = [{"rc": rc}]
+    o = out.cpu()
+    for r in range(12):
+        ref = a[r:r + 128].float() @ w.float().t()
+        res.append({"shift": r, "err_base0": float((o[r, 0] - ref).abs().max()),
+                    "err_base_r": float((o[r, 1] - ref).abs().max())})
+    return res
+
+
+GROUPS = {"probe": group_probe, "simt": group_simt, "conv_small": group_conv_small, "convT": group_convT, "gemm": group_gemm,
           "conv_big": group_conv_big, "perf": group_perf}
 
 

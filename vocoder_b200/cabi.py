@@ -25,6 +25,7 @@ EXPORTS = [
     "fv_last_error", "fv_abi_version", "fv_launch_count", "fv_reset_launch_count", "fv_conv1d",
     "fv_set_tc_tuning", "fv_pack_input", "fv_unpack_output", "fv_conv_post_tanh", "fv_snake_aa",
     "fv_dwconv_layernorm", "fv_istft_ola", "fv_noise_conv", "fv_act_cast", "fv_resample_linear",
+    "fv_debug_rowshift_probe",
 ]
 
 
@@ -79,6 +80,7 @@ def lib() -> ctypes.CDLL:
     L.fv_noise_conv.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, vp]
     L.fv_act_cast.argtypes = [vp, vp, vp, vp, vp, ci, cf, ci, ci, ci, ci, ci, ci, vp]
     L.fv_resample_linear.argtypes = [vp, vp, vp, ci, cf, ci, ci, ci, ci, ci, ci, ci, cf, vp]
+    L.fv_debug_rowshift_probe.argtypes = [vp, vp, vp, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("fv_last_error", "fv_launch_count", "fv_reset_launch_count", "fv_set_tc_tuning"):

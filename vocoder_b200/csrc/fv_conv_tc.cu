@@ -4,7 +4,9 @@
 // epilogue.  One persistent CTA per SM, warp-specialised:
 //     warp 0    : TMA producer  (one elected lane)
 //     warp 1    : tcgen05.mma issuer (one elected lane) + TMEM allocator
-//     warps 2-5 : epilogue (TMEM -> registers -> global), one TMEM lane quarter each
+//     warps 2-9 : epilogue, two warps per TMEM lane quarter: TMEM -> registers -> per-warp smem transpose ->
+//                 coalesced global I/O (every warp instruction touches whole 128-byte rows of the channels-last
+//                 tensors: residual / MRF-accumulator reads, fp32 + fp16 writes)
 //
 // GEMM view (time on M, C_out on N, K = taps x C_in):
 //     D[q, o] = sum_tap sum_c A[b, q + off[phase][tap], c] * W[phase][tap][o][c]
@@ -20,7 +22,9 @@
 
 namespace fv {
 
-constexpr int kTcThreads = 192;
+constexpr int kEpiWarps = 8;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kTcThreads = 64 + kEpiThreads;
 constexpr int kSmemLimit = 232448;  // 227 KB opt-in maximum per CTA on sm_100
 
 struct ConvTcParams {
@@ -52,11 +56,17 @@ struct TcCfg {
   static constexpr int TMEM_COLS_RAW = ACC_BUFS * ACC_COLS;
   static constexpr int TMEM_COLS = TMEM_COLS_RAW <= 32 ? 32 : TMEM_COLS_RAW <= 64 ? 64 : TMEM_COLS_RAW <= 128 ? 128
                                    : TMEM_COLS_RAW <= 256 ? 256 : 512;
-  static constexpr int TAIL_BYTES = 512 + 2 * BLOCK_N * 4;  // barriers + tmem ptr + bias/gamma staging
+  static constexpr int CH = BLOCK_N < 32 ? BLOCK_N : 32;  // epilogue column chunk
+  static constexpr int STG_STRIDE = CH + 1;               // padded row stride (words) of the transpose buffer
+  static constexpr int STG_BYTES = kEpiWarps * 32 * STG_STRIDE * 4;
+  static constexpr int TAIL_BYTES = 512 + 2 * BLOCK_N * 4 + STG_BYTES;  // barriers, tmem ptr, bias/gamma, staging
   static constexpr int STAGES_RAW = (kSmemLimit - 1024 - TAIL_BYTES) / STAGE;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE + TAIL_BYTES;
-  static constexpr int CH = BLOCK_N < 32 ? BLOCK_N : 32;  // epilogue column chunk
+  static constexpr int NCH = BLOCK_N / CH;                // column chunks per 128-row accumulator
+  static constexpr int LPR = CH / 4;                      // lanes per row in the coalesced phase (float4 each)
+  static constexpr int RPI = 32 / LPR;                    // rows per warp instruction
+  static constexpr int ITERS = 32 / RPI;                  // warp instructions per 32-row chunk
   static_assert(STAGES >= 2, "pipeline needs at least two stages");
   static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 16 && BLOCK_N <= 256, "invalid UMMA N");
   static_assert(TMEM_COLS_RAW <= 512, "accumulators exceed TMEM");
@@ -74,6 +84,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float* s_bias = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE + 512);
   float* s_gamma = s_bias + BLOCK_N;
+  float* s_stage = s_gamma + BLOCK_N;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -87,7 +98,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 128);
+      mbar_init(&tempty_bar[i], kEpiThreads);
     }
     fence_barrier_init();
   } else if (warp == 1) {
@@ -160,8 +171,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps
-    const int quarter = warp & 3;            // TMEM lane quarter this warp may access
-    const int tid_e = threadIdx.x - 64;      // 0..127
+    const int ew = warp - 2;                 // 0..7
+    const int quarter = warp & 3;            // TMEM lane quarter this warp may access (hardware: warp id % 4)
+    const int cgrp = ew >> 2;                // work items (sub, chunk) are split between the two warps of a quarter
+    const int tid_e = threadIdx.x - 64;      // 0..255
+    float* stg = s_stage + ew * (32 * Cfg::STG_STRIDE);
+    const int r_in = lane / Cfg::LPR;        // row within a warp instruction (coalesced phase)
+    const int c4 = (lane % Cfg::LPR) * 4;    // first of this lane's 4 consecutive columns within the chunk
+    constexpr int N_ITEMS = M_SUB * Cfg::NCH;
     uint32_t tile_i = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tile_i) {
       int r = tile;
@@ -172,112 +189,128 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
       const int q0 = m_t * (M_SUB * 128);
       const int n0 = n_t * BLOCK_N;
       const uint32_t buf = tile_i % Cfg::ACC_BUFS;
+      const size_t brow0 = static_cast<size_t>(b) * p.L_out;
 
-      named_bar_sync(1, 128);  // previous tile's readers of s_bias/s_gamma are done
-      for (int i = tid_e; i < BLOCK_N; i += 128) {
+      named_bar_sync(1, kEpiThreads);  // previous tile's readers of s_bias/s_gamma are done
+      for (int i = tid_e; i < BLOCK_N; i += kEpiThreads) {
         const int col = n0 + i;
         s_bias[i] = (p.bias != nullptr && col < p.C_out) ? p.bias[col] : 0.f;
         s_gamma[i] = (p.gamma != nullptr && col < p.C_out) ? p.gamma[col] : 1.f;
       }
-      named_bar_sync(1, 128);
+      named_bar_sync(1, kEpiThreads);
+
+      // residual prefetch for one work item: the rows/columns this lane handles in the coalesced phase
+      auto load_res = [&](int item, float4 (&res)[Cfg::ITERS]) {
+        const int sub = item / Cfg::NCH, ch = item % Cfg::NCH;
+        const int col = n0 + ch * Cfg::CH + c4;
+#pragma unroll
+        for (int it = 0; it < Cfg::ITERS; ++it) {
+          res[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+          const int q = q0 + sub * 128 + quarter * 32 + it * Cfg::RPI + r_in;
+          const int orow = q * p.n_phase + phase;
+          if (p.residual != nullptr && q < p.q_rows && orow < p.L_out && col < p.C_out_r8)
+            res[it] = *reinterpret_cast<const float4*>(p.residual + (brow0 + orow) * p.res_pitch + col);
+        }
+      };
+
+      float4 res_cur[Cfg::ITERS];
+      if (cgrp < N_ITEMS) load_res(cgrp, res_cur);
 
       mbar_wait(&tfull_bar[buf], (tile_i / Cfg::ACC_BUFS) & 1);
       tc_fence_after();
 
 #pragma unroll 1
-      for (int sub = 0; sub < M_SUB; ++sub) {
-        const int q = q0 + sub * 128 + quarter * 32 + lane;
-        const int orow = q * p.n_phase + phase;
-        const bool row_ok = (q < p.q_rows) && (orow < p.L_out);
-        const size_t grow = static_cast<size_t>(b) * p.L_out + orow;
-#pragma unroll 1
-        for (int ch = 0; ch < BLOCK_N / Cfg::CH; ++ch) {
-          const int cbase = n0 + ch * Cfg::CH;
-          uint32_t acc[32];
-          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
-                                 (buf * M_SUB + sub) * BLOCK_N + ch * Cfg::CH;
-          if constexpr (Cfg::CH == 32) tmem_ld_32x32b_x32(taddr, acc);
-          else tmem_ld_32x32b_x16(taddr, acc);
+      for (int item = cgrp; item < N_ITEMS; item += 2) {
+        const int sub = item / Cfg::NCH, ch = item % Cfg::NCH;
+        uint32_t acc[32];
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                               (buf * M_SUB + sub) * BLOCK_N + ch * Cfg::CH;
+        if constexpr (Cfg::CH == 32) tmem_ld_32x32b_x32(taddr, acc);
+        else tmem_ld_32x32b_x16(taddr, acc);
+        tmem_ld_wait();
+        if (item + 2 >= N_ITEMS) {  // this warp's last TMEM read of the tile: hand the accumulator back
+          tc_fence_before();
+          mbar_arrive(&tempty_bar[buf]);
+        }
+        // transpose through this warp's private smem patch: thread = row  ->  lanes along the channel axis
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < Cfg::CH; ++i) stg[lane * Cfg::STG_STRIDE + i] = __uint_as_float(acc[i]);
+        __syncwarp();
 
-          // issue the global reads this chunk needs while the TMEM load is in flight
-          float4 res[Cfg::CH / 4];
-          float4 old[Cfg::CH / 4];
-#pragma unroll
-          for (int g = 0; g < Cfg::CH / 4; ++g) {
-            res[g] = make_float4(0.f, 0.f, 0.f, 0.f);
-            old[g] = make_float4(0.f, 0.f, 0.f, 0.f);
-            const int col = cbase + 4 * g;
-            if (row_ok && col < p.C_out_r8) {
-              if (p.residual != nullptr)
-                res[g] = *reinterpret_cast<const float4*>(p.residual + grow * p.res_pitch + col);
-              if (p.accumulate && p.out32 != nullptr)
-                old[g] = *reinterpret_cast<const float4*>(p.out32 + grow * p.out32_pitch + col);
-            }
-          }
-          tmem_ld_wait();
-          if (sub == M_SUB - 1 && ch == BLOCK_N / Cfg::CH - 1) {
-            // every TMEM read of this accumulator buffer is complete: hand it back to the MMA warp
-            tc_fence_before();
-            mbar_arrive(&tempty_bar[buf]);
-          }
+        // prefetch the next item's residual while this one is processed
+        float4 res_nxt[Cfg::ITERS];
+        const bool has_next = item + 2 < N_ITEMS;
+        if (has_next) load_res(item + 2, res_nxt);
 
-          float o[Cfg::CH];
+        const int ccol = ch * Cfg::CH + c4;  // column within the N tile
+        const int col = n0 + ccol;
+        const bool col_ok = col < p.C_out_r8;
+        const float4 bia = *reinterpret_cast<const float4*>(s_bias + ccol);
+        const float4 gam = *reinterpret_cast<const float4*>(s_gamma + ccol);
 #pragma unroll
-          for (int g = 0; g < Cfg::CH / 4; ++g) {
-            const float rr[4] = {res[g].x, res[g].y, res[g].z, res[g].w};
-            const float oo[4] = {old[g].x, old[g].y, old[g].z, old[g].w};
+        for (int it = 0; it < Cfg::ITERS; ++it) {
+          const int rl = it * Cfg::RPI + r_in;
+          const int q = q0 + sub * 128 + quarter * 32 + rl;
+          const int orow = q * p.n_phase + phase;
+          const bool ok = col_ok && (q < p.q_rows) && (orow < p.L_out);
+          const size_t grow = brow0 + orow;
+          const float* sp = stg + rl * Cfg::STG_STRIDE + c4;
+          float o[4];
+          o[0] = (sp[0] + bia.x) * gam.x + res_cur[it].x;
+          o[1] = (sp[1] + bia.y) * gam.y + res_cur[it].y;
+          o[2] = (sp[2] + bia.z) * gam.z + res_cur[it].z;
+          o[3] = (sp[3] + bia.w) * gam.w + res_cur[it].w;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int i = 4 * g + e;
-              float v = __uint_as_float(acc[i]) + s_bias[ch * Cfg::CH + i];
-              v = v * s_gamma[ch * Cfg::CH + i] + rr[e];
-              o[i] = v * p.out_scale + oo[e];
-            }
-          }
-          if (p.out32 != nullptr && row_ok) {
-#pragma unroll
-            for (int g = 0; g < Cfg::CH / 4; ++g) {
-              const int col = cbase + 4 * g;
-              if (col < p.C_out_r8)
-                *reinterpret_cast<float4*>(p.out32 + grow * p.out32_pitch + col) =
-                    make_float4(o[4 * g], o[4 * g + 1], o[4 * g + 2], o[4 * g + 3]);
-            }
-          }
-          if (p.out16 != nullptr && row_ok) {
-            if (p.act == FV_ACT_POLAR) {
-#pragma unroll
-              for (int i = 0; i < Cfg::CH; i += 2) {
-                const float m = fminf(expf(o[i]), 100.f);
-                float sn, cs;
-                sincosf(o[i + 1], &sn, &cs);
-                o[i] = m * cs;
-                o[i + 1] = m * sn;
+          for (int e = 0; e < 4; ++e) o[e] *= p.out_scale;
+          if (ok) {
+            if (p.out32 != nullptr) {
+              float* dst = p.out32 + grow * p.out32_pitch + col;
+              if (p.accumulate) {
+                const float4 old = *reinterpret_cast<const float4*>(dst);
+                o[0] += old.x; o[1] += old.y; o[2] += old.z; o[3] += old.w;
               }
-            } else if (p.act != FV_ACT_NONE) {
-#pragma unroll
-              for (int i = 0; i < Cfg::CH; ++i) o[i] = act_apply(o[i], p.act, p.act_param);
+              *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
             }
+            if (p.out16 != nullptr) {
+              if (p.act == FV_ACT_POLAR) {
 #pragma unroll
-            for (int g = 0; g < Cfg::CH / 8; ++g) {
-              const int col = cbase + 8 * g;
-              if (col < p.C_out_r8) {
-                uint4 pk;
-                pk.x = pack_half2_sat(o[8 * g + 0], o[8 * g + 1]);
-                pk.y = pack_half2_sat(o[8 * g + 2], o[8 * g + 3]);
-                pk.z = pack_half2_sat(o[8 * g + 4], o[8 * g + 5]);
-                pk.w = pack_half2_sat(o[8 * g + 6], o[8 * g + 7]);
-                *reinterpret_cast<uint4*>(p.out16 + grow * p.out16_pitch + col) = pk;
+                for (int e = 0; e < 4; e += 2) {
+                  const float m = fminf(expf(o[e]), 100.f);
+                  float sn, cs;
+                  sincosf(o[e + 1], &sn, &cs);
+                  o[e] = m * cs;
+                  o[e + 1] = m * sn;
+                }
+              } else if (p.act != FV_ACT_NONE) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) o[e] = act_apply(o[e], p.act, p.act_param);
               }
+              uint2 pk;
+              pk.x = pack_half2_sat(o[0], o[1]);
+              pk.y = pack_half2_sat(o[2], o[3]);
+              *reinterpret_cast<uint2*>(p.out16 + grow * p.out16_pitch + col) = pk;
             }
           }
         }
+        if (has_next) {
+#pragma unroll
+          for (int it = 0; it < Cfg::ITERS; ++it) res_cur[it] = res_nxt[it];
+        }
+      }
+      if (cgrp >= N_ITEMS) {  // idle warp of this tile shape still owes its TMEM-release arrivals
+        tc_fence_before();
+        mbar_arrive(&tempty_bar[buf]);
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
