@@ -65,8 +65,12 @@ def ref_conv(a16, pc, L_out, bias=None, gamma=None, residual=None, scale=1.0, ol
     return o32, o16
 
 
+EPILOGUE = 0
+
+
 def run_conv_case(name, B, L, c_in, c_out, k=3, d=1, convT=None, act=0, use_res=False, use_gamma=False,
-                  accumulate=False, scale=1.0, engines=("tc", "simt"), seed=0, time_it=False, check=True):
+                  accumulate=False, scale=1.0, engines=("tc", "simt"), seed=0, time_it=False, check=True,
+                  want32=True):
     dev = "cuda"
     g = torch.Generator().manual_seed(seed)
     ap = cabi.pitch_of(c_in)
@@ -93,14 +97,15 @@ def run_conv_case(name, B, L, c_in, c_out, k=3, d=1, convT=None, act=0, use_res=
     res = {"name": name, "shape": [B, L, c_in, c_out, k, d, convT], "L_out": L_out}
     outs = {}
     for eng in engines:
-        out32 = old.clone() if accumulate else torch.full((B, L_out, r8), float("nan"), device=dev)
+        out32 = old.clone() if accumulate else (torch.full((B, L_out, r8), float("nan"), device=dev)
+                                                if want32 else None)
         out16 = torch.full((B, L_out, r8), float("nan"), dtype=torch.float16, device=dev)
         e = cabi.ENGINE_TC if eng == "tc" else cabi.ENGINE_SIMT
         kw = dict(gamma=gamma, residual=residual, out32=out32, accumulate=accumulate, out_scale=scale,
                   out16=out16, act=act, act_param=0.2, engine=e)
         cabi.conv1d(a16, pc, L_out, **kw)
         torch.cuda.synchronize()
-        outs[eng] = (out32.cpu(), out16.float().cpu())
+        outs[eng] = (None if out32 is None else out32.cpu(), out16.float().cpu())
         if time_it and eng == "tc":
             kw["accumulate"] = False
             for _ in range(3):
@@ -203,6 +208,19 @@ def group_perf():
                              engines=("tc",), check=False, time_it=True))
     out.append(run_conv_case(name="perf_lin_5632_1408", B=128, L=94, c_in=5632, c_out=1408, k=1, act=A.ACT_NONE,
                              use_res=True, use_gamma=True, engines=("tc",), check=False, time_it=True))
+    out.append(run_conv_case(name="perf_lin_2816_11264", B=128, L=94, c_in=2816, c_out=11264, k=1, act=A.ACT_GELU,
+                             engines=("tc",), check=False, time_it=True))
+    out.append(run_conv_case(name="perf_c128_k7_c1", B=64, L=6016, c_in=128, c_out=128, k=7, d=1, act=A.ACT_SILU,
+                             use_res=False, engines=("tc",), check=False, time_it=True, want32=False))
+    for msub in (1, 2):
+        cabi.set_tc_tuning(0, msub, EPILOGUE)
+        out.append(run_conv_case(name=f"perf_c256_k7_msub{msub}", B=64, L=752, c_in=256, c_out=256, k=7, d=1,
+                                 act=A.ACT_SILU, use_res=True, engines=("tc",), check=False, time_it=True))
+        out.append(run_conv_case(name=f"perf_c128_k7_msub{msub}", B=64, L=6016, c_in=128, c_out=128, k=7, d=1,
+                                 act=A.ACT_SILU, use_res=True, engines=("tc",), check=False, time_it=True))
+        out.append(run_conv_case(name=f"perf_lin_1408_5632_msub{msub}", B=128, L=94, c_in=1408, c_out=5632, k=1,
+                                 act=A.ACT_GELU, engines=("tc",), check=False, time_it=True))
+    cabi.set_tc_tuning(0, 0, EPILOGUE)
     return out
 
 
@@ -305,7 +323,8 @@ def group_probe():
     a = torch.randn(144, 64, generator=g).half()
     w = torch.randn(64, 64, generator=g).half()
     out = torch.full((12, 2, 128, 64), float("nan"), device="cuda")
-    rc = cabi.lib().fv_debug_rowshift_probe(a.cuda().data_ptr(), w.cuda().data_ptr(), out.data_ptr(), None)
+    a_d, w_d = a.cuda(), w.cuda()  # keep the device copies alive across the launch
+    rc = cabi.lib().fv_debug_rowshift_probe(a_d.data_ptr(), w_d.data_ptr(), out.data_ptr(), None)
     torch.cuda.synchronize()
     res = [{"rc": rc}]
     o = out.cpu()
@@ -324,18 +343,24 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--group", default=None)
     ap.add_argument("--timeout", type=int, default=240)
-    ap.add_argument("--only", default=None, help="comma separated group names")
+    ap.add_argument("--only", default=None, help="comma separated group names (name@E runs with epilogue E)")
     args = ap.parse_args()
     os.makedirs(OUT_DIR, exist_ok=True)
     if args.group:
+        global EPILOGUE
+        gname = args.group
+        if "@" in gname:
+            gname, e = gname.split("@")
+            EPILOGUE = int(e)
+            cabi.set_tc_tuning(0, 0, EPILOGUE)
         t0 = time.time()
         try:
-            out = {"ok": True, "results": GROUPS[args.group]()}
+            out = {"ok": True, "results": GROUPS[gname]()}
         except Exception as e:  # noqa: BLE001
             import traceback
             out = {"ok": False, "error": repr(e), "trace": traceback.format_exc()}
         out["seconds"] = time.time() - t0
-        with open(os.path.join(OUT_DIR, f"diag_{args.group}.json"), "w") as f:
+        with open(os.path.join(OUT_DIR, f"diag_{args.group.replace('@', '_e')}.json"), "w") as f:
             json.dump(out, f, indent=1)
         print(json.dumps(out, indent=1))
         return
@@ -345,7 +370,7 @@ def main():
         try:
             p = subprocess.run([sys.executable, os.path.abspath(__file__), "--group", name], timeout=args.timeout,
                                capture_output=True, text=True)
-            path = os.path.join(OUT_DIR, f"diag_{name}.json")
+            path = os.path.join(OUT_DIR, f"diag_{name.replace('@', '_e')}.json")
             if os.path.exists(path):
                 summary[name] = json.load(open(path))
             else:

@@ -30,6 +30,10 @@ constexpr int kSmemLimit = 232448;  // 227 KB opt-in maximum per CTA on sm_100
 struct ConvTcParams {
   CUtensorMap tmA;  // 3D {pitch, L_in, B} fp16, box {BLOCK_K, rows, 1}
   CUtensorMap tmW;  // 2D {w_pitch, n_phase*n_taps*C_out_pad} fp16, box {BLOCK_K, BLOCK_N}
+  // epilogue maps, 4D {C_out_r8, n_phase, L_out / n_phase, B}, box {32, 1, 32, 1} (TMA epilogue only)
+  CUtensorMap tmR;    // residual fp32 (SWIZZLE_128B)
+  CUtensorMap tmO32;  // out32 fp32    (SWIZZLE_128B): accumulate-load and store
+  CUtensorMap tmO16;  // out16 fp16    (SWIZZLE_64B)
   int B, n_phase, n_taps, k_chunks, C_out, C_out_r8, C_out_pad, q_rows, L_out;
   int m_tiles, n_tiles, total_tiles;
   const float* bias;
@@ -42,7 +46,7 @@ struct ConvTcParams {
   int16_t tap_off[FV_MAX_TAPS];
 };
 
-template <int BLOCK_N, int M_SUB, int BLOCK_K>
+template <int BLOCK_N, int M_SUB, int BLOCK_K, bool EPI_TMA>
 struct TcCfg {
   static constexpr int ROW_BYTES = BLOCK_K * 2;
   static constexpr int A_SUB_BYTES = 128 * ROW_BYTES;
@@ -58,11 +62,15 @@ struct TcCfg {
                                    : TMEM_COLS_RAW <= 256 ? 256 : 512;
   static constexpr int CH = BLOCK_N < 32 ? BLOCK_N : 32;  // epilogue column chunk
   static constexpr int STG_STRIDE = CH + 1;               // padded row stride (words) of the transpose buffer
-  static constexpr int STG_BYTES = kEpiWarps * 32 * STG_STRIDE * 4;
-  static constexpr int TAIL_BYTES = 512 + 2 * BLOCK_N * 4 + STG_BYTES;  // barriers, tmem ptr, bias/gamma, staging
-  static constexpr int STAGES_RAW = (kSmemLimit - 1024 - TAIL_BYTES) / STAGE;
+  // epilogue staging.  LSU flavour: per-warp padded transpose patch.  TMA flavour: per-warp swizzled boxes, a
+  // 32x32 fp32 patch (4 KB, SWIZZLE_128B; residual lands here and is overwritten in place by out32) and a 32x32
+  // fp16 patch (2 KB, SWIZZLE_64B).
+  static constexpr int EPI_WARP_BYTES = EPI_TMA ? (4096 + 2048) : (32 * STG_STRIDE * 4);
+  static constexpr int STG_BYTES = ((kEpiWarps * EPI_WARP_BYTES + 1023) / 1024) * 1024;
+  static constexpr int TAIL_BYTES = 1024 + 2 * BLOCK_N * 4;  // barriers, tmem ptr, bias/gamma
+  static constexpr int STAGES_RAW = (kSmemLimit - 1024 - TAIL_BYTES - STG_BYTES) / STAGE;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE + TAIL_BYTES;
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE + STG_BYTES + TAIL_BYTES;
   static constexpr int NCH = BLOCK_N / CH;                // column chunks per 128-row accumulator
   static constexpr int LPR = CH / 4;                      // lanes per row in the coalesced phase (float4 each)
   static constexpr int RPI = 32 / LPR;                    // rows per warp instruction
@@ -72,19 +80,22 @@ struct TcCfg {
   static_assert(TMEM_COLS_RAW <= 512, "accumulators exceed TMEM");
 };
 
-template <int BLOCK_N, int M_SUB, int BLOCK_K>
+template <int BLOCK_N, int M_SUB, int BLOCK_K, bool EPI_TMA>
 __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
-  using Cfg = TcCfg<BLOCK_N, M_SUB, BLOCK_K>;
+  using Cfg = TcCfg<BLOCK_N, M_SUB, BLOCK_K, EPI_TMA>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE);
+  uint8_t* s_stage_raw = smem + Cfg::STAGES * Cfg::STAGE;  // 1024-aligned (stage sizes are multiples of 1024 / 512)
+  uint8_t* tail = s_stage_raw + Cfg::STG_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty_bar = full_bar + Cfg::STAGES;
   uint64_t* tfull_bar = empty_bar + Cfg::STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  float* s_bias = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE + 512);
+  uint64_t* epi_bar = tempty_bar + 2;  // one per epilogue warp (TMA epilogue loads)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(epi_bar + kEpiWarps);
+  float* s_bias = reinterpret_cast<float*>(tail + 1024);
   float* s_gamma = s_bias + BLOCK_N;
-  float* s_stage = s_gamma + BLOCK_N;
+  float* s_stage = reinterpret_cast<float*>(s_stage_raw);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -99,6 +110,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], kEpiThreads);
+    }
+    for (int i = 0; i < kEpiWarps; ++i) mbar_init(&epi_bar[i], 1);
+    if (EPI_TMA) {
+      if (p.residual) tma_prefetch_desc(&p.tmR);
+      if (p.out32) tma_prefetch_desc(&p.tmO32);
+      if (p.out16) tma_prefetch_desc(&p.tmO16);
     }
     fence_barrier_init();
   } else if (warp == 1) {
@@ -171,6 +188,171 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps
+    if constexpr (EPI_TMA) {
+      // thread = accumulator row throughout (the native TMEM layout); all global traffic of the epilogue is TMA:
+      // the residual patch is bulk-loaded into a swizzled smem box, combined in place, and bulk-stored as out32;
+      // the activated fp16 patch goes out through a second box.  No per-element address math, no LSU global ops.
+      const int ew = warp - 2;
+      const int quarter = warp & 3;
+      const int cgrp = ew >> 2;
+      const int tid_e = threadIdx.x - 64;
+      uint8_t* Rp = s_stage_raw + ew * 4096;                       // 32 rows x 128 B, SWIZZLE_128B
+      uint8_t* Hp = s_stage_raw + kEpiWarps * 4096 + ew * 2048;    // 32 rows x  64 B, SWIZZLE_64B
+      uint64_t* my_bar = &epi_bar[ew];
+      uint32_t ld_phase = 0;
+      const uint32_t r_row = smem_u32(Rp) + lane * 128;
+      const uint32_t h_row = smem_u32(Hp) + lane * 64;
+      const uint32_t r_xor = static_cast<uint32_t>(lane & 7);
+      const uint32_t h_xor = static_cast<uint32_t>((lane >> 1) & 3);
+      const bool has_res = p.residual != nullptr, has_o32 = p.out32 != nullptr, has_o16 = p.out16 != nullptr;
+      uint32_t tile_i = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tile_i) {
+        int r = tile;
+        const int n_t = r % p.n_tiles; r /= p.n_tiles;
+        const int m_t = r % p.m_tiles; r /= p.m_tiles;
+        const int b = r % p.B;
+        const int phase = r / p.B;
+        const int q0 = m_t * (M_SUB * 128);
+        const int n0 = n_t * BLOCK_N;
+        const uint32_t buf = tile_i % Cfg::ACC_BUFS;
+
+        named_bar_sync(1, kEpiThreads);
+        for (int i = tid_e; i < BLOCK_N; i += kEpiThreads) {
+          const int col = n0 + i;
+          s_bias[i] = (p.bias != nullptr && col < p.C_out) ? p.bias[col] : 0.f;
+          s_gamma[i] = (p.gamma != nullptr && col < p.C_out) ? p.gamma[col] : 1.f;
+        }
+        named_bar_sync(1, kEpiThreads);
+
+        int n_ch = (p.C_out_r8 - n0 + 31) / 32;  // column chunks of this tile that hold real channels
+        n_ch = n_ch < Cfg::NCH ? n_ch : Cfg::NCH;
+        const int n_items = M_SUB * n_ch;
+
+        auto issue_res_load = [&](int item) {  // lane 0 only
+          const int sub = item / n_ch, ch = item % n_ch;
+          tma_store_wait_read();  // previous stores of this warp no longer read Rp / Hp
+          mbar_arrive_expect_tx(my_bar, 4096);
+          tma_load_4d(Rp, &p.tmR, my_bar, n0 + ch * 32, phase, q0 + sub * 128 + quarter * 32, b);
+        };
+        if (has_res && cgrp < n_items && lane == 0) issue_res_load(cgrp);
+
+        mbar_wait(&tfull_bar[buf], (tile_i / Cfg::ACC_BUFS) & 1);
+        tc_fence_after();
+
+#pragma unroll 1
+        for (int item = cgrp; item < n_items; item += 2) {
+          const int sub = item / n_ch, ch = item % n_ch;
+          const int qb = q0 + sub * 128 + quarter * 32;
+          const int col0 = n0 + ch * 32;
+          uint32_t acc[32];
+          tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + (buf * M_SUB + sub) * BLOCK_N +
+                                 ch * 32, acc);
+          tmem_ld_wait();
+          if (item + 2 >= n_items) {
+            tc_fence_before();
+            mbar_arrive(&tempty_bar[buf]);
+          }
+          if (has_res) {
+            mbar_wait(my_bar, ld_phase);
+            ld_phase ^= 1;
+          } else if (lane == 0) {
+            tma_store_wait_read();
+          }
+          __syncwarp();
+          float o[32];
+          const float4* bp = reinterpret_cast<const float4*>(s_bias + ch * 32);
+          const float4* gp = reinterpret_cast<const float4*>(s_gamma + ch * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 bb = bp[j];
+            float4 rr = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (has_res) {
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                           : "=f"(rr.x), "=f"(rr.y), "=f"(rr.z), "=f"(rr.w)
+                           : "r"(r_row + ((static_cast<uint32_t>(j) ^ r_xor) << 4)));
+            }
+            o[4 * j + 0] = __uint_as_float(acc[4 * j + 0]) + bb.x;
+            o[4 * j + 1] = __uint_as_float(acc[4 * j + 1]) + bb.y;
+            o[4 * j + 2] = __uint_as_float(acc[4 * j + 2]) + bb.z;
+            o[4 * j + 3] = __uint_as_float(acc[4 * j + 3]) + bb.w;
+            if (p.gamma != nullptr) {
+              const float4 gg = gp[j];
+              o[4 * j + 0] *= gg.x; o[4 * j + 1] *= gg.y; o[4 * j + 2] *= gg.z; o[4 * j + 3] *= gg.w;
+            }
+            o[4 * j + 0] = (o[4 * j + 0] + rr.x) * p.out_scale;
+            o[4 * j + 1] = (o[4 * j + 1] + rr.y) * p.out_scale;
+            o[4 * j + 2] = (o[4 * j + 2] + rr.z) * p.out_scale;
+            o[4 * j + 3] = (o[4 * j + 3] + rr.w) * p.out_scale;
+          }
+          if (p.accumulate) {  // MRF mean: add the running sum already in out32 (second bulk load into the patch)
+            __syncwarp();
+            if (lane == 0) {
+              mbar_arrive_expect_tx(my_bar, 4096);
+              tma_load_4d(Rp, &p.tmO32, my_bar, col0, phase, qb, b);
+            }
+            mbar_wait(my_bar, ld_phase);
+            ld_phase ^= 1;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 oo;
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                           : "=f"(oo.x), "=f"(oo.y), "=f"(oo.z), "=f"(oo.w)
+                           : "r"(r_row + ((static_cast<uint32_t>(j) ^ r_xor) << 4)));
+              o[4 * j + 0] += oo.x; o[4 * j + 1] += oo.y; o[4 * j + 2] += oo.z; o[4 * j + 3] += oo.w;
+            }
+            __syncwarp();
+          }
+          if (has_o32) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(r_row + ((static_cast<uint32_t>(j) ^ r_xor) << 4)),
+                           "f"(o[4 * j + 0]), "f"(o[4 * j + 1]), "f"(o[4 * j + 2]), "f"(o[4 * j + 3])
+                           : "memory");
+          }
+          if (has_o16) {
+            if (p.act == FV_ACT_POLAR) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 2) {
+                const float m = fminf(expf(o[i]), 100.f);
+                float sn, cs;
+                sincosf(o[i + 1], &sn, &cs);
+                o[i] = m * cs;
+                o[i + 1] = m * sn;
+              }
+            } else if (p.act == FV_ACT_SILU) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] = __fdividef(o[i], 1.0f + __expf(-o[i]));
+            } else if (p.act != FV_ACT_NONE) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] = act_apply(o[i], p.act, p.act_param);
+            }
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              const uint32_t w0 = pack_half2_sat(o[8 * jj + 0], o[8 * jj + 1]);
+              const uint32_t w1 = pack_half2_sat(o[8 * jj + 2], o[8 * jj + 3]);
+              const uint32_t w2 = pack_half2_sat(o[8 * jj + 4], o[8 * jj + 5]);
+              const uint32_t w3 = pack_half2_sat(o[8 * jj + 6], o[8 * jj + 7]);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(h_row + ((static_cast<uint32_t>(jj) ^ h_xor) << 4)),
+                           "r"(w0), "r"(w1), "r"(w2), "r"(w3)
+                           : "memory");
+            }
+          }
+          fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the bulk-copy engine
+          __syncwarp();
+          if (lane == 0) {
+            if (has_o32) tma_store_4d(&p.tmO32, Rp, col0, phase, qb, b);
+            if (has_o16) tma_store_4d(&p.tmO16, Hp, col0, phase, qb, b);
+            tma_store_commit();
+            if (has_res && item + 2 < n_items) issue_res_load(item + 2);
+          }
+        }
+        if (cgrp >= n_items) {
+          tc_fence_before();
+          mbar_arrive(&tempty_bar[buf]);
+        }
+      }
+      if (lane == 0) tma_store_wait_all();  // global writes complete before the CTA retires
+    } else {
     const int ew = warp - 2;                 // 0..7
     const int quarter = warp & 3;            // TMEM lane quarter this warp may access (hardware: warp id % 4)
     const int cgrp = ew >> 2;                // work items (sub, chunk) are split between the two warps of a quarter
@@ -303,6 +485,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
         mbar_arrive(&tempty_bar[buf]);
       }
     }
+    }  // LSU epilogue
   }
 
   tc_fence_before();
@@ -349,9 +532,27 @@ static CUtensorMapSwizzle swizzle_for(int row_bytes) {
                           : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
 }
 
-template <int BLOCK_N, int M_SUB, int BLOCK_K>
+// 4D view of an output-side tensor [B][L_out][pitch]: {channel, phase, q, batch} with row = q * n_phase + phase
+static int encode_epi_map(EncodeTiledFn enc, CUtensorMap* tm, const void* base, bool fp16, const fv_conv_desc* d,
+                          int pitch, int c_out_r8) {
+  const cuuint64_t es = fp16 ? 2 : 4;
+  cuuint64_t dims[4] = {(cuuint64_t)c_out_r8, (cuuint64_t)d->n_phase, (cuuint64_t)(d->L_out / d->n_phase),
+                        (cuuint64_t)d->B};
+  cuuint64_t strides[3] = {(cuuint64_t)pitch * es, (cuuint64_t)pitch * es * d->n_phase,
+                           (cuuint64_t)pitch * es * d->L_out};
+  cuuint32_t box[4] = {32, 1, 32, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(tm, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
+                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   fp16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FV_REQUIRE(r == CUDA_SUCCESS, FV_E_DRIVER, "cuTensorMapEncodeTiled(epilogue) failed: %d", (int)r);
+  return 0;
+}
+
+template <int BLOCK_N, int M_SUB, int BLOCK_K, bool EPI_TMA>
 static int launch_tc(const fv_conv_desc* d, ConvTcParams& p, cudaStream_t stream) {
-  using Cfg = TcCfg<BLOCK_N, M_SUB, BLOCK_K>;
+  using Cfg = TcCfg<BLOCK_N, M_SUB, BLOCK_K, EPI_TMA>;
   EncodeTiledFn enc = get_encode_fn();
   FV_REQUIRE(enc != nullptr, FV_E_DRIVER, "cuTensorMapEncodeTiled not available from the driver");
 
@@ -375,6 +576,13 @@ static int launch_tc(const fv_conv_desc* d, ConvTcParams& p, cudaStream_t stream
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     FV_REQUIRE(r == CUDA_SUCCESS, FV_E_DRIVER, "cuTensorMapEncodeTiled(W) failed: %d", (int)r);
   }
+  if constexpr (EPI_TMA) {
+    int rc = 0;
+    if (d->residual) rc = encode_epi_map(enc, &p.tmR, d->residual, false, d, d->res_pitch, p.C_out_r8);
+    if (!rc && d->out32) rc = encode_epi_map(enc, &p.tmO32, d->out32, false, d, d->out32_pitch, p.C_out_r8);
+    if (!rc && d->out16) rc = encode_epi_map(enc, &p.tmO16, d->out16, true, d, d->out16_pitch, p.C_out_r8);
+    if (rc) return rc;
+  }
   p.k_chunks = ceil_div(d->a_pitch, BLOCK_K);
   p.m_tiles = ceil_div(p.q_rows, M_SUB * 128);
   p.n_tiles = ceil_div(d->C_out, BLOCK_N);
@@ -387,32 +595,38 @@ static int launch_tc(const fv_conv_desc* d, ConvTcParams& p, cudaStream_t stream
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, M_SUB, BLOCK_K>,
+    attr_err = cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, M_SUB, BLOCK_K, EPI_TMA>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
   });
   int rc = check_cuda(attr_err, "cudaFuncSetAttribute(conv_tc_kernel)");
   if (rc) return rc;
   const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  conv_tc_kernel<BLOCK_N, M_SUB, BLOCK_K><<<grid, kTcThreads, Cfg::SMEM_BYTES, stream>>>(p);
+  conv_tc_kernel<BLOCK_N, M_SUB, BLOCK_K, EPI_TMA><<<grid, kTcThreads, Cfg::SMEM_BYTES, stream>>>(p);
   FV_CHECK_LAUNCH("conv_tc_kernel");
   return 0;
 }
 
-template <int BLOCK_N, int M_SUB>
+template <int BLOCK_N, int M_SUB, bool EPI_TMA>
 static int dispatch_k(const fv_conv_desc* d, ConvTcParams& p, cudaStream_t s) {
-  if (d->a_pitch > 32) return launch_tc<BLOCK_N, M_SUB, 64>(d, p, s);
+  if (d->a_pitch > 32) return launch_tc<BLOCK_N, M_SUB, 64, EPI_TMA>(d, p, s);
   if constexpr (M_SUB == 2) {
-    if (d->a_pitch > 16) return launch_tc<BLOCK_N, 2, 32>(d, p, s);
-    return launch_tc<BLOCK_N, 2, 16>(d, p, s);
+    if (d->a_pitch > 16) return launch_tc<BLOCK_N, 2, 32, EPI_TMA>(d, p, s);
+    return launch_tc<BLOCK_N, 2, 16, EPI_TMA>(d, p, s);
   } else {
-    return launch_tc<BLOCK_N, M_SUB, 64>(d, p, s);  // small-K variants only exist for M_SUB == 2
+    return launch_tc<BLOCK_N, M_SUB, 64, EPI_TMA>(d, p, s);  // small-K variants only exist for M_SUB == 2
   }
 }
 
 template <int BLOCK_N>
-static int dispatch_m(const fv_conv_desc* d, ConvTcParams& p, cudaStream_t s, int m_sub) {
-  if (m_sub == 1) return dispatch_k<BLOCK_N, 1>(d, p, s);
-  return dispatch_k<BLOCK_N, 2>(d, p, s);
+static int dispatch_m(const fv_conv_desc* d, ConvTcParams& p, cudaStream_t s, int m_sub, bool epi_tma) {
+  if constexpr (BLOCK_N >= 32) {
+    if (epi_tma) {
+      if (m_sub == 1) return dispatch_k<BLOCK_N, 1, true>(d, p, s);
+      return dispatch_k<BLOCK_N, 2, true>(d, p, s);
+    }
+  }
+  if (m_sub == 1) return dispatch_k<BLOCK_N, 1, false>(d, p, s);
+  return dispatch_k<BLOCK_N, 2, false>(d, p, s);
 }
 
 int pick_block_n(int C_out) {
@@ -425,7 +639,7 @@ int pick_block_n(int C_out) {
 }
 
 // Called by fv_conv1d (fv_api.cu) after argument validation.  m_sub_override / block_n_override: 0 = heuristic.
-int conv1d_tc(const fv_conv_desc* d, cudaStream_t stream, int block_n_override, int m_sub_override) {
+int conv1d_tc(const fv_conv_desc* d, cudaStream_t stream, int block_n_override, int m_sub_override, int epilogue) {
   ConvTcParams p;
   memset(&p, 0, sizeof(p));
   p.B = d->B;
@@ -452,14 +666,17 @@ int conv1d_tc(const fv_conv_desc* d, cudaStream_t stream, int block_n_override, 
 
   const int bn = block_n_override ? block_n_override : pick_block_n(d->C_out);
   // two 128-row accumulators per CTA share every weight tile; a single one when the sequence is short
-  int m_sub = m_sub_override ? m_sub_override : (p.q_rows > 128 ? 2 : 1);
+  int m_sub = m_sub_override ? m_sub_override : ((p.q_rows > 128 && bn < 256) ? 2 : 1);
   if (d->a_pitch <= 32) m_sub = 2;
+  // TMA epilogue needs a rectangular {phase, q} view of the output rows; epilogue: 0 = auto, 1 = LSU, 2 = TMA
+  const bool tma_ok = (d->L_out % d->n_phase) == 0 && bn >= 32;
+  const bool epi_tma = tma_ok && epilogue != 1;
   switch (bn) {
-    case 16: return dispatch_m<16>(d, p, stream, m_sub);
-    case 32: return dispatch_m<32>(d, p, stream, m_sub);
-    case 64: return dispatch_m<64>(d, p, stream, m_sub);
-    case 128: return dispatch_m<128>(d, p, stream, m_sub);
-    case 256: return dispatch_m<256>(d, p, stream, m_sub);
+    case 16: return dispatch_m<16>(d, p, stream, m_sub, epi_tma);
+    case 32: return dispatch_m<32>(d, p, stream, m_sub, epi_tma);
+    case 64: return dispatch_m<64>(d, p, stream, m_sub, epi_tma);
+    case 128: return dispatch_m<128>(d, p, stream, m_sub, epi_tma);
+    case 256: return dispatch_m<256>(d, p, stream, m_sub, epi_tma);
     default: return set_error(FV_E_BADARG, "unsupported BLOCK_N %d", bn);
   }
 }
