@@ -177,3 +177,21 @@ def test_pack_conv_same_padding(k, d):
                    padding=(k * d - d) // 2).permute(0, 2, 1)
     assert float((_ref_from_pack(a, pc, L) - ref).abs().max()) < 1e-9
     assert pc.c_out_pad % 16 == 0 and pc.w_pitch % 8 == 0
+
+
+def test_compat_package_provides_reference_dotted_paths():
+    import importlib
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "compat"))
+    try:
+        for mod, name in [("fish_vocoder.modules.generators.hifigan", "HiFiGANGenerator"),
+                          ("fish_vocoder.modules.generators.bigvgan", "BigVGANGenerator"),
+                          ("fish_vocoder.modules.generators.unify", "UnifyGenerator"),
+                          ("fish_vocoder.modules.generators.vocos", "ISTFTHead"),
+                          ("fish_vocoder.modules.encoders.convnext", "ConvNeXtEncoder")]:
+            cls = getattr(importlib.import_module(mod), name)
+            assert cls.__module__.startswith("vocoder_b200.")
+    finally:
+        sys.path.remove(os.path.join(ROOT, "compat"))
+        for k in [k for k in sys.modules if k == "fish_vocoder" or k.startswith("fish_vocoder.")]:
+            del sys.modules[k]

@@ -197,8 +197,17 @@ struct SnakeFilt {
   float dn[12];
 };
 
+// sin with a two-constant Cody-Waite reduction to [-pi, pi] followed by the SFU sine: absolute error ~1e-6 for
+// |t| up to ~1e4 (the reduced argument is exact to ~2e-7 * |t| / 2pi), against ~30 instructions for sinf().
+__device__ __forceinline__ float fast_sin(float t) {
+  const float k = rintf(t * 0.15915494309189535f);
+  float r = fmaf(k, -6.2831854820251465f, t);      // 2pi hi (fp32)
+  r = fmaf(k, 1.7484556000744883e-07f, r);          // 2pi hi - 2pi
+  return __sinf(r);
+}
+
 __device__ __forceinline__ float snake_fn(float u, float a, float inv_b) {
-  const float s = sinf(u * a);
+  const float s = fast_sin(u * a);
   return fmaf(inv_b * s, s, u);
 }
 
