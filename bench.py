@@ -189,6 +189,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=0, help="utterances in the CPU baseline sample (0 = auto)")
+    ap.add_argument("--micro-batch", type=int, default=0,
+                    help="utterances per residual-block pass (0 = whole batch, the measured optimum)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -245,6 +247,8 @@ def main():
     for m in model.modules():
         if hasattr(m, "use_cuda_graph"):
             m.use_cuda_graph = False
+        if args.micro_batch > 0 and hasattr(m, "micro_batch"):
+            m.micro_batch = args.micro_batch
     mel_host = synthetic_mel(B, n_mels, T, 1234 + rank).pin_memory()
     mel = mel_host.to(dev)
     wav_host = torch.empty(B, 1, T * hop).pin_memory()
@@ -344,6 +348,7 @@ def main():
         config["l2"] = ("L2 flushed between timed steps (256 MiB memset outside the per-step event pairs); per-step "
                         f"working set {sum(m._ws.nbytes() for m in model.modules() if hasattr(m, '_ws')) / 1e9:.2f} GB > 126 MB L2")
         config["cuda_graph"] = not args.no_graph
+        config["micro_batch"] = args.micro_batch if args.micro_batch > 0 else "whole batch"
         line = {"metric": "audio samples/sec, mel->wav generator forward", "value": value, "unit": "samples/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -191,14 +191,14 @@ __global__ void conv_post_kernel(const __half* __restrict__ a, const float* __re
 // anti-aliased Snake: up 2x (polyphase 6+6 taps) -> x + sin^2(a x)/(b+1e-9) -> down 2x (12 taps), one pass.
 // One thread = one channel x SN_T consecutive time steps; the activated 2x signal lives only in registers.
 // ------------------------------------------------------------------------------------------------
-constexpr int SN_T = 16;
+constexpr int SN_SEG = 48;  // time steps per thread (a multiple of 6, the period of the register rings)
 struct SnakeFilt {
   float up[12];
   float dn[12];
 };
 
 // sin with a two-constant Cody-Waite reduction to [-pi, pi] followed by the SFU sine: absolute error ~1e-6 for
-// |t| up to ~1e4 (the reduced argument is exact to ~2e-7 * |t| / 2pi), against ~30 instructions for sinf().
+// |t| up to ~1e4 (the reduced argument is exact to ~1e-7), against ~30 instructions for sinf().
 __device__ __forceinline__ float fast_sin(float t) {
   const float k = rintf(t * 0.15915494309189535f);
   float r = fmaf(k, -6.2831854820251465f, t);      // 2pi hi (fp32)
@@ -211,20 +211,27 @@ __device__ __forceinline__ float snake_fn(float u, float a, float inv_b) {
   return fmaf(inv_b * s, s, u);
 }
 
-__global__ void __launch_bounds__(256) snake_aa_kernel(const float* __restrict__ x, __half* __restrict__ out,
+// Streaming formulation (Appendix B4 of SURVEY.md).  With x~ the edge-replicated input and v~ the edge-replicated
+// activated 2x signal:   out[t] = sum_j f[j] * v~[2t - 5 + j],  and both new values a step needs,
+//   v[2t+7] = act(2 * sum_q f[2q]   * x~[t+6-q]),   v[2t+8] = act(2 * sum_q f[2q+1] * x~[t+6-q]),
+// read the same 6-sample window.  A thread owns one channel and marches over SN_SEG steps keeping x~[t+1..t+6] in a
+// 6-register ring and v~[2t-5..2t+6] in a 12-register ring (unrolled by 6 so ring slots are compile-time registers):
+// one 4-byte load, 24 FMA, 2 SFU sines and one 2-byte store per sample; six "pre-roll" steps fill the rings.
+__global__ void __launch_bounds__(256, 3) snake_aa_kernel(const float* __restrict__ x, __half* __restrict__ out,
                                                        const float* __restrict__ alpha, const float* __restrict__ beta,
                                                        const SnakeFilt f, int logscale, int B, int L, int C, int pitch,
-                                                       int n_chunks) {
-  const long long total = (long long)B * n_chunks * pitch;
+                                                       int n_seg) {
+  const long long total = (long long)B * n_seg * pitch;
   const long long item = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (item >= total) return;
   const int c = (int)(item % pitch);
-  const int chunk = (int)((item / pitch) % n_chunks);
-  const int b = (int)(item / ((long long)pitch * n_chunks));
-  const int t0 = chunk * SN_T;
+  const int seg = (int)((item / pitch) % n_seg);
+  const int b = (int)(item / ((long long)pitch * n_seg));
+  const int t0 = seg * SN_SEG;
+  const int t_end = min(t0 + SN_SEG, L);
   __half* orow = out + ((size_t)b * L) * pitch + c;
   if (c >= C) {  // padded channels stay zero
-    for (int tt = 0; tt < SN_T && t0 + tt < L; ++tt) orow[(size_t)(t0 + tt) * pitch] = __float2half_rn(0.f);
+    for (int t = t0; t < t_end; ++t) orow[(size_t)t * pitch] = __float2half_rn(0.f);
     return;
   }
   float a = alpha[c];
@@ -235,55 +242,63 @@ __global__ void __launch_bounds__(256) snake_aa_kernel(const float* __restrict__
   }
   const float inv_b = 1.0f / (bb + 1e-9f);
   const float* xc = x + ((size_t)b * L) * pitch + c;
+  const int nl = 2 * L - 1;
+  auto ldx = [&](int t) {
+    t = t < 0 ? 0 : (t > L - 1 ? L - 1 : t);  // replicate edge of the INPUT (first filter pads its own input)
+    return xc[(size_t)t * pitch];
+  };
 
-  float xs[SN_T + 10];
+  float X[6];   // ring: x~[t+6-q] lives in X[(k - q) mod 6] at unrolled position k
+  float V[12];  // ring: v~[2t-5+j] lives in V[(2k + j) mod 12]
+  float vlast = 0.f;
+  // window before the first pre-roll step (t = t0 - 6): x~[t+1 .. t+5] = x~[t0-5 .. t0-1] in X[1..5]
 #pragma unroll
-  for (int i = 0; i < SN_T + 10; ++i) {
-    int t = t0 - 5 + i;
-    t = t < 0 ? 0 : (t > L - 1 ? L - 1 : t);  // replicate edge of the INPUT (first filter)
-    xs[i] = xc[(size_t)t * pitch];
-  }
-  // v[i] = act(up[n]), n = 2*t0 - 5 + i
-  float v[2 * SN_T + 10];
+  for (int i = 1; i < 6; ++i) X[i] = ldx(t0 - 6 + i);
 #pragma unroll
-  for (int i = 0; i < 2 * SN_T + 10; ++i) {
-    float u = 0.f;
-    if ((i & 1) == 0) {  // n odd: up[2s+1] = 2 * sum_q f[2q] * x[s+3-q],  xs index i/2 + 5 - q
-#pragma unroll
-      for (int q = 0; q < 6; ++q) u = fmaf(f.up[2 * q], xs[i / 2 + 5 - q], u);
-    } else {             // n even: up[2s] = 2 * sum_q f[2q+1] * x[s+2-q],  xs index (i+9)/2 - q
-#pragma unroll
-      for (int q = 0; q < 6; ++q) u = fmaf(f.up[2 * q + 1], xs[(i + 9) / 2 - q], u);
-    }
-    v[i] = snake_fn(2.0f * u, a, inv_b);
-  }
-  // replicate edges of the ACTIVATED 2x signal (second filter pads its own input)
-  if (t0 == 0) {
-#pragma unroll
-    for (int i = 0; i < 5; ++i) v[i] = v[5];  // n < 0 -> v[n = 0]
-  }
-  const int n_last = 2 * L - 1;
-  if (2 * t0 - 5 + (2 * SN_T + 9) > n_last) {
-    // v[n = 2L-1] = act(2 * sum_q f[2q] * x~[L+2-q])
-    float u = 0.f;
+  for (int k = 0; k < 6; ++k) {  // pre-roll: t = t0 - 6 + k produces v[2t0-5+2k], v[2t0-4+2k]
+    const int t = t0 - 6 + k;
+    X[k] = ldx(t + 6);
+    float uo = 0.f, ue = 0.f;
 #pragma unroll
     for (int q = 0; q < 6; ++q) {
-      int t = L + 2 - q;
-      t = t > L - 1 ? L - 1 : (t < 0 ? 0 : t);
-      u = fmaf(f.up[2 * q], xc[(size_t)t * pitch], u);
+      const float xv = X[(k - q + 6) % 6];
+      uo = fmaf(f.up[2 * q], xv, uo);
+      ue = fmaf(f.up[2 * q + 1], xv, ue);
     }
-    const float vl = snake_fn(2.0f * u, a, inv_b);
-#pragma unroll
-    for (int i = 0; i < 2 * SN_T + 10; ++i)
-      if (2 * t0 - 5 + i > n_last) v[i] = vl;
+    float va = snake_fn(2.0f * uo, a, inv_b), vb = snake_fn(2.0f * ue, a, inv_b);
+    if (2 * t + 7 <= nl) vlast = va; else va = vlast;
+    if (2 * t + 8 <= nl) vlast = vb; else vb = vlast;
+    V[(2 * k) % 12] = va;
+    V[(2 * k + 1) % 12] = vb;
   }
+  if (t0 == 0) {  // v~[n < 0] = v[0]: replicate edge of the ACTIVATED signal (second filter pads its own input)
 #pragma unroll
-  for (int tt = 0; tt < SN_T; ++tt) {
-    if (t0 + tt < L) {
+    for (int j = 0; j < 5; ++j) V[j] = V[5];
+  }
+  for (int tb = t0; tb < t_end; tb += 6) {
+    float xn[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) xn[k] = ldx(tb + k + 6);  // six independent loads in flight
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const int t = tb + k;
       float o = 0.f;
 #pragma unroll
-      for (int j = 0; j < 12; ++j) o = fmaf(f.dn[j], v[2 * tt + j], o);
-      orow[(size_t)(t0 + tt) * pitch] = to_half_sat(o);
+      for (int j = 0; j < 12; ++j) o = fmaf(f.dn[j], V[(2 * k + j) % 12], o);
+      if (t < t_end) orow[(size_t)t * pitch] = to_half_sat(o);
+      X[k] = xn[k];
+      float uo = 0.f, ue = 0.f;
+#pragma unroll
+      for (int q = 0; q < 6; ++q) {
+        const float xv = X[(k - q + 6) % 6];
+        uo = fmaf(f.up[2 * q], xv, uo);
+        ue = fmaf(f.up[2 * q + 1], xv, ue);
+      }
+      float va = snake_fn(2.0f * uo, a, inv_b), vb = snake_fn(2.0f * ue, a, inv_b);
+      if (2 * t + 7 <= nl) vlast = va; else va = vlast;
+      if (2 * t + 8 <= nl) vlast = vb; else vb = vlast;
+      V[(2 * k) % 12] = va;
+      V[(2 * k + 1) % 12] = vb;
     }
   }
 }
@@ -493,10 +508,10 @@ extern "C" int fv_snake_aa(const float* x32, void* out16, const float* alpha, co
     f.up[i] = filt_up[i];
     f.dn[i] = filt_down[i];
   }
-  const int n_chunks = ceil_div(L, SN_T);
-  const long long total = (long long)B * n_chunks * pitch;
+  const int n_seg = ceil_div(L, SN_SEG);
+  const long long total = (long long)B * n_seg * pitch;
   snake_aa_kernel<<<grid1d(total, 256), 256, 0, (cudaStream_t)stream>>>(x32, (__half*)out16, alpha, beta, f, logscale,
-                                                                       B, L, C, pitch, n_chunks);
+                                                                       B, L, C, pitch, n_seg);
   FV_CHECK_LAUNCH("snake_aa_kernel");
   return 0;
 }

@@ -202,33 +202,44 @@ class MRFGeneratorBase(nn.Module):
                 cabi.conv1d(h16, up, Lo, residual=nz, out32=x0, out16=xa0, act=cabi.ACT_SILU, engine=eng)
             acc = ws.f32(f"acc_{i}", B, Lo, C, dev)
             h_next = ws.f16(f"h_{i}", B, Lo, C, dev)
-            xr_w = ws.f32(f"xr_{i}", B, Lo, C, dev)
-            xa_w = ws.f16(f"xa_{i}", B, Lo, C, dev)
-            ta = ws.f16(f"ta_{i}", B, Lo, C, dev)
-            t32 = ws.f32(f"t32_{i}", B, Lo, C, dev) if self.snake_blocks else None
+            # The residual blocks can run per micro-batch of utterances (working set resident in the 126 MB L2).
+            # Measured on B200 (HiFiGAN cfg B): 64 -> 8.6 ms, 32 -> 9.4 ms, 16 -> 10.6 ms, 8 -> 13.7 ms per forward:
+            # tail and launch effects outweigh the L2 hits, so the default is the whole batch.
+            mb = self._micro_batch(B, Lo, C)
+            xr_w = ws.f32(f"xr_{i}", mb, Lo, C, dev)
+            xa_w = ws.f16(f"xa_{i}", mb, Lo, C, dev)
+            ta = ws.f16(f"ta_{i}", mb, Lo, C, dev)
+            t32 = ws.f32(f"t32_{i}", mb, Lo, C, dev) if self.snake_blocks else None
             blocks = P["blocks"][i]
             nk = len(blocks)
             out_act, out_act_p = self._stage_out_act(last_stage)
-            for j, (c1s, c2s, blk) in enumerate(blocks):
-                xr, xa = x0, xa0
-                n_pairs = len(c1s)
-                for p_i in range(n_pairs):
-                    last_pair = p_i == n_pairs - 1
-                    if self.snake_blocks:
-                        self._snake(blk.activations[2 * p_i], xr, xa_w, C)
-                        cabi.conv1d(xa_w, c1s[p_i], out32=t32, engine=eng)
-                        self._snake(blk.activations[2 * p_i + 1], t32, ta, C)
-                    else:
-                        cabi.conv1d(xa, c1s[p_i], out16=ta, act=cabi.ACT_SILU, engine=eng)
-                    if not last_pair:
-                        cabi.conv1d(ta, c2s[p_i], residual=xr, out32=xr_w,
-                                    out16=None if self.snake_blocks else xa_w, act=cabi.ACT_SILU, engine=eng)
-                        xr, xa = xr_w, xa_w
-                    else:
-                        want16 = (j == nk - 1) and out_act is not None
-                        cabi.conv1d(ta, c2s[p_i], residual=xr, out32=acc, accumulate=j > 0, out_scale=1.0 / nk,
-                                    out16=h_next if want16 else None, act=out_act if want16 else cabi.ACT_NONE,
-                                    act_param=out_act_p, engine=eng)
+            for b0 in range(0, B, mb):
+                b1 = min(B, b0 + mb)
+                n = b1 - b0
+                x0_m, acc_m, h_m = x0[b0:b1], acc[b0:b1], h_next[b0:b1]
+                xa0_m = None if xa0 is None else xa0[b0:b1]
+                xr_m, xa_m, ta_m = xr_w[:n], xa_w[:n], ta[:n]
+                t32_m = None if t32 is None else t32[:n]
+                for j, (c1s, c2s, blk) in enumerate(blocks):
+                    xr, xa = x0_m, xa0_m
+                    n_pairs = len(c1s)
+                    for p_i in range(n_pairs):
+                        last_pair = p_i == n_pairs - 1
+                        if self.snake_blocks:
+                            self._snake(blk.activations[2 * p_i], xr, xa_m, C)
+                            cabi.conv1d(xa_m, c1s[p_i], out32=t32_m, engine=eng)
+                            self._snake(blk.activations[2 * p_i + 1], t32_m, ta_m, C)
+                        else:
+                            cabi.conv1d(xa, c1s[p_i], out16=ta_m, act=cabi.ACT_SILU, engine=eng)
+                        if not last_pair:
+                            cabi.conv1d(ta_m, c2s[p_i], residual=xr, out32=xr_m,
+                                        out16=None if self.snake_blocks else xa_m, act=cabi.ACT_SILU, engine=eng)
+                            xr, xa = xr_m, xa_m
+                        else:
+                            want16 = (j == nk - 1) and out_act is not None
+                            cabi.conv1d(ta_m, c2s[p_i], residual=xr, out32=acc_m, accumulate=j > 0,
+                                        out_scale=1.0 / nk, out16=h_m if want16 else None,
+                                        act=out_act if want16 else cabi.ACT_NONE, act_param=out_act_p, engine=eng)
             if last_stage:
                 self._final_activation(acc, h_next, C)
             h16, L = h_next, Lo
@@ -237,3 +248,21 @@ class MRFGeneratorBase(nn.Module):
 
     def _snake(self, act_module, x32, out16, C):
         raise NotImplementedError
+
+    #: utterances per residual-block pass; None = whole batch; 0 = size the block working set for L2 (_micro_batch)
+    micro_batch = None
+    l2_budget_bytes = 96 * 1024 * 1024
+
+    def _micro_batch(self, B: int, L: int, C: int) -> int:
+        if self.micro_batch is None:
+            return B
+        if self.micro_batch > 0:
+            return max(1, min(B, int(self.micro_batch)))
+        # live set of one (c1, c2) pair per utterance: xr fp32 (read + written in place), xa + ta fp16 (+ t32 fp32)
+        per_utt = L * cabi.pitch_of(C) * (4 + 2 + 2 + (4 if self.snake_blocks else 0))
+        mb = max(1, self.l2_budget_bytes // max(1, per_utt))
+        # keep at least ~2 waves of 256-row tiles on 148 SMs when the batch allows it
+        tiles_per_utt = -(-L // 256)
+        mb = min(B, max(mb, -(-296 // tiles_per_utt)))
+        n_chunks = -(-B // mb)
+        return int(-(-B // n_chunks))  # equal-sized chunks
