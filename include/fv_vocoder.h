@@ -149,13 +149,18 @@ FV_API int fv_istft_ola(const float* frames, const float* window, float* wav, in
 FV_API int fv_noise_conv(const float* tpl, const float* w, const float* bias, float* out32, int B, int L_audio, int L_out,
                   int C, int pitch, int k, int stride, int pad, void* stream);
 
-/* RefineGAN helpers (refinegan.py:124-127,222,252,302-313): elementwise/linear-resample glue, channels-last.
- * fv_act_cast: out16 = fp16(act(x32 [+ noise*noise_w[c]]))   (AdaIN when noise != NULL, plain leaky otherwise)
- * fv_resample_linear: F.interpolate(mode="linear", align_corners=False) along L; scale = 1/scale_factor. */
+/* RefineGAN helpers (refinegan.py:124-127,222,252,302-313): elementwise / linear-resample glue, channels-last.
+ * fv_act_cast:  v = act(x32 [+ noise * noise_w[c]]);   (noise != NULL: AdaIN, refinegan.py:124-127)
+ *               out32[.., c]              = v * out_scale (+ out32 if accumulate)        fp32 [B][L][out32_pitch]
+ *               out16[.., out16_coff + c] = fp16(act16(v))    (channel slice of a wider buffer = torch.cat for free)
+ * fv_resample_linear: F.interpolate(mode="linear", align_corners=False) along L of pre_act(x32), then act;
+ *               scale = 1 / scale_factor (what torch uses when scale_factor is given). */
 FV_API int fv_act_cast(const float* x32, const float* noise, const float* noise_w, void* out16, float* out32, int act,
-                float act_param, int B, int L, int C, int in_pitch, int out_pitch, int out_coff, void* stream);
-FV_API int fv_resample_linear(const float* x32, float* out32, void* out16, int act, float act_param, int B, int L_in,
-                       int L_out, int C, int in_pitch, int out_pitch, int out_coff, float scale, void* stream);
+                       float act_param, int act16, float act16_param, float out_scale, int accumulate, int B, int L,
+                       int C, int in_pitch, int out16_pitch, int out16_coff, int out32_pitch, void* stream);
+FV_API int fv_resample_linear(const float* x32, float* out32, void* out16, int pre_act, float pre_param, int act,
+                              float act_param, int B, int L_in, int L_out, int C, int in_pitch, int out_pitch,
+                              int out_coff, float scale, void* stream);
 
 /* bring-up probe (not on the product path): 12 row shifts x {base_offset 0, base_offset r&7} of a 128x64x64 UMMA whose
  * A descriptor starts r rows into a TMA-written 144x64 fp16 slab.  a16 [144][64], w16 [64][64], out [12][2][128][64]. */

@@ -12,7 +12,8 @@ import torch.nn.functional as F
 from tests.util import GOLDEN, load_golden
 from vocoder_b200 import cabi
 from vocoder_b200.encoders import ConvNeXtEncoder
-from vocoder_b200.generators import BigVGANGenerator, HiFiGANGenerator, ISTFTHead, UnifyGenerator
+from vocoder_b200.generators import (BigVGANGenerator, HiFiGANGenerator, ISTFTHead, RefineGANGenerator,
+                                     UnifyGenerator)
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -35,10 +36,12 @@ def _build(name):
             backbone=ConvNeXtEncoder(input_channels=128, depths=[3, 3, 27, 3], dims=[128, 256, 512, 1024],
                                      drop_path_rate=0.4, kernel_size=7),
             head=ISTFTHead(dim=1024, n_fft=2048, hop_length=512, win_length=2048, padding="same"))
+    if name == "refinegan_default":
+        return RefineGANGenerator()
     raise KeyError(name)
 
 
-@pytest.mark.parametrize("name", ["hifigan_cfgA", "hifigan_yaml_44k", "bigvgan_cfgC", "vocos_yaml"])
+@pytest.mark.parametrize("name", ["hifigan_cfgA", "hifigan_yaml_44k", "bigvgan_cfgC", "vocos_yaml", "refinegan_default"])
 def test_state_dict_layout_matches_reference(name):
     want = _contract()[name]
     got = {k: list(v.shape) for k, v in _build(name).state_dict().items()}
@@ -47,7 +50,8 @@ def test_state_dict_layout_matches_reference(name):
 
 @pytest.mark.parametrize("name,cls", [("hifigan_small_ref", HiFiGANGenerator),
                                       ("hifigan_template_stress", HiFiGANGenerator),
-                                      ("bigvgan_small_stress", BigVGANGenerator)])
+                                      ("bigvgan_small_stress", BigVGANGenerator),
+                                      ("refinegan_small_stress", RefineGANGenerator)])
 def test_reference_state_dict_loads_strict(name, cls):
     kwargs, sd, _, _, _ = load_golden(name)
     m = cls(**kwargs)

@@ -311,8 +311,18 @@ def group_simt():
     nw = torch.randn(16, generator=g)
     ref = F.leaky_relu(xx + nz * nw, 0.2)
     o = torch.empty(2, 64, 16, device=dev)
-    cabi.act_cast(xx.to(dev), 16, cabi.ACT_LEAKY, 0.2, noise=nz.to(dev), noise_w=nw.to(dev), out32=o)
-    res.append({"name": "act_cast_adain", "err": float((o.cpu() - ref).abs().max())})
+    o16 = torch.zeros(2, 64, 24, dtype=torch.float16, device=dev)
+    cabi.act_cast(xx.to(dev), 16, cabi.ACT_LEAKY, 0.2, noise=nz.to(dev), noise_w=nw.to(dev), out32=o, out16=o16,
+                  out16_coff=8, act16=cabi.ACT_LEAKY, act16_param=0.2)
+    res.append({"name": "act_cast_adain", "err": float((o.cpu() - ref).abs().max()),
+                "err16": float((o16.float().cpu()[..., 8:24] - F.leaky_relu(ref, 0.2)).abs().max())})
+    o2 = o.clone()
+    cabi.act_cast(xx.to(dev), 16, cabi.ACT_NONE, out32=o2, out_scale=0.5, accumulate=True)
+    res.append({"name": "act_cast_accumulate", "err": float((o2.cpu() - (ref + 0.5 * xx)).abs().max())})
+    ref = F.interpolate(F.leaky_relu(xx, 0.2).permute(0, 2, 1), scale_factor=2.0, mode="linear").permute(0, 2, 1)
+    o = torch.empty(2, 128, 16, device=dev)
+    cabi.resample_linear(xx.to(dev), 16, 128, 0.5, pre_act=cabi.ACT_LEAKY, pre_param=0.2, out32=o)
+    res.append({"name": "resample_preact", "err": float((o.cpu() - ref).abs().max())})
     torch.cuda.synchronize()
     return res
 

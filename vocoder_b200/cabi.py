@@ -78,8 +78,8 @@ def lib() -> ctypes.CDLL:
     L.fv_dwconv_layernorm.argtypes = [vp, vp, vp, vp, vp, vp, vp, cf, ci, ci, ci, ci, ci, vp]
     L.fv_istft_ola.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, vp]
     L.fv_noise_conv.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, vp]
-    L.fv_act_cast.argtypes = [vp, vp, vp, vp, vp, ci, cf, ci, ci, ci, ci, ci, ci, vp]
-    L.fv_resample_linear.argtypes = [vp, vp, vp, ci, cf, ci, ci, ci, ci, ci, ci, ci, cf, vp]
+    L.fv_act_cast.argtypes = [vp, vp, vp, vp, vp, ci, cf, ci, cf, cf, ci, ci, ci, ci, ci, ci, ci, ci, vp]
+    L.fv_resample_linear.argtypes = [vp, vp, vp, ci, cf, ci, cf, ci, ci, ci, ci, ci, ci, ci, cf, vp]
     L.fv_debug_rowshift_probe.argtypes = [vp, vp, vp, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
@@ -310,21 +310,24 @@ def noise_conv(tpl: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, out32: to
 
 
 def act_cast(x32: torch.Tensor, C: int, act: int, act_param: float = 0.0, *, noise=None, noise_w=None,
-             out16=None, out32=None, out_coff: int = 0) -> None:
+             out16=None, out16_coff: int = 0, act16: int = ACT_NONE, act16_param: float = 0.0, out32=None,
+             out_scale: float = 1.0, accumulate: bool = False) -> None:
     B, L, in_pitch = x32.shape
-    o = out16 if out16 is not None else out32
     _check(lib().fv_act_cast(_ptr(x32, torch.float32), _ptr(noise, torch.float32), _ptr(noise_w, torch.float32),
                              _ptr(out16, torch.float16), _ptr(out32, torch.float32), int(act), float(act_param),
-                             B, L, C, in_pitch, o.shape[2], out_coff, _stream()), "fv_act_cast")
+                             int(act16), float(act16_param), float(out_scale), int(bool(accumulate)), B, L, C,
+                             in_pitch, 0 if out16 is None else out16.shape[2], out16_coff,
+                             0 if out32 is None else out32.shape[2], _stream()), "fv_act_cast")
 
 
-def resample_linear(x32: torch.Tensor, C: int, L_out: int, scale: float, *, act=ACT_NONE, act_param=0.0,
-                    out16=None, out32=None, out_coff: int = 0) -> None:
+def resample_linear(x32: torch.Tensor, C: int, L_out: int, scale: float, *, pre_act=ACT_NONE, pre_param=0.0,
+                    act=ACT_NONE, act_param=0.0, out16=None, out32=None, out_coff: int = 0) -> None:
     B, L_in, in_pitch = x32.shape
     o = out16 if out16 is not None else out32
     _check(lib().fv_resample_linear(_ptr(x32, torch.float32), _ptr(out32, torch.float32),
-                                    _ptr(out16, torch.float16), int(act), float(act_param), B, L_in, L_out, C,
-                                    in_pitch, o.shape[2], out_coff, float(scale), _stream()), "fv_resample_linear")
+                                    _ptr(out16, torch.float16), int(pre_act), float(pre_param), int(act),
+                                    float(act_param), B, L_in, L_out, C, in_pitch, o.shape[2], out_coff, float(scale),
+                                    _stream()), "fv_resample_linear")
 
 
 def launch_count() -> int:

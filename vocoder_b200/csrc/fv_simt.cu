@@ -408,8 +408,9 @@ __global__ void noise_conv_kernel(const float* __restrict__ tpl, const float* __
 // ------------------------------------------------------------------------------------------------
 __global__ void act_cast_kernel(const float* __restrict__ x, const float* __restrict__ noise,
                                 const float* __restrict__ noise_w, __half* __restrict__ out16,
-                                float* __restrict__ out32, int act, float param, long long rows, int C, int in_pitch,
-                                int out_pitch, int out_coff) {
+                                float* __restrict__ out32, int act, float param, int act16, float param16,
+                                float out_scale, int accumulate, long long rows, int C, int in_pitch,
+                                int out16_pitch, int out16_coff, int out32_pitch) {
   const long long total = rows * C;
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (idx >= total) return;
@@ -418,13 +419,18 @@ __global__ void act_cast_kernel(const float* __restrict__ x, const float* __rest
   float v = x[r * in_pitch + c];
   if (noise) v = fmaf(noise[r * in_pitch + c], noise_w[c], v);
   v = act_apply(v, act, param);
-  if (out16) out16[r * out_pitch + out_coff + c] = to_half_sat(v);
-  if (out32) out32[r * out_pitch + out_coff + c] = v;
+  if (out32) {
+    float o = v * out_scale;
+    if (accumulate) o += out32[r * out32_pitch + c];
+    out32[r * out32_pitch + c] = o;
+  }
+  if (out16) out16[r * out16_pitch + out16_coff + c] = to_half_sat(act_apply(v, act16, param16));
 }
 
 __global__ void resample_linear_kernel(const float* __restrict__ x, float* __restrict__ out32,
-                                       __half* __restrict__ out16, int act, float param, int B, int L_in, int L_out,
-                                       int C, int in_pitch, int out_pitch, int out_coff, float scale) {
+                                       __half* __restrict__ out16, int pre_act, float pre_param, int act, float param,
+                                       int B, int L_in, int L_out, int C, int in_pitch, int out_pitch, int out_coff,
+                                       float scale) {
   const long long total = (long long)B * L_out * C;
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (idx >= total) return;
@@ -438,7 +444,9 @@ __global__ void resample_linear_kernel(const float* __restrict__ x, float* __res
   const int i1 = i0 + 1 < L_in ? i0 + 1 : L_in - 1;
   const float lam = src - (float)i0;
   const float* xb = x + (size_t)b * L_in * in_pitch + c;
-  float v = (1.0f - lam) * xb[(size_t)i0 * in_pitch] + lam * xb[(size_t)i1 * in_pitch];
+  const float v0 = act_apply(xb[(size_t)i0 * in_pitch], pre_act, pre_param);
+  const float v1 = act_apply(xb[(size_t)i1 * in_pitch], pre_act, pre_param);
+  float v = (1.0f - lam) * v0 + lam * v1;
   v = act_apply(v, act, param);
   if (out32) out32[grow * out_pitch + out_coff + c] = v;
   if (out16) out16[grow * out_pitch + out_coff + c] = to_half_sat(v);
@@ -557,27 +565,32 @@ extern "C" int fv_noise_conv(const float* tpl, const float* w, const float* bias
 }
 
 extern "C" int fv_act_cast(const float* x32, const float* noise, const float* noise_w, void* out16, float* out32,
-                           int act, float act_param, int B, int L, int C, int in_pitch, int out_pitch, int out_coff,
+                           int act, float act_param, int act16, float act16_param, float out_scale, int accumulate,
+                           int B, int L, int C, int in_pitch, int out16_pitch, int out16_coff, int out32_pitch,
                            void* stream) {
-  FV_REQUIRE(x32 && (out16 || out32) && B > 0 && L > 0 && C > 0 && in_pitch >= C && out_pitch >= out_coff + C &&
+  FV_REQUIRE(x32 && (out16 || out32) && B > 0 && L > 0 && C > 0 && in_pitch >= C &&
                  (noise == nullptr || noise_w != nullptr),
              FV_E_BADARG, "fv_act_cast: bad arguments");
+  FV_REQUIRE(!out16 || out16_pitch >= out16_coff + C, FV_E_BADARG, "fv_act_cast: out16 slice exceeds its pitch");
+  FV_REQUIRE(!out32 || out32_pitch >= C, FV_E_BADARG, "fv_act_cast: out32 pitch too small");
   const long long rows = (long long)B * L;
   act_cast_kernel<<<grid1d(rows * C, 256), 256, 0, (cudaStream_t)stream>>>(
-      x32, noise, noise_w, (__half*)out16, out32, act, act_param, rows, C, in_pitch, out_pitch, out_coff);
+      x32, noise, noise_w, (__half*)out16, out32, act, act_param, act16, act16_param, out_scale, accumulate, rows, C,
+      in_pitch, out16_pitch, out16_coff, out32_pitch);
   FV_CHECK_LAUNCH("act_cast_kernel");
   return 0;
 }
 
-extern "C" int fv_resample_linear(const float* x32, float* out32, void* out16, int act, float act_param, int B,
-                                  int L_in, int L_out, int C, int in_pitch, int out_pitch, int out_coff, float scale,
-                                  void* stream) {
+extern "C" int fv_resample_linear(const float* x32, float* out32, void* out16, int pre_act, float pre_param, int act,
+                                  float act_param, int B, int L_in, int L_out, int C, int in_pitch, int out_pitch,
+                                  int out_coff, float scale, void* stream) {
   FV_REQUIRE(x32 && (out16 || out32) && B > 0 && L_in > 0 && L_out > 0 && C > 0 && in_pitch >= C &&
                  out_pitch >= out_coff + C && scale > 0.f,
              FV_E_BADARG, "fv_resample_linear: bad arguments");
   const long long total = (long long)B * L_out * C;
   resample_linear_kernel<<<grid1d(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      x32, out32, (__half*)out16, act, act_param, B, L_in, L_out, C, in_pitch, out_pitch, out_coff, scale);
+      x32, out32, (__half*)out16, pre_act, pre_param, act, act_param, B, L_in, L_out, C, in_pitch, out_pitch,
+      out_coff, scale);
   FV_CHECK_LAUNCH("resample_linear_kernel");
   return 0;
 }

@@ -17,11 +17,11 @@ class Workspace:
     def __init__(self):
         self._bufs: Dict[Tuple, torch.Tensor] = {}
 
-    def get(self, name: str, shape: Tuple[int, ...], dtype: torch.dtype, device) -> torch.Tensor:
+    def get(self, name: str, shape: Tuple[int, ...], dtype: torch.dtype, device, zero: bool = False) -> torch.Tensor:
         key = (name, tuple(shape), dtype, str(device))
         t = self._bufs.get(key)
         if t is None:
-            t = torch.empty(shape, dtype=dtype, device=device)
+            t = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=device)
             self._bufs[key] = t
         return t
 
