@@ -189,6 +189,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=0, help="utterances in the CPU baseline sample (0 = auto)")
+    ap.add_argument("--dump-launches", default=None, help="write the per-launch conv timing table (json) here")
     ap.add_argument("--micro-batch", type=int, default=0,
                     help="utterances per residual-block pass (0 = whole batch, the measured optimum)")
     args = ap.parse_args()
@@ -315,6 +316,9 @@ def main():
         with torch.no_grad():
             for _ in range(2):
                 recs = profile_conv_launches(model, mel)
+        if args.dump_launches:
+            with open(args.dump_launches, "w") as f:
+                json.dump(recs, f)
         t_conv = sum(r["ms"] for r in recs) * 1e-3
         fl = sum(r["flops"] for r in recs)
         by = sum(r["bytes"] for r in recs)

@@ -70,7 +70,7 @@ EPILOGUE = 0
 
 def run_conv_case(name, B, L, c_in, c_out, k=3, d=1, convT=None, act=0, use_res=False, use_gamma=False,
                   accumulate=False, scale=1.0, engines=("tc", "simt"), seed=0, time_it=False, check=True,
-                  want32=True):
+                  want32=True, want16=True):
     dev = "cuda"
     g = torch.Generator().manual_seed(seed)
     ap = cabi.pitch_of(c_in)
@@ -99,13 +99,13 @@ def run_conv_case(name, B, L, c_in, c_out, k=3, d=1, convT=None, act=0, use_res=
     for eng in engines:
         out32 = old.clone() if accumulate else (torch.full((B, L_out, r8), float("nan"), device=dev)
                                                 if want32 else None)
-        out16 = torch.full((B, L_out, r8), float("nan"), dtype=torch.float16, device=dev)
+        out16 = torch.full((B, L_out, r8), float("nan"), dtype=torch.float16, device=dev) if want16 else None
         e = cabi.ENGINE_TC if eng == "tc" else cabi.ENGINE_SIMT
         kw = dict(gamma=gamma, residual=residual, out32=out32, accumulate=accumulate, out_scale=scale,
                   out16=out16, act=act, act_param=0.2, engine=e)
         cabi.conv1d(a16, pc, L_out, **kw)
         torch.cuda.synchronize()
-        outs[eng] = (None if out32 is None else out32.cpu(), out16.float().cpu())
+        outs[eng] = (None if out32 is None else out32.cpu(), None if out16 is None else out16.float().cpu())
         if time_it and eng == "tc":
             kw["accumulate"] = False
             for _ in range(3):
@@ -345,7 +345,29 @@ def group_probe():
     return res
 
 
-GROUPS = {"probe": group_probe, "simt": group_simt, "conv_small": group_conv_small, "convT": group_convT, "gemm": group_gemm,
+def group_perf2():
+    """epilogue / pipeline floor experiments on the HiFiGAN stage-2 shape (B=64, L=6016, C=128)"""
+    A = cabi
+    out = []
+    kw = dict(B=64, L=6016, c_in=128, c_out=128, engines=("tc",), check=False, time_it=True)
+    out.append(run_conv_case(name="c1_k1_none", k=1, act=A.ACT_NONE, want32=False, **kw))
+    out.append(run_conv_case(name="c1_k1_silu", k=1, act=A.ACT_SILU, want32=False, **kw))
+    out.append(run_conv_case(name="c1_k3_none", k=3, act=A.ACT_NONE, want32=False, **kw))
+    out.append(run_conv_case(name="c1_k3_silu", k=3, act=A.ACT_SILU, want32=False, **kw))
+    out.append(run_conv_case(name="c1_k7_none", k=7, act=A.ACT_NONE, want32=False, **kw))
+    out.append(run_conv_case(name="c1_k7_silu", k=7, act=A.ACT_SILU, want32=False, **kw))
+    out.append(run_conv_case(name="o32only_k3", k=3, act=A.ACT_NONE, want32=True, want16=False, **kw))
+    out.append(run_conv_case(name="c2_k3_res_silu", k=3, act=A.ACT_SILU, use_res=True, **kw))
+    for msub in (1, 2):
+        cabi.set_tc_tuning(0, msub, EPILOGUE)
+        out.append(run_conv_case(name=f"c1_k3_silu_msub{msub}", k=3, act=A.ACT_SILU, want32=False, **kw))
+    cabi.set_tc_tuning(64, 2, EPILOGUE)
+    out.append(run_conv_case(name="c1_k3_silu_bn64", k=3, act=A.ACT_SILU, want32=False, **kw))
+    cabi.set_tc_tuning(0, 0, EPILOGUE)
+    return out
+
+
+GROUPS = {"perf2": group_perf2, "probe": group_probe, "simt": group_simt, "conv_small": group_conv_small, "convT": group_convT, "gemm": group_gemm,
           "conv_big": group_conv_big, "perf": group_perf}
 
 

@@ -38,11 +38,26 @@ static inline int ceil_div(int x, int m) { return (x + m - 1) / m; }
 // ------------------------------------------------------------------------------------------------
 // activation math shared by the tensor-core epilogue and the CUDA-core kernels
 // ------------------------------------------------------------------------------------------------
+// exact-erf GELU (nn.GELU default) with erf from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7): one SFU reciprocal,
+// one SFU exp2 and a degree-5 Horner polynomial instead of erff()'s ~25 instructions.
+__device__ __forceinline__ float gelu_erf_fast(float v) {
+  const float z = fabsf(v) * 0.70710678118654752f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float e = (poly * t) * __expf(-z * z);          // 1 - erf(z), z >= 0
+  const float erf_abs = 1.0f - e;
+  const float erfv = copysignf(erf_abs, v);
+  return 0.5f * v * (1.0f + erfv);
+}
+
 __device__ __forceinline__ float act_apply(float v, int act, float param) {
   switch (act) {
     case FV_ACT_SILU: return __fdividef(v, 1.0f + __expf(-v));
     case FV_ACT_LEAKY: return v > 0.f ? v : v * param;
-    case FV_ACT_GELU: return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
+    case FV_ACT_GELU: return gelu_erf_fast(v);
     case FV_ACT_TANH: return tanhf(v);
     default: return v;
   }
@@ -146,6 +161,10 @@ __device__ __forceinline__ void tma_store_4d(const void* tmap, const void* smem_
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // wait until every committed bulk store of this thread has finished READING its shared-memory source
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// same, but the most recent committed group may still be in flight (double-buffered staging)
+__device__ __forceinline__ void tma_store_wait_read_keep1() {
+  asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+}
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------

@@ -62,15 +62,15 @@ struct TcCfg {
                                    : TMEM_COLS_RAW <= 256 ? 256 : 512;
   static constexpr int CH = BLOCK_N < 32 ? BLOCK_N : 32;  // epilogue column chunk
   static constexpr int STG_STRIDE = CH + 1;               // padded row stride (words) of the transpose buffer
-  // epilogue staging.  LSU flavour: per-warp padded transpose patch.  TMA flavour: per-warp swizzled boxes, a
-  // 32x32 fp32 patch (4 KB, SWIZZLE_128B; residual lands here and is overwritten in place by out32) and a 32x32
-  // fp16 patch (2 KB, SWIZZLE_64B).
-  static constexpr int EPI_WARP_BYTES = EPI_TMA ? (4096 + 2048) : (32 * STG_STRIDE * 4);
+  // epilogue staging.  LSU flavour: per-warp padded transpose patch.  TMA flavour: per-warp swizzled boxes, two
+  // 32x32 fp32 patches (4 KB each, SWIZZLE_128B: residual-in / out32, or ping-pong outputs when there is no
+  // residual) and a 32x32 fp16 patch (2 KB, SWIZZLE_64B).
+  static constexpr int EPI_WARP_BYTES = EPI_TMA ? (2 * 4096 + 2048) : (32 * STG_STRIDE * 4);
   static constexpr int STG_BYTES = ((kEpiWarps * EPI_WARP_BYTES + 1023) / 1024) * 1024;
   static constexpr int TAIL_BYTES = 1024 + 2 * BLOCK_N * 4;  // barriers, tmem ptr, bias/gamma
-  static constexpr int STAGES_RAW = (kSmemLimit - 1024 - TAIL_BYTES - STG_BYTES) / STAGE;
+  static constexpr int STAGES_RAW = (kSmemLimit - TAIL_BYTES - STG_BYTES) / STAGE;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE + STG_BYTES + TAIL_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE + STG_BYTES + TAIL_BYTES;
   static constexpr int NCH = BLOCK_N / CH;                // column chunks per 128-row accumulator
   static constexpr int LPR = CH / 4;                      // lanes per row in the coalesced phase (float4 each)
   static constexpr int RPI = 32 / LPR;                    // rows per warp instruction
@@ -83,16 +83,20 @@ struct TcCfg {
 template <int BLOCK_N, int M_SUB, int BLOCK_K, bool EPI_TMA>
 __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
   using Cfg = TcCfg<BLOCK_N, M_SUB, BLOCK_K, EPI_TMA>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0) {  // swizzled TMA/UMMA tiles need a 1024-byte aligned window
+    if (threadIdx.x == 0) printf("fv: dynamic shared memory is not 1024-byte aligned\n");
+    __trap();
+  }
   uint8_t* s_stage_raw = smem + Cfg::STAGES * Cfg::STAGE;  // 1024-aligned (stage sizes are multiples of 1024 / 512)
   uint8_t* tail = s_stage_raw + Cfg::STG_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty_bar = full_bar + Cfg::STAGES;
   uint64_t* tfull_bar = empty_bar + Cfg::STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint64_t* epi_bar = tempty_bar + 2;  // one per epilogue warp (TMA epilogue loads)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(epi_bar + kEpiWarps);
+  uint64_t* epi_bar = tempty_bar + 2;  // two per epilogue warp (TMA epilogue: residual prefetch, running-sum load)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(epi_bar + 2 * kEpiWarps);
   float* s_bias = reinterpret_cast<float*>(tail + 1024);
   float* s_gamma = s_bias + BLOCK_N;
   float* s_stage = reinterpret_cast<float*>(s_stage_raw);
@@ -111,7 +115,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], kEpiThreads);
     }
-    for (int i = 0; i < kEpiWarps; ++i) mbar_init(&epi_bar[i], 1);
+    for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&epi_bar[i], 1);
     if (EPI_TMA) {
       if (p.residual) tma_prefetch_desc(&p.tmR);
       if (p.out32) tma_prefetch_desc(&p.tmO32);
@@ -196,12 +200,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
       const int quarter = warp & 3;
       const int cgrp = ew >> 2;
       const int tid_e = threadIdx.x - 64;
-      uint8_t* Rp = s_stage_raw + ew * 4096;                       // 32 rows x 128 B, SWIZZLE_128B
-      uint8_t* Hp = s_stage_raw + kEpiWarps * 4096 + ew * 2048;    // 32 rows x  64 B, SWIZZLE_64B
+      uint8_t* R0 = s_stage_raw + ew * 8192;                       // 32 rows x 128 B, SWIZZLE_128B
+      uint8_t* R1 = R0 + 4096;
+      uint8_t* Hp = s_stage_raw + kEpiWarps * 8192 + ew * 2048;    // 32 rows x  64 B, SWIZZLE_64B
       uint64_t* my_bar = &epi_bar[ew];
-      uint32_t ld_phase = 0;
-      const uint32_t r_row = smem_u32(Rp) + lane * 128;
-      const uint32_t h_row = smem_u32(Hp) + lane * 64;
+      uint64_t* acc_bar = &epi_bar[kEpiWarps + ew];  // separate barrier: a residual prefetch may be in flight
+      uint32_t ld_phase = 0, acc_phase = 0;
+      uint32_t parity = 0;  // ping-pong of the output staging when no residual is loaded
       const uint32_t r_xor = static_cast<uint32_t>(lane & 7);
       const uint32_t h_xor = static_cast<uint32_t>((lane >> 1) & 3);
       const bool has_res = p.residual != nullptr, has_o32 = p.out32 != nullptr, has_o16 = p.out16 != nullptr;
@@ -228,11 +233,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
         n_ch = n_ch < Cfg::NCH ? n_ch : Cfg::NCH;
         const int n_items = M_SUB * n_ch;
 
+        // residual patches are bulk-loaded into R0 one item ahead; nothing but these loads ever writes R0 in that
+        // mode, so the next load is issued as soon as the current patch has been read into registers.
         auto issue_res_load = [&](int item) {  // lane 0 only
           const int sub = item / n_ch, ch = item % n_ch;
-          tma_store_wait_read();  // previous stores of this warp no longer read Rp / Hp
           mbar_arrive_expect_tx(my_bar, 4096);
-          tma_load_4d(Rp, &p.tmR, my_bar, n0 + ch * 32, phase, q0 + sub * 128 + quarter * 32, b);
+          tma_load_4d(R0, &p.tmR, my_bar, n0 + ch * 32, phase, q0 + sub * 128 + quarter * 32, b);
         };
         if (has_res && cgrp < n_items && lane == 0) issue_res_load(cgrp);
 
@@ -252,16 +258,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
             tc_fence_before();
             mbar_arrive(&tempty_bar[buf]);
           }
-          if (has_res) {
-            mbar_wait(my_bar, ld_phase);
-            ld_phase ^= 1;
-          } else if (lane == 0) {
-            tma_store_wait_read();
-          }
-          __syncwarp();
           float o[32];
           const float4* bp = reinterpret_cast<const float4*>(s_bias + ch * 32);
           const float4* gp = reinterpret_cast<const float4*>(s_gamma + ch * 32);
+          if (has_res) {
+            mbar_wait(my_bar, ld_phase);
+            ld_phase ^= 1;
+          }
+          const uint32_t r0_row = smem_u32(R0) + lane * 128;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 bb = bp[j];
@@ -269,7 +273,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
             if (has_res) {
               asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                            : "=f"(rr.x), "=f"(rr.y), "=f"(rr.z), "=f"(rr.w)
-                           : "r"(r_row + ((static_cast<uint32_t>(j) ^ r_xor) << 4)));
+                           : "r"(r0_row + ((static_cast<uint32_t>(j) ^ r_xor) << 4)));
             }
             o[4 * j + 0] = __uint_as_float(acc[4 * j + 0]) + bb.x;
             o[4 * j + 1] = __uint_as_float(acc[4 * j + 1]) + bb.y;
@@ -284,14 +288,30 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
             o[4 * j + 2] = (o[4 * j + 2] + rr.z) * p.out_scale;
             o[4 * j + 3] = (o[4 * j + 3] + rr.w) * p.out_scale;
           }
-          if (p.accumulate) {  // MRF mean: add the running sum already in out32 (second bulk load into the patch)
+          if (has_res && item + 2 < n_items) {  // R0 has been consumed: prefetch the next residual patch right away
             __syncwarp();
+            if (lane == 0) issue_res_load(item + 2);
+          }
+          // output staging: with a residual R1 + Hp (single); without, ping-pong R0/R1 (and the fp16 patch in the
+          // other half of the same buffer when there is no fp32 output) so stores of the previous item may still drain
+          uint8_t* Rout = has_res ? R1 : (parity ? R1 : R0);
+          uint8_t* Hout = (has_res || has_o32) ? Hp : Rout;
+          const bool pingpong = !has_res && !(has_o32 && has_o16) && !p.accumulate;
+          parity ^= 1;
+          if (lane == 0) {
+            if (pingpong) tma_store_wait_read_keep1();
+            else tma_store_wait_read();
+          }
+          __syncwarp();
+          const uint32_t r_row = smem_u32(Rout) + lane * 128;
+          const uint32_t h_row = smem_u32(Hout) + lane * 64;
+          if (p.accumulate) {  // MRF mean: add the running sum already in out32 (bulk load into the output patch)
             if (lane == 0) {
-              mbar_arrive_expect_tx(my_bar, 4096);
-              tma_load_4d(Rp, &p.tmO32, my_bar, col0, phase, qb, b);
+              mbar_arrive_expect_tx(acc_bar, 4096);
+              tma_load_4d(Rout, &p.tmO32, acc_bar, col0, phase, qb, b);
             }
-            mbar_wait(my_bar, ld_phase);
-            ld_phase ^= 1;
+            mbar_wait(acc_bar, acc_phase);
+            acc_phase ^= 1;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               float4 oo;
@@ -322,6 +342,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
             } else if (p.act == FV_ACT_SILU) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) o[i] = __fdividef(o[i], 1.0f + __expf(-o[i]));
+            } else if (p.act == FV_ACT_GELU) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] = gelu_erf_fast(o[i]);
             } else if (p.act != FV_ACT_NONE) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) o[i] = act_apply(o[i], p.act, p.act_param);
@@ -340,10 +363,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
           fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the bulk-copy engine
           __syncwarp();
           if (lane == 0) {
-            if (has_o32) tma_store_4d(&p.tmO32, Rp, col0, phase, qb, b);
-            if (has_o16) tma_store_4d(&p.tmO16, Hp, col0, phase, qb, b);
+            if (has_o32) tma_store_4d(&p.tmO32, Rout, col0, phase, qb, b);
+            if (has_o16) tma_store_4d(&p.tmO16, Hout, col0, phase, qb, b);
             tma_store_commit();
-            if (has_res && item + 2 < n_items) issue_res_load(item + 2);
           }
         }
         if (cgrp >= n_items) {
