@@ -361,8 +361,6 @@ def group_perf2():
     for msub in (1, 2):
         cabi.set_tc_tuning(0, msub, EPILOGUE)
         out.append(run_conv_case(name=f"c1_k3_silu_msub{msub}", k=3, act=A.ACT_SILU, want32=False, **kw))
-    cabi.set_tc_tuning(64, 2, EPILOGUE)
-    out.append(run_conv_case(name="c1_k3_silu_bn64", k=3, act=A.ACT_SILU, want32=False, **kw))
     cabi.set_tc_tuning(0, 0, EPILOGUE)
     return out
 

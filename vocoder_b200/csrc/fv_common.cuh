@@ -68,9 +68,11 @@ __device__ __forceinline__ __half to_half_sat(float v) {
   v = fminf(fmaxf(v, -65504.f), 65504.f);
   return __float2half_rn(v);
 }
+// two floats -> packed fp16x2 (a in the low half), round-to-nearest, saturating to +-65504: one F2FP instruction
 __device__ __forceinline__ uint32_t pack_half2_sat(float a, float b) {
-  __half2 h = __halves2half2(to_half_sat(a), to_half_sat(b));
-  return *reinterpret_cast<uint32_t*>(&h);
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -143,6 +145,18 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* tmap, ui
       : "memory");
 }
 
+// L2 prefetch of a tile (no shared-memory destination): warms L2 for a later tma_load of the same box
+__device__ __forceinline__ void tma_prefetch_l2_3d(const void* tmap, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(reinterpret_cast<uint64_t>(tmap)),
+               "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_l2_4d(const void* tmap, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global [%0, {%1, %2, %3, %4}];" ::"l"(
+                   reinterpret_cast<uint64_t>(tmap)),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2,
                                             int c3) {
   asm volatile(

@@ -80,7 +80,10 @@ struct TcCfg {
   static_assert(TMEM_COLS_RAW <= 512, "accumulators exceed TMEM");
 };
 
-template <int BLOCK_N, int M_SUB, int BLOCK_K, bool EPI_TMA>
+// HEAVY_ACT = false keeps only the cheap activations (none / SiLU / leaky / GELU) in the epilogue body; tanh and the
+// polar map (expf + sincosf with its Payne-Hanek slow path) live in the HEAVY_ACT = true instantiations, so the hot
+// kernels stay small enough for the instruction cache.
+template <int BLOCK_N, int M_SUB, int BLOCK_K, bool EPI_TMA, bool HEAVY_ACT>
 __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
   using Cfg = TcCfg<BLOCK_N, M_SUB, BLOCK_K, EPI_TMA>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -207,6 +210,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
       uint64_t* acc_bar = &epi_bar[kEpiWarps + ew];  // separate barrier: a residual prefetch may be in flight
       uint32_t ld_phase = 0, acc_phase = 0;
       uint32_t parity = 0;  // ping-pong of the output staging when no residual is loaded
+      int staged_n_t = -1;
       const uint32_t r_xor = static_cast<uint32_t>(lane & 7);
       const uint32_t h_xor = static_cast<uint32_t>((lane >> 1) & 3);
       const bool has_res = p.residual != nullptr, has_o32 = p.out32 != nullptr, has_o16 = p.out16 != nullptr;
@@ -221,13 +225,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
         const int n0 = n_t * BLOCK_N;
         const uint32_t buf = tile_i % Cfg::ACC_BUFS;
 
-        named_bar_sync(1, kEpiThreads);
-        for (int i = tid_e; i < BLOCK_N; i += kEpiThreads) {
-          const int col = n0 + i;
-          s_bias[i] = (p.bias != nullptr && col < p.C_out) ? p.bias[col] : 0.f;
-          s_gamma[i] = (p.gamma != nullptr && col < p.C_out) ? p.gamma[col] : 1.f;
+        if (n_t != staged_n_t) {  // bias / layer-scale of this N tile -> smem (once per CTA when there is one N tile)
+          named_bar_sync(1, kEpiThreads);
+          for (int i = tid_e; i < BLOCK_N; i += kEpiThreads) {
+            const int col = n0 + i;
+            s_bias[i] = (p.bias != nullptr && col < p.C_out) ? p.bias[col] : 0.f;
+            s_gamma[i] = (p.gamma != nullptr && col < p.C_out) ? p.gamma[col] : 1.f;
+          }
+          named_bar_sync(1, kEpiThreads);
+          staged_n_t = n_t;
         }
-        named_bar_sync(1, kEpiThreads);
 
         int n_ch = (p.C_out_r8 - n0 + 31) / 32;  // column chunks of this tile that hold real channels
         n_ch = n_ch < Cfg::NCH ? n_ch : Cfg::NCH;
@@ -330,24 +337,30 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
                            : "memory");
           }
           if (has_o16) {
-            if (p.act == FV_ACT_POLAR) {
-#pragma unroll
-              for (int i = 0; i < 32; i += 2) {
-                const float m = fminf(expf(o[i]), 100.f);
-                float sn, cs;
-                sincosf(o[i + 1], &sn, &cs);
-                o[i] = m * cs;
-                o[i + 1] = m * sn;
-              }
-            } else if (p.act == FV_ACT_SILU) {
+            if (p.act == FV_ACT_SILU) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) o[i] = __fdividef(o[i], 1.0f + __expf(-o[i]));
             } else if (p.act == FV_ACT_GELU) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) o[i] = gelu_erf_fast(o[i]);
-            } else if (p.act != FV_ACT_NONE) {
+            } else if (p.act == FV_ACT_LEAKY) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) o[i] = act_apply(o[i], p.act, p.act_param);
+              for (int i = 0; i < 32; ++i) o[i] = o[i] > 0.f ? o[i] : o[i] * p.act_param;
+            }
+            if constexpr (HEAVY_ACT) {
+              if (p.act == FV_ACT_POLAR) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                  const float m = fminf(expf(o[i]), 100.f);
+                  float sn, cs;
+                  sincosf(o[i + 1], &sn, &cs);
+                  o[i] = m * cs;
+                  o[i + 1] = m * sn;
+                }
+              } else if (p.act == FV_ACT_TANH) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) o[i] = tanhf(o[i]);
+              }
             }
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
@@ -477,18 +490,30 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
               *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
             }
             if (p.out16 != nullptr) {
-              if (p.act == FV_ACT_POLAR) {
+              if (p.act == FV_ACT_SILU) {
 #pragma unroll
-                for (int e = 0; e < 4; e += 2) {
-                  const float m = fminf(expf(o[e]), 100.f);
-                  float sn, cs;
-                  sincosf(o[e + 1], &sn, &cs);
-                  o[e] = m * cs;
-                  o[e + 1] = m * sn;
+                for (int e = 0; e < 4; ++e) o[e] = __fdividef(o[e], 1.0f + __expf(-o[e]));
+              } else if (p.act == FV_ACT_GELU) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) o[e] = gelu_erf_fast(o[e]);
+              } else if (p.act == FV_ACT_LEAKY) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) o[e] = o[e] > 0.f ? o[e] : o[e] * p.act_param;
+              }
+              if constexpr (HEAVY_ACT) {
+                if (p.act == FV_ACT_POLAR) {
+#pragma unroll
+                  for (int e = 0; e < 4; e += 2) {
+                    const float m = fminf(expf(o[e]), 100.f);
+                    float sn, cs;
+                    sincosf(o[e + 1], &sn, &cs);
+                    o[e] = m * cs;
+                    o[e + 1] = m * sn;
+                  }
+                } else if (p.act == FV_ACT_TANH) {
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) o[e] = tanhf(o[e]);
                 }
-              } else if (p.act != FV_ACT_NONE) {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) o[e] = act_apply(o[e], p.act, p.act_param);
               }
               uint2 pk;
               pk.x = pack_half2_sat(o[0], o[1]);
@@ -572,8 +597,8 @@ static int encode_epi_map(EncodeTiledFn enc, CUtensorMap* tm, const void* base, 
   return 0;
 }
 
-template <int BLOCK_N, int M_SUB, int BLOCK_K, bool EPI_TMA>
-static int launch_tc(const fv_conv_desc* d, ConvTcParams& p, cudaStream_t stream) {
+template <int BLOCK_N, int M_SUB, int BLOCK_K, bool EPI_TMA, bool HEAVY_ACT>
+static int launch_tc_impl(const fv_conv_desc* d, ConvTcParams& p, cudaStream_t stream) {
   using Cfg = TcCfg<BLOCK_N, M_SUB, BLOCK_K, EPI_TMA>;
   EncodeTiledFn enc = get_encode_fn();
   FV_REQUIRE(enc != nullptr, FV_E_DRIVER, "cuTensorMapEncodeTiled not available from the driver");
@@ -617,15 +642,22 @@ static int launch_tc(const fv_conv_desc* d, ConvTcParams& p, cudaStream_t stream
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, M_SUB, BLOCK_K, EPI_TMA>,
+    attr_err = cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, M_SUB, BLOCK_K, EPI_TMA, HEAVY_ACT>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
   });
   int rc = check_cuda(attr_err, "cudaFuncSetAttribute(conv_tc_kernel)");
   if (rc) return rc;
   const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  conv_tc_kernel<BLOCK_N, M_SUB, BLOCK_K, EPI_TMA><<<grid, kTcThreads, Cfg::SMEM_BYTES, stream>>>(p);
+  conv_tc_kernel<BLOCK_N, M_SUB, BLOCK_K, EPI_TMA, HEAVY_ACT><<<grid, kTcThreads, Cfg::SMEM_BYTES, stream>>>(p);
   FV_CHECK_LAUNCH("conv_tc_kernel");
   return 0;
+}
+
+template <int BLOCK_N, int M_SUB, int BLOCK_K, bool EPI_TMA>
+static int launch_tc(const fv_conv_desc* d, ConvTcParams& p, cudaStream_t stream) {
+  const bool heavy = d->out16 != nullptr && (d->act == FV_ACT_POLAR || d->act == FV_ACT_TANH);
+  if (heavy) return launch_tc_impl<BLOCK_N, M_SUB, BLOCK_K, EPI_TMA, true>(d, p, stream);
+  return launch_tc_impl<BLOCK_N, M_SUB, BLOCK_K, EPI_TMA, false>(d, p, stream);
 }
 
 template <int BLOCK_N, int M_SUB, bool EPI_TMA>
