@@ -106,9 +106,10 @@ FV_API void fv_reset_launch_count(void);
 
 FV_API int fv_conv1d(const fv_conv_desc* d, int engine, void* stream);
 /* tuning overrides for the tcgen05 engine (0 = built-in heuristic): N tile in {16,32,64,128,256}, 128-row
- * accumulators per CTA in {1,2}, epilogue flavour (1 = LSU + smem transpose, 2 = TMA bulk load/store).
+ * accumulators per CTA in {1,2}, epilogue flavour (1 = LSU + smem transpose, 2 = TMA bulk load/store), mainloop
+ * (1 = one smem stage per tap, 2 = one operand slab per K chunk with row-shifted UMMA descriptors per tap).
  * Process-global; meant for benchmarking sweeps. */
-FV_API void fv_set_tc_tuning(int block_n, int m_sub, int epilogue);
+FV_API void fv_set_tc_tuning(int block_n, int m_sub, int epilogue, int mainloop);
 
 /* mel [B][C][T] fp32 channels-first -> fp16 channels-last [B][T][pitch] (zero padded channels).
  * Entry of the path: the tensor handed to Generator.forward (hifigan.py:226, convnext.py:206). */

@@ -66,6 +66,7 @@ def ref_conv(a16, pc, L_out, bias=None, gamma=None, residual=None, scale=1.0, ol
 
 
 EPILOGUE = 0
+MAINLOOP = 0
 
 
 def run_conv_case(name, B, L, c_in, c_out, k=3, d=1, convT=None, act=0, use_res=False, use_gamma=False,
@@ -213,14 +214,14 @@ def group_perf():
     out.append(run_conv_case(name="perf_c128_k7_c1", B=64, L=6016, c_in=128, c_out=128, k=7, d=1, act=A.ACT_SILU,
                              use_res=False, engines=("tc",), check=False, time_it=True, want32=False))
     for msub in (1, 2):
-        cabi.set_tc_tuning(0, msub, EPILOGUE)
+        cabi.set_tc_tuning(0, msub, EPILOGUE, MAINLOOP)
         out.append(run_conv_case(name=f"perf_c256_k7_msub{msub}", B=64, L=752, c_in=256, c_out=256, k=7, d=1,
                                  act=A.ACT_SILU, use_res=True, engines=("tc",), check=False, time_it=True))
         out.append(run_conv_case(name=f"perf_c128_k7_msub{msub}", B=64, L=6016, c_in=128, c_out=128, k=7, d=1,
                                  act=A.ACT_SILU, use_res=True, engines=("tc",), check=False, time_it=True))
         out.append(run_conv_case(name=f"perf_lin_1408_5632_msub{msub}", B=128, L=94, c_in=1408, c_out=5632, k=1,
                                  act=A.ACT_GELU, engines=("tc",), check=False, time_it=True))
-    cabi.set_tc_tuning(0, 0, EPILOGUE)
+    cabi.set_tc_tuning(0, 0, EPILOGUE, MAINLOOP)
     return out
 
 
@@ -359,9 +360,9 @@ def group_perf2():
     out.append(run_conv_case(name="o32only_k3", k=3, act=A.ACT_NONE, want32=True, want16=False, **kw))
     out.append(run_conv_case(name="c2_k3_res_silu", k=3, act=A.ACT_SILU, use_res=True, **kw))
     for msub in (1, 2):
-        cabi.set_tc_tuning(0, msub, EPILOGUE)
+        cabi.set_tc_tuning(0, msub, EPILOGUE, MAINLOOP)
         out.append(run_conv_case(name=f"c1_k3_silu_msub{msub}", k=3, act=A.ACT_SILU, want32=False, **kw))
-    cabi.set_tc_tuning(0, 0, EPILOGUE)
+    cabi.set_tc_tuning(0, 0, EPILOGUE, MAINLOOP)
     return out
 
 
@@ -377,12 +378,15 @@ def main():
     args = ap.parse_args()
     os.makedirs(OUT_DIR, exist_ok=True)
     if args.group:
-        global EPILOGUE
+        global EPILOGUE, MAINLOOP
         gname = args.group
-        if "@" in gname:
+        if "@" in gname:  # name@E or name@E.M  (epilogue flavour, mainloop flavour)
             gname, e = gname.split("@")
+            if "." in e:
+                e, m = e.split(".")
+                MAINLOOP = int(m)
             EPILOGUE = int(e)
-            cabi.set_tc_tuning(0, 0, EPILOGUE)
+            cabi.set_tc_tuning(0, 0, EPILOGUE, MAINLOOP)
         t0 = time.time()
         try:
             out = {"ok": True, "results": GROUPS[gname]()}
@@ -390,7 +394,7 @@ def main():
             import traceback
             out = {"ok": False, "error": repr(e), "trace": traceback.format_exc()}
         out["seconds"] = time.time() - t0
-        with open(os.path.join(OUT_DIR, f"diag_{args.group.replace('@', '_e')}.json"), "w") as f:
+        with open(os.path.join(OUT_DIR, f"diag_{args.group.replace('@', '_e').replace('.', '_m')}.json"), "w") as f:
             json.dump(out, f, indent=1)
         print(json.dumps(out, indent=1))
         return
@@ -400,7 +404,7 @@ def main():
         try:
             p = subprocess.run([sys.executable, os.path.abspath(__file__), "--group", name], timeout=args.timeout,
                                capture_output=True, text=True)
-            path = os.path.join(OUT_DIR, f"diag_{name.replace('@', '_e')}.json")
+            path = os.path.join(OUT_DIR, f"diag_{name.replace('@', '_e').replace('.', '_m')}.json")
             if os.path.exists(path):
                 summary[name] = json.load(open(path))
             else:

@@ -68,7 +68,7 @@ def lib() -> ctypes.CDLL:
     L.fv_launch_count.restype = ctypes.c_int64
     L.fv_reset_launch_count.restype = None
     L.fv_set_tc_tuning.restype = None
-    L.fv_set_tc_tuning.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    L.fv_set_tc_tuning.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
     vp, ci, cf = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
     L.fv_conv1d.argtypes = [ctypes.POINTER(ConvDesc), ci, vp]
     L.fv_pack_input.argtypes = [vp, vp, ci, ci, ci, ci, vp]
@@ -338,6 +338,7 @@ def reset_launch_count() -> None:
     lib().fv_reset_launch_count()
 
 
-def set_tc_tuning(block_n: int = 0, m_sub: int = 0, epilogue: int = 0) -> None:
-    """epilogue: 0 auto, 1 LSU (smem transpose + coalesced ld/st.global), 2 TMA (bulk tensor load/store)."""
-    lib().fv_set_tc_tuning(int(block_n), int(m_sub), int(epilogue))
+def set_tc_tuning(block_n: int = 0, m_sub: int = 0, epilogue: int = 0, mainloop: int = 0) -> None:
+    """epilogue: 0 auto, 1 LSU (smem transpose + coalesced ld/st.global), 2 TMA (bulk tensor load/store);
+    mainloop: 0 auto, 1 per-tap stages, 2 operand slab + row-shifted descriptors."""
+    lib().fv_set_tc_tuning(int(block_n), int(m_sub), int(epilogue), int(mainloop))

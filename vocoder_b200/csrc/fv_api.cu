@@ -13,6 +13,7 @@ static std::atomic<long long> g_launches{0};
 static std::atomic<int> g_tune_block_n{0};
 static std::atomic<int> g_tune_m_sub{0};
 static std::atomic<int> g_tune_epilogue{0};
+static std::atomic<int> g_tune_mainloop{0};
 
 int set_error(int code, const char* fmt, ...) {
   va_list ap;
@@ -30,7 +31,8 @@ int check_cuda(cudaError_t e, const char* what) {
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
-int conv1d_tc(const fv_conv_desc* d, cudaStream_t stream, int block_n_override, int m_sub_override, int epilogue);
+int conv1d_tc(const fv_conv_desc* d, cudaStream_t stream, int block_n_override, int m_sub_override, int epilogue,
+              int mainloop);
 int conv1d_simt(const fv_conv_desc* d, cudaStream_t stream);
 
 }  // namespace fv
@@ -41,10 +43,11 @@ extern "C" const char* fv_last_error(void) { return g_err; }
 extern "C" int fv_abi_version(void) { return FV_ABI_VERSION; }
 extern "C" int64_t fv_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 extern "C" void fv_reset_launch_count(void) { g_launches.store(0, std::memory_order_relaxed); }
-extern "C" void fv_set_tc_tuning(int block_n, int m_sub, int epilogue) {
+extern "C" void fv_set_tc_tuning(int block_n, int m_sub, int epilogue, int mainloop) {
   g_tune_block_n.store(block_n);
   g_tune_m_sub.store(m_sub);
   g_tune_epilogue.store(epilogue);
+  g_tune_mainloop.store(mainloop);
 }
 
 extern "C" int fv_conv1d(const fv_conv_desc* d, int engine, void* stream) {
@@ -77,5 +80,6 @@ extern "C" int fv_conv1d(const fv_conv_desc* d, int engine, void* stream) {
     FV_REQUIRE(d->tap_off[i] > -30000 && d->tap_off[i] < 30000, FV_E_BADARG, "fv_conv1d: tap offset out of range");
   if (engine == FV_ENGINE_SIMT) return conv1d_simt(d, (cudaStream_t)stream);
   FV_REQUIRE(engine == FV_ENGINE_TC, FV_E_BADARG, "fv_conv1d: unknown engine %d", engine);
-  return conv1d_tc(d, (cudaStream_t)stream, g_tune_block_n.load(), g_tune_m_sub.load(), g_tune_epilogue.load());
+  return conv1d_tc(d, (cudaStream_t)stream, g_tune_block_n.load(), g_tune_m_sub.load(), g_tune_epilogue.load(),
+                   g_tune_mainloop.load());
 }

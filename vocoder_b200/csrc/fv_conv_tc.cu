@@ -22,7 +22,8 @@
 
 namespace fv {
 
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 8;            // a multiple of 4: kEpiWarps / 4 warps share each TMEM lane quarter
+constexpr int kEpiStride = kEpiWarps / 4;  // work items (sub-tile, column chunk) are dealt round-robin to them
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kTcThreads = 64 + kEpiThreads;
 constexpr int kSmemLimit = 232448;  // 227 KB opt-in maximum per CTA on sm_100
@@ -30,12 +31,14 @@ constexpr int kSmemLimit = 232448;  // 227 KB opt-in maximum per CTA on sm_100
 struct ConvTcParams {
   CUtensorMap tmA;  // 3D {pitch, L_in, B} fp16, box {BLOCK_K, rows, 1}
   CUtensorMap tmW;  // 2D {w_pitch, n_phase*n_taps*C_out_pad} fp16, box {BLOCK_K, BLOCK_N}
+  CUtensorMap tmA2; // slab mainloop: same tensor as tmA, box {BLOCK_K, 64 rows, 1}
   // epilogue maps, 4D {C_out_r8, n_phase, L_out / n_phase, B}, box {32, 1, 32, 1} (TMA epilogue only)
   CUtensorMap tmR;    // residual fp32 (SWIZZLE_128B)
   CUtensorMap tmO32;  // out32 fp32    (SWIZZLE_128B): accumulate-load and store
   CUtensorMap tmO16;  // out16 fp16    (SWIZZLE_64B)
   int B, n_phase, n_taps, k_chunks, C_out, C_out_r8, C_out_pad, q_rows, L_out;
   int m_tiles, n_tiles, total_tiles;
+  int use_slab, off_min, slab_boxes, w_resident;  // slab mainloop: smallest tap offset, 64-row boxes per slab, weights stay in smem
   const float* bias;
   const float* gamma;
   const float* residual;
@@ -46,7 +49,7 @@ struct ConvTcParams {
   int16_t tap_off[FV_MAX_TAPS];
 };
 
-template <int BLOCK_N, int M_SUB, int BLOCK_K, bool EPI_TMA>
+template <int BLOCK_N, int M_SUB, int BLOCK_K, bool EPI_TMA, bool SLAB = false>
 struct TcCfg {
   static constexpr int ROW_BYTES = BLOCK_K * 2;
   static constexpr int A_SUB_BYTES = 128 * ROW_BYTES;
@@ -68,14 +71,21 @@ struct TcCfg {
   static constexpr int EPI_WARP_BYTES = EPI_TMA ? (2 * 4096 + 2048) : (32 * STG_STRIDE * 4);
   static constexpr int STG_BYTES = ((kEpiWarps * EPI_WARP_BYTES + 1023) / 1024) * 1024;
   static constexpr int TAIL_BYTES = 1024 + 2 * BLOCK_N * 4;  // barriers, tmem ptr, bias/gamma
+  // per-tap mainloop: ring of (operand tile, weight tile) stages.  Slab mainloop: two operand slabs of
+  // M_SUB*128 + 64 rows (one per K chunk, every tap is a row-shifted UMMA descriptor into it) + a ring of weight tiles.
+  static constexpr int SLAB_ROWS = M_SUB * 128 + 64;
+  static constexpr int A_SLAB = SLAB_ROWS * ROW_BYTES;
+  static constexpr int NB_RAW = (kSmemLimit - TAIL_BYTES - STG_BYTES - 2 * A_SLAB) / B_STAGE;
+  static constexpr int NB = NB_RAW > 16 ? 16 : NB_RAW;
   static constexpr int STAGES_RAW = (kSmemLimit - TAIL_BYTES - STG_BYTES) / STAGE;
-  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr int SMEM_BYTES = STAGES * STAGE + STG_BYTES + TAIL_BYTES;
+  static constexpr int STAGES = SLAB ? NB : (STAGES_RAW > 8 ? 8 : STAGES_RAW);
+  static constexpr int MAIN_BYTES = SLAB ? (2 * A_SLAB + NB * B_STAGE) : STAGES * STAGE;
+  static constexpr int SMEM_BYTES = MAIN_BYTES + STG_BYTES + TAIL_BYTES;
   static constexpr int NCH = BLOCK_N / CH;                // column chunks per 128-row accumulator
   static constexpr int LPR = CH / 4;                      // lanes per row in the coalesced phase (float4 each)
   static constexpr int RPI = 32 / LPR;                    // rows per warp instruction
   static constexpr int ITERS = 32 / RPI;                  // warp instructions per 32-row chunk
-  static_assert(STAGES >= 2, "pipeline needs at least two stages");
+  static constexpr bool VALID = STAGES >= 2;  // configurations whose pipeline does not fit are never instantiated
   static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 16 && BLOCK_N <= 256, "invalid UMMA N");
   static_assert(TMEM_COLS_RAW <= 512, "accumulators exceed TMEM");
 };
@@ -83,20 +93,22 @@ struct TcCfg {
 // HEAVY_ACT = false keeps only the cheap activations (none / SiLU / leaky / GELU) in the epilogue body; tanh and the
 // polar map (expf + sincosf with its Payne-Hanek slow path) live in the HEAVY_ACT = true instantiations, so the hot
 // kernels stay small enough for the instruction cache.
-template <int BLOCK_N, int M_SUB, int BLOCK_K, bool EPI_TMA, bool HEAVY_ACT>
+template <int BLOCK_N, int M_SUB, int BLOCK_K, bool EPI_TMA, bool HEAVY_ACT, bool SLAB>
 __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
-  using Cfg = TcCfg<BLOCK_N, M_SUB, BLOCK_K, EPI_TMA>;
+  using Cfg = TcCfg<BLOCK_N, M_SUB, BLOCK_K, EPI_TMA, SLAB>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   if ((smem_u32(smem) & 1023u) != 0) {  // swizzled TMA/UMMA tiles need a 1024-byte aligned window
     if (threadIdx.x == 0) printf("fv: dynamic shared memory is not 1024-byte aligned\n");
     __trap();
   }
-  uint8_t* s_stage_raw = smem + Cfg::STAGES * Cfg::STAGE;  // 1024-aligned (stage sizes are multiples of 1024 / 512)
+  uint8_t* s_stage_raw = smem + Cfg::MAIN_BYTES;  // 1024-aligned (tile sizes are multiples of the swizzle atom)
   uint8_t* tail = s_stage_raw + Cfg::STG_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);   // per-tap: stage ring; slab: weight-tile ring
   uint64_t* empty_bar = full_bar + Cfg::STAGES;
-  uint64_t* tfull_bar = empty_bar + Cfg::STAGES;
+  uint64_t* afull_bar = empty_bar + Cfg::STAGES;            // slab mainloop: the two operand slabs
+  uint64_t* aempty_bar = afull_bar + 2;
+  uint64_t* tfull_bar = aempty_bar + 2;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* epi_bar = tempty_bar + 2;  // two per epilogue warp (TMA epilogue: residual prefetch, running-sum load)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(epi_bar + 2 * kEpiWarps);
@@ -117,7 +129,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], kEpiThreads);
+      mbar_init(&afull_bar[i], 1);
+      mbar_init(&aempty_bar[i], 1);
     }
+    if (SLAB) tma_prefetch_desc(&p.tmA2);
     for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&epi_bar[i], 1);
     if (EPI_TMA) {
       if (p.residual) tma_prefetch_desc(&p.tmR);
@@ -138,7 +153,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      uint32_t it = 0;
+      uint32_t it = 0, ita = 0;
+      bool w_loaded = false;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         int r = tile;
         const int n_t = r % p.n_tiles; r /= p.n_tiles;
@@ -147,19 +163,41 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
         const int phase = r / p.B;
         const int q0 = m_t * (M_SUB * 128);
         const int n0 = n_t * BLOCK_N;
-        for (int tap = 0; tap < p.n_taps; ++tap) {
-          const int row0 = q0 + p.tap_off[phase * p.n_taps + tap];
-          const int wrow = (phase * p.n_taps + tap) * p.C_out_pad + n0;
-          for (int kc = 0; kc < p.k_chunks; ++kc, ++it) {
-            const int s = it % Cfg::STAGES;
-            mbar_wait(&empty_bar[s], ((it / Cfg::STAGES) & 1) ^ 1);
-            mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE);
-            uint8_t* sa = smem + s * Cfg::STAGE;
-#pragma unroll
-            for (int bx = 0; bx < Cfg::N_A_BOX; ++bx)
-              tma_load_3d(sa + bx * Cfg::A_BOX_ROWS * Cfg::ROW_BYTES, &p.tmA, &full_bar[s], kc * BLOCK_K,
-                          row0 + bx * Cfg::A_BOX_ROWS, b);
-            tma_load_2d(sa + Cfg::A_STAGE, &p.tmW, &full_bar[s], kc * BLOCK_K, wrow);
+        if constexpr (SLAB) {
+          uint8_t* b_ring = smem + 2 * Cfg::A_SLAB;
+          for (int kc = 0; kc < p.k_chunks; ++kc, ++ita) {
+            const int sa = ita & 1;
+            mbar_wait(&aempty_bar[sa], ((ita >> 1) & 1) ^ 1);
+            mbar_arrive_expect_tx(&afull_bar[sa], p.slab_boxes * 64 * Cfg::ROW_BYTES);
+            for (int bx = 0; bx < p.slab_boxes; ++bx)
+              tma_load_3d(smem + sa * Cfg::A_SLAB + bx * 64 * Cfg::ROW_BYTES, &p.tmA2, &afull_bar[sa], kc * BLOCK_K,
+                          q0 + p.off_min + bx * 64, b);
+            if (!(p.w_resident && w_loaded)) {
+              for (int tap = 0; tap < p.n_taps; ++tap, ++it) {
+                const int s = it % Cfg::NB;
+                mbar_wait(&empty_bar[s], ((it / Cfg::NB) & 1) ^ 1);
+                mbar_arrive_expect_tx(&full_bar[s], Cfg::B_STAGE);
+                tma_load_2d(b_ring + s * Cfg::B_STAGE, &p.tmW, &full_bar[s], kc * BLOCK_K,
+                            (phase * p.n_taps + tap) * p.C_out_pad + n0);
+              }
+            }
+          }
+          w_loaded = true;
+        } else {
+          for (int tap = 0; tap < p.n_taps; ++tap) {
+            const int row0 = q0 + p.tap_off[phase * p.n_taps + tap];
+            const int wrow = (phase * p.n_taps + tap) * p.C_out_pad + n0;
+            for (int kc = 0; kc < p.k_chunks; ++kc, ++it) {
+              const int s = it % Cfg::STAGES;
+              mbar_wait(&empty_bar[s], ((it / Cfg::STAGES) & 1) ^ 1);
+              mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE);
+              uint8_t* sa = smem + s * Cfg::STAGE;
+  #pragma unroll
+              for (int bx = 0; bx < Cfg::N_A_BOX; ++bx)
+                tma_load_3d(sa + bx * Cfg::A_BOX_ROWS * Cfg::ROW_BYTES, &p.tmA, &full_bar[s], kc * BLOCK_K,
+                            row0 + bx * Cfg::A_BOX_ROWS, b);
+              tma_load_2d(sa + Cfg::A_STAGE, &p.tmW, &full_bar[s], kc * BLOCK_K, wrow);
+            }
           }
         }
       }
@@ -168,27 +206,71 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_f16(128, BLOCK_N);
-      uint32_t it = 0, tile_i = 0;
+      uint32_t it = 0, ita = 0, tile_i = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tile_i) {
         const uint32_t buf = tile_i % Cfg::ACC_BUFS;
         mbar_wait(&tempty_bar[buf], ((tile_i / Cfg::ACC_BUFS) & 1) ^ 1);
         tc_fence_after();
-        for (int st = 0; st < k_steps; ++st, ++it) {
-          const int s = it % Cfg::STAGES;
-          mbar_wait(&full_bar[s], (it / Cfg::STAGES) & 1);
-          tc_fence_after();
-          const uint32_t a_base = smem_u32(smem + s * Cfg::STAGE);
-          const uint32_t b_base = a_base + Cfg::A_STAGE;
+        if constexpr (SLAB) {
+          int r = tile;
+          r /= p.n_tiles;
+          r /= p.m_tiles;
+          const int phase = r / p.B;
+          const uint32_t b_ring = smem_u32(smem + 2 * Cfg::A_SLAB);
+          for (int kc = 0; kc < p.k_chunks; ++kc, ++ita) {
+            const int sa = ita & 1;
+            mbar_wait(&afull_bar[sa], (ita >> 1) & 1);
+            tc_fence_after();
+            const uint32_t slab = smem_u32(smem + sa * Cfg::A_SLAB);
+            for (int tap = 0; tap < p.n_taps; ++tap) {
+              int s;
+              if (p.w_resident) {
+                s = kc * p.n_taps + tap;
+                if (tile_i == 0) mbar_wait(&full_bar[s], 0);
+              } else {
+                s = it % Cfg::NB;
+                mbar_wait(&full_bar[s], (it / Cfg::NB) & 1);
+              }
+              tc_fence_after();
+              // the tap is a row shift into the slab: descriptor start += rows * row_bytes (swizzle is a function
+              // of the absolute smem address, verified by fv_debug_rowshift_probe)
+              const uint32_t a_tap = slab + (p.tap_off[phase * p.n_taps + tap] - p.off_min) * Cfg::ROW_BYTES;
+              const uint32_t b_base = b_ring + s * Cfg::B_STAGE;
 #pragma unroll
-          for (int sub = 0; sub < M_SUB; ++sub) {
+              for (int sub = 0; sub < M_SUB; ++sub) {
 #pragma unroll
-            for (int kk = 0; kk < BLOCK_K / 16; ++kk) {
-              const uint64_t da = make_kmajor_desc(a_base + sub * Cfg::A_SUB_BYTES + kk * 32, Cfg::ROW_BYTES);
-              const uint64_t db = make_kmajor_desc(b_base + kk * 32, Cfg::ROW_BYTES);
-              umma_f16_ss(tmem_base + (buf * M_SUB + sub) * BLOCK_N, da, db, idesc, (st > 0 || kk > 0) ? 1u : 0u);
+                for (int kk = 0; kk < BLOCK_K / 16; ++kk) {
+                  const uint64_t da = make_kmajor_desc(a_tap + sub * Cfg::A_SUB_BYTES + kk * 32, Cfg::ROW_BYTES);
+                  const uint64_t db = make_kmajor_desc(b_base + kk * 32, Cfg::ROW_BYTES);
+                  umma_f16_ss(tmem_base + (buf * M_SUB + sub) * BLOCK_N, da, db, idesc,
+                              (kc > 0 || tap > 0 || kk > 0) ? 1u : 0u);
+                }
+              }
+              if (!p.w_resident) {
+                umma_commit(&empty_bar[s]);  // weight tile consumed
+                ++it;
+              }
             }
+            umma_commit(&aempty_bar[sa]);  // slab consumed by every tap of this K chunk
           }
-          umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
+        } else {
+          for (int st = 0; st < k_steps; ++st, ++it) {
+            const int s = it % Cfg::STAGES;
+            mbar_wait(&full_bar[s], (it / Cfg::STAGES) & 1);
+            tc_fence_after();
+            const uint32_t a_base = smem_u32(smem + s * Cfg::STAGE);
+            const uint32_t b_base = a_base + Cfg::A_STAGE;
+  #pragma unroll
+            for (int sub = 0; sub < M_SUB; ++sub) {
+  #pragma unroll
+              for (int kk = 0; kk < BLOCK_K / 16; ++kk) {
+                const uint64_t da = make_kmajor_desc(a_base + sub * Cfg::A_SUB_BYTES + kk * 32, Cfg::ROW_BYTES);
+                const uint64_t db = make_kmajor_desc(b_base + kk * 32, Cfg::ROW_BYTES);
+                umma_f16_ss(tmem_base + (buf * M_SUB + sub) * BLOCK_N, da, db, idesc, (st > 0 || kk > 0) ? 1u : 0u);
+              }
+            }
+            umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
+          }
         }
         umma_commit(&tfull_bar[buf]);  // accumulator complete -> epilogue
       }
@@ -253,7 +335,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
         tc_fence_after();
 
 #pragma unroll 1
-        for (int item = cgrp; item < n_items; item += 2) {
+        for (int item = cgrp; item < n_items; item += kEpiStride) {
           const int sub = item / n_ch, ch = item % n_ch;
           const int qb = q0 + sub * 128 + quarter * 32;
           const int col0 = n0 + ch * 32;
@@ -261,7 +343,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
           tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + (buf * M_SUB + sub) * BLOCK_N +
                                  ch * 32, acc);
           tmem_ld_wait();
-          if (item + 2 >= n_items) {
+          if (item + kEpiStride >= n_items) {
             tc_fence_before();
             mbar_arrive(&tempty_bar[buf]);
           }
@@ -295,9 +377,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
             o[4 * j + 2] = (o[4 * j + 2] + rr.z) * p.out_scale;
             o[4 * j + 3] = (o[4 * j + 3] + rr.w) * p.out_scale;
           }
-          if (has_res && item + 2 < n_items) {  // R0 has been consumed: prefetch the next residual patch right away
+          if (has_res && item + kEpiStride < n_items) {  // R0 has been consumed: prefetch the next residual patch right away
             __syncwarp();
-            if (lane == 0) issue_res_load(item + 2);
+            if (lane == 0) issue_res_load(item + kEpiStride);
           }
           // output staging: with a residual R1 + Hp (single); without, ping-pong R0/R1 (and the fp16 patch in the
           // other half of the same buffer when there is no fp32 output) so stores of the previous item may still drain
@@ -437,7 +519,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
       tc_fence_after();
 
 #pragma unroll 1
-      for (int item = cgrp; item < N_ITEMS; item += 2) {
+      for (int item = cgrp; item < N_ITEMS; item += kEpiStride) {
         const int sub = item / Cfg::NCH, ch = item % Cfg::NCH;
         uint32_t acc[32];
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
@@ -445,7 +527,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
         if constexpr (Cfg::CH == 32) tmem_ld_32x32b_x32(taddr, acc);
         else tmem_ld_32x32b_x16(taddr, acc);
         tmem_ld_wait();
-        if (item + 2 >= N_ITEMS) {  // this warp's last TMEM read of the tile: hand the accumulator back
+        if (item + kEpiStride >= N_ITEMS) {  // this warp's last TMEM read of the tile: hand the accumulator back
           tc_fence_before();
           mbar_arrive(&tempty_bar[buf]);
         }
@@ -457,8 +539,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
 
         // prefetch the next item's residual while this one is processed
         float4 res_nxt[Cfg::ITERS];
-        const bool has_next = item + 2 < N_ITEMS;
-        if (has_next) load_res(item + 2, res_nxt);
+        const bool has_next = item + kEpiStride < N_ITEMS;
+        if (has_next) load_res(item + kEpiStride, res_nxt);
 
         const int ccol = ch * Cfg::CH + c4;  // column within the N tile
         const int col = n0 + ccol;
@@ -597,9 +679,13 @@ static int encode_epi_map(EncodeTiledFn enc, CUtensorMap* tm, const void* base, 
   return 0;
 }
 
-template <int BLOCK_N, int M_SUB, int BLOCK_K, bool EPI_TMA, bool HEAVY_ACT>
+template <int BLOCK_N, int M_SUB, int BLOCK_K, bool EPI_TMA, bool HEAVY_ACT, bool SLAB>
 static int launch_tc_impl(const fv_conv_desc* d, ConvTcParams& p, cudaStream_t stream) {
-  using Cfg = TcCfg<BLOCK_N, M_SUB, BLOCK_K, EPI_TMA>;
+  using Cfg = TcCfg<BLOCK_N, M_SUB, BLOCK_K, EPI_TMA, SLAB>;
+  if constexpr (!Cfg::VALID) {
+    return set_error(FV_E_UNSUPPORTED, "tile configuration N=%d M_SUB=%d K=%d does not fit in shared memory", BLOCK_N,
+                     M_SUB, BLOCK_K);
+  } else {
   EncodeTiledFn enc = get_encode_fn();
   FV_REQUIRE(enc != nullptr, FV_E_DRIVER, "cuTensorMapEncodeTiled not available from the driver");
 
@@ -612,6 +698,23 @@ static int launch_tc_impl(const fv_conv_desc* d, ConvTcParams& p, cudaStream_t s
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(Cfg::ROW_BYTES), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     FV_REQUIRE(r == CUDA_SUCCESS, FV_E_DRIVER, "cuTensorMapEncodeTiled(A) failed: %d", (int)r);
+  }
+  if constexpr (SLAB) {  // same activations, 64-row boxes (slab pieces)
+    cuuint64_t dims[3] = {(cuuint64_t)d->a_pitch, (cuuint64_t)d->L_in, (cuuint64_t)d->B};
+    cuuint64_t strides[2] = {(cuuint64_t)d->a_pitch * 2, (cuuint64_t)d->a_pitch * 2 * (cuuint64_t)d->L_in};
+    cuuint32_t box[3] = {(cuuint32_t)BLOCK_K, 64, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&p.tmA2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(d->a), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(Cfg::ROW_BYTES), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    FV_REQUIRE(r == CUDA_SUCCESS, FV_E_DRIVER, "cuTensorMapEncodeTiled(A slab) failed: %d", (int)r);
+    int omin = d->tap_off[0], omax = d->tap_off[0];
+    for (int i = 0; i < d->n_phase * d->n_taps; ++i) {
+      omin = d->tap_off[i] < omin ? d->tap_off[i] : omin;
+      omax = d->tap_off[i] > omax ? d->tap_off[i] : omax;
+    }
+    p.off_min = omin;
+    p.slab_boxes = ceil_div(M_SUB * 128 + (omax - omin), 64);
   }
   {  // weights: {w_pitch, n_phase*n_taps*C_out_pad}
     cuuint64_t dims[2] = {(cuuint64_t)d->w_pitch, (cuuint64_t)d->n_phase * d->n_taps * d->C_out_pad};
@@ -638,26 +741,43 @@ static int launch_tc_impl(const fv_conv_desc* d, ConvTcParams& p, cudaStream_t s
   const long long total = (long long)p.m_tiles * p.n_tiles * d->B * d->n_phase;
   FV_REQUIRE(total > 0 && total < (1ll << 30), FV_E_BADARG, "bad tile count %lld", total);
   p.total_tiles = (int)total;
+  if constexpr (SLAB) {
+    // all weight tiles of the conv fit in the ring and every tile of a CTA uses the same ones: load them once
+    p.w_resident = (d->n_taps * p.k_chunks <= Cfg::NB && p.n_tiles == 1 && d->n_phase == 1) ? 1 : 0;
+  }
 
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, M_SUB, BLOCK_K, EPI_TMA, HEAVY_ACT>,
+    attr_err = cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, M_SUB, BLOCK_K, EPI_TMA, HEAVY_ACT, SLAB>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
   });
   int rc = check_cuda(attr_err, "cudaFuncSetAttribute(conv_tc_kernel)");
   if (rc) return rc;
   const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  conv_tc_kernel<BLOCK_N, M_SUB, BLOCK_K, EPI_TMA, HEAVY_ACT><<<grid, kTcThreads, Cfg::SMEM_BYTES, stream>>>(p);
+  conv_tc_kernel<BLOCK_N, M_SUB, BLOCK_K, EPI_TMA, HEAVY_ACT, SLAB><<<grid, kTcThreads, Cfg::SMEM_BYTES, stream>>>(p);
   FV_CHECK_LAUNCH("conv_tc_kernel");
   return 0;
+  }
 }
 
 template <int BLOCK_N, int M_SUB, int BLOCK_K, bool EPI_TMA>
 static int launch_tc(const fv_conv_desc* d, ConvTcParams& p, cudaStream_t stream) {
   const bool heavy = d->out16 != nullptr && (d->act == FV_ACT_POLAR || d->act == FV_ACT_TANH);
-  if (heavy) return launch_tc_impl<BLOCK_N, M_SUB, BLOCK_K, EPI_TMA, true>(d, p, stream);
-  return launch_tc_impl<BLOCK_N, M_SUB, BLOCK_K, EPI_TMA, false>(d, p, stream);
+  if (heavy) return launch_tc_impl<BLOCK_N, M_SUB, BLOCK_K, EPI_TMA, true, false>(d, p, stream);
+  if constexpr (EPI_TMA) {
+    // slab mainloop: every tap offset must fall inside the 64 extra slab rows
+    int omin = d->tap_off[0], omax = d->tap_off[0];
+    for (int i = 0; i < d->n_phase * d->n_taps; ++i) {
+      omin = d->tap_off[i] < omin ? d->tap_off[i] : omin;
+      omax = d->tap_off[i] > omax ? d->tap_off[i] : omax;
+    }
+    const bool slab_ok = (omax - omin) <= 64 && d->n_taps > 1;
+    if constexpr (TcCfg<BLOCK_N, M_SUB, BLOCK_K, true, true>::VALID) {
+      if (slab_ok && p.use_slab) return launch_tc_impl<BLOCK_N, M_SUB, BLOCK_K, true, false, true>(d, p, stream);
+    }
+  }
+  return launch_tc_impl<BLOCK_N, M_SUB, BLOCK_K, EPI_TMA, false, false>(d, p, stream);
 }
 
 template <int BLOCK_N, int M_SUB, bool EPI_TMA>
@@ -693,7 +813,8 @@ int pick_block_n(int C_out) {
 }
 
 // Called by fv_conv1d (fv_api.cu) after argument validation.  m_sub_override / block_n_override: 0 = heuristic.
-int conv1d_tc(const fv_conv_desc* d, cudaStream_t stream, int block_n_override, int m_sub_override, int epilogue) {
+int conv1d_tc(const fv_conv_desc* d, cudaStream_t stream, int block_n_override, int m_sub_override, int epilogue,
+              int mainloop) {
   ConvTcParams p;
   memset(&p, 0, sizeof(p));
   p.B = d->B;
@@ -716,11 +837,15 @@ int conv1d_tc(const fv_conv_desc* d, cudaStream_t stream, int block_n_override, 
   p.act = d->act;
   p.out_scale = d->out_scale;
   p.act_param = d->act_param;
+  // mainloop: 0 = auto, 1 = per-tap stages, 2 = slab.  Measured on B200 the two are equivalent (the epilogue, not the
+  // mainloop, bounds these kernels), so auto keeps the simpler per-tap ring; the slab path is the base for fusion.
+  p.use_slab = mainloop == 2;
   for (int i = 0; i < d->n_phase * d->n_taps; ++i) p.tap_off[i] = (int16_t)d->tap_off[i];
 
   const int bn = block_n_override ? block_n_override : pick_block_n(d->C_out);
   // two 128-row accumulators per CTA share every weight tile; a single one when the sequence is short
   int m_sub = m_sub_override ? m_sub_override : ((p.q_rows > 128 && bn < 256) ? 2 : 1);
+  if (bn == 256) m_sub = 1;  // two 256-column accumulators do not leave room for a pipelined smem ring
   if (d->a_pitch <= 32) m_sub = 2;
   // TMA epilogue needs a rectangular {phase, q} view of the output rows; epilogue: 0 = auto, 1 = LSU, 2 = TMA
   const bool tma_ok = (d->L_out % d->n_phase) == 0 && bn >= 32;
