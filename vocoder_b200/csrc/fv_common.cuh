@@ -65,8 +65,9 @@ __device__ __forceinline__ float act_apply(float v, int act, float param) {
 
 // fp16 conversion that cannot produce inf for finite inputs (tensor-core operands must stay finite)
 __device__ __forceinline__ __half to_half_sat(float v) {
-  v = fminf(fmaxf(v, -65504.f), 65504.f);
-  return __float2half_rn(v);
+  unsigned short r;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(v));
+  return __ushort_as_half(r);
 }
 // two floats -> packed fp16x2 (a in the low half), round-to-nearest, saturating to +-65504: one F2FP instruction
 __device__ __forceinline__ uint32_t pack_half2_sat(float a, float b) {

@@ -217,10 +217,87 @@ __device__ __forceinline__ float snake_fn(float u, float a, float inv_b) {
 // read the same 6-sample window.  A thread owns one channel and marches over SN_SEG steps keeping x~[t+1..t+6] in a
 // 6-register ring and v~[2t-5..2t+6] in a 12-register ring (unrolled by 6 so ring slots are compile-time registers):
 // one 4-byte load, 24 FMA, 2 SFU sines and one 2-byte store per sample; six "pre-roll" steps fill the rings.
+// EDGE = false is the interior fast path (no index clamps, no replicate logic, pointer increments only): ncu showed
+// the kernel issue-bound with a third of its instructions being integer/predicate work of the edge handling.
+template <bool EDGE>
+__device__ __forceinline__ void snake_segment(const float* __restrict__ xc, __half* __restrict__ orow,
+                                              const SnakeFilt& f, float a, float inv_b, int t0, int t_end, int L,
+                                              int pitch) {
+  const int nl = 2 * L - 1;
+  auto ldx = [&](int t) {
+    if (EDGE) t = t < 0 ? 0 : (t > L - 1 ? L - 1 : t);  // replicate edge of the INPUT (first filter pads its own input)
+    return xc[(size_t)t * pitch];
+  };
+  float X[6];   // ring: x~[t+6-q] lives in X[(k - q) mod 6] at unrolled position k
+  float V[12];  // ring: v~[2t-5+j] lives in V[(2k + j) mod 12]
+  float vlast = 0.f;
+  // window before the first pre-roll step (t = t0 - 6): x~[t+1 .. t+5] = x~[t0-5 .. t0-1] in X[1..5]
+#pragma unroll
+  for (int i = 1; i < 6; ++i) X[i] = ldx(t0 - 6 + i);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {  // pre-roll: t = t0 - 6 + k produces v[2t0-5+2k], v[2t0-4+2k]
+    const int t = t0 - 6 + k;
+    X[k] = ldx(t + 6);
+    float uo = 0.f, ue = 0.f;
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+      const float xv = X[(k - q + 6) % 6];
+      uo = fmaf(f.up[2 * q], xv, uo);
+      ue = fmaf(f.up[2 * q + 1], xv, ue);
+    }
+    float va = snake_fn(uo, a, inv_b), vb = snake_fn(ue, a, inv_b);  // f.up carries the 2x gain
+    if (EDGE) {
+      if (2 * t + 7 <= nl) vlast = va; else va = vlast;
+      if (2 * t + 8 <= nl) vlast = vb; else vb = vlast;
+    }
+    V[(2 * k) % 12] = va;
+    V[(2 * k + 1) % 12] = vb;
+  }
+  if (EDGE && t0 == 0) {  // v~[n < 0] = v[0]: replicate edge of the ACTIVATED signal (second filter pads its own input)
+#pragma unroll
+    for (int j = 0; j < 5; ++j) V[j] = V[5];
+  }
+  const float* px = xc + (size_t)(t0 + 6) * pitch;  // interior path: running pointers instead of index math
+  __half* po = orow + (size_t)t0 * pitch;
+  for (int tb = t0; tb < t_end; tb += 6) {
+    float xn[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {  // six independent loads in flight
+      if (EDGE) xn[k] = ldx(tb + k + 6);
+      else xn[k] = px[(size_t)k * pitch];
+    }
+    px += (size_t)6 * pitch;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const int t = tb + k;
+      float o = 0.f;
+#pragma unroll
+      for (int j = 0; j < 12; ++j) o = fmaf(f.dn[j], V[(2 * k + j) % 12], o);
+      if (!EDGE || t < t_end) po[(size_t)k * pitch] = to_half_sat(o);
+      X[k] = xn[k];
+      float uo = 0.f, ue = 0.f;
+#pragma unroll
+      for (int q = 0; q < 6; ++q) {
+        const float xv = X[(k - q + 6) % 6];
+        uo = fmaf(f.up[2 * q], xv, uo);
+        ue = fmaf(f.up[2 * q + 1], xv, ue);
+      }
+      float va = snake_fn(uo, a, inv_b), vb = snake_fn(ue, a, inv_b);  // f.up carries the 2x gain
+      if (EDGE) {
+        if (2 * t + 7 <= nl) vlast = va; else va = vlast;
+        if (2 * t + 8 <= nl) vlast = vb; else vb = vlast;
+      }
+      V[(2 * k) % 12] = va;
+      V[(2 * k + 1) % 12] = vb;
+    }
+    po += (size_t)6 * pitch;
+  }
+}
+
 __global__ void __launch_bounds__(256, 3) snake_aa_kernel(const float* __restrict__ x, __half* __restrict__ out,
-                                                       const float* __restrict__ alpha, const float* __restrict__ beta,
-                                                       const SnakeFilt f, int logscale, int B, int L, int C, int pitch,
-                                                       int n_seg) {
+                                                          const float* __restrict__ alpha,
+                                                          const float* __restrict__ beta, const SnakeFilt f,
+                                                          int logscale, int B, int L, int C, int pitch, int n_seg) {
   const long long total = (long long)B * n_seg * pitch;
   const long long item = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (item >= total) return;
@@ -242,65 +319,10 @@ __global__ void __launch_bounds__(256, 3) snake_aa_kernel(const float* __restric
   }
   const float inv_b = 1.0f / (bb + 1e-9f);
   const float* xc = x + ((size_t)b * L) * pitch + c;
-  const int nl = 2 * L - 1;
-  auto ldx = [&](int t) {
-    t = t < 0 ? 0 : (t > L - 1 ? L - 1 : t);  // replicate edge of the INPUT (first filter pads its own input)
-    return xc[(size_t)t * pitch];
-  };
-
-  float X[6];   // ring: x~[t+6-q] lives in X[(k - q) mod 6] at unrolled position k
-  float V[12];  // ring: v~[2t-5+j] lives in V[(2k + j) mod 12]
-  float vlast = 0.f;
-  // window before the first pre-roll step (t = t0 - 6): x~[t+1 .. t+5] = x~[t0-5 .. t0-1] in X[1..5]
-#pragma unroll
-  for (int i = 1; i < 6; ++i) X[i] = ldx(t0 - 6 + i);
-#pragma unroll
-  for (int k = 0; k < 6; ++k) {  // pre-roll: t = t0 - 6 + k produces v[2t0-5+2k], v[2t0-4+2k]
-    const int t = t0 - 6 + k;
-    X[k] = ldx(t + 6);
-    float uo = 0.f, ue = 0.f;
-#pragma unroll
-    for (int q = 0; q < 6; ++q) {
-      const float xv = X[(k - q + 6) % 6];
-      uo = fmaf(f.up[2 * q], xv, uo);
-      ue = fmaf(f.up[2 * q + 1], xv, ue);
-    }
-    float va = snake_fn(2.0f * uo, a, inv_b), vb = snake_fn(2.0f * ue, a, inv_b);
-    if (2 * t + 7 <= nl) vlast = va; else va = vlast;
-    if (2 * t + 8 <= nl) vlast = vb; else vb = vlast;
-    V[(2 * k) % 12] = va;
-    V[(2 * k + 1) % 12] = vb;
-  }
-  if (t0 == 0) {  // v~[n < 0] = v[0]: replicate edge of the ACTIVATED signal (second filter pads its own input)
-#pragma unroll
-    for (int j = 0; j < 5; ++j) V[j] = V[5];
-  }
-  for (int tb = t0; tb < t_end; tb += 6) {
-    float xn[6];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) xn[k] = ldx(tb + k + 6);  // six independent loads in flight
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      const int t = tb + k;
-      float o = 0.f;
-#pragma unroll
-      for (int j = 0; j < 12; ++j) o = fmaf(f.dn[j], V[(2 * k + j) % 12], o);
-      if (t < t_end) orow[(size_t)t * pitch] = to_half_sat(o);
-      X[k] = xn[k];
-      float uo = 0.f, ue = 0.f;
-#pragma unroll
-      for (int q = 0; q < 6; ++q) {
-        const float xv = X[(k - q + 6) % 6];
-        uo = fmaf(f.up[2 * q], xv, uo);
-        ue = fmaf(f.up[2 * q + 1], xv, ue);
-      }
-      float va = snake_fn(2.0f * uo, a, inv_b), vb = snake_fn(2.0f * ue, a, inv_b);
-      if (2 * t + 7 <= nl) vlast = va; else va = vlast;
-      if (2 * t + 8 <= nl) vlast = vb; else vb = vlast;
-      V[(2 * k) % 12] = va;
-      V[(2 * k + 1) % 12] = vb;
-    }
-  }
+  // interior segment: every x index in [t0-5, t0+SN_SEG+5] and every v index up to 2(t0+SN_SEG)+6 is in range
+  const bool interior = (t0 >= 6) && (t0 + SN_SEG + 6 <= L - 1);
+  if (interior) snake_segment<false>(xc, orow, f, a, inv_b, t0, t_end, L, pitch);
+  else snake_segment<true>(xc, orow, f, a, inv_b, t0, t_end, L, pitch);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -513,7 +535,7 @@ extern "C" int fv_snake_aa(const float* x32, void* out16, const float* alpha, co
   // the 12 taps are tiny, deterministic buffers of the module; fetch them once per call (async, stream ordered
   // copies would need a staging buffer - the module passes HOST copies of the taps instead, see python side)
   for (int i = 0; i < 12; ++i) {
-    f.up[i] = filt_up[i];
+    f.up[i] = 2.0f * filt_up[i];  // the up-sampler's gain of `ratio` (= 2) is folded into its taps
     f.dn[i] = filt_down[i];
   }
   const int n_seg = ceil_div(L, SN_SEG);
