@@ -133,7 +133,8 @@ FV_API int fv_snake_aa(const float* x32, void* out16, const float* alpha, const 
                 const float* filt_down, int logscale, int B, int L, int C, int pitch, void* stream);
 
 /* ConvNeXt block front half (convnext.py:127-129): depthwise conv k (zero pad) + LayerNorm over C (eps) -> fp16.
- * x32 [B][T][pitch] -> out16 [B][T][pitch].  dw_w [C][k], dw_b [C], ln_w/ln_b [C]. k <= 0 means "no conv"
+ * x32 [B][T][pitch] -> out16 [B][T][pitch].  dw_w [k][C] (tap-major, i.e. the module's [C,1,k] weight transposed so
+ * that channel-parallel threads read it coalesced), dw_b [C], ln_w/ln_b [C]. k <= 0 means "no conv"
  * (plain LayerNorm over C: convnext.py:64-74).  out32 (optional) receives the fp32 result as well. */
 FV_API int fv_dwconv_layernorm(const float* x32, void* out16, float* out32, const float* dw_w, const float* dw_b,
                         const float* ln_w, const float* ln_b, float eps, int B, int T, int C, int pitch, int k,

@@ -124,7 +124,7 @@ def pitch_of(channels: int) -> int:
 def c_out_pad_of(c_out: int) -> int:
     """Weight rows per tap: a multiple of every N tile the kernel may pick for this C_out."""
     if c_out <= 128:
-        p = 16
+        p = 32  # the smallest N tile the tcgen05 engine picks (TMA epilogue boxes are 32 columns wide)
         while p < c_out:
             p *= 2
         return p

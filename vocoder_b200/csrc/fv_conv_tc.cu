@@ -803,9 +803,9 @@ static int dispatch_m(const fv_conv_desc* d, ConvTcParams& p, cudaStream_t s, in
   return dispatch_k<BLOCK_N, 2, false>(d, p, s);
 }
 
-int pick_block_n(int C_out) {
-  if (C_out <= 16) return 16;
-  if (C_out <= 32) return 32;
+int pick_block_n(int C_out, int C_out_pad) {
+  if (C_out <= 16 && C_out_pad < 32) return 16;  // weights packed for 16-row tiles only
+  if (C_out <= 32) return 32;                    // N = 32 keeps the TMA epilogue (32-column boxes) even for C <= 16
   if (C_out <= 64) return 64;
   if (C_out <= 128) return 128;
   const int pad128 = round_up(C_out, 128), pad256 = round_up(C_out, 256);
@@ -842,7 +842,7 @@ int conv1d_tc(const fv_conv_desc* d, cudaStream_t stream, int block_n_override, 
   p.use_slab = mainloop == 2;
   for (int i = 0; i < d->n_phase * d->n_taps; ++i) p.tap_off[i] = (int16_t)d->tap_off[i];
 
-  const int bn = block_n_override ? block_n_override : pick_block_n(d->C_out);
+  const int bn = block_n_override ? block_n_override : pick_block_n(d->C_out, d->C_out_pad);
   // two 128-row accumulators per CTA share every weight tile; a single one when the sequence is short
   int m_sub = m_sub_override ? m_sub_override : ((p.q_rows > 128 && bn < 256) ? 2 : 1);
   if (bn == 256) m_sub = 1;  // two 256-column accumulators do not leave room for a pipelined smem ring

@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(128) dwconv_ln_kernel(const float* __restrict_
       acc = dw_b[c];
       for (int j = 0; j < k; ++j) {
         const int r = t + j - half_k;
-        if (r >= 0 && r < T) acc = fmaf(dw_w[c * k + j], xb[(size_t)r * pitch + c], acc);
+        if (r >= 0 && r < T) acc = fmaf(dw_w[(size_t)j * C + c], xb[(size_t)r * pitch + c], acc);
       }
     } else {
       acc = xb[(size_t)t * pitch + c];
@@ -371,6 +371,112 @@ __global__ void __launch_bounds__(128) dwconv_ln_kernel(const float* __restrict_
     const float y = c < C ? fmaf((h[c] - mean) * rstd, ln_w[c], ln_b[c]) : 0.f;
     if (out16) out16[(size_t)row * pitch + c] = to_half_sat(y);
     if (out32) out32[(size_t)row * pitch + c] = y;
+  }
+}
+
+// Tiled version for the ConvNeXt shapes: one CTA = DW_R consecutive time steps x all channels.  Each thread walks
+// channels c = tid, tid + 256, ...: the DW_R + K - 1 input rows and the K taps (weights stored [k][C]) are read once
+// per channel with coalesced 128-byte warp accesses (2.5 loads per output instead of 7), the depthwise results stay in
+// shared memory for the two LayerNorm reductions and the normalised write.  K = 0: plain LayerNorm over C.
+constexpr int DW_R = 4;
+
+template <int K>
+__global__ void __launch_bounds__(256) dwconv_ln_tiled_kernel(const float* __restrict__ x, __half* __restrict__ out16,
+                                                              float* __restrict__ out32,
+                                                              const float* __restrict__ dw_wT,
+                                                              const float* __restrict__ dw_b,
+                                                              const float* __restrict__ ln_w,
+                                                              const float* __restrict__ ln_b, float eps, int T, int C,
+                                                              int pitch, int tiles_per_b) {
+  extern __shared__ float s_h[];  // [DW_R][pitch]
+  __shared__ float s_red[8][DW_R];
+  __shared__ float s_mean[DW_R], s_rstd[DW_R];
+  const int b = blockIdx.x / tiles_per_b;
+  const int t0 = (blockIdx.x % tiles_per_b) * DW_R;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float* xb = x + (size_t)b * T * pitch;
+  constexpr int HALF = K > 0 ? (K - 1) / 2 : 0;
+  constexpr int WIN = DW_R + (K > 0 ? K - 1 : 0);
+  float sum[DW_R];
+#pragma unroll
+  for (int r = 0; r < DW_R; ++r) sum[r] = 0.f;
+  for (int c = tid; c < C; c += 256) {
+    float xw[WIN];
+#pragma unroll
+    for (int i = 0; i < WIN; ++i) {
+      const int t = t0 - HALF + i;
+      xw[i] = (t >= 0 && t < T) ? xb[(size_t)t * pitch + c] : 0.f;
+    }
+    float acc[DW_R];
+    if constexpr (K > 0) {
+      const float bias = dw_b[c];
+#pragma unroll
+      for (int r = 0; r < DW_R; ++r) acc[r] = bias;
+#pragma unroll
+      for (int j = 0; j < K; ++j) {
+        const float w = dw_wT[(size_t)j * C + c];
+#pragma unroll
+        for (int r = 0; r < DW_R; ++r) acc[r] = fmaf(w, xw[r + j], acc[r]);
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < DW_R; ++r) acc[r] = xw[r];
+    }
+#pragma unroll
+    for (int r = 0; r < DW_R; ++r) {
+      s_h[r * pitch + c] = acc[r];
+      sum[r] += acc[r];
+    }
+  }
+  // block reduction of the DW_R row sums -> means
+#pragma unroll
+  for (int r = 0; r < DW_R; ++r) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], off);
+    if (lane == 0) s_red[warp][r] = sum[r];
+  }
+  __syncthreads();
+  if (tid < DW_R) {
+    float m = 0.f;
+    for (int w = 0; w < 8; ++w) m += s_red[w][tid];
+    s_mean[tid] = m / C;
+  }
+  __syncthreads();
+  float var[DW_R];
+#pragma unroll
+  for (int r = 0; r < DW_R; ++r) var[r] = 0.f;
+  for (int c = tid; c < C; c += 256) {
+#pragma unroll
+    for (int r = 0; r < DW_R; ++r) {
+      const float dlt = s_h[r * pitch + c] - s_mean[r];
+      var[r] = fmaf(dlt, dlt, var[r]);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < DW_R; ++r) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) var[r] += __shfl_xor_sync(0xffffffffu, var[r], off);
+    if (lane == 0) s_red[warp][r] = var[r];
+  }
+  __syncthreads();
+  if (tid < DW_R) {
+    float v = 0.f;
+    for (int w = 0; w < 8; ++w) v += s_red[w][tid];
+    s_rstd[tid] = 1.0f / sqrtf(v / C + eps);
+  }
+  __syncthreads();
+  for (int c = tid; c < pitch; c += 256) {
+    const float g = c < C ? ln_w[c] : 0.f, be = c < C ? ln_b[c] : 0.f;
+#pragma unroll
+    for (int r = 0; r < DW_R; ++r) {
+      const int t = t0 + r;
+      if (t < T) {
+        const float y = c < C ? fmaf((s_h[r * pitch + c] - s_mean[r]) * s_rstd[r], g, be) : 0.f;
+        const size_t o = ((size_t)b * T + t) * pitch + c;
+        if (out16) out16[o] = to_half_sat(y);
+        if (out32) out32[o] = y;
+      }
+    }
   }
 }
 
@@ -552,6 +658,19 @@ extern "C" int fv_dwconv_layernorm(const float* x32, void* out16, float* out32, 
   FV_REQUIRE(x32 && (out16 || out32) && ln_w && ln_b && B > 0 && T > 0 && C > 0 && pitch >= C, FV_E_BADARG,
              "fv_dwconv_layernorm: bad arguments");
   FV_REQUIRE(k <= 0 || (dw_w && dw_b && (k & 1)), FV_E_BADARG, "fv_dwconv_layernorm: bad depthwise kernel");
+  const int tiled_smem = DW_R * pitch * (int)sizeof(float);
+  if ((k <= 0 || k == 7) && tiled_smem <= 48 * 1024) {
+    const int tiles_per_b = ceil_div(T, DW_R);
+    const int grid = B * tiles_per_b;
+    if (k == 7)
+      dwconv_ln_tiled_kernel<7><<<grid, 256, tiled_smem, (cudaStream_t)stream>>>(
+          x32, (__half*)out16, out32, dw_w, dw_b, ln_w, ln_b, eps, T, C, pitch, tiles_per_b);
+    else
+      dwconv_ln_tiled_kernel<0><<<grid, 256, tiled_smem, (cudaStream_t)stream>>>(
+          x32, (__half*)out16, out32, dw_w, dw_b, ln_w, ln_b, eps, T, C, pitch, tiles_per_b);
+    FV_CHECK_LAUNCH("dwconv_ln_tiled_kernel");
+    return 0;
+  }
   const int warps = 4;
   const int smem = warps * pitch * (int)sizeof(float);
   FV_REQUIRE(smem <= 48 * 1024, FV_E_UNSUPPORTED, "fv_dwconv_layernorm: C too large (%d)", C);

@@ -125,7 +125,7 @@ class ConvNeXtEncoder(nn.Module):
                 for blk in stage:
                     C = blk.dwconv.weight.shape[0]
                     blocks.append(dict(
-                        C=C, k=blk.dwconv.kernel_size[0], dw_w=f32(blk.dwconv.weight).reshape(C, -1).contiguous(),
+                        C=C, k=blk.dwconv.kernel_size[0], dw_w=f32(blk.dwconv.weight).reshape(C, -1).t().contiguous(),
                         dw_b=f32(blk.dwconv.bias), ln_w=f32(blk.norm.weight), ln_b=f32(blk.norm.bias),
                         eps=blk.norm.eps, pw1=cabi.pack_linear(blk.pwconv1.weight, blk.pwconv1.bias),
                         pw2=cabi.pack_linear(blk.pwconv2.weight, blk.pwconv2.bias),
