@@ -125,6 +125,19 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// one lane of a fully converged warp (the canonical way to issue TMA / tcgen05 work: the role loops stay warp-uniform,
+// so descriptors live in uniform registers instead of being re-broadcast around every instruction)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, %1;\n\t"
+      "@px mov.s32 %0, 1;\n\t}"
+      : "+r"(pred)
+      : "r"(0xffffffffu));
+  return pred != 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // PTX: TMA tiled loads (global -> swizzled shared), completion on an mbarrier
 // ------------------------------------------------------------------------------------------------
@@ -249,6 +262,12 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, uint32_
   d |= static_cast<uint64_t>(base_offset & 7u) << 49;
   d |= layout << 61;
   return d;
+}
+
+// Advancing a descriptor by a byte offset inside the same swizzled tile: add (bytes >> 4) to the start-address field
+// (shared-memory addresses are < 256 KB, so the 14-bit field cannot overflow).
+__device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t bytes) {
+  return desc + static_cast<uint64_t>(bytes >> 4);
 }
 
 // Instruction descriptor for kind::f16: fp16 A/B (K-major both), fp32 accumulate, shape M x N

@@ -152,7 +152,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // (whole warp runs the loops and the barrier waits; one elected lane issues the bulk copies)
+    {
+      const bool leader = elect_one();
       uint32_t it = 0, ita = 0;
       bool w_loaded = false;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -168,17 +170,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
           for (int kc = 0; kc < p.k_chunks; ++kc, ++ita) {
             const int sa = ita & 1;
             mbar_wait(&aempty_bar[sa], ((ita >> 1) & 1) ^ 1);
-            mbar_arrive_expect_tx(&afull_bar[sa], p.slab_boxes * 64 * Cfg::ROW_BYTES);
-            for (int bx = 0; bx < p.slab_boxes; ++bx)
-              tma_load_3d(smem + sa * Cfg::A_SLAB + bx * 64 * Cfg::ROW_BYTES, &p.tmA2, &afull_bar[sa], kc * BLOCK_K,
-                          q0 + p.off_min + bx * 64, b);
+            if (leader) {
+              mbar_arrive_expect_tx(&afull_bar[sa], p.slab_boxes * 64 * Cfg::ROW_BYTES);
+              for (int bx = 0; bx < p.slab_boxes; ++bx)
+                tma_load_3d(smem + sa * Cfg::A_SLAB + bx * 64 * Cfg::ROW_BYTES, &p.tmA2, &afull_bar[sa], kc * BLOCK_K,
+                            q0 + p.off_min + bx * 64, b);
+            }
             if (!(p.w_resident && w_loaded)) {
               for (int tap = 0; tap < p.n_taps; ++tap, ++it) {
                 const int s = it % Cfg::NB;
                 mbar_wait(&empty_bar[s], ((it / Cfg::NB) & 1) ^ 1);
-                mbar_arrive_expect_tx(&full_bar[s], Cfg::B_STAGE);
-                tma_load_2d(b_ring + s * Cfg::B_STAGE, &p.tmW, &full_bar[s], kc * BLOCK_K,
-                            (phase * p.n_taps + tap) * p.C_out_pad + n0);
+                if (leader) {
+                  mbar_arrive_expect_tx(&full_bar[s], Cfg::B_STAGE);
+                  tma_load_2d(b_ring + s * Cfg::B_STAGE, &p.tmW, &full_bar[s], kc * BLOCK_K,
+                              (phase * p.n_taps + tap) * p.C_out_pad + n0);
+                }
               }
             }
           }
@@ -190,13 +196,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
             for (int kc = 0; kc < p.k_chunks; ++kc, ++it) {
               const int s = it % Cfg::STAGES;
               mbar_wait(&empty_bar[s], ((it / Cfg::STAGES) & 1) ^ 1);
-              mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE);
-              uint8_t* sa = smem + s * Cfg::STAGE;
-  #pragma unroll
-              for (int bx = 0; bx < Cfg::N_A_BOX; ++bx)
-                tma_load_3d(sa + bx * Cfg::A_BOX_ROWS * Cfg::ROW_BYTES, &p.tmA, &full_bar[s], kc * BLOCK_K,
-                            row0 + bx * Cfg::A_BOX_ROWS, b);
-              tma_load_2d(sa + Cfg::A_STAGE, &p.tmW, &full_bar[s], kc * BLOCK_K, wrow);
+              if (leader) {
+                mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE);
+                uint8_t* sa = smem + s * Cfg::STAGE;
+#pragma unroll
+                for (int bx = 0; bx < Cfg::N_A_BOX; ++bx)
+                  tma_load_3d(sa + bx * Cfg::A_BOX_ROWS * Cfg::ROW_BYTES, &p.tmA, &full_bar[s], kc * BLOCK_K,
+                              row0 + bx * Cfg::A_BOX_ROWS, b);
+                tma_load_2d(sa + Cfg::A_STAGE, &p.tmW, &full_bar[s], kc * BLOCK_K, wrow);
+              }
             }
           }
         }
@@ -204,7 +212,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // (whole warp runs the loops and the barrier waits; one elected lane issues tcgen05.mma / tcgen05.commit)
+    {
+      const bool leader = elect_one();
       constexpr uint32_t idesc = make_idesc_f16(128, BLOCK_N);
       uint32_t it = 0, ita = 0, tile_i = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tile_i) {
@@ -236,22 +246,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
               // of the absolute smem address, verified by fv_debug_rowshift_probe)
               const uint32_t a_tap = slab + (p.tap_off[phase * p.n_taps + tap] - p.off_min) * Cfg::ROW_BYTES;
               const uint32_t b_base = b_ring + s * Cfg::B_STAGE;
+              if (leader) {
+                const uint64_t da0 = make_kmajor_desc(a_tap, Cfg::ROW_BYTES);
+                const uint64_t db0 = make_kmajor_desc(b_base, Cfg::ROW_BYTES);
 #pragma unroll
-              for (int sub = 0; sub < M_SUB; ++sub) {
+                for (int sub = 0; sub < M_SUB; ++sub) {
 #pragma unroll
-                for (int kk = 0; kk < BLOCK_K / 16; ++kk) {
-                  const uint64_t da = make_kmajor_desc(a_tap + sub * Cfg::A_SUB_BYTES + kk * 32, Cfg::ROW_BYTES);
-                  const uint64_t db = make_kmajor_desc(b_base + kk * 32, Cfg::ROW_BYTES);
-                  umma_f16_ss(tmem_base + (buf * M_SUB + sub) * BLOCK_N, da, db, idesc,
-                              (kc > 0 || tap > 0 || kk > 0) ? 1u : 0u);
+                  for (int kk = 0; kk < BLOCK_K / 16; ++kk) {
+                    umma_f16_ss(tmem_base + (buf * M_SUB + sub) * BLOCK_N,
+                                desc_advance(da0, sub * Cfg::A_SUB_BYTES + kk * 32), desc_advance(db0, kk * 32), idesc,
+                                (kc > 0 || tap > 0 || kk > 0) ? 1u : 0u);
+                  }
                 }
+                if (!p.w_resident) umma_commit(&empty_bar[s]);  // weight tile consumed
               }
-              if (!p.w_resident) {
-                umma_commit(&empty_bar[s]);  // weight tile consumed
-                ++it;
-              }
+              __syncwarp();
+              if (!p.w_resident) ++it;
             }
-            umma_commit(&aempty_bar[sa]);  // slab consumed by every tap of this K chunk
+            if (leader) umma_commit(&aempty_bar[sa]);  // slab consumed by every tap of this K chunk
+            __syncwarp();
           }
         } else {
           for (int st = 0; st < k_steps; ++st, ++it) {
@@ -260,19 +273,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
             tc_fence_after();
             const uint32_t a_base = smem_u32(smem + s * Cfg::STAGE);
             const uint32_t b_base = a_base + Cfg::A_STAGE;
-  #pragma unroll
-            for (int sub = 0; sub < M_SUB; ++sub) {
-  #pragma unroll
-              for (int kk = 0; kk < BLOCK_K / 16; ++kk) {
-                const uint64_t da = make_kmajor_desc(a_base + sub * Cfg::A_SUB_BYTES + kk * 32, Cfg::ROW_BYTES);
-                const uint64_t db = make_kmajor_desc(b_base + kk * 32, Cfg::ROW_BYTES);
-                umma_f16_ss(tmem_base + (buf * M_SUB + sub) * BLOCK_N, da, db, idesc, (st > 0 || kk > 0) ? 1u : 0u);
+            if (leader) {
+              const uint64_t da0 = make_kmajor_desc(a_base, Cfg::ROW_BYTES);
+              const uint64_t db0 = make_kmajor_desc(b_base, Cfg::ROW_BYTES);
+#pragma unroll
+              for (int sub = 0; sub < M_SUB; ++sub) {
+#pragma unroll
+                for (int kk = 0; kk < BLOCK_K / 16; ++kk) {
+                  umma_f16_ss(tmem_base + (buf * M_SUB + sub) * BLOCK_N,
+                              desc_advance(da0, sub * Cfg::A_SUB_BYTES + kk * 32), desc_advance(db0, kk * 32), idesc,
+                              (st > 0 || kk > 0) ? 1u : 0u);
+                }
               }
+              umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
             }
-            umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
+            __syncwarp();
           }
         }
-        umma_commit(&tfull_bar[buf]);  // accumulator complete -> epilogue
+        if (leader) umma_commit(&tfull_bar[buf]);  // accumulator complete -> epilogue
+        __syncwarp();
       }
     }
   } else {
