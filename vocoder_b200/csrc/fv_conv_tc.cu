@@ -802,11 +802,11 @@ static int launch_tc(const fv_conv_desc* d, ConvTcParams& p, cudaStream_t stream
 template <int BLOCK_N, int M_SUB, bool EPI_TMA>
 static int dispatch_k(const fv_conv_desc* d, ConvTcParams& p, cudaStream_t s) {
   if (d->a_pitch > 32) return launch_tc<BLOCK_N, M_SUB, 64, EPI_TMA>(d, p, s);
-  if constexpr (M_SUB == 2) {
-    if (d->a_pitch > 16) return launch_tc<BLOCK_N, 2, 32, EPI_TMA>(d, p, s);
-    return launch_tc<BLOCK_N, 2, 16, EPI_TMA>(d, p, s);
+  if constexpr (M_SUB >= 2) {  // small-K variants exist for the multi-accumulator tiles only
+    if (d->a_pitch > 16) return launch_tc<BLOCK_N, M_SUB, 32, EPI_TMA>(d, p, s);
+    return launch_tc<BLOCK_N, M_SUB, 16, EPI_TMA>(d, p, s);
   } else {
-    return launch_tc<BLOCK_N, M_SUB, 64, EPI_TMA>(d, p, s);  // small-K variants only exist for M_SUB == 2
+    return launch_tc<BLOCK_N, M_SUB, 64, EPI_TMA>(d, p, s);
   }
 }
 
@@ -815,6 +815,9 @@ static int dispatch_m(const fv_conv_desc* d, ConvTcParams& p, cudaStream_t s, in
   if constexpr (BLOCK_N >= 32) {
     if (epi_tma) {
       if (m_sub == 1) return dispatch_k<BLOCK_N, 1, true>(d, p, s);
+      if constexpr (BLOCK_N <= 64) {  // four 128-row accumulators: 512-row tiles amortise the per-tile cost at small C
+        if (m_sub == 4) return dispatch_k<BLOCK_N, 4, true>(d, p, s);
+      }
       return dispatch_k<BLOCK_N, 2, true>(d, p, s);
     }
   }
@@ -865,7 +868,8 @@ int conv1d_tc(const fv_conv_desc* d, cudaStream_t stream, int block_n_override, 
   // two 128-row accumulators per CTA share every weight tile; a single one when the sequence is short
   int m_sub = m_sub_override ? m_sub_override : ((p.q_rows > 128 && bn < 256) ? 2 : 1);
   if (bn == 256) m_sub = 1;  // two 256-column accumulators do not leave room for a pipelined smem ring
-  if (d->a_pitch <= 32) m_sub = 2;
+  if (!m_sub_override && bn <= 64 && p.q_rows >= 2048) m_sub = 4;
+  if (d->a_pitch <= 32 && m_sub < 2) m_sub = 2;
   // TMA epilogue needs a rectangular {phase, q} view of the output rows; epilogue: 0 = auto, 1 = LSU, 2 = TMA
   const bool tma_ok = (d->L_out % d->n_phase) == 0 && bn >= 32;
   const bool epi_tma = tma_ok && epilogue != 1;
