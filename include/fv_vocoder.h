@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define FV_ABI_VERSION 1
+#define FV_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define FV_API __attribute__((visibility("default")))
@@ -96,6 +96,12 @@ typedef struct fv_conv_desc {
   int32_t out16_pitch;
   int32_t act; /* enum fv_act applied to the value written to out16 */
   float act_param;
+  /* strict ("f16x3") precision: operands carry a second fp16 word so that hi + lo is fp32-grade (22-bit mantissa).
+   * a_split = P > 0: `a` is [B][L_in][2P] = [hi | lo]; `w` rows are [Whi | Whi | Wlo] (w_pitch = 3P) and the K loop
+   *   reads A columns {0..2P, 0..P}: acc = hi*Whi + lo*Whi + hi*Wlo  (the lo*Wlo term, ~2^-22 relative, is dropped).
+   * out16_split = Po > 0: out16 is [B][L_out][2 Po]; the epilogue writes hi at [o] and lo = fp16(v - hi) at [Po + o]. */
+  int32_t a_split;
+  int32_t out16_split;
 } fv_conv_desc;
 
 FV_API const char* fv_last_error(void);
@@ -112,17 +118,19 @@ FV_API int fv_conv1d(const fv_conv_desc* d, int engine, void* stream);
 FV_API void fv_set_tc_tuning(int block_n, int m_sub, int epilogue, int mainloop);
 
 /* mel [B][C][T] fp32 channels-first -> fp16 channels-last [B][T][pitch] (zero padded channels).
- * Entry of the path: the tensor handed to Generator.forward (hifigan.py:226, convnext.py:206). */
-FV_API int fv_pack_input(const float* x, void* out16, int B, int C, int T, int pitch, void* stream);
+ * Entry of the path: the tensor handed to Generator.forward (hifigan.py:226, convnext.py:206).
+ * Every fp16-producing entry point takes `split`: 0 = plain fp16; P > 0 = strict mode, the row holds 2P halfs, hi at [c]
+ * and lo = fp16(v - hi) at [P + c] (see fv_conv_desc.a_split). */
+FV_API int fv_pack_input(const float* x, void* out16, int B, int C, int T, int pitch, int split, void* stream);
 
 /* fp32 channels-last [B][L][pitch] -> fp32 channels-first [B][C][L]  (leaving the path; debugging) */
 FV_API int fv_unpack_output(const float* x32, float* out, int B, int C, int L, int pitch, void* stream);
 
 /* conv_post + tanh (hifigan.py:214-222,246-247): a16 [B][L][pitch] (already activated) * w32 [k][C] + bias
  * -> wav fp32 [B][L] (== [B,1,L]).  C_out == 1, so this is a CUDA-core dot product with a warp-shuffle
- * reduction along the channel axis. */
+ * reduction along the channel axis.  split = pitch in strict mode (rows are [hi | lo], the operand is hi + lo). */
 FV_API int fv_conv_post_tanh(const void* a16, const float* w32, const float* bias, float* wav, int B, int L, int C,
-                      int pitch, int k, int apply_tanh, void* stream);
+                      int pitch, int k, int apply_tanh, int split, void* stream);
 
 /* Anti-aliased Snake / SnakeBeta = alias_free_torch.Activation1d(SnakeBeta) (bigvgan.py:226-233,335-337;
  * SURVEY B4): 2x Kaiser-sinc up (12 taps, replicate edges) -> x + sin^2(a x)/(b+1e-9) -> 2x down, ONE kernel.
@@ -130,7 +138,7 @@ FV_API int fv_conv_post_tanh(const void* a16, const float* w32, const float* bia
  * beta == NULL selects Snake (beta := alpha).  filt_up / filt_down = HOST pointers to the 12 fp32 taps (the
  * module's `upsample.filter` / `downsample.lowpass.filter` buffers; passed by value to the kernel). */
 FV_API int fv_snake_aa(const float* x32, void* out16, const float* alpha, const float* beta, const float* filt_up,
-                const float* filt_down, int logscale, int B, int L, int C, int pitch, void* stream);
+                const float* filt_down, int logscale, int B, int L, int C, int pitch, int split, void* stream);
 
 /* ConvNeXt block front half (convnext.py:127-129): depthwise conv k (zero pad) + LayerNorm over C (eps) -> fp16.
  * x32 [B][T][pitch] -> out16 [B][T][pitch].  dw_w [k][C] (tap-major, i.e. the module's [C,1,k] weight transposed so
@@ -138,7 +146,7 @@ FV_API int fv_snake_aa(const float* x32, void* out16, const float* alpha, const 
  * (plain LayerNorm over C: convnext.py:64-74).  out32 (optional) receives the fp32 result as well. */
 FV_API int fv_dwconv_layernorm(const float* x32, void* out16, float* out32, const float* dw_w, const float* dw_b,
                         const float* ln_w, const float* ln_b, float eps, int B, int T, int C, int pitch, int k,
-                        void* stream);
+                        int split, void* stream);
 
 /* ISTFT("same") tail (vocos==0.0.2 spectral_ops.ISTFT): windowed frames [B][T][n_fft] fp32 (window
  * already folded into the inverse-DFT basis) -> overlap-add, trim (win-hop)/2, divide by the hann^2 envelope.
@@ -159,10 +167,10 @@ FV_API int fv_noise_conv(const float* tpl, const float* w, const float* bias, fl
  *               scale = 1 / scale_factor (what torch uses when scale_factor is given). */
 FV_API int fv_act_cast(const float* x32, const float* noise, const float* noise_w, void* out16, float* out32, int act,
                        float act_param, int act16, float act16_param, float out_scale, int accumulate, int B, int L,
-                       int C, int in_pitch, int out16_pitch, int out16_coff, int out32_pitch, void* stream);
+                       int C, int in_pitch, int out16_pitch, int out16_coff, int out32_pitch, int split, void* stream);
 FV_API int fv_resample_linear(const float* x32, float* out32, void* out16, int pre_act, float pre_param, int act,
                               float act_param, int B, int L_in, int L_out, int C, int in_pitch, int out_pitch,
-                              int out_coff, float scale, void* stream);
+                              int out_coff, float scale, int split, void* stream);
 
 /* bring-up probe (not on the product path): 12 row shifts x {base_offset 0, base_offset r&7} of a 128x64x64 UMMA whose
  * A descriptor starts r rows into a TMA-written 144x64 fp16 slab.  a16 [144][64], w16 [64][64], out [12][2][128][64]. */

@@ -110,7 +110,7 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(cabi.LIB_PATH)
     for name in declared:
         assert hasattr(lib, name), f"{name} not exported"
-    assert cabi.lib().fv_abi_version() == 1
+    assert cabi.lib().fv_abi_version() == 2
 
 
 def test_conv_desc_struct_matches_header_layout():
@@ -135,7 +135,7 @@ def test_argument_validation_returns_error_not_crash():
     lib = cabi.lib()
     assert lib.fv_conv1d(None, 0, None) == -1
     assert b"null" in lib.fv_last_error()
-    assert lib.fv_pack_input(None, None, 1, 1, 1, 8, None) == -1
+    assert lib.fv_pack_input(None, None, 1, 1, 1, 8, 0, None) == -1
 
 
 def _ref_from_pack(a, pc, L_out):

@@ -85,6 +85,51 @@ def test_generator_matches_reference_golden(name):
         assert err_emu <= max(5e-4 * peak, gap), f"{name}: vs rounded oracle {err_emu:.3e}"
 
 
+def _set_precision(m, mode):
+    for sub in m.modules():
+        if hasattr(sub, "_ws"):
+            sub.precision = mode
+    m.precision = mode
+
+
+@pytest.mark.parametrize("engine", ["tc", "simt"])
+@pytest.mark.parametrize("name", GOLDEN_GPU)
+def test_strict_precision_meets_1e3_on_every_fixture(name, engine):
+    """precision="strict" (fp16 hi+lo operands, 3 tensor-core passes): fp32-grade, so the north_star bar
+    max|delta| < 1e-3 vs the fp32 reference golden holds for EVERY fixture, the TF32-limited ones included."""
+    kwargs, sd, ins, out, extra = load_golden(name)
+    m = _build(name, kwargs)
+    m.load_state_dict(sd, strict=True)
+    m = m.eval().cuda()
+    _set_precision(m, "strict")
+    if engine == "simt":
+        for sub in m.modules():
+            if hasattr(sub, "engine"):
+                sub.engine = cabi.ENGINE_SIMT
+    with torch.no_grad():
+        y = _run(name, m, ins, extra).cpu()
+    peak = max(1.0, float(out.abs().max()))
+    err = float((y - out).abs().max())
+    print(f"{name} strict/{engine}: vs fp32 reference {err:.3e} (peak {peak:.3f})")
+    assert y.shape == out.shape
+    assert err <= 2e-4 * peak, f"{name}: strict max|delta|={err:.3e} (peak {peak:.3f})"
+
+
+def test_precision_switch_repacks_and_restores_default():
+    kwargs, sd, ins, out, extra = load_golden("hifigan_small_stress")
+    m = _build("hifigan_small_stress", kwargs)
+    m.load_state_dict(sd)
+    m = m.eval().cuda()
+    with torch.no_grad():
+        y0 = _run("hifigan_small_stress", m, ins, extra).clone()
+        m.precision = "strict"
+        ys = _run("hifigan_small_stress", m, ins, extra).clone()
+        m.precision = "fp16"
+        y1 = _run("hifigan_small_stress", m, ins, extra).clone()
+    assert torch.equal(y0, y1)
+    assert float((ys.cpu() - out).abs().max()) < float((y0.cpu() - out).abs().max())
+
+
 @pytest.mark.parametrize("name", ["hifigan_small_stress", "bigvgan_small_ref"])
 def test_simt_engine_agrees_with_tensor_core_engine(name):
     kwargs, sd, ins, out, extra = load_golden(name)

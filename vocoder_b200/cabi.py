@@ -6,8 +6,10 @@ shared library is missing or a tensor is not on a CUDA device the call raises.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes
 import os
+import threading
 from dataclasses import dataclass
 from typing import Optional, Sequence
 
@@ -47,6 +49,7 @@ class ConvDesc(ctypes.Structure):
         ("out_scale", ctypes.c_float),
         ("out16", ctypes.c_void_p), ("out16_pitch", ctypes.c_int32), ("act", ctypes.c_int32),
         ("act_param", ctypes.c_float),
+        ("a_split", ctypes.c_int32), ("out16_split", ctypes.c_int32),
     ]
 
 
@@ -71,21 +74,21 @@ def lib() -> ctypes.CDLL:
     L.fv_set_tc_tuning.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
     vp, ci, cf = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
     L.fv_conv1d.argtypes = [ctypes.POINTER(ConvDesc), ci, vp]
-    L.fv_pack_input.argtypes = [vp, vp, ci, ci, ci, ci, vp]
+    L.fv_pack_input.argtypes = [vp, vp, ci, ci, ci, ci, ci, vp]
     L.fv_unpack_output.argtypes = [vp, vp, ci, ci, ci, ci, vp]
-    L.fv_conv_post_tanh.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, vp]
-    L.fv_snake_aa.argtypes = [vp, vp, vp, vp, ctypes.POINTER(cf), ctypes.POINTER(cf), ci, ci, ci, ci, ci, vp]
-    L.fv_dwconv_layernorm.argtypes = [vp, vp, vp, vp, vp, vp, vp, cf, ci, ci, ci, ci, ci, vp]
+    L.fv_conv_post_tanh.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, vp]
+    L.fv_snake_aa.argtypes = [vp, vp, vp, vp, ctypes.POINTER(cf), ctypes.POINTER(cf), ci, ci, ci, ci, ci, ci, vp]
+    L.fv_dwconv_layernorm.argtypes = [vp, vp, vp, vp, vp, vp, vp, cf, ci, ci, ci, ci, ci, ci, vp]
     L.fv_istft_ola.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, vp]
     L.fv_noise_conv.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, vp]
-    L.fv_act_cast.argtypes = [vp, vp, vp, vp, vp, ci, cf, ci, cf, cf, ci, ci, ci, ci, ci, ci, ci, ci, vp]
-    L.fv_resample_linear.argtypes = [vp, vp, vp, ci, cf, ci, cf, ci, ci, ci, ci, ci, ci, ci, cf, vp]
+    L.fv_act_cast.argtypes = [vp, vp, vp, vp, vp, ci, cf, ci, cf, cf, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp]
+    L.fv_resample_linear.argtypes = [vp, vp, vp, ci, cf, ci, cf, ci, ci, ci, ci, ci, ci, ci, cf, ci, vp]
     L.fv_debug_rowshift_probe.argtypes = [vp, vp, vp, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("fv_last_error", "fv_launch_count", "fv_reset_launch_count", "fv_set_tc_tuning"):
             fn.restype = ctypes.c_int
-    if L.fv_abi_version() != 1:
+    if L.fv_abi_version() != 2:
         raise FvError("libfv_b200.so ABI version mismatch")
     _lib = L
     return L
@@ -116,9 +119,57 @@ def round_up(x: int, m: int) -> int:
     return (x + m - 1) // m * m
 
 
+# ----------------------------------------------------------------------------------------------
+# operand precision
+#   "fp16"   (default) tensor-core operands are IEEE fp16 (10-bit mantissa = TF32 grade, the grade the reference
+#            itself runs at on GPU: test.py:15 enables TF32), fp32 everywhere else.
+#   "strict" operands carry a second fp16 word (value = hi + lo, 21+ mantissa bits) and every contraction is
+#            evaluated as hi*Whi + lo*Whi + hi*Wlo in the same kernel (fv_conv_desc.a_split): fp32-grade results
+#            at 3x the tensor work and 2x the operand bytes.  Activation buffers are then [B][L][2*pitch] = [hi | lo].
+# The mode is thread-local state entered by the module's forward (``module.precision``).
+# ----------------------------------------------------------------------------------------------
+PRECISIONS = ("fp16", "strict")
+_tls = threading.local()
+
+
+def is_strict() -> bool:
+    return getattr(_tls, "strict", False)
+
+
+@contextlib.contextmanager
+def precision(mode: str):
+    if mode not in PRECISIONS:
+        raise ValueError(f"precision must be one of {PRECISIONS}, got {mode!r}")
+    old = is_strict()
+    _tls.strict = mode == "strict"
+    try:
+        yield
+    finally:
+        _tls.strict = old
+
+
 def pitch_of(channels: int) -> int:
-    """Channel pitch of a channels-last activation buffer."""
+    """Channel pitch of a channels-last activation buffer (strict mode: K chunks must not straddle hi | lo)."""
+    if is_strict():
+        return 16 if channels <= 16 else (32 if channels <= 32 else round_up(channels, 64))
     return round_up(channels, 8)
+
+
+def f16_width(channels: int) -> int:
+    """Halfs per row of an fp16 operand buffer: pitch, or [hi | lo] = 2 * pitch in strict mode."""
+    p = pitch_of(channels)
+    return 2 * p if is_strict() else p
+
+
+def split_of(t16: Optional[torch.Tensor]) -> int:
+    """The `split` argument of the fp16-producing entry points for operand buffer `t16`."""
+    return t16.shape[-1] // 2 if (is_strict() and t16 is not None) else 0
+
+
+def _hi_lo(w32: torch.Tensor):
+    hi = w32.to(torch.float16)
+    lo = (w32 - hi.float()).to(torch.float16)
+    return hi, lo
 
 
 def c_out_pad_of(c_out: int) -> int:
@@ -146,6 +197,7 @@ class PackedConv:
     c_out: int
     c_out_pad: int
     w_pitch: int
+    split: int = 0  # strict mode: operand pitch P; the K axis of `w` is [Whi | Whi | Wlo] (w_pitch = 3P)
 
     def __post_init__(self):
         assert self.n_phase * self.n_taps <= MAX_TAPS, "too many taps for one call"
@@ -154,7 +206,25 @@ class PackedConv:
     def to(self, device) -> "PackedConv":
         return PackedConv(self.w.to(device), None if self.bias is None else self.bias.to(device),
                           list(self.tap_off), self.n_phase, self.n_taps, self.c_in, self.c_out,
-                          self.c_out_pad, self.w_pitch)
+                          self.c_out_pad, self.w_pitch, self.split)
+
+
+def _alloc_w(n_phase: int, n_taps: int, cp: int, wp: int, device):
+    """Zeroed packed-weight tensor and the `put(phase, tap, W[c_out, c_in])` writer for the active precision."""
+    strict = is_strict()
+    w = torch.zeros(n_phase, n_taps, cp, 3 * wp if strict else wp, dtype=torch.float16, device=device)
+
+    def put(r: int, i: int, m32: torch.Tensor):
+        co, ci = m32.shape
+        if strict:
+            hi, lo = _hi_lo(m32)
+            w[r, i, :co, :ci] = hi
+            w[r, i, :co, wp:wp + ci] = hi
+            w[r, i, :co, 2 * wp:2 * wp + ci] = lo
+        else:
+            w[r, i, :co, :ci] = m32.to(torch.float16)
+
+    return w, put, (wp if strict else 0)
 
 
 def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], dilation: int = 1) -> PackedConv:
@@ -162,11 +232,13 @@ def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], dilation: int 
     c_out, c_in, k = weight.shape
     assert k % 2 == 1, "same-padded convs on this path have odd kernels"
     cp, wp = c_out_pad_of(c_out), pitch_of(c_in)
-    w = torch.zeros(1, k, cp, wp, dtype=torch.float16, device=weight.device)
-    w[0, :, :c_out, :c_in] = weight.detach().float().permute(2, 0, 1).to(torch.float16)
+    w, put, split = _alloc_w(1, k, cp, wp, weight.device)
+    wf = weight.detach().float()
+    for j in range(k):
+        put(0, j, wf[:, :, j])
     offs = [(j - (k - 1) // 2) * dilation for j in range(k)]
     b = None if bias is None else bias.detach().float().contiguous()
-    return PackedConv(w.contiguous(), b, offs, 1, k, c_in, c_out, cp, wp)
+    return PackedConv(w.contiguous(), b, offs, 1, k, c_in, c_out, cp, w.shape[-1], split)
 
 
 def pack_linear(weight: torch.Tensor, bias: Optional[torch.Tensor]) -> PackedConv:
@@ -192,19 +264,19 @@ def pack_conv_transpose(weight: torch.Tensor, bias: Optional[torch.Tensor], stri
         phases.append(taps)
     n_taps = max(1, max(len(t) for t in phases))
     cp, wp = c_out_pad_of(c_out), pitch_of(c_in)
-    w = torch.zeros(u, n_taps, cp, wp, dtype=torch.float16, device=weight.device)
+    w, put, split = _alloc_w(u, n_taps, cp, wp, weight.device)
     offs = []
     wf = weight.detach().float()
     for r, taps in enumerate(phases):
         for i in range(n_taps):
             if i < len(taps):
                 off, j = taps[i]
-                w[r, i, :c_out, :c_in] = wf[:, :, j].t().to(torch.float16)
+                put(r, i, wf[:, :, j].t())
                 offs.append(off)
             else:
                 offs.append(0)
     b = None if bias is None else bias.detach().float().contiguous()
-    return PackedConv(w.contiguous(), b, offs, u, n_taps, c_in, c_out, cp, wp)
+    return PackedConv(w.contiguous(), b, offs, u, n_taps, c_in, c_out, cp, w.shape[-1], split)
 
 
 def conv_transpose_out_len(L: int, k: int, u: int) -> int:
@@ -237,6 +309,12 @@ def conv1d(a16: torch.Tensor, pc: PackedConv, L_out: Optional[int] = None, *, ga
     d.accumulate, d.out_scale = int(bool(accumulate)), float(out_scale)
     d.out16, d.out16_pitch = _ptr(out16, torch.float16), (0 if out16 is None else out16.shape[2])
     d.act, d.act_param = int(act), float(act_param)
+    if pc.split and a_pitch != 2 * pc.split:
+        raise FvError(f"strict-precision weights (operand pitch {pc.split}) need a [hi | lo] operand of "
+                      f"{2 * pc.split} halfs per row, got {a_pitch}")
+    if not pc.split and is_strict():
+        raise FvError("weights were packed in fp16 mode but the call runs in strict mode: repack")
+    d.a_split, d.out16_split = pc.split, split_of(out16)
     _check(lib().fv_conv1d(ctypes.byref(d), int(engine), _stream()), "fv_conv1d")
 
 
@@ -244,8 +322,10 @@ def pack_input(x: torch.Tensor, pitch: Optional[int] = None) -> torch.Tensor:
     """[B, C, T] fp32 channels-first -> [B, T, pitch] fp16 channels-last."""
     B, C, T = x.shape
     pitch = pitch or pitch_of(C)
-    out = torch.empty(B, T, pitch, dtype=torch.float16, device=x.device)
-    _check(lib().fv_pack_input(_ptr(x, torch.float32), _ptr(out), B, C, T, pitch, _stream()), "fv_pack_input")
+    split = pitch if is_strict() else 0
+    out = torch.empty(B, T, pitch + split, dtype=torch.float16, device=x.device)
+    _check(lib().fv_pack_input(_ptr(x, torch.float32), _ptr(out), B, C, T, pitch, split, _stream()),
+           "fv_pack_input")
     return out
 
 
@@ -260,13 +340,14 @@ def unpack_output(x32: torch.Tensor, C: int) -> torch.Tensor:
 def conv_post_tanh(a16: torch.Tensor, w32: torch.Tensor, bias: Optional[torch.Tensor], C: int,
                    apply_tanh: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """a16 [B, L, pitch] fp16, w32 [k, C] fp32 -> wav [B, 1, L] fp32."""
-    B, L, pitch = a16.shape
+    B, L, width = a16.shape
+    split = split_of(a16)
     k = w32.shape[0]
     if out is None:
         out = torch.empty(B, 1, L, dtype=torch.float32, device=a16.device)
     _check(lib().fv_conv_post_tanh(_ptr(a16, torch.float16), _ptr(w32, torch.float32), _ptr(bias, torch.float32),
-                                   _ptr(out, torch.float32), B, L, C, pitch, k, int(apply_tanh), _stream()),
-           "fv_conv_post_tanh")
+                                   _ptr(out, torch.float32), B, L, C, width - split, k, int(apply_tanh), split,
+                                   _stream()), "fv_conv_post_tanh")
     return out
 
 
@@ -276,7 +357,8 @@ def snake_aa(x32: torch.Tensor, out16: torch.Tensor, alpha: torch.Tensor, beta: 
     fu = (ctypes.c_float * 12)(*[float(v) for v in filt_up])
     fd = (ctypes.c_float * 12)(*[float(v) for v in filt_down])
     _check(lib().fv_snake_aa(_ptr(x32, torch.float32), _ptr(out16, torch.float16), _ptr(alpha, torch.float32),
-                             _ptr(beta, torch.float32), fu, fd, int(logscale), B, L, C, pitch, _stream()),
+                             _ptr(beta, torch.float32), fu, fd, int(logscale), B, L, C, pitch, split_of(out16),
+                             _stream()),
            "fv_snake_aa")
 
 
@@ -286,7 +368,8 @@ def dwconv_layernorm(x32: torch.Tensor, C: int, dw_w, dw_b, ln_w, ln_b, eps: flo
     _check(lib().fv_dwconv_layernorm(_ptr(x32, torch.float32), _ptr(out16, torch.float16),
                                      _ptr(out32, torch.float32), _ptr(dw_w, torch.float32),
                                      _ptr(dw_b, torch.float32), _ptr(ln_w, torch.float32),
-                                     _ptr(ln_b, torch.float32), float(eps), B, T, C, pitch, int(k), _stream()),
+                                     _ptr(ln_b, torch.float32), float(eps), B, T, C, pitch, int(k),
+                                     split_of(out16), _stream()),
            "fv_dwconv_layernorm")
 
 
@@ -317,7 +400,7 @@ def act_cast(x32: torch.Tensor, C: int, act: int, act_param: float = 0.0, *, noi
                              _ptr(out16, torch.float16), _ptr(out32, torch.float32), int(act), float(act_param),
                              int(act16), float(act16_param), float(out_scale), int(bool(accumulate)), B, L, C,
                              in_pitch, 0 if out16 is None else out16.shape[2], out16_coff,
-                             0 if out32 is None else out32.shape[2], _stream()), "fv_act_cast")
+                             0 if out32 is None else out32.shape[2], split_of(out16), _stream()), "fv_act_cast")
 
 
 def resample_linear(x32: torch.Tensor, C: int, L_out: int, scale: float, *, pre_act=ACT_NONE, pre_param=0.0,
@@ -327,7 +410,7 @@ def resample_linear(x32: torch.Tensor, C: int, L_out: int, scale: float, *, pre_
     _check(lib().fv_resample_linear(_ptr(x32, torch.float32), _ptr(out32, torch.float32),
                                     _ptr(out16, torch.float16), int(pre_act), float(pre_param), int(act),
                                     float(act_param), B, L_in, L_out, C, in_pitch, o.shape[2], out_coff, float(scale),
-                                    _stream()), "fv_resample_linear")
+                                    split_of(out16), _stream()), "fv_resample_linear")
 
 
 def launch_count() -> int:

@@ -74,6 +74,14 @@ extern "C" int fv_conv1d(const fv_conv_desc* d, int engine, void* stream) {
   if (d->residual)
     FV_REQUIRE(d->res_pitch >= r8 && d->res_pitch % 4 == 0 && (reinterpret_cast<uintptr_t>(d->residual) & 15) == 0,
                FV_E_ALIGN, "fv_conv1d: residual pitch/alignment (pitch %d, need >= %d)", d->res_pitch, r8);
+  if (d->a_split > 0)
+    FV_REQUIRE(d->a_split % 16 == 0 && d->a_pitch == 2 * d->a_split && d->w_pitch >= 3 * d->a_split, FV_E_BADARG,
+               "fv_conv1d: strict operand layout needs a_pitch == 2*a_split (16 | a_split) and w_pitch >= 3*a_split "
+               "(a_split=%d a_pitch=%d w_pitch=%d)", d->a_split, d->a_pitch, d->w_pitch);
+  if (d->out16_split > 0)
+    FV_REQUIRE(d->out16 && d->out16_split % 8 == 0 && d->out16_split >= r8 && d->out16_pitch >= d->out16_split + r8,
+               FV_E_BADARG, "fv_conv1d: strict output layout needs out16_pitch >= out16_split + C_out (split=%d pitch=%d)",
+               d->out16_split, d->out16_pitch);
   FV_REQUIRE(d->act >= FV_ACT_NONE && d->act <= FV_ACT_POLAR, FV_E_BADARG, "fv_conv1d: bad activation %d", d->act);
   FV_REQUIRE(!(d->accumulate && !d->out32), FV_E_BADARG, "fv_conv1d: accumulate needs out32");
   for (int i = 0; i < d->n_phase * d->n_taps; ++i)

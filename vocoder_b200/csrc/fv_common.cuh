@@ -69,6 +69,13 @@ __device__ __forceinline__ __half to_half_sat(float v) {
   asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(v));
   return __ushort_as_half(r);
 }
+// store v as fp16 at dst[0]; in strict mode (split > 0) also store the residual fp16(v - hi) `split` halfs further on
+__device__ __forceinline__ void store_half_split(__half* dst, float v, int split) {
+  const __half h = to_half_sat(v);
+  dst[0] = h;
+  if (split > 0) dst[split] = to_half_sat(v - __half2float(h));
+}
+
 // two floats -> packed fp16x2 (a in the low half), round-to-nearest, saturating to +-65504: one F2FP instruction
 __device__ __forceinline__ uint32_t pack_half2_sat(float a, float b) {
   uint32_t r;

@@ -38,6 +38,7 @@ struct ConvTcParams {
   CUtensorMap tmO16;  // out16 fp16    (SWIZZLE_64B)
   int B, n_phase, n_taps, k_chunks, C_out, C_out_r8, C_out_pad, q_rows, L_out;
   int m_tiles, n_tiles, total_tiles;
+  int a_split, out16_split;  // strict precision: [hi | lo] operand / output layout (0 = plain fp16), see fv_conv_desc
   int use_slab, off_min, slab_boxes, w_resident;  // slab mainloop: smallest tap offset, 64-row boxes per slab, weights stay in smem
   const float* bias;
   const float* gamma;
@@ -157,6 +158,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
       const bool leader = elect_one();
       uint32_t it = 0, ita = 0;
       bool w_loaded = false;
+      // strict precision: the weight K axis is [Whi | Whi | Wlo] (3P), the operand holds [hi | lo] (2P): the third
+      // segment re-reads the hi block
+      auto a_col = [&](int kc) {
+        const int col = kc * BLOCK_K;
+        return (p.a_split > 0 && col >= 2 * p.a_split) ? col - 2 * p.a_split : col;
+      };
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         int r = tile;
         const int n_t = r % p.n_tiles; r /= p.n_tiles;
@@ -173,7 +180,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
             if (leader) {
               mbar_arrive_expect_tx(&afull_bar[sa], p.slab_boxes * 64 * Cfg::ROW_BYTES);
               for (int bx = 0; bx < p.slab_boxes; ++bx)
-                tma_load_3d(smem + sa * Cfg::A_SLAB + bx * 64 * Cfg::ROW_BYTES, &p.tmA2, &afull_bar[sa], kc * BLOCK_K,
+                tma_load_3d(smem + sa * Cfg::A_SLAB + bx * 64 * Cfg::ROW_BYTES, &p.tmA2, &afull_bar[sa], a_col(kc),
                             q0 + p.off_min + bx * 64, b);
             }
             if (!(p.w_resident && w_loaded)) {
@@ -201,7 +208,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
                 uint8_t* sa = smem + s * Cfg::STAGE;
 #pragma unroll
                 for (int bx = 0; bx < Cfg::N_A_BOX; ++bx)
-                  tma_load_3d(sa + bx * Cfg::A_BOX_ROWS * Cfg::ROW_BYTES, &p.tmA, &full_bar[s], kc * BLOCK_K,
+                  tma_load_3d(sa + bx * Cfg::A_BOX_ROWS * Cfg::ROW_BYTES, &p.tmA, &full_bar[s], a_col(kc),
                               row0 + bx * Cfg::A_BOX_ROWS, b);
                 tma_load_2d(sa + Cfg::A_STAGE, &p.tmW, &full_bar[s], kc * BLOCK_K, wrow);
               }
@@ -404,7 +411,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
           // other half of the same buffer when there is no fp32 output) so stores of the previous item may still drain
           uint8_t* Rout = has_res ? R1 : (parity ? R1 : R0);
           uint8_t* Hout = (has_res || has_o32) ? Hp : Rout;
-          const bool pingpong = !has_res && !(has_o32 && has_o16) && !p.accumulate;
+          const bool pingpong = !has_res && !(has_o32 && has_o16) && !p.accumulate && p.out16_split == 0;
           parity ^= 1;
           if (lane == 0) {
             if (pingpong) tma_store_wait_read_keep1();
@@ -463,6 +470,33 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
                 for (int i = 0; i < 32; ++i) o[i] = tanhf(o[i]);
               }
             }
+            uint32_t hw[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) hw[i] = pack_half2_sat(o[2 * i], o[2 * i + 1]);
+            if (p.out16_split > 0) {  // strict precision: o := v - fp16(v), stored as the "lo" word after the hi patch
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hw[i]));
+                o[2 * i] -= f.x;
+                o[2 * i + 1] -= f.y;
+              }
+            }
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(h_row + ((static_cast<uint32_t>(jj) ^ h_xor) << 4)),
+                           "r"(hw[4 * jj + 0]), "r"(hw[4 * jj + 1]), "r"(hw[4 * jj + 2]), "r"(hw[4 * jj + 3])
+                           : "memory");
+          }
+          fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the bulk-copy engine
+          __syncwarp();
+          if (lane == 0) {
+            if (has_o32) tma_store_4d(&p.tmO32, Rout, col0, phase, qb, b);
+            if (has_o16) tma_store_4d(&p.tmO16, Hout, col0, phase, qb, b);
+            tma_store_commit();
+          }
+          if (has_o16 && p.out16_split > 0) {  // second pass through the same fp16 staging patch for the lo words
+            if (lane == 0) tma_store_wait_read();
+            __syncwarp();
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
               const uint32_t w0 = pack_half2_sat(o[8 * jj + 0], o[8 * jj + 1]);
@@ -473,13 +507,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
                            "r"(w0), "r"(w1), "r"(w2), "r"(w3)
                            : "memory");
             }
-          }
-          fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the bulk-copy engine
-          __syncwarp();
-          if (lane == 0) {
-            if (has_o32) tma_store_4d(&p.tmO32, Rout, col0, phase, qb, b);
-            if (has_o16) tma_store_4d(&p.tmO16, Hout, col0, phase, qb, b);
-            tma_store_commit();
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_4d(&p.tmO16, Hout, p.out16_split + col0, phase, qb, b);
+              tma_store_commit();
+            }
           }
         }
         if (cgrp >= n_items) {
@@ -620,6 +653,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
               pk.x = pack_half2_sat(o[0], o[1]);
               pk.y = pack_half2_sat(o[2], o[3]);
               *reinterpret_cast<uint2*>(p.out16 + grow * p.out16_pitch + col) = pk;
+              if (p.out16_split > 0) {
+                const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&pk.x));
+                const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&pk.y));
+                uint2 lo;
+                lo.x = pack_half2_sat(o[0] - f0.x, o[1] - f0.y);
+                lo.y = pack_half2_sat(o[2] - f1.x, o[3] - f1.y);
+                *reinterpret_cast<uint2*>(p.out16 + grow * p.out16_pitch + p.out16_split + col) = lo;
+              }
             }
           }
         }
@@ -684,6 +725,7 @@ static CUtensorMapSwizzle swizzle_for(int row_bytes) {
 static int encode_epi_map(EncodeTiledFn enc, CUtensorMap* tm, const void* base, bool fp16, const fv_conv_desc* d,
                           int pitch, int c_out_r8) {
   const cuuint64_t es = fp16 ? 2 : 4;
+  if (fp16 && d->out16_split > 0) c_out_r8 += d->out16_split;  // [hi | lo]: the lo words live out16_split columns on
   cuuint64_t dims[4] = {(cuuint64_t)c_out_r8, (cuuint64_t)d->n_phase, (cuuint64_t)(d->L_out / d->n_phase),
                         (cuuint64_t)d->B};
   cuuint64_t strides[3] = {(cuuint64_t)pitch * es, (cuuint64_t)pitch * es * d->n_phase,
@@ -752,7 +794,7 @@ static int launch_tc_impl(const fv_conv_desc* d, ConvTcParams& p, cudaStream_t s
     if (!rc && d->out16) rc = encode_epi_map(enc, &p.tmO16, d->out16, true, d, d->out16_pitch, p.C_out_r8);
     if (rc) return rc;
   }
-  p.k_chunks = ceil_div(d->a_pitch, BLOCK_K);
+  p.k_chunks = d->a_split > 0 ? (3 * d->a_split) / BLOCK_K : ceil_div(d->a_pitch, BLOCK_K);
   p.m_tiles = ceil_div(p.q_rows, M_SUB * 128);
   p.n_tiles = ceil_div(d->C_out, BLOCK_N);
   FV_REQUIRE(p.n_tiles * BLOCK_N <= d->C_out_pad, FV_E_BADARG, "C_out_pad %d too small for %d tiles of %d",
@@ -801,12 +843,15 @@ static int launch_tc(const fv_conv_desc* d, ConvTcParams& p, cudaStream_t stream
 
 template <int BLOCK_N, int M_SUB, bool EPI_TMA>
 static int dispatch_k(const fv_conv_desc* d, ConvTcParams& p, cudaStream_t s) {
-  if (d->a_pitch > 32) return launch_tc<BLOCK_N, M_SUB, 64, EPI_TMA>(d, p, s);
+  // K chunk: 64 channels when the operand is wide enough; in strict mode a chunk must not straddle the hi/lo blocks
+  int bk = d->a_pitch > 32 ? 64 : (d->a_pitch > 16 ? 32 : 16);
+  if (d->a_split > 0) bk = (d->a_split % 64 == 0) ? 64 : ((d->a_split % 32 == 0) ? 32 : 16);
+  if (bk == 64) return launch_tc<BLOCK_N, M_SUB, 64, EPI_TMA>(d, p, s);
   if constexpr (M_SUB >= 2) {  // small-K variants exist for the multi-accumulator tiles only
-    if (d->a_pitch > 16) return launch_tc<BLOCK_N, M_SUB, 32, EPI_TMA>(d, p, s);
+    if (bk == 32) return launch_tc<BLOCK_N, M_SUB, 32, EPI_TMA>(d, p, s);
     return launch_tc<BLOCK_N, M_SUB, 16, EPI_TMA>(d, p, s);
   } else {
-    return launch_tc<BLOCK_N, M_SUB, 64, EPI_TMA>(d, p, s);
+    return set_error(FV_E_UNSUPPORTED, "no single-accumulator kernel for K chunk %d", bk);
   }
 }
 
@@ -859,6 +904,8 @@ int conv1d_tc(const fv_conv_desc* d, cudaStream_t stream, int block_n_override, 
   p.act = d->act;
   p.out_scale = d->out_scale;
   p.act_param = d->act_param;
+  p.a_split = d->a_split;
+  p.out16_split = d->out16_split;
   // mainloop: 0 = auto, 1 = per-tap stages, 2 = slab.  Measured on B200 the two are equivalent (the epilogue, not the
   // mainloop, bounds these kernels), so auto keeps the simpler per-tap ring; the slab path is the base for fusion.
   p.use_slab = mainloop == 2;
@@ -870,6 +917,7 @@ int conv1d_tc(const fv_conv_desc* d, cudaStream_t stream, int block_n_override, 
   if (bn == 256) m_sub = 1;  // two 256-column accumulators do not leave room for a pipelined smem ring
   if (!m_sub_override && bn <= 64 && p.q_rows >= 2048) m_sub = 4;
   if (d->a_pitch <= 32 && m_sub < 2) m_sub = 2;
+  if (d->a_split > 0 && d->a_split % 64 != 0 && m_sub < 2) m_sub = 2;
   // TMA epilogue needs a rectangular {phase, q} view of the output rows; epilogue: 0 = auto, 1 = LSU, 2 = TMA
   const bool tma_ok = (d->L_out % d->n_phase) == 0 && bn >= 32;
   const bool epi_tma = tma_ok && epilogue != 1;

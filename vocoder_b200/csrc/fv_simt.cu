@@ -22,6 +22,7 @@ struct ConvSimtParams {
   __half* out16;
   int res_pitch, out32_pitch, out16_pitch, accumulate, act;
   float out_scale, act_param;
+  int a_split, out16_split;
   int16_t tap_off[FV_MAX_TAPS];
 };
 
@@ -37,7 +38,8 @@ __global__ void conv_simt_kernel(const __grid_constant__ ConvSimtParams p) {
     const int phase = orow % p.n_phase;
     const int q = orow / p.n_phase;
     float acc[2] = {0.f, 0.f};
-    const int kmax = p.a_pitch < p.w_pitch ? p.a_pitch : p.w_pitch;
+    // strict precision: weight columns [Whi | Whi | Wlo] (3P) against operand columns [hi | lo | hi again]
+    const int kmax = p.a_split > 0 ? 3 * p.a_split : (p.a_pitch < p.w_pitch ? p.a_pitch : p.w_pitch);
     for (int tap = 0; tap < p.n_taps; ++tap) {
       const int r = q + p.tap_off[phase * p.n_taps + tap];
       if (r < 0 || r >= p.L_in) continue;
@@ -46,7 +48,10 @@ __global__ void conv_simt_kernel(const __grid_constant__ ConvSimtParams p) {
         if (col + e >= p.C_out) continue;
         const __half* wrow = p.w + ((size_t)(phase * p.n_taps + tap) * p.C_out_pad + col + e) * p.w_pitch;
         float s = 0.f;
-        for (int c = 0; c < kmax; ++c) s = fmaf(__half2float(arow[c]), __half2float(wrow[c]), s);
+        for (int c = 0; c < kmax; ++c) {
+          const int ca = (p.a_split > 0 && c >= 2 * p.a_split) ? c - 2 * p.a_split : c;
+          s = fmaf(__half2float(arow[ca]), __half2float(wrow[c]), s);
+        }
         acc[e] += s;
       }
     }
@@ -75,8 +80,8 @@ __global__ void conv_simt_kernel(const __grid_constant__ ConvSimtParams p) {
         o[0] = act_apply(o[0], p.act, p.act_param);
         o[1] = act_apply(o[1], p.act, p.act_param);
       }
-      p.out16[grow * p.out16_pitch + col] = to_half_sat(o[0]);
-      p.out16[grow * p.out16_pitch + col + 1] = to_half_sat(o[1]);
+      store_half_split(p.out16 + grow * p.out16_pitch + col, o[0], p.out16_split);
+      store_half_split(p.out16 + grow * p.out16_pitch + col + 1, o[1], p.out16_split);
     }
   }
 }
@@ -92,6 +97,8 @@ int conv1d_simt(const fv_conv_desc* d, cudaStream_t stream) {
   p.out16 = reinterpret_cast<__half*>(d->out16); p.res_pitch = d->res_pitch; p.out32_pitch = d->out32_pitch;
   p.out16_pitch = d->out16_pitch; p.accumulate = d->accumulate; p.act = d->act; p.out_scale = d->out_scale;
   p.act_param = d->act_param;
+  p.a_split = d->a_split;
+  p.out16_split = d->out16_split;
   for (int i = 0; i < d->n_phase * d->n_taps; ++i) p.tap_off[i] = (int16_t)d->tap_off[i];
   const long long total = (long long)p.B * p.L_out * (p.C_out_r8 / 2);
   const int threads = 128;
@@ -105,7 +112,8 @@ int conv1d_simt(const fv_conv_desc* d, cudaStream_t stream) {
 // ------------------------------------------------------------------------------------------------
 // layout entry / exit: [B][C][T] fp32 <-> channels-last
 // ------------------------------------------------------------------------------------------------
-__global__ void pack_input_kernel(const float* __restrict__ x, __half* __restrict__ out, int C, int T, int pitch) {
+__global__ void pack_input_kernel(const float* __restrict__ x, __half* __restrict__ out, int C, int T, int pitch,
+                                  int split) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -116,7 +124,7 @@ __global__ void pack_input_kernel(const float* __restrict__ x, __half* __restric
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {  // write: c fastest
     const int t = t0 + i, c = c0 + threadIdx.x;
-    if (t < T && c < pitch) out[((size_t)b * T + t) * pitch + c] = __float2half_rn(tile[threadIdx.x][i]);
+    if (t < T && c < pitch) store_half_split(out + ((size_t)b * T + t) * (pitch + split) + c, tile[threadIdx.x][i], split);
   }
 }
 
@@ -141,8 +149,10 @@ __global__ void unpack_output_kernel(const float* __restrict__ x, float* __restr
 // ------------------------------------------------------------------------------------------------
 template <int G>
 __global__ void conv_post_kernel(const __half* __restrict__ a, const float* __restrict__ w, const float* bias,
-                                 float* __restrict__ wav, int B, int L, int C, int pitch, int k, int apply_tanh) {
+                                 float* __restrict__ wav, int B, int L, int C, int pitch, int k, int apply_tanh,
+                                 int split) {
   extern __shared__ float s_w[];  // [k][pitch]
+  const int rpitch = pitch + split;  // strict precision: the row holds [hi | lo], the operand value is hi + lo
   for (int i = threadIdx.x; i < k * pitch; i += blockDim.x) {
     const int j = i / pitch, c = i % pitch;
     s_w[i] = c < C ? w[j * C + c] : 0.f;
@@ -164,7 +174,7 @@ __global__ void conv_post_kernel(const __half* __restrict__ a, const float* __re
       for (int j = 0; j < k; ++j) {
         const int r = t + j - half_k;
         if (r < 0 || r >= L) continue;
-        const __half* row = a + ((size_t)b * L + r) * pitch;
+        const __half* row = a + ((size_t)b * L + r) * rpitch;
         for (int ci = g; ci < chunks; ci += G) {
           const uint4 pk = *reinterpret_cast<const uint4*>(row + ci * 8);
           const __half2* h2 = reinterpret_cast<const __half2*>(&pk);
@@ -174,6 +184,16 @@ __global__ void conv_post_kernel(const __half* __restrict__ a, const float* __re
             const float2 f = __half22float2(h2[e]);
             acc = fmaf(f.x, wj[2 * e], acc);
             acc = fmaf(f.y, wj[2 * e + 1], acc);
+          }
+          if (split > 0) {
+            const uint4 pl = *reinterpret_cast<const uint4*>(row + split + ci * 8);
+            const __half2* l2 = reinterpret_cast<const __half2*>(&pl);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = __half22float2(l2[e]);
+              acc = fmaf(f.x, wj[2 * e], acc);
+              acc = fmaf(f.y, wj[2 * e + 1], acc);
+            }
           }
         }
       }
@@ -222,7 +242,7 @@ __device__ __forceinline__ float snake_fn(float u, float a, float inv_b) {
 template <bool EDGE>
 __device__ __forceinline__ void snake_segment(const float* __restrict__ xc, __half* __restrict__ orow,
                                               const SnakeFilt& f, float a, float inv_b, int t0, int t_end, int L,
-                                              int pitch) {
+                                              int pitch, int opitch, int split) {
   const int nl = 2 * L - 1;
   auto ldx = [&](int t) {
     if (EDGE) t = t < 0 ? 0 : (t > L - 1 ? L - 1 : t);  // replicate edge of the INPUT (first filter pads its own input)
@@ -258,7 +278,7 @@ __device__ __forceinline__ void snake_segment(const float* __restrict__ xc, __ha
     for (int j = 0; j < 5; ++j) V[j] = V[5];
   }
   const float* px = xc + (size_t)(t0 + 6) * pitch;  // interior path: running pointers instead of index math
-  __half* po = orow + (size_t)t0 * pitch;
+  __half* po = orow + (size_t)t0 * opitch;
   for (int tb = t0; tb < t_end; tb += 6) {
     float xn[6];
 #pragma unroll
@@ -273,7 +293,7 @@ __device__ __forceinline__ void snake_segment(const float* __restrict__ xc, __ha
       float o = 0.f;
 #pragma unroll
       for (int j = 0; j < 12; ++j) o = fmaf(f.dn[j], V[(2 * k + j) % 12], o);
-      if (!EDGE || t < t_end) po[(size_t)k * pitch] = to_half_sat(o);
+      if (!EDGE || t < t_end) store_half_split(po + (size_t)k * opitch, o, split);
       X[k] = xn[k];
       float uo = 0.f, ue = 0.f;
 #pragma unroll
@@ -290,14 +310,15 @@ __device__ __forceinline__ void snake_segment(const float* __restrict__ xc, __ha
       V[(2 * k) % 12] = va;
       V[(2 * k + 1) % 12] = vb;
     }
-    po += (size_t)6 * pitch;
+    po += (size_t)6 * opitch;
   }
 }
 
 __global__ void __launch_bounds__(256, 3) snake_aa_kernel(const float* __restrict__ x, __half* __restrict__ out,
                                                           const float* __restrict__ alpha,
                                                           const float* __restrict__ beta, const SnakeFilt f,
-                                                          int logscale, int B, int L, int C, int pitch, int n_seg) {
+                                                          int logscale, int B, int L, int C, int pitch, int n_seg,
+                                                          int split) {
   const long long total = (long long)B * n_seg * pitch;
   const long long item = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (item >= total) return;
@@ -306,9 +327,10 @@ __global__ void __launch_bounds__(256, 3) snake_aa_kernel(const float* __restric
   const int b = (int)(item / ((long long)pitch * n_seg));
   const int t0 = seg * SN_SEG;
   const int t_end = min(t0 + SN_SEG, L);
-  __half* orow = out + ((size_t)b * L) * pitch + c;
+  const int opitch = pitch + split;
+  __half* orow = out + ((size_t)b * L) * opitch + c;
   if (c >= C) {  // padded channels stay zero
-    for (int t = t0; t < t_end; ++t) orow[(size_t)t * pitch] = __float2half_rn(0.f);
+    for (int t = t0; t < t_end; ++t) store_half_split(orow + (size_t)t * opitch, 0.f, split);
     return;
   }
   float a = alpha[c];
@@ -321,8 +343,8 @@ __global__ void __launch_bounds__(256, 3) snake_aa_kernel(const float* __restric
   const float* xc = x + ((size_t)b * L) * pitch + c;
   // interior segment: every x index in [t0-5, t0+SN_SEG+5] and every v index up to 2(t0+SN_SEG)+6 is in range
   const bool interior = (t0 >= 6) && (t0 + SN_SEG + 6 <= L - 1);
-  if (interior) snake_segment<false>(xc, orow, f, a, inv_b, t0, t_end, L, pitch);
-  else snake_segment<true>(xc, orow, f, a, inv_b, t0, t_end, L, pitch);
+  if (interior) snake_segment<false>(xc, orow, f, a, inv_b, t0, t_end, L, pitch, opitch, split);
+  else snake_segment<true>(xc, orow, f, a, inv_b, t0, t_end, L, pitch, opitch, split);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -332,7 +354,7 @@ __global__ void __launch_bounds__(128) dwconv_ln_kernel(const float* __restrict_
                                                         float* __restrict__ out32, const float* __restrict__ dw_w,
                                                         const float* __restrict__ dw_b, const float* __restrict__ ln_w,
                                                         const float* __restrict__ ln_b, float eps, int B, int T, int C,
-                                                        int pitch, int k) {
+                                                        int pitch, int k, int split) {
   extern __shared__ float s_h[];  // [warps][pitch]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + warp;
@@ -369,7 +391,7 @@ __global__ void __launch_bounds__(128) dwconv_ln_kernel(const float* __restrict_
   const float rstd = 1.0f / sqrtf(var / C + eps);
   for (int c = lane; c < pitch; c += 32) {
     const float y = c < C ? fmaf((h[c] - mean) * rstd, ln_w[c], ln_b[c]) : 0.f;
-    if (out16) out16[(size_t)row * pitch + c] = to_half_sat(y);
+    if (out16) store_half_split(out16 + (size_t)row * (pitch + split) + c, y, split);
     if (out32) out32[(size_t)row * pitch + c] = y;
   }
 }
@@ -387,7 +409,7 @@ __global__ void __launch_bounds__(256) dwconv_ln_tiled_kernel(const float* __res
                                                               const float* __restrict__ dw_b,
                                                               const float* __restrict__ ln_w,
                                                               const float* __restrict__ ln_b, float eps, int T, int C,
-                                                              int pitch, int tiles_per_b) {
+                                                              int pitch, int tiles_per_b, int split) {
   extern __shared__ float s_h[];  // [DW_R][pitch]
   __shared__ float s_red[8][DW_R];
   __shared__ float s_mean[DW_R], s_rstd[DW_R];
@@ -473,7 +495,7 @@ __global__ void __launch_bounds__(256) dwconv_ln_tiled_kernel(const float* __res
       if (t < T) {
         const float y = c < C ? fmaf((s_h[r * pitch + c] - s_mean[r]) * s_rstd[r], g, be) : 0.f;
         const size_t o = ((size_t)b * T + t) * pitch + c;
-        if (out16) out16[o] = to_half_sat(y);
+        if (out16) store_half_split(out16 + ((size_t)b * T + t) * (pitch + split) + c, y, split);
         if (out32) out32[o] = y;
       }
     }
@@ -538,7 +560,7 @@ __global__ void act_cast_kernel(const float* __restrict__ x, const float* __rest
                                 const float* __restrict__ noise_w, __half* __restrict__ out16,
                                 float* __restrict__ out32, int act, float param, int act16, float param16,
                                 float out_scale, int accumulate, long long rows, int C, int in_pitch,
-                                int out16_pitch, int out16_coff, int out32_pitch) {
+                                int out16_pitch, int out16_coff, int out32_pitch, int split) {
   const long long total = rows * C;
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (idx >= total) return;
@@ -552,13 +574,13 @@ __global__ void act_cast_kernel(const float* __restrict__ x, const float* __rest
     if (accumulate) o += out32[r * out32_pitch + c];
     out32[r * out32_pitch + c] = o;
   }
-  if (out16) out16[r * out16_pitch + out16_coff + c] = to_half_sat(act_apply(v, act16, param16));
+  if (out16) store_half_split(out16 + r * out16_pitch + out16_coff + c, act_apply(v, act16, param16), split);
 }
 
 __global__ void resample_linear_kernel(const float* __restrict__ x, float* __restrict__ out32,
                                        __half* __restrict__ out16, int pre_act, float pre_param, int act, float param,
                                        int B, int L_in, int L_out, int C, int in_pitch, int out_pitch, int out_coff,
-                                       float scale) {
+                                       float scale, int split) {
   const long long total = (long long)B * L_out * C;
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (idx >= total) return;
@@ -577,7 +599,7 @@ __global__ void resample_linear_kernel(const float* __restrict__ x, float* __res
   float v = (1.0f - lam) * v0 + lam * v1;
   v = act_apply(v, act, param);
   if (out32) out32[grow * out_pitch + out_coff + c] = v;
-  if (out16) out16[grow * out_pitch + out_coff + c] = to_half_sat(v);
+  if (out16) store_half_split(out16 + grow * out_pitch + out_coff + c, v, split);
 }
 
 }  // namespace fv
@@ -589,11 +611,11 @@ using namespace fv;
 
 static inline int grid1d(long long total, int threads) { return (int)((total + threads - 1) / threads); }
 
-extern "C" int fv_pack_input(const float* x, void* out16, int B, int C, int T, int pitch, void* stream) {
-  FV_REQUIRE(x && out16 && B > 0 && C > 0 && T > 0 && pitch >= C && pitch % 8 == 0, FV_E_BADARG,
-             "fv_pack_input: bad arguments (B=%d C=%d T=%d pitch=%d)", B, C, T, pitch);
+extern "C" int fv_pack_input(const float* x, void* out16, int B, int C, int T, int pitch, int split, void* stream) {
+  FV_REQUIRE(x && out16 && B > 0 && C > 0 && T > 0 && pitch >= C && pitch % 8 == 0 && (split == 0 || split == pitch),
+             FV_E_BADARG, "fv_pack_input: bad arguments (B=%d C=%d T=%d pitch=%d split=%d)", B, C, T, pitch, split);
   dim3 grid(ceil_div(T, 32), ceil_div(pitch, 32), B), block(32, 8);
-  pack_input_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(x, (__half*)out16, C, T, pitch);
+  pack_input_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(x, (__half*)out16, C, T, pitch, split);
   FV_CHECK_LAUNCH("pack_input_kernel");
   return 0;
 }
@@ -607,9 +629,10 @@ extern "C" int fv_unpack_output(const float* x32, float* out, int B, int C, int 
 }
 
 extern "C" int fv_conv_post_tanh(const void* a16, const float* w32, const float* bias, float* wav, int B, int L, int C,
-                                 int pitch, int k, int apply_tanh, void* stream) {
-  FV_REQUIRE(a16 && w32 && wav && B > 0 && L > 0 && C > 0 && pitch >= C && pitch % 8 == 0 && k > 0 && (k & 1),
-             FV_E_BADARG, "fv_conv_post_tanh: bad arguments (C=%d pitch=%d k=%d)", C, pitch, k);
+                                 int pitch, int k, int apply_tanh, int split, void* stream) {
+  FV_REQUIRE(a16 && w32 && wav && B > 0 && L > 0 && C > 0 && pitch >= C && pitch % 8 == 0 && k > 0 && (k & 1) &&
+                 (split == 0 || split == pitch),
+             FV_E_BADARG, "fv_conv_post_tanh: bad arguments (C=%d pitch=%d k=%d split=%d)", C, pitch, k, split);
   const int smem = k * pitch * (int)sizeof(float);
   FV_REQUIRE(smem <= 48 * 1024, FV_E_UNSUPPORTED, "fv_conv_post_tanh: k*pitch too large (%d bytes)", smem);
   const int chunks = pitch / 8;
@@ -620,7 +643,7 @@ extern "C" int fv_conv_post_tanh(const void* a16, const float* w32, const float*
     long long blocks = (total + (threads / G) - 1) / (threads / G);                                         \
     if (blocks > 148 * 16) blocks = 148 * 16;                                                               \
     conv_post_kernel<G><<<(int)blocks, threads, smem, (cudaStream_t)stream>>>(                              \
-        (const __half*)a16, w32, bias, wav, B, L, C, pitch, k, apply_tanh);                                 \
+        (const __half*)a16, w32, bias, wav, B, L, C, pitch, k, apply_tanh, split);                          \
   }
   if (chunks <= 1) FV_POST(1)
   else if (chunks <= 2) FV_POST(2)
@@ -634,9 +657,11 @@ extern "C" int fv_conv_post_tanh(const void* a16, const float* w32, const float*
 }
 
 extern "C" int fv_snake_aa(const float* x32, void* out16, const float* alpha, const float* beta, const float* filt_up,
-                           const float* filt_down, int logscale, int B, int L, int C, int pitch, void* stream) {
-  FV_REQUIRE(x32 && out16 && alpha && filt_up && filt_down && B > 0 && L > 0 && C > 0 && pitch >= C, FV_E_BADARG,
-             "fv_snake_aa: bad arguments");
+                           const float* filt_down, int logscale, int B, int L, int C, int pitch, int split,
+                           void* stream) {
+  FV_REQUIRE(x32 && out16 && alpha && filt_up && filt_down && B > 0 && L > 0 && C > 0 && pitch >= C &&
+                 (split == 0 || split == pitch),
+             FV_E_BADARG, "fv_snake_aa: bad arguments");
   SnakeFilt f;
   // the 12 taps are tiny, deterministic buffers of the module; fetch them once per call (async, stream ordered
   // copies would need a staging buffer - the module passes HOST copies of the taps instead, see python side)
@@ -647,16 +672,17 @@ extern "C" int fv_snake_aa(const float* x32, void* out16, const float* alpha, co
   const int n_seg = ceil_div(L, SN_SEG);
   const long long total = (long long)B * n_seg * pitch;
   snake_aa_kernel<<<grid1d(total, 256), 256, 0, (cudaStream_t)stream>>>(x32, (__half*)out16, alpha, beta, f, logscale,
-                                                                       B, L, C, pitch, n_seg);
+                                                                       B, L, C, pitch, n_seg, split);
   FV_CHECK_LAUNCH("snake_aa_kernel");
   return 0;
 }
 
 extern "C" int fv_dwconv_layernorm(const float* x32, void* out16, float* out32, const float* dw_w, const float* dw_b,
                                    const float* ln_w, const float* ln_b, float eps, int B, int T, int C, int pitch,
-                                   int k, void* stream) {
-  FV_REQUIRE(x32 && (out16 || out32) && ln_w && ln_b && B > 0 && T > 0 && C > 0 && pitch >= C, FV_E_BADARG,
-             "fv_dwconv_layernorm: bad arguments");
+                                   int k, int split, void* stream) {
+  FV_REQUIRE(x32 && (out16 || out32) && ln_w && ln_b && B > 0 && T > 0 && C > 0 && pitch >= C &&
+                 (split == 0 || split == pitch),
+             FV_E_BADARG, "fv_dwconv_layernorm: bad arguments");
   FV_REQUIRE(k <= 0 || (dw_w && dw_b && (k & 1)), FV_E_BADARG, "fv_dwconv_layernorm: bad depthwise kernel");
   const int tiled_smem = DW_R * pitch * (int)sizeof(float);
   if ((k <= 0 || k == 7) && tiled_smem <= 48 * 1024) {
@@ -664,10 +690,10 @@ extern "C" int fv_dwconv_layernorm(const float* x32, void* out16, float* out32, 
     const int grid = B * tiles_per_b;
     if (k == 7)
       dwconv_ln_tiled_kernel<7><<<grid, 256, tiled_smem, (cudaStream_t)stream>>>(
-          x32, (__half*)out16, out32, dw_w, dw_b, ln_w, ln_b, eps, T, C, pitch, tiles_per_b);
+          x32, (__half*)out16, out32, dw_w, dw_b, ln_w, ln_b, eps, T, C, pitch, tiles_per_b, split);
     else
       dwconv_ln_tiled_kernel<0><<<grid, 256, tiled_smem, (cudaStream_t)stream>>>(
-          x32, (__half*)out16, out32, dw_w, dw_b, ln_w, ln_b, eps, T, C, pitch, tiles_per_b);
+          x32, (__half*)out16, out32, dw_w, dw_b, ln_w, ln_b, eps, T, C, pitch, tiles_per_b, split);
     FV_CHECK_LAUNCH("dwconv_ln_tiled_kernel");
     return 0;
   }
@@ -676,7 +702,7 @@ extern "C" int fv_dwconv_layernorm(const float* x32, void* out16, float* out32, 
   FV_REQUIRE(smem <= 48 * 1024, FV_E_UNSUPPORTED, "fv_dwconv_layernorm: C too large (%d)", C);
   const long long rows = (long long)B * T;
   dwconv_ln_kernel<<<(int)((rows + warps - 1) / warps), warps * 32, smem, (cudaStream_t)stream>>>(
-      x32, (__half*)out16, out32, dw_w, dw_b, ln_w, ln_b, eps, B, T, C, pitch, k);
+      x32, (__half*)out16, out32, dw_w, dw_b, ln_w, ln_b, eps, B, T, C, pitch, k, split);
   FV_CHECK_LAUNCH("dwconv_ln_kernel");
   return 0;
 }
@@ -708,30 +734,31 @@ extern "C" int fv_noise_conv(const float* tpl, const float* w, const float* bias
 extern "C" int fv_act_cast(const float* x32, const float* noise, const float* noise_w, void* out16, float* out32,
                            int act, float act_param, int act16, float act16_param, float out_scale, int accumulate,
                            int B, int L, int C, int in_pitch, int out16_pitch, int out16_coff, int out32_pitch,
-                           void* stream) {
+                           int split, void* stream) {
   FV_REQUIRE(x32 && (out16 || out32) && B > 0 && L > 0 && C > 0 && in_pitch >= C &&
                  (noise == nullptr || noise_w != nullptr),
              FV_E_BADARG, "fv_act_cast: bad arguments");
-  FV_REQUIRE(!out16 || out16_pitch >= out16_coff + C, FV_E_BADARG, "fv_act_cast: out16 slice exceeds its pitch");
+  FV_REQUIRE(!out16 || out16_pitch >= out16_coff + C + split, FV_E_BADARG,
+             "fv_act_cast: out16 slice exceeds its pitch");
   FV_REQUIRE(!out32 || out32_pitch >= C, FV_E_BADARG, "fv_act_cast: out32 pitch too small");
   const long long rows = (long long)B * L;
   act_cast_kernel<<<grid1d(rows * C, 256), 256, 0, (cudaStream_t)stream>>>(
       x32, noise, noise_w, (__half*)out16, out32, act, act_param, act16, act16_param, out_scale, accumulate, rows, C,
-      in_pitch, out16_pitch, out16_coff, out32_pitch);
+      in_pitch, out16_pitch, out16_coff, out32_pitch, split);
   FV_CHECK_LAUNCH("act_cast_kernel");
   return 0;
 }
 
 extern "C" int fv_resample_linear(const float* x32, float* out32, void* out16, int pre_act, float pre_param, int act,
                                   float act_param, int B, int L_in, int L_out, int C, int in_pitch, int out_pitch,
-                                  int out_coff, float scale, void* stream) {
+                                  int out_coff, float scale, int split, void* stream) {
   FV_REQUIRE(x32 && (out16 || out32) && B > 0 && L_in > 0 && L_out > 0 && C > 0 && in_pitch >= C &&
-                 out_pitch >= out_coff + C && scale > 0.f,
+                 out_pitch >= out_coff + C + split && scale > 0.f && !(split > 0 && out32),
              FV_E_BADARG, "fv_resample_linear: bad arguments");
   const long long total = (long long)B * L_out * C;
   resample_linear_kernel<<<grid1d(total, 256), 256, 0, (cudaStream_t)stream>>>(
       x32, out32, (__half*)out16, pre_act, pre_param, act, act_param, B, L_in, L_out, C, in_pitch, out_pitch,
-      out_coff, scale);
+      out_coff, scale, split);
   FV_CHECK_LAUNCH("resample_linear_kernel");
   return 0;
 }

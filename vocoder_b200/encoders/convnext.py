@@ -15,7 +15,7 @@ import torch
 from torch import nn
 
 from .. import cabi
-from ..runtime import GraphedForward, Workspace, params_key, require_cuda
+from ..runtime import GraphedForward, Workspace, params_key, require_cuda, with_precision
 
 
 class LayerNorm(nn.Module):
@@ -177,6 +177,7 @@ class ConvNeXtEncoder(nn.Module):
         _, out32 = self._encode_cl(a0, want32=True)
         return cabi.unpack_output(out32, self.dims[-1])
 
+    @with_precision
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         """[B, input_channels, T] -> [B, dims[-1], T] fp32 (convnext.py:206-214)."""
         require_cuda(x, "ConvNeXtEncoder")

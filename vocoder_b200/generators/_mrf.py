@@ -23,7 +23,7 @@ from torch.nn.utils.parametrizations import weight_norm
 from torch.nn.utils.parametrize import remove_parametrizations as _torch_remove_parametrizations
 
 from .. import cabi
-from ..runtime import GraphedForward, Workspace, params_key, require_cuda
+from ..runtime import GraphedForward, Workspace, params_key, require_cuda, with_precision
 
 
 def same_padding(kernel_size: int, dilation: int = 1) -> int:
@@ -111,6 +111,7 @@ class MRFGeneratorBase(nn.Module):
         strip_weight_norm(self)
         self._packed = None
 
+    @with_precision
     def forward(self, x: torch.Tensor, template: Optional[torch.Tensor] = None) -> torch.Tensor:
         require_cuda(x, type(self).__name__)
         if self.use_template and template is None:

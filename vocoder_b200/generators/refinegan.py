@@ -22,7 +22,7 @@ from torch import nn
 from torch.nn.utils.parametrizations import weight_norm
 
 from .. import cabi
-from ..runtime import GraphedForward, Workspace, params_key, require_cuda
+from ..runtime import GraphedForward, Workspace, params_key, require_cuda, with_precision
 from ._mrf import same_padding, strip_weight_norm
 
 
@@ -191,7 +191,7 @@ class RefineGANGenerator(nn.Module):
         for i in range(len(self.upsample_rates)):
             skip_i = n_down - 1 - i
             # zero-initialised once: the channel padding of the operand buffer is never written afterwards
-            cats.append(ws.get(f"cat_{i}", (B, down_L[skip_i], cabi.pitch_of(Cx + down_C[skip_i])), torch.float16, dev,
+            cats.append(ws.get(f"cat_{i}", (B, down_L[skip_i], cabi.f16_width(Cx + down_C[skip_i])), torch.float16, dev,
                                zero=True))
             cat_x.append(Cx)
             Cx //= 2
@@ -244,6 +244,7 @@ class RefineGANGenerator(nn.Module):
         cabi.act_cast(x, C, LK, sl, out16=h16)
         return cabi.conv_post_tanh(h16, P["post_w"], P["post_b"], C, apply_tanh=True)
 
+    @with_precision
     def forward(self, mel: torch.Tensor, template: torch.Tensor) -> torch.Tensor:
         require_cuda(mel, "RefineGANGenerator")
         return self._forward_eager(mel.contiguous().float(), template.contiguous().float())

@@ -10,7 +10,7 @@ import torch
 from torch import nn
 
 from .. import cabi
-from ..runtime import GraphedForward, require_cuda
+from ..runtime import GraphedForward, require_cuda, with_precision
 
 
 class UnifyGenerator(nn.Module):
@@ -34,6 +34,7 @@ class UnifyGenerator(nn.Module):
             y = self.head._forward_cl(h16)
         return y[:, None, :] if y.ndim == 2 else y
 
+    @with_precision
     def forward(self, x: torch.Tensor, template=None):
         require_cuda(x, "UnifyGenerator")
         if self._fused_ok():

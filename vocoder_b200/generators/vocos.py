@@ -18,7 +18,7 @@ import torch
 from torch import nn
 
 from .. import cabi
-from ..runtime import GraphedForward, Workspace, params_key, require_cuda
+from ..runtime import GraphedForward, Workspace, params_key, require_cuda, with_precision
 
 
 class ISTFT(nn.Module):
@@ -96,6 +96,7 @@ class ISTFTHead(nn.Module):
     def _forward_eager(self, x):
         return self._forward_cl(cabi.pack_input(x))
 
+    @with_precision
     def forward(self, x: torch.Tensor, template=None) -> torch.Tensor:
         """[B, dim, T] -> [B, T*hop]  (vocos.py:43-69).  ``template`` is accepted and ignored: the reference's
         UnifyGenerator passes it (unify.py:25) although the reference head cannot take it."""

@@ -4,6 +4,7 @@ Nothing here computes: torch is used for device memory, streams and graph captur
 """
 from __future__ import annotations
 
+import functools
 from typing import Callable, Dict, Iterable, Tuple
 
 import torch
@@ -21,7 +22,9 @@ class Workspace:
         key = (name, tuple(shape), dtype, str(device))
         t = self._bufs.get(key)
         if t is None:
-            t = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=device)
+            # always zero-filled at creation: kernels that write only c < C (act_cast, resample_linear, snake_aa) rely
+            # on the channel padding of operand buffers being zero (0-weights x NaN garbage would still be NaN)
+            t = torch.zeros(shape, dtype=dtype, device=device)
             self._bufs[key] = t
         return t
 
@@ -29,7 +32,7 @@ class Workspace:
         return self.get(name, (B, L, cabi.pitch_of(C)), torch.float32, device)
 
     def f16(self, name, B, L, C, device):
-        return self.get(name, (B, L, cabi.pitch_of(C)), torch.float16, device)
+        return self.get(name, (B, L, cabi.f16_width(C)), torch.float16, device)  # strict mode: [hi | lo]
 
     def clear(self):
         self._bufs.clear()
@@ -40,7 +43,7 @@ class Workspace:
 
 def params_key(tensors: Iterable[torch.Tensor]) -> Tuple:
     """Cheap fingerprint of a parameter set: changes when any tensor is updated in place, replaced or moved."""
-    return tuple((t.data_ptr(), t._version, t.device.index) for t in tensors)
+    return (cabi.is_strict(),) + tuple((t.data_ptr(), t._version, t.device.index) for t in tensors)
 
 
 def require_cuda(x: torch.Tensor, who: str) -> None:
@@ -49,6 +52,17 @@ def require_cuda(x: torch.Tensor, who: str) -> None:
             f"{who}: the generator forward runs only in the sm_100a CUDA kernels of libfv_b200.so; got a "
             f"{x.device} tensor. Move the module and its input to a CUDA device (there is no CPU fallback).")
     cabi.lib()  # raises loudly when the extension has not been built
+
+
+def with_precision(fn):
+    """Run a module's forward under its ``precision`` attribute ("fp16" default | "strict", see cabi.precision)."""
+
+    @functools.wraps(fn)
+    def wrapper(self, *args, **kwargs):
+        with cabi.precision(getattr(self, "precision", "fp16")):
+            return fn(self, *args, **kwargs)
+
+    return wrapper
 
 
 class GraphedForward:
@@ -67,7 +81,8 @@ class GraphedForward:
         self._graphs.clear()
 
     def __call__(self, *inputs: torch.Tensor) -> torch.Tensor:
-        sig = tuple((tuple(t.shape), t.dtype, t.device.index) if t is not None else None for t in inputs)
+        sig = (cabi.is_strict(),) + tuple((tuple(t.shape), t.dtype, t.device.index) if t is not None else None
+                                          for t in inputs)
         entry = self._graphs.get(sig)
         if entry is None:
             static_in = [None if t is None else t.clone() for t in inputs]
