@@ -172,6 +172,42 @@ FV_API int fv_resample_linear(const float* x32, float* out32, void* out16, int p
                               float act_param, int B, int L_in, int L_out, int C, int in_pitch, int out_pitch,
                               int out_coff, float scale, int split, void* stream);
 
+/*
+ * Fused MRF stage: mean over `n_blocks` residual blocks, each a chain of `n_pairs` pairs
+ *     xt = act(x); xt = conv_{k, dil1}(xt) + b1; xt = act(xt); xt = conv_{k, dil2}(xt) + b2; x = x + xt
+ * evaluated ENTIRELY ON CHIP per 512-row time tile (halo recomputed): the fp32 residual stream lives in TMEM as the
+ * accumulator the second conv of every pair adds onto, the fp16 operands of the 2*n_pairs convs live in swizzled shared
+ * memory (taps = row-shifted UMMA descriptors), weights stream through a TMA ring.  HBM traffic per stage: x read,
+ * result written - instead of 16 bytes per element per conv pair for the layer-wise path.
+ *     out32[b, t, c] = (1/n_blocks) * sum_j block_j(x)[b, t, c]        (also the running-sum scratch: required)
+ *     out16          = fp16(out_act(out32))                            (optional)
+ * Replaces ParralelBlock.forward / ResBlock1.forward (hifigan.py:101-108,117-133): the stack([...]).mean(0) over
+ * kernel sizes (3,7,11) of 3 x {silu, conv(k,d), silu, conv(k,1), +x}.  C in {32, 64}; tap reach (k-1)/2*dil <= 32.
+ */
+#define FV_MRF_MAX_BLOCKS 4
+#define FV_MRF_MAX_PAIRS 4
+typedef struct fv_mrf_desc {
+  const float* x; /* [B][L][x_pitch] fp32 channels-last stage input */
+  int32_t B, L, C, x_pitch;
+  const void* w;  /* fp16 [w_rows][C]: the [C_out][C_in] tap tiles of every conv, concatenated */
+  int32_t w_rows;
+  const float* bias; /* fp32 [n_blocks][n_pairs][2][C]: b1, b2 of every pair */
+  int32_t n_blocks, n_pairs;
+  int32_t ksize[FV_MRF_MAX_BLOCKS];
+  int32_t dil1[FV_MRF_MAX_BLOCKS][FV_MRF_MAX_PAIRS];
+  int32_t dil2[FV_MRF_MAX_BLOCKS][FV_MRF_MAX_PAIRS];
+  int32_t w_row0[FV_MRF_MAX_BLOCKS][FV_MRF_MAX_PAIRS][2]; /* first row in `w` of tap 0 of (block, pair, conv) */
+  int32_t act; /* FV_ACT_SILU | FV_ACT_LEAKY */
+  float act_param;
+  float* out32;
+  int32_t out32_pitch;
+  void* out16;
+  int32_t out16_pitch;
+  int32_t out_act;
+  float out_act_param;
+} fv_mrf_desc;
+FV_API int fv_mrf_fused(const fv_mrf_desc* d, void* stream);
+
 /* bring-up probe (not on the product path): 12 row shifts x {base_offset 0, base_offset r&7} of a 128x64x64 UMMA whose
  * A descriptor starts r rows into a TMA-written 144x64 fp16 slab.  a16 [144][64], w16 [64][64], out [12][2][128][64]. */
 FV_API int fv_debug_rowshift_probe(const void* a16, const void* w16, float* out, void* stream);

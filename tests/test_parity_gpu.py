@@ -236,6 +236,75 @@ def test_receptive_field_locality():
 
 
 # ------------------------------------------------------------------------------------------------
+# fused MRF stage (fv_mrf_fused): the whole stack of dilated convs on chip
+# ------------------------------------------------------------------------------------------------
+def _mrf_reference(x, blocks, out_act):
+    """fp64 evaluation of the fv_mrf_fused contract: fp16-rounded operands, everything else exact."""
+    r = lambda t: t.float().half().double()
+    xs = x.double().permute(0, 2, 1)      # [B, C, L]
+    total = torch.zeros_like(xs)
+    for c1s, c2s in blocks:
+        xk = xs.clone()
+        for c1, c2 in zip(c1s, c2s):
+            xt = r(F.silu(xk))
+            xt = F.conv1d(xt, r(c1.weight), c1.bias.double(), padding=c1.padding[0], dilation=c1.dilation[0])
+            xt = r(F.silu(xt))
+            xt = F.conv1d(xt, r(c2.weight), c2.bias.double(), padding=c2.padding[0], dilation=c2.dilation[0])
+            xk = xk + xt
+        total += xk
+    mean = total / len(blocks)
+    act = F.silu(mean) if out_act == cabi.ACT_SILU else mean
+    return mean.permute(0, 2, 1), act.permute(0, 2, 1)
+
+
+@pytest.mark.parametrize("C,L,B,ks", [(32, 52, 2, (3, 7, 11)), (64, 1000, 2, (3, 7, 11)), (32, 1537, 3, (3, 7, 11)),
+                                        (64, 384, 1, (11,)), (64, 4000, 5, (3, 5)), (32, 6016, 40, (3, 7, 11))])
+def test_mrf_fused_kernel(C, L, B, ks):
+    torch.manual_seed(C + L)
+    blocks = []
+    for k in ks:
+        mk = lambda d: torch.nn.Conv1d(C, C, k, dilation=d, padding=(k * d - d) // 2)
+        c1s, c2s = [mk(d) for d in (1, 3, 5)], [mk(1) for _ in range(3)]
+        for c in c1s + c2s:
+            c.weight.data.normal_(0, 0.5 / math.sqrt(C * k))
+            c.bias.data.normal_(0, 0.05)
+        blocks.append((c1s, c2s))
+    assert cabi.mrf_fusable(C, blocks)
+    x = torch.randn(B, L, C)
+    with torch.no_grad():
+        want32, want16 = _mrf_reference(x, blocks, cabi.ACT_SILU)
+        pm = cabi.pack_mrf(C, blocks)
+        pm.w, pm.bias = pm.w.cuda(), pm.bias.cuda()
+        out32 = torch.full((B, L, C), float("nan"), device="cuda")
+        out16 = torch.full((B, L, C), float("nan"), device="cuda", dtype=torch.float16)
+        cabi.mrf_fused(x.cuda(), pm, out32, out16=out16, act=cabi.ACT_SILU, out_act=cabi.ACT_SILU)
+        torch.cuda.synchronize()
+    scale = max(1.0, float(want32.abs().max()))
+    e32 = float((out32.cpu().double() - want32).abs().max())
+    e16 = float((out16.cpu().double() - want16).abs().max())
+    print(f"mrf_fused C={C} L={L} B={B} ks={ks}: out32 err {e32:.3e}, out16 err {e16:.3e}, scale {scale:.2f}")
+    assert e32 <= 3e-4 * scale, f"out32 err {e32:.3e} (scale {scale:.2f})"
+    assert e16 <= 2e-3 * scale, f"out16 err {e16:.3e}"
+
+
+def test_mrf_fused_generator_matches_layerwise():
+    m, n_mels, hop = _full("hifigan")
+    m = m.eval().cuda()
+    torch.manual_seed(11)
+    mel = torch.empty(3, n_mels, 70).uniform_(-11.5129, 2.0).cuda()
+    with torch.no_grad():
+        cabi.reset_launch_count()
+        fused = m(mel).clone()
+        n_fused = cabi.launch_count()
+        m.fuse_mrf = False
+        cabi.reset_launch_count()
+        layer = m(mel).clone()
+        n_layer = cabi.launch_count()
+    assert n_fused < n_layer            # stages with C <= 64 collapse into one launch each
+    assert float((fused - layer).abs().max()) <= 2e-4
+
+
+# ------------------------------------------------------------------------------------------------
 # kernel-level parity (tcgen05 implicit GEMM + CUDA-core kernels) against CPU torch
 # ------------------------------------------------------------------------------------------------
 def _diag():

@@ -27,8 +27,9 @@ EXPORTS = [
     "fv_last_error", "fv_abi_version", "fv_launch_count", "fv_reset_launch_count", "fv_conv1d",
     "fv_set_tc_tuning", "fv_pack_input", "fv_unpack_output", "fv_conv_post_tanh", "fv_snake_aa",
     "fv_dwconv_layernorm", "fv_istft_ola", "fv_noise_conv", "fv_act_cast", "fv_resample_linear",
-    "fv_debug_rowshift_probe",
+    "fv_mrf_fused", "fv_debug_rowshift_probe",
 ]
+MRF_MAX_BLOCKS, MRF_MAX_PAIRS, MRF_MAX_REACH = 4, 4, 32
 
 
 class FvError(RuntimeError):
@@ -50,6 +51,24 @@ class ConvDesc(ctypes.Structure):
         ("out16", ctypes.c_void_p), ("out16_pitch", ctypes.c_int32), ("act", ctypes.c_int32),
         ("act_param", ctypes.c_float),
         ("a_split", ctypes.c_int32), ("out16_split", ctypes.c_int32),
+    ]
+
+
+class MrfDesc(ctypes.Structure):
+    """Mirror of ``struct fv_mrf_desc``."""
+    _fields_ = [
+        ("x", ctypes.c_void_p), ("B", ctypes.c_int32), ("L", ctypes.c_int32), ("C", ctypes.c_int32),
+        ("x_pitch", ctypes.c_int32),
+        ("w", ctypes.c_void_p), ("w_rows", ctypes.c_int32),
+        ("bias", ctypes.c_void_p), ("n_blocks", ctypes.c_int32), ("n_pairs", ctypes.c_int32),
+        ("ksize", ctypes.c_int32 * MRF_MAX_BLOCKS),
+        ("dil1", (ctypes.c_int32 * MRF_MAX_PAIRS) * MRF_MAX_BLOCKS),
+        ("dil2", (ctypes.c_int32 * MRF_MAX_PAIRS) * MRF_MAX_BLOCKS),
+        ("w_row0", ((ctypes.c_int32 * 2) * MRF_MAX_PAIRS) * MRF_MAX_BLOCKS),
+        ("act", ctypes.c_int32), ("act_param", ctypes.c_float),
+        ("out32", ctypes.c_void_p), ("out32_pitch", ctypes.c_int32),
+        ("out16", ctypes.c_void_p), ("out16_pitch", ctypes.c_int32),
+        ("out_act", ctypes.c_int32), ("out_act_param", ctypes.c_float),
     ]
 
 
@@ -83,6 +102,7 @@ def lib() -> ctypes.CDLL:
     L.fv_noise_conv.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, vp]
     L.fv_act_cast.argtypes = [vp, vp, vp, vp, vp, ci, cf, ci, cf, cf, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp]
     L.fv_resample_linear.argtypes = [vp, vp, vp, ci, cf, ci, cf, ci, ci, ci, ci, ci, ci, ci, cf, ci, vp]
+    L.fv_mrf_fused.argtypes = [ctypes.POINTER(MrfDesc), vp]
     L.fv_debug_rowshift_probe.argtypes = [vp, vp, vp, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
@@ -411,6 +431,90 @@ def resample_linear(x32: torch.Tensor, C: int, L_out: int, scale: float, *, pre_
                                     _ptr(out16, torch.float16), int(pre_act), float(pre_param), int(act),
                                     float(act_param), B, L_in, L_out, C, in_pitch, o.shape[2], out_coff, float(scale),
                                     split_of(out16), _stream()), "fv_resample_linear")
+
+
+# ----------------------------------------------------------------------------------------------
+# fused MRF stage (fv_mrf_fused)
+# ----------------------------------------------------------------------------------------------
+@dataclass
+class PackedMrf:
+    """Weights of one fused MRF stage: every [C_out, C_in] tap tile of every conv, concatenated row-wise."""
+    w: torch.Tensor        # fp16 [rows, C]
+    bias: torch.Tensor     # fp32 [n_blocks, n_pairs, 2, C]
+    C: int
+    ksize: Sequence[int]
+    dil1: Sequence[Sequence[int]]
+    dil2: Sequence[Sequence[int]]
+    w_row0: Sequence[Sequence[Sequence[int]]]
+
+
+def mrf_fusable(C: int, blocks) -> bool:
+    """blocks: [(convs1, convs2)] of nn.Conv1d-like modules.  True when fv_mrf_fused covers the stage."""
+    if is_strict() or C not in (32, 64) or not 1 <= len(blocks) <= MRF_MAX_BLOCKS:
+        return False
+    n_pairs = len(blocks[0][0])
+    halo = 0
+    for c1s, c2s in blocks:
+        if len(c1s) != n_pairs or len(c2s) != n_pairs or not 1 <= n_pairs <= MRF_MAX_PAIRS:
+            return False
+        k = c1s[0].kernel_size[0]
+        h = 0
+        for c in list(c1s) + list(c2s):
+            if c.kernel_size[0] != k or k % 2 == 0 or c.in_channels != C or c.out_channels != C or c.bias is None:
+                return False
+            reach = (k - 1) // 2 * c.dilation[0]
+            if reach > MRF_MAX_REACH:
+                return False
+            h += reach
+        halo = max(halo, h)
+    return 512 - round_up(halo, 32) - halo >= 32
+
+
+def pack_mrf(C: int, blocks) -> PackedMrf:
+    """blocks: [(convs1, convs2)] with folded weights [C, C, k] (hifigan.py:29-98)."""
+    tiles, biases, ksize, dil1, dil2, row0 = [], [], [], [], [], []
+    rows = 0
+    for c1s, c2s in blocks:
+        k = c1s[0].kernel_size[0]
+        ksize.append(k)
+        dil1.append([c.dilation[0] for c in c1s])
+        dil2.append([c.dilation[0] for c in c2s])
+        r_blk, b_blk = [], []
+        for c1, c2 in zip(c1s, c2s):
+            r_pair = []
+            for c in (c1, c2):
+                w = c.weight.detach().float()                         # [C_out, C_in, k]
+                tiles.append(w.permute(2, 0, 1).reshape(k * C, C).to(torch.float16))
+                r_pair.append(rows)
+                rows += k * C
+            r_blk.append(r_pair)
+            b_blk.append(torch.stack([c1.bias.detach().float(), c2.bias.detach().float()]))
+        row0.append(r_blk)
+        biases.append(torch.stack(b_blk))
+    return PackedMrf(torch.cat(tiles).contiguous(), torch.stack(biases).contiguous(), C, ksize, dil1, dil2, row0)
+
+
+def mrf_fused(x32: torch.Tensor, pm: PackedMrf, out32: torch.Tensor, *, out16: Optional[torch.Tensor] = None,
+              act: int = ACT_SILU, act_param: float = 0.0, out_act: int = ACT_NONE, out_act_param: float = 0.0) -> None:
+    """x32 [B, L, pitch] fp32 -> out32 = mean over residual blocks (and out16 = fp16(out_act(out32)))."""
+    B, L, pitch = x32.shape
+    d = MrfDesc()
+    d.x, d.B, d.L, d.C, d.x_pitch = _ptr(x32, torch.float32), B, L, pm.C, pitch
+    d.w, d.w_rows, d.bias = _ptr(pm.w, torch.float16), pm.w.shape[0], _ptr(pm.bias, torch.float32)
+    d.n_blocks, d.n_pairs = len(pm.ksize), len(pm.dil1[0])
+    for j, k in enumerate(pm.ksize):
+        d.ksize[j] = k
+        for i in range(d.n_pairs):
+            d.dil1[j][i], d.dil2[j][i] = pm.dil1[j][i], pm.dil2[j][i]
+            d.w_row0[j][i][0], d.w_row0[j][i][1] = pm.w_row0[j][i]
+    d.act, d.act_param = int(act), float(act_param)
+    for name, t in (("out32", out32), ("out16", out16)):
+        if t is not None and (t.shape[0] != B or t.shape[1] != L):
+            raise FvError(f"{name} has shape {tuple(t.shape)}, expected [{B}, {L}, pitch]")
+    d.out32, d.out32_pitch = _ptr(out32, torch.float32), out32.shape[2]
+    d.out16, d.out16_pitch = _ptr(out16, torch.float16), (0 if out16 is None else out16.shape[2])
+    d.out_act, d.out_act_param = int(out_act), float(out_act_param)
+    _check(lib().fv_mrf_fused(ctypes.byref(d), _stream()), "fv_mrf_fused")
 
 
 def launch_count() -> int:

@@ -136,20 +136,28 @@ class MRFGeneratorBase(nn.Module):
         raise NotImplementedError
 
     def _ensure_packed(self, device):
-        key = params_key(list(self.parameters()) + list(self.buffers()))
+        key = params_key(list(self.parameters()) + list(self.buffers())) + (self.fuse_mrf, self.engine)
         if self._packed is not None and self._packed_key == key:
             return self._packed
         with torch.no_grad():
             P = {"pre": cabi.pack_conv(self.conv_pre.weight, self.conv_pre.bias), "ups": [], "blocks": [],
-                 "noise": []}
+                 "noise": [], "fused": []}
             for i, up in enumerate(self.ups):
                 P["ups"].append(cabi.pack_conv_transpose(up.weight, up.bias, self.upsample_rates[i]))
                 blocks = []
-                for blk in self._block_modules(i):
-                    c1 = [cabi.pack_conv(c.weight, c.bias, c.dilation[0]) for c in blk.convs1]
-                    c2 = [cabi.pack_conv(c.weight, c.bias, c.dilation[0]) for c in blk.convs2]
-                    blocks.append((c1, c2, blk))
+                mods = self._block_modules(i)
+                pairs = [(list(blk.convs1), list(blk.convs2)) for blk in mods]
+                fused = None
+                if (self.fuse_mrf and not self.snake_blocks and self.engine == cabi.ENGINE_TC
+                        and cabi.mrf_fusable(self.stage_channels[i], pairs)):
+                    fused = cabi.pack_mrf(self.stage_channels[i], pairs)   # whole stage = one fv_mrf_fused launch
+                else:
+                    for blk in mods:
+                        c1 = [cabi.pack_conv(c.weight, c.bias, c.dilation[0]) for c in blk.convs1]
+                        c2 = [cabi.pack_conv(c.weight, c.bias, c.dilation[0]) for c in blk.convs2]
+                        blocks.append((c1, c2, blk))
                 P["blocks"].append(blocks)
+                P["fused"].append(fused)
             for nc in self.noise_convs:
                 P["noise"].append((nc.weight.detach().float().reshape(nc.out_channels, -1).contiguous(),
                                    nc.bias.detach().float().contiguous(), nc.kernel_size[0], nc.stride[0],
@@ -195,6 +203,20 @@ class MRFGeneratorBase(nn.Module):
                 nz = ws.f32(f"nz_{i}", B, Lo, C, dev)
                 cabi.noise_conv(tpl.reshape(B, -1), w, b, nz, C, k, s, p)
             last_stage = i == n_stage - 1
+            fused = P["fused"][i]
+            if fused is not None:
+                # C <= 64 SiLU stages: ups writes only the fp32 stage input; the whole MRF (3 kernel sizes x 3 pairs)
+                # runs on chip per time tile and leaves the mean (+ the activated fp16 operand of the next layer)
+                cabi.conv1d(h16, up, Lo, residual=nz, out32=x0, engine=eng)
+                acc = ws.f32(f"acc_{i}", B, Lo, C, dev)
+                h_next = ws.f16(f"h_{i}", B, Lo, C, dev)
+                out_act, out_act_p = self._stage_out_act(last_stage)
+                cabi.mrf_fused(x0, fused, acc, out16=h_next if out_act is not None else None,
+                               act=cabi.ACT_SILU, out_act=out_act or cabi.ACT_NONE, out_act_param=out_act_p)
+                if last_stage:
+                    self._final_activation(acc, h_next, C)
+                h16, L = h_next, Lo
+                continue
             if self.snake_blocks:
                 cabi.conv1d(h16, up, Lo, residual=nz, out32=x0, engine=eng)
                 xa0 = None
@@ -249,6 +271,9 @@ class MRFGeneratorBase(nn.Module):
 
     def _snake(self, act_module, x32, out16, C):
         raise NotImplementedError
+
+    #: C <= 64 SiLU stages as one on-chip kernel per stage (fv_mrf_fused); False = layer-wise fv_conv1d launches
+    fuse_mrf = True
 
     #: utterances per residual-block pass; None = whole batch; 0 = size the block working set for L2 (_micro_batch)
     micro_batch = None
