@@ -140,43 +140,127 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "tensor_tflops": 1590.0, "tensor_tflops_sustained": 1400.0, "source": "fallback"}
 
 
-def profile_conv_launches(model, mel):
-    """One instrumented eager forward: CUDA-event duration + algorithmic flops/bytes of every fv_conv1d launch
-    (the tcgen05 implicit-GEMM kernel, dominant kernel of the step)."""
+def _alg_conv1d(a16, pc, L_out=None, **kw):
+    B, L_in, _ = a16.shape
+    rows = B * (L_in if L_out is None else L_out)
+    flops = 2.0 * rows * pc.c_out * pc.c_in * pc.n_taps
+    byts = 2.0 * B * L_in * pc.c_in + 2.0 * pc.n_phase * pc.n_taps * pc.c_out * pc.c_in
+    if kw.get("residual") is not None:
+        byts += 4.0 * rows * pc.c_out
+    if kw.get("out32") is not None:
+        byts += 4.0 * rows * pc.c_out * (2 if kw.get("accumulate") else 1)
+    if kw.get("out16") is not None:
+        byts += 2.0 * rows * pc.c_out
+    return flops, byts
+
+
+def _alg_mrf_fused(x32, pm, out32, **kw):
+    # whole MRF stage: x read once, mean written once (+ fp16 operand of the next layer), every tap tile read once
+    B, L, _ = x32.shape
+    taps = sum(k * 2 * len(pm.dil1[j]) for j, k in enumerate(pm.ksize))
+    flops = 2.0 * B * L * pm.C * pm.C * taps
+    byts = 8.0 * B * L * pm.C + 2.0 * taps * pm.C * pm.C + (2.0 * B * L * pm.C if kw.get("out16") is not None else 0.0)
+    return flops, byts
+
+
+def _alg_snake(x32, out16, alpha, beta, fu, fd, C, *a, **kw):
+    B, L, _ = x32.shape
+    return 0.0, 6.0 * B * L * C
+
+
+def _alg_dwln(x32, C, *a, out16=None, out32=None, **kw):
+    B, T, _ = x32.shape
+    return 0.0, B * T * C * (4.0 + (2.0 if out16 is not None else 0.0) + (4.0 if out32 is not None else 0.0))
+
+
+def _alg_post(a16, w32, bias, C, *a, **kw):
+    B, L, _ = a16.shape
+    return 2.0 * B * L * C * w32.shape[0], 2.0 * B * L * C + 4.0 * B * L
+
+
+def _alg_pack(x, *a, **kw):
+    return 0.0, 6.0 * x.numel()
+
+
+def _alg_ola(frames, window, n_fft, hop, *a, **kw):
+    B, T, _ = frames.shape
+    return 0.0, 4.0 * B * T * (n_fft + hop)
+
+
+# C-ABI wrapper -> (kernel family, algorithmic (flops, bytes) of one launch); formulas in DESIGN.md section 4
+FAMILIES = {"conv1d": ("conv_tc_kernel", _alg_conv1d), "mrf_fused": ("mrf_fused_kernel", _alg_mrf_fused),
+            "snake_aa": ("snake_aa_kernel", _alg_snake), "dwconv_layernorm": ("dwconv_ln_kernel", _alg_dwln),
+            "conv_post_tanh": ("conv_post_kernel", _alg_post), "pack_input": ("pack_input_kernel", _alg_pack),
+            "istft_ola": ("istft_ola_kernel", _alg_ola)}
+
+
+def profile_launches(model, mel):
+    """One instrumented eager forward: CUDA-event duration (events recorded on the launching stream) and algorithmic
+    flops/bytes of every launch of the kernel families above."""
     from vocoder_b200 import cabi
-    recs = []
-    orig = cabi.conv1d
+    recs, saved = [], {}
     stream = torch.cuda.current_stream()
 
-    def wrapped(a16, pc, L_out=None, **kw):
-        B, L_in, ap = a16.shape
-        Lo = L_in if L_out is None else L_out
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        orig(a16, pc, L_out, **kw)
-        e1.record(stream)
-        rows = B * Lo
-        flops = 2.0 * rows * pc.c_out * pc.c_in * pc.n_taps
-        byts = 2.0 * B * L_in * pc.c_in + 2.0 * pc.n_phase * pc.n_taps * pc.c_out * pc.c_in
-        if kw.get("residual") is not None:
-            byts += 4.0 * rows * pc.c_out
-        if kw.get("out32") is not None:
-            byts += 4.0 * rows * pc.c_out * (2 if kw.get("accumulate") else 1)
-        if kw.get("out16") is not None:
-            byts += 2.0 * rows * pc.c_out
-        recs.append((e0, e1, flops, byts, pc.c_in, pc.c_out, pc.n_taps))
+    def make(name, fam, alg, orig):
+        def wrapped(*a, **kw):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            out = orig(*a, **kw)
+            e1.record(stream)
+            fl, by = alg(*a, **kw)
+            recs.append((fam, e0, e1, fl, by))
+            return out
+        return wrapped
 
-    cabi.conv1d = wrapped
+    for name, (fam, alg) in FAMILIES.items():
+        saved[name] = getattr(cabi, name)
+        setattr(cabi, name, make(name, fam, alg, saved[name]))
     try:
         with torch.no_grad():
             model(mel)
         torch.cuda.synchronize()
     finally:
-        cabi.conv1d = orig
-    out = []
-    for e0, e1, fl, by, ci, co, nt in recs:
-        out.append({"ms": e0.elapsed_time(e1), "flops": fl, "bytes": by, "c_in": ci, "c_out": co, "taps": nt})
-    return out
+        for name, fn in saved.items():
+            setattr(cabi, name, fn)
+    return [{"kernel": fam, "ms": e0.elapsed_time(e1), "flops": fl, "bytes": by} for fam, e0, e1, fl, by in recs]
+
+
+def roofline_of(recs, peaks, step_ms):
+    """Per-family totals; the roofline object describes the family with the largest share of the step."""
+    fams = {}
+    for r in recs:
+        f = fams.setdefault(r["kernel"], {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0, "t_roof": 0.0})
+        f["launches"] += 1
+        f["ms"] += r["ms"]
+        f["flops"] += r["flops"]
+        f["bytes"] += r["bytes"]
+        f["t_roof"] += max(r["flops"] / (peaks["tensor_tflops"] * 1e12), r["bytes"] / (peaks["hbm_gbs"] * 1e9))
+    table = {}
+    for k, f in fams.items():
+        t = f["ms"] * 1e-3
+        table[k] = {"launches": f["launches"], "ms_per_step": f["ms"], "share_of_step": f["ms"] / step_ms,
+                    "alg_tflop": f["flops"] / 1e12, "alg_gbytes": f["bytes"] / 1e9,
+                    "tflops": f["flops"] / t / 1e12, "gbs": f["bytes"] / t / 1e9,
+                    "roofline_frac": f["t_roof"] / t}
+    top = max(fams, key=lambda k: fams[k]["ms"])
+    f = fams[top]
+    t = f["ms"] * 1e-3
+    t_tensor = f["flops"] / (peaks["tensor_tflops"] * 1e12)
+    t_hbm = f["bytes"] / (peaks["hbm_gbs"] * 1e9)
+    if t_hbm >= t_tensor:
+        roof = {"bound": "hbm", "achieved": f["bytes"] / t / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s"}
+    else:
+        roof = {"bound": "tensor", "achieved": f["flops"] / t / 1e12, "peak": peaks["tensor_tflops"], "unit": "TFLOP/s"}
+    roof["frac"] = roof["achieved"] / roof["peak"]
+    roof["traffic"] = None
+    roof.update({"kernel": f"{top} (all {f['launches']} launches of one step)", "launches": f["launches"],
+                 "kernel_ms_per_step": f["ms"], "share_of_step": f["ms"] / step_ms,
+                 "alg_tflop_per_step": f["flops"] / 1e12, "alg_gbytes_per_step": f["bytes"] / 1e9,
+                 "tensor_frac": f["flops"] / t / 1e12 / peaks["tensor_tflops"],
+                 "hbm_frac": f["bytes"] / t / 1e9 / peaks["hbm_gbs"],
+                 "per_launch_roofline_frac": f["t_roof"] / t, "peak_source": peaks["source"] + " (burst)",
+                 "families": table})
+    return roof
 
 
 def main():
@@ -188,6 +272,7 @@ def main():
     ap.add_argument("--workload", default="hifigan_b64", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-fuse-mrf", action="store_true", help="layer-wise fv_conv1d launches instead of fv_mrf_fused")
     ap.add_argument("--cpu-sample", type=int, default=0, help="utterances in the CPU baseline sample (0 = auto)")
     ap.add_argument("--dump-launches", default=None, help="write the per-launch conv timing table (json) here")
     ap.add_argument("--micro-batch", type=int, default=0,
@@ -250,6 +335,8 @@ def main():
             m.use_cuda_graph = False
         if args.micro_batch > 0 and hasattr(m, "micro_batch"):
             m.micro_batch = args.micro_batch
+        if args.no_fuse_mrf and hasattr(m, "fuse_mrf"):
+            m.fuse_mrf = False
     mel_host = synthetic_mel(B, n_mels, T, 1234 + rank).pin_memory()
     mel = mel_host.to(dev)
     wav_host = torch.empty(B, 1, T * hop).pin_memory()
@@ -315,31 +402,11 @@ def main():
         model.use_cuda_graph = False
         with torch.no_grad():
             for _ in range(2):
-                recs = profile_conv_launches(model, mel)
+                recs = profile_launches(model, mel)
         if args.dump_launches:
             with open(args.dump_launches, "w") as f:
                 json.dump(recs, f)
-        t_conv = sum(r["ms"] for r in recs) * 1e-3
-        fl = sum(r["flops"] for r in recs)
-        by = sum(r["bytes"] for r in recs)
-        t_roof_tensor = fl / (peaks["tensor_tflops"] * 1e12)
-        t_roof_hbm = by / (peaks["hbm_gbs"] * 1e9)
-        roof_each = sum(max(r["flops"] / (peaks["tensor_tflops"] * 1e12), r["bytes"] / (peaks["hbm_gbs"] * 1e9))
-                        for r in recs)
-        if t_roof_hbm >= t_roof_tensor:
-            roofline = {"bound": "hbm", "achieved": by / t_conv / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s"}
-        else:
-            roofline = {"bound": "tensor", "achieved": fl / t_conv / 1e12, "peak": peaks["tensor_tflops"],
-                        "unit": "TFLOP/s"}
-        roofline["frac"] = roofline["achieved"] / roofline["peak"]
-        roofline["traffic"] = None
-        roofline.update({
-            "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv, all launches of one step)",
-            "launches": len(recs), "kernel_ms_per_step": t_conv * 1e3,
-            "share_of_step": t_conv * 1e3 / (dev_ms / args.steps),
-            "alg_tflop_per_step": fl / 1e12, "alg_gbytes_per_step": by / 1e9,
-            "tensor_frac": fl / t_conv / 1e12 / peaks["tensor_tflops"], "hbm_frac": by / t_conv / 1e9 / peaks["hbm_gbs"],
-            "per_launch_roofline_frac": roof_each / t_conv, "peak_source": peaks["source"] + " (burst)"})
+        roofline = roofline_of(recs, peaks, dev_ms / args.steps)
 
         cpu_baseline = None
         if not args.no_cpu_baseline and world == 1:
@@ -352,6 +419,7 @@ def main():
         config["l2"] = ("L2 flushed between timed steps (256 MiB memset outside the per-step event pairs); per-step "
                         f"working set {sum(m._ws.nbytes() for m in model.modules() if hasattr(m, '_ws')) / 1e9:.2f} GB > 126 MB L2")
         config["cuda_graph"] = not args.no_graph
+        config["fuse_mrf"] = not args.no_fuse_mrf
         config["micro_batch"] = args.micro_batch if args.micro_batch > 0 else "whole batch"
         line = {"metric": "audio samples/sec, mel->wav generator forward", "value": value, "unit": "samples/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
