@@ -46,8 +46,10 @@ enum fv_act {
   FV_ACT_LEAKY = 2, /* F.leaky_relu(o, act_param): refinegan.py:89,91,302,313,319                  */
   FV_ACT_GELU = 3,  /* nn.GELU() exact erf: encoders/convnext.py:115                               */
   FV_ACT_TANH = 4,  /* torch.tanh: hifigan.py:247                                                  */
-  FV_ACT_POLAR = 5  /* column pairs (2k,2k+1) = (log-mag, phase) -> (min(exp(m),100)cos p, ..sin p):
+  FV_ACT_POLAR = 5, /* column pairs (2k,2k+1) = (log-mag, phase) -> (min(exp(m),100)cos p, ..sin p):
                        generators/vocos.py:57-67                                                  */
+  FV_ACT_SILU_TANH = 6 /* F.silu as x/2 + x/2 tanh(x/2) with tanh.approx (one SFU op, |err| <= 2.4e-4 |x|):
+                          opt-in inner activation of fv_mrf_fused only                             */
 };
 
 /* which kernel family executes fv_conv1d */
@@ -197,7 +199,7 @@ typedef struct fv_mrf_desc {
   int32_t dil1[FV_MRF_MAX_BLOCKS][FV_MRF_MAX_PAIRS];
   int32_t dil2[FV_MRF_MAX_BLOCKS][FV_MRF_MAX_PAIRS];
   int32_t w_row0[FV_MRF_MAX_BLOCKS][FV_MRF_MAX_PAIRS][2]; /* first row in `w` of tap 0 of (block, pair, conv) */
-  int32_t act; /* FV_ACT_SILU | FV_ACT_LEAKY */
+  int32_t act; /* FV_ACT_SILU | FV_ACT_LEAKY | FV_ACT_SILU_TANH */
   float act_param;
   float* out32;
   int32_t out32_pitch;

@@ -287,6 +287,28 @@ def test_mrf_fused_kernel(C, L, B, ks):
     assert e16 <= 2e-3 * scale, f"out16 err {e16:.3e}"
 
 
+@pytest.mark.parametrize("variant", ["layerwise", "fused", "fused_silu_tanh"])
+def test_full_width_stress_hifigan_vs_oracle(variant):
+    """Full-width HiFiGAN (cfg A/B channels) with SURVEY-8d stress weights, so the residual branches of the C = 64 / 32
+    stages (the ones fv_mrf_fused evaluates on chip) carry signal: every MRF variant within 1e-3 of the fp32 oracle."""
+    from tests.util import stress_init
+    m, n_mels, hop = _full("hifigan")
+    stress_init(m, seed=3)
+    m = m.eval()
+    torch.manual_seed(4321)
+    mel = torch.empty(2, n_mels, 19).uniform_(-11.5129, 2.0)
+    want = _oracle_full("hifigan", m, mel)
+    m = m.cuda()
+    m.fuse_mrf = variant != "layerwise"
+    m.mrf_silu_tanh = variant == "fused_silu_tanh"
+    with torch.no_grad():
+        y = m(mel.cuda()).cpu()
+    peak = max(1.0, float(want.abs().max()))
+    err = float((y - want).abs().max())
+    print(f"full-width stress hifigan [{variant}]: max|delta| vs fp32 oracle {err:.3e} (peak {peak:.3f})")
+    assert err <= TOL * peak, f"{variant}: max|delta|={err:.3e}"
+
+
 def test_mrf_fused_generator_matches_layerwise():
     m, n_mels, hop = _full("hifigan")
     m = m.eval().cuda()

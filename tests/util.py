@@ -90,3 +90,29 @@ class emulate_f16_operands:
     def __exit__(self, *exc):
         self.F.conv1d, self.F.conv_transpose1d, self.F.linear = self.saved
         return False
+
+
+def stress_init(model: torch.nn.Module, seed: int = 1) -> None:
+    """SURVEY 8d "stress-init" (same distributions as oracle/make_golden.py): weight-norm directions ~ N(0, (s/sqrt(fan_in))^2)
+    with s = 0.5 for the residual-block convs and 1 elsewhere, g = ||v||, biases ~ N(0, 0.02^2), Snake alpha/beta ~
+    N(0, 0.5^2), ConvNeXt gamma ~ U(0.05, 0.5): residual branches carry signal like a trained network's."""
+    g = torch.Generator().manual_seed(seed)
+    sd = model.state_dict()
+    new = {}
+    for k, v in sd.items():
+        if k.endswith("parametrizations.weight.original1"):
+            fan_in = v.shape[0] * v.shape[2] if "ups." in k else v[0].numel()
+            s = 0.5 if (".convs1." in k or ".convs2." in k) else 1.0
+            new[k] = torch.randn(v.shape, generator=g) * (s / fan_in ** 0.5)
+        elif k.endswith(".bias") and v.ndim == 1:
+            new[k] = torch.randn(v.shape, generator=g) * 0.02
+        elif k.endswith(".act.alpha") or k.endswith(".act.beta"):
+            new[k] = torch.randn(v.shape, generator=g) * 0.5
+        elif k.endswith(".gamma"):
+            new[k] = torch.rand(v.shape, generator=g) * 0.45 + 0.05
+    for k, v in list(new.items()):
+        if k.endswith("original1"):
+            k0 = k[:-1] + "0"
+            new[k0] = v.reshape(v.shape[0], -1).norm(dim=1).reshape(sd[k0].shape)
+    sd.update(new)
+    model.load_state_dict(sd)

@@ -18,7 +18,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libfv_b200.so")
 
-ACT_NONE, ACT_SILU, ACT_LEAKY, ACT_GELU, ACT_TANH, ACT_POLAR = range(6)
+ACT_NONE, ACT_SILU, ACT_LEAKY, ACT_GELU, ACT_TANH, ACT_POLAR, ACT_SILU_TANH = range(7)
 ENGINE_TC, ENGINE_SIMT = 0, 1
 MAX_TAPS = 64
 

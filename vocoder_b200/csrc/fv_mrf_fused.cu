@@ -18,6 +18,7 @@
 // Warp roles: warp 0 = weight-tile TMA producer, warp 1 = tcgen05.mma issuer + TMEM owner, warps 4-19 = epilogue
 // (one thread per tile row: TMEM -> bias/activation -> fp16 operand row in smem; tile entry/exit through TMA boxes).
 // HBM traffic per element of the stage: 4 B in (x) + 2..6 B out, against 16 B per conv pair for the layer-wise path.
+#include <cstdlib>
 #include <mutex>
 
 #include "fv_common.cuh"
@@ -27,9 +28,7 @@ namespace fv {
 constexpr int kFrTile = 512;     // rows per tile = 4 UMMA M blocks of 128
 constexpr int kFrMBlocks = 4;
 constexpr int kFrGuard = 32;     // guard rows either side of an operand slab = largest tap reach supported
-constexpr int kFrEpiWarps = 16;  // one epilogue thread per tile row
-constexpr int kFrThreads = 128 + kFrEpiWarps * 32;
-constexpr int kFrSmemLimit = 232448;
+constexpr int kFrSmemSm = 233472;  // shared memory of one SM; every resident CTA also pays 1 KB of driver reservation
 constexpr int kFrMaxConvs = FV_MRF_MAX_BLOCKS * FV_MRF_MAX_PAIRS * 2;
 
 struct MrfParams {
@@ -48,16 +47,21 @@ struct MrfParams {
   float act_param, out_act_param, out_scale;
 };
 
-template <int C>
+// EW epilogue warps (a multiple of 4, at most 16: warp w owns TMEM lane quarter w % 4 and walks 16 / EW row groups),
+// NCTA co-resident CTAs per SM: with C = 32 two CTAs fit (256 TMEM columns and < 113 KB each), so the tensor pipe
+// works on one CTA's conv while the other CTA's epilogue warps turn accumulators into the next operand.
+template <int C, int EW, int NCTA>
 struct FrCfg {
+  static constexpr int THREADS = 64 + EW * 32;                // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
+  static constexpr int SMEM_LIMIT = kFrSmemSm / NCTA - 1024;
   static constexpr int ROWB = C * 2;                          // bytes per operand row = swizzle span
   static constexpr int SLAB_ROWS = kFrTile + 2 * kFrGuard;
   static constexpr int SLAB = SLAB_ROWS * ROWB;               // multiple of 1024
   static constexpr int W_TILE = C * ROWB;
-  static constexpr int STG32 = kFrEpiWarps * 4096;            // per-warp 32 x 32 fp32 patch, SWIZZLE_128B
-  static constexpr int STG16 = kFrEpiWarps * 2048;            // per-warp 32 x 32 fp16 patch, SWIZZLE_64B
-  // C = 64: the staging patches alias the operand slabs (dead at tile entry / exit); C = 32: own region
-  static constexpr bool ALIAS = 2 * SLAB + STG32 + STG16 + 8 * W_TILE + 16384 > kFrSmemLimit;
+  static constexpr int STG32 = EW * 4096;                     // per-warp 32 x 32 fp32 patch, SWIZZLE_128B
+  static constexpr int STG16 = EW * 2048;                     // per-warp 32 x 32 fp16 patch, SWIZZLE_64B
+  // when the staging patches do not fit next to the slabs they alias them (slabs are dead at tile entry / exit)
+  static constexpr bool ALIAS = 2 * SLAB + STG32 + STG16 + 8 * W_TILE + 16384 > SMEM_LIMIT;
   static constexpr int XA_OFF = 0;
   static constexpr int TA_OFF = SLAB;
   static constexpr int STG32_OFF = ALIAS ? TA_OFF : 2 * SLAB;
@@ -65,10 +69,14 @@ struct FrCfg {
   static constexpr int RING_OFF = ALIAS ? 2 * SLAB : 2 * SLAB + STG32 + STG16;
   static constexpr int BIAS_BYTES = kFrMaxConvs * C * 4;
   static constexpr int TAIL = 1024 + BIAS_BYTES;
-  static constexpr int NS_RAW = (kFrSmemLimit - RING_OFF - TAIL) / W_TILE;
+  static constexpr int NS_RAW = (SMEM_LIMIT - RING_OFF - TAIL) / W_TILE;
   static constexpr int NS = NS_RAW > 16 ? 16 : NS_RAW;
   static constexpr int SMEM = RING_OFF + NS * W_TILE + TAIL;
   static constexpr int TMEM_COLS = 2 * kFrMBlocks * C;        // 512 (C = 64) / 256 (C = 32)
+  static constexpr int GROUPS = EW / 4;                       // epilogue warps per TMEM lane quarter
+  static constexpr int RR = kFrMBlocks / GROUPS;              // 128-row blocks each epilogue warp walks
+  static_assert(EW % 4 == 0 && EW >= 4 && EW <= 16 && kFrMBlocks % GROUPS == 0, "bad epilogue warp count");
+  static_assert(TMEM_COLS * NCTA <= 512, "co-resident CTAs exceed TMEM");
   static_assert(!ALIAS || (STG32 <= SLAB && STG16 <= SLAB), "staging does not fit in the slabs it aliases");
   static_assert(NS >= 4, "weight ring too shallow");
   static_assert(SLAB % 1024 == 0 && W_TILE % 1024 == 0, "swizzled tiles must stay 1024-byte aligned");
@@ -81,9 +89,32 @@ __device__ __forceinline__ uint32_t swz_off(int row, int chunk) {
   else return row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4);
 }
 
-template <int C>
-__global__ void __launch_bounds__(kFrThreads, 1) mrf_fused_kernel(const __grid_constant__ MrfParams p) {
-  using Cfg = FrCfg<C>;
+// Inner activation of the residual blocks, resolved at compile time: the epilogue body must be straight-line code
+// (a per-element switch costs a uniform branch + BSSY/BSYNC per element and serialises the SFU latencies).
+//   kActSilu     x / (1 + 2^(-x log2 e)): ex2.approx.ftz + rcp.approx.ftz (2 SFU ops, ~1e-7 relative)
+//   kActSiluTanh x/2 + x/2 * tanh(x/2):   tanh.approx (1 SFU op, |error| <= 2.4e-4 |x|) - opt-in, see fv_set_mrf_tuning
+//   kActLeaky    x > 0 ? x : slope * x
+constexpr int kActSilu = 0, kActSiluTanh = 1, kActLeaky = 2;
+template <int ACT>
+__device__ __forceinline__ float fr_act(float v, float param) {
+  if constexpr (ACT == kActSilu) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * -1.4426950408889634f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return v * r;
+  } else if constexpr (ACT == kActSiluTanh) {
+    const float h = 0.5f * v;
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    return fmaf(h, t, h);
+  } else {
+    return v > 0.f ? v : v * param;
+  }
+}
+
+template <int C, int ACT, int EW, int NCTA>
+__global__ void __launch_bounds__(FrCfg<C, EW, NCTA>::THREADS, NCTA) mrf_fused_kernel(const __grid_constant__ MrfParams p) {
+  using Cfg = FrCfg<C, EW, NCTA>;
   constexpr int ROWB = Cfg::ROWB;
   constexpr int NCH = C / 32;  // 32-column chunks per row
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -97,7 +128,7 @@ __global__ void __launch_bounds__(kFrThreads, 1) mrf_fused_kernel(const __grid_c
   uint64_t* a_ready = w_empty + Cfg::NS;   // epilogue warps -> MMA: operand of the next conv is in smem / X is in TMEM
   uint64_t* acc_full = a_ready + 1;        // MMA -> epilogue: accumulators of the current conv are complete
   uint64_t* stg_bar = acc_full + 1;        // one per epilogue warp: TMA loads into its staging patch
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stg_bar + kFrEpiWarps);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stg_bar + EW);
   float* s_bias = reinterpret_cast<float*>(tail + 1024);  // [block][pair][2][C]: b1, cumulative b2
 
   const int warp = threadIdx.x >> 5;
@@ -112,9 +143,9 @@ __global__ void __launch_bounds__(kFrThreads, 1) mrf_fused_kernel(const __grid_c
       mbar_init(&w_full[i], 1);
       mbar_init(&w_empty[i], 1);
     }
-    mbar_init(a_ready, kFrEpiWarps);
+    mbar_init(a_ready, EW);
     mbar_init(acc_full, 1);
-    for (int i = 0; i < kFrEpiWarps; ++i) mbar_init(&stg_bar[i], 1);
+    for (int i = 0; i < EW; ++i) mbar_init(&stg_bar[i], 1);
     fence_barrier_init();
   } else if (warp == 1) {
     tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -201,34 +232,46 @@ __global__ void __launch_bounds__(kFrThreads, 1) mrf_fused_kernel(const __grid_c
           }
       }
     }
-  } else if (warp >= 4) {
-    // ---------------------------------------------------------------- epilogue: thread = tile row
-    const int e = warp - 4;             // rows 32e .. 32e+31 of the tile; TMEM lane quarter = warp % 4 = e % 4
-    const int m = e >> 2;
-    const int row_l = e * 32 + lane;
-    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>((e & 3) * 32) << 16);
+  } else {
+    // ---------------------------------------------------------------- epilogue: thread = tile row (RR rows in turn)
+    // warp w may only touch TMEM lanes 32 (w % 4) .. +31: it owns that lane quarter of the 128-row blocks
+    // m = g, g + GROUPS, ... (g = its index among the warps of the quarter); local row = 128 m + 32 q + lane
+    const int e = warp - 2;
+    const int q = warp & 3;
+    const int g = e >> 2;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     uint8_t* patch32 = smem + Cfg::STG32_OFF + e * 4096;
     uint8_t* patch16 = smem + Cfg::STG16_OFF + e * 2048;
     const uint32_t p32_row = smem_u32(patch32) + lane * 128;
     const uint32_t p16_row = smem_u32(patch16) + lane * 64;
     const uint32_t r_xor = lane & 7, h_xor = (lane >> 1) & 3;
     const uint32_t xa_base = smem_u32(smem + Cfg::XA_OFF), ta_base = smem_u32(smem + Cfg::TA_OFF);
-    const int srow = kFrGuard + row_l;  // this thread's row inside the operand slabs
     uint64_t* my_bar = &stg_bar[e];
     uint32_t stg_phase = 0, n = 0;
-    const bool in_window = (e * 32 >= p.h0) && (e * 32 < p.h0 + p.V);
 
-    // activation -> fp16 -> this thread's 64 bytes (32 columns) of an operand row
-    auto put_operand = [&](uint32_t slab_base, int cc, const float (&v)[32]) {
+    // activation -> fp16 -> this thread's 64 bytes (32 columns) of operand row `srow`
+    auto put_operand = [&](uint32_t slab_base, int srow, int cc, const float (&v)[32]) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const uint32_t w0 = pack_half2_sat(v[8 * q + 0], v[8 * q + 1]);
-        const uint32_t w1 = pack_half2_sat(v[8 * q + 2], v[8 * q + 3]);
-        const uint32_t w2 = pack_half2_sat(v[8 * q + 4], v[8 * q + 5]);
-        const uint32_t w3 = pack_half2_sat(v[8 * q + 6], v[8 * q + 7]);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(slab_base + swz_off<ROWB>(srow, cc * 4 + q)),
+      for (int qq = 0; qq < 4; ++qq) {
+        const uint32_t w0 = pack_half2_sat(v[8 * qq + 0], v[8 * qq + 1]);
+        const uint32_t w1 = pack_half2_sat(v[8 * qq + 2], v[8 * qq + 3]);
+        const uint32_t w2 = pack_half2_sat(v[8 * qq + 4], v[8 * qq + 5]);
+        const uint32_t w3 = pack_half2_sat(v[8 * qq + 6], v[8 * qq + 7]);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(slab_base + swz_off<ROWB>(srow, cc * 4 + qq)),
                      "r"(w0), "r"(w1), "r"(w2), "r"(w3)
                      : "memory");
+      }
+    };
+    // v = accumulator + bias (32 consecutive channels; the bias row is 16-byte aligned: broadcast LDS.128)
+    auto add_bias = [&](float (&v)[32], const uint32_t (&r)[32], const float* bias) {
+      const float4* b4 = reinterpret_cast<const float4*>(bias);
+#pragma unroll
+      for (int qq = 0; qq < 8; ++qq) {
+        const float4 bb = b4[qq];
+        v[4 * qq] = __uint_as_float(r[4 * qq]) + bb.x;
+        v[4 * qq + 1] = __uint_as_float(r[4 * qq + 1]) + bb.y;
+        v[4 * qq + 2] = __uint_as_float(r[4 * qq + 2]) + bb.z;
+        v[4 * qq + 3] = __uint_as_float(r[4 * qq + 3]) + bb.w;
       }
     };
     auto publish = [&]() {  // operand rows / TMEM stores of this warp are done -> MMA warp
@@ -237,36 +280,60 @@ __global__ void __launch_bounds__(kFrThreads, 1) mrf_fused_kernel(const __grid_c
       __syncwarp();
       if (lane == 0) mbar_arrive(a_ready);
     };
+    // accumulator (TMEM column base `col`) + bias -> activation -> operand slab, for every row this thread owns
+    auto acc_to_operand = [&](uint32_t col, const float* bias, uint32_t slab_base, int g0) {
+#pragma unroll 1
+      for (int rr = 0; rr < Cfg::RR; ++rr) {
+        const int m = g + rr * Cfg::GROUPS;
+        const int row_l = m * 128 + q * 32 + lane;
+        const int gr = g0 + row_l;
+        const bool in_seq = gr >= 0 && gr < p.L;
+#pragma unroll 1
+        for (int cc = 0; cc < NCH; ++cc) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(t_lane + col + m * C + cc * 32, r);
+          tmem_ld_wait();
+          float v[32];
+          add_bias(v, r, bias + cc * 32);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = in_seq ? fr_act<ACT>(v[i], p.act_param) : 0.f;
+          put_operand(slab_base, kFrGuard + row_l, cc, v);
+        }
+      }
+    };
 
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int b = tile / p.tiles_per_b;
       const int g0 = (tile % p.tiles_per_b) * p.V - p.h0;  // global row of tile row 0
-      const int g = g0 + row_l;
-      const bool in_seq = g >= 0 && g < p.L;
-      const bool live = in_window && (g0 + e * 32 < p.L);
       for (int j = 0; j < p.n_blocks; ++j) {
         // ---- tile entry: x -> X (TMEM, fp32) and act(x) -> XA (fp16); rows outside the sequence arrive as zeros
-        for (int cc = 0; cc < NCH; ++cc) {
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_wait_read();
-            mbar_arrive_expect_tx(my_bar, 4096);
-            tma_load_3d(patch32, &p.tmX, my_bar, cc * 32, g0 + e * 32, b);
+#pragma unroll 1
+        for (int rr = 0; rr < Cfg::RR; ++rr) {
+          const int m = g + rr * Cfg::GROUPS;
+          const int blk0 = m * 128 + q * 32;  // first tile row of this warp's 32-row group
+#pragma unroll 1
+          for (int cc = 0; cc < NCH; ++cc) {
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_wait_read();
+              mbar_arrive_expect_tx(my_bar, 4096);
+              tma_load_3d(patch32, &p.tmX, my_bar, cc * 32, g0 + blk0, b);
+            }
+            __syncwarp();
+            mbar_wait(my_bar, stg_phase);
+            stg_phase ^= 1;
+            uint32_t r[32];
+#pragma unroll
+            for (int qq = 0; qq < 8; ++qq)
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(r[4 * qq]), "=r"(r[4 * qq + 1]), "=r"(r[4 * qq + 2]), "=r"(r[4 * qq + 3])
+                           : "r"(p32_row + ((static_cast<uint32_t>(qq) ^ r_xor) << 4)));
+            tmem_st_32x32b_x32(t_lane + X_COL + m * C + cc * 32, r);
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fr_act<ACT>(__uint_as_float(r[i]), p.act_param);
+            put_operand(xa_base, kFrGuard + blk0 + lane, cc, v);
           }
-          __syncwarp();
-          mbar_wait(my_bar, stg_phase);
-          stg_phase ^= 1;
-          uint32_t r[32];
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                         : "=r"(r[4 * q]), "=r"(r[4 * q + 1]), "=r"(r[4 * q + 2]), "=r"(r[4 * q + 3])
-                         : "r"(p32_row + ((static_cast<uint32_t>(q) ^ r_xor) << 4)));
-          tmem_st_32x32b_x32(t_lane + X_COL + m * C + cc * 32, r);
-          float v[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = act_apply(__uint_as_float(r[i]), p.act, p.act_param);
-          put_operand(xa_base, cc, v);
         }
         tmem_st_wait();
         publish();
@@ -277,111 +344,105 @@ __global__ void __launch_bounds__(kFrThreads, 1) mrf_fused_kernel(const __grid_c
           mbar_wait(acc_full, n & 1);
           ++n;
           tc_fence_after();
-#pragma unroll 1
-          for (int cc = 0; cc < NCH; ++cc) {
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(t_lane + T_COL + m * C + cc * 32, r);
-            tmem_ld_wait();
-            float v[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float t = __uint_as_float(r[i]) + b1[cc * 32 + i];
-              v[i] = in_seq ? act_apply(t, p.act, p.act_param) : 0.f;
-            }
-            put_operand(ta_base, cc, v);
-          }
+          acc_to_operand(T_COL, b1, ta_base, g0);
           publish();
           // ---- conv2 done: X (+ cumulative b2) is the residual stream after this pair
           mbar_wait(acc_full, n & 1);
           ++n;
           tc_fence_after();
           if (pi + 1 < p.n_pairs) {
-#pragma unroll 1
-            for (int cc = 0; cc < NCH; ++cc) {
-              uint32_t r[32];
-              tmem_ld_32x32b_x32(t_lane + X_COL + m * C + cc * 32, r);
-              tmem_ld_wait();
-              float v[32];
-#pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                const float t = __uint_as_float(r[i]) + b2c[cc * 32 + i];
-                v[i] = in_seq ? act_apply(t, p.act, p.act_param) : 0.f;
-              }
-              put_operand(xa_base, cc, v);
-            }
+            acc_to_operand(X_COL, b2c, xa_base, g0);
             publish();
-          } else if (live) {
+          } else {
             // ---- tile exit: block output -> running mean in out32 (-> activated fp16 after the last block)
             const bool last = j == p.n_blocks - 1;
-            const int grow = g0 + e * 32;
 #pragma unroll 1
-            for (int cc = 0; cc < NCH; ++cc) {
-              __syncwarp();
-              if (lane == 0) {
+            for (int rr = 0; rr < Cfg::RR; ++rr) {
+              const int m = g + rr * Cfg::GROUPS;
+              const int blk0 = m * 128 + q * 32;
+              const int grow = g0 + blk0;
+              if (!(blk0 >= p.h0 && blk0 < p.h0 + p.V && grow < p.L)) continue;  // halo rows / past the sequence
+#pragma unroll 1
+              for (int cc = 0; cc < NCH; ++cc) {
+                __syncwarp();
+                if (lane == 0) {
+                  if (j > 0) {
+                    tma_store_wait_all();  // the partial sums this warp stored for block j-1 are visible
+                    mbar_arrive_expect_tx(my_bar, 4096);
+                    tma_load_3d(patch32, &p.tmO32, my_bar, cc * 32, grow, b);
+                  } else {
+                    tma_store_wait_read();
+                  }
+                }
+                __syncwarp();
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(t_lane + X_COL + m * C + cc * 32, r);
+                tmem_ld_wait();
+                float v[32];
+                add_bias(v, r, b2c + cc * 32);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] *= p.out_scale;
                 if (j > 0) {
-                  tma_store_wait_all();  // the partial sums this warp stored for block j-1 are visible
-                  mbar_arrive_expect_tx(my_bar, 4096);
-                  tma_load_3d(patch32, &p.tmO32, my_bar, cc * 32, grow, b);
-                } else {
-                  tma_store_wait_read();
+                  mbar_wait(my_bar, stg_phase);
+                  stg_phase ^= 1;
+#pragma unroll
+                  for (int qq = 0; qq < 8; ++qq) {
+                    float4 a;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w)
+                                 : "r"(p32_row + ((static_cast<uint32_t>(qq) ^ r_xor) << 4)));
+                    v[4 * qq] += a.x;
+                    v[4 * qq + 1] += a.y;
+                    v[4 * qq + 2] += a.z;
+                    v[4 * qq + 3] += a.w;
+                  }
                 }
-              }
-              __syncwarp();
-              uint32_t r[32];
-              tmem_ld_32x32b_x32(t_lane + X_COL + m * C + cc * 32, r);
-              tmem_ld_wait();
-              float v[32];
 #pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = (__uint_as_float(r[i]) + b2c[cc * 32 + i]) * p.out_scale;
-              if (j > 0) {
-                mbar_wait(my_bar, stg_phase);
-                stg_phase ^= 1;
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                  float4 a;
-                  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w)
-                               : "r"(p32_row + ((static_cast<uint32_t>(q) ^ r_xor) << 4)));
-                  v[4 * q] += a.x;
-                  v[4 * q + 1] += a.y;
-                  v[4 * q + 2] += a.z;
-                  v[4 * q + 3] += a.w;
-                }
-              }
-#pragma unroll
-              for (int q = 0; q < 8; ++q)
-                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(p32_row +
-                                                                              ((static_cast<uint32_t>(q) ^ r_xor) << 4)),
-                             "f"(v[4 * q]), "f"(v[4 * q + 1]), "f"(v[4 * q + 2]), "f"(v[4 * q + 3])
-                             : "memory");
-              if (last && p.has_o16) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  uint32_t w[4];
-#pragma unroll
-                  for (int u = 0; u < 4; ++u)
-                    w[u] = pack_half2_sat(act_apply(v[8 * q + 2 * u], p.out_act, p.out_act_param),
-                                          act_apply(v[8 * q + 2 * u + 1], p.out_act, p.out_act_param));
-                  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p16_row +
-                                                                                ((static_cast<uint32_t>(q) ^ h_xor) << 4)),
-                               "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
+                for (int qq = 0; qq < 8; ++qq)
+                  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(
+                                   p32_row + ((static_cast<uint32_t>(qq) ^ r_xor) << 4)),
+                               "f"(v[4 * qq]), "f"(v[4 * qq + 1]), "f"(v[4 * qq + 2]), "f"(v[4 * qq + 3])
                                : "memory");
+                if (last && p.has_o16) {
+                  if (p.out_act == FV_ACT_SILU) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = fr_act<kActSilu>(v[i], 0.f);
+                  } else if (p.out_act == FV_ACT_LEAKY) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = fr_act<kActLeaky>(v[i], p.out_act_param);
+                  } else if (p.out_act == FV_ACT_TANH) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = tanhf(v[i]);
+                  } else if (p.out_act == FV_ACT_GELU) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = gelu_erf_fast(v[i]);
+                  }
+#pragma unroll
+                  for (int qq = 0; qq < 4; ++qq) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) w[u] = pack_half2_sat(v[8 * qq + 2 * u], v[8 * qq + 2 * u + 1]);
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(
+                                     p16_row + ((static_cast<uint32_t>(qq) ^ h_xor) << 4)),
+                                 "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
+                                 : "memory");
+                  }
                 }
-              }
-              fence_proxy_async_smem();
-              __syncwarp();
-              if (lane == 0) {
-                tma_store_3d(&p.tmO32, patch32, cc * 32, grow, b);
-                if (last && p.has_o16) tma_store_3d(&p.tmO16, patch16, cc * 32, grow, b);
-                tma_store_commit();
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                  tma_store_3d(&p.tmO32, patch32, cc * 32, grow, b);
+                  if (last && p.has_o16) tma_store_3d(&p.tmO16, patch16, cc * 32, grow, b);
+                  tma_store_commit();
+                }
               }
             }
-          }
-          if (Cfg::ALIAS && pi + 1 == p.n_pairs && j == p.n_blocks - 1 && p.has_o16) {
-            // the fp16 exit patches alias XA: nobody may start the next tile's entry before every store has read them
-            if (lane == 0) tma_store_wait_read();
-            __syncwarp();
-            named_bar_sync(1, kFrEpiWarps * 32);
+            if (Cfg::ALIAS && last && p.has_o16) {
+              // the fp16 exit patches alias XA: nobody may start the next tile's entry before every store has read them
+              if (lane == 0) tma_store_wait_read();
+              __syncwarp();
+              named_bar_sync(1, EW * 32);
+            }
           }
         }
       }
@@ -414,9 +475,15 @@ static int encode_rows_map(EncodeTiledFn enc, CUtensorMap* tm, const void* base,
   return 0;
 }
 
-template <int C>
+// FV_MRF_C32_CTAS=1 selects the one-CTA-per-SM configuration for C = 32 (A/B measurements); default 2
+static const int g_mrf_c32_ctas = [] {
+  const char* e = getenv("FV_MRF_C32_CTAS");
+  return (e && e[0] == '1') ? 1 : 2;
+}();
+
+template <int C, int ACT, int EW, int NCTA>
 static int launch_mrf(const fv_mrf_desc* d, MrfParams& p, cudaStream_t stream) {
-  using Cfg = FrCfg<C>;
+  using Cfg = FrCfg<C, EW, NCTA>;
   EncodeTiledFn enc = get_encode_fn();
   FV_REQUIRE(enc != nullptr, FV_E_DRIVER, "cuTensorMapEncodeTiled not available from the driver");
   int rc = encode_rows_map(enc, &p.tmX, d->x, false, C, d->x_pitch, d->L, d->B);
@@ -437,12 +504,13 @@ static int launch_mrf(const fv_mrf_desc* d, MrfParams& p, cudaStream_t stream) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(mrf_fused_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    attr_err = cudaFuncSetAttribute(mrf_fused_kernel<C, ACT, EW, NCTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
   });
   rc = check_cuda(attr_err, "cudaFuncSetAttribute(mrf_fused_kernel)");
   if (rc) return rc;
-  const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  mrf_fused_kernel<C><<<grid, kFrThreads, Cfg::SMEM, stream>>>(p);
+  const int slots = num_sms() * NCTA;
+  const int grid = p.total_tiles < slots ? p.total_tiles : slots;
+  mrf_fused_kernel<C, ACT, EW, NCTA><<<grid, Cfg::THREADS, Cfg::SMEM, stream>>>(p);
   FV_CHECK_LAUNCH("mrf_fused_kernel");
   return 0;
 }
@@ -458,7 +526,7 @@ extern "C" int fv_mrf_fused(const fv_mrf_desc* d, void* stream) {
   FV_REQUIRE(d->C == 32 || d->C == 64, FV_E_UNSUPPORTED, "fv_mrf_fused: C must be 32 or 64 (got %d)", d->C);
   FV_REQUIRE(d->n_blocks >= 1 && d->n_blocks <= FV_MRF_MAX_BLOCKS && d->n_pairs >= 1 && d->n_pairs <= FV_MRF_MAX_PAIRS,
              FV_E_BADARG, "fv_mrf_fused: n_blocks=%d n_pairs=%d out of range", d->n_blocks, d->n_pairs);
-  FV_REQUIRE(d->act == FV_ACT_SILU || d->act == FV_ACT_LEAKY, FV_E_UNSUPPORTED,
+  FV_REQUIRE(d->act == FV_ACT_SILU || d->act == FV_ACT_LEAKY || d->act == FV_ACT_SILU_TANH, FV_E_UNSUPPORTED,
              "fv_mrf_fused: inner activation must be SiLU or leaky ReLU");
   FV_REQUIRE(d->out_act >= FV_ACT_NONE && d->out_act <= FV_ACT_TANH, FV_E_BADARG, "fv_mrf_fused: bad out_act");
   FV_REQUIRE(d->x_pitch >= d->C && d->x_pitch % 4 == 0 && d->out32_pitch >= d->C && d->out32_pitch % 4 == 0 &&
@@ -509,6 +577,20 @@ extern "C" int fv_mrf_fused(const fv_mrf_desc* d, void* stream) {
   p.out_act_param = d->out_act_param;
   p.has_o16 = d->out16 != nullptr;
   p.out_scale = 1.0f / (float)d->n_blocks;
-  if (d->C == 64) return launch_mrf<64>(d, p, (cudaStream_t)stream);
-  return launch_mrf<32>(d, p, (cudaStream_t)stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  // C = 64: the residual stream + conv1 accumulator of a 512-row tile fill TMEM -> one CTA per SM, 16 epilogue warps;
+  // C = 32: two co-resident CTAs with 8 epilogue warps each (MMA of one overlaps the epilogue of the other)
+  if (d->C == 64) {
+    if (d->act == FV_ACT_SILU) return launch_mrf<64, kActSilu, 16, 1>(d, p, st);
+    if (d->act == FV_ACT_SILU_TANH) return launch_mrf<64, kActSiluTanh, 16, 1>(d, p, st);
+    return launch_mrf<64, kActLeaky, 16, 1>(d, p, st);
+  }
+  if (g_mrf_c32_ctas == 1) {
+    if (d->act == FV_ACT_SILU) return launch_mrf<32, kActSilu, 16, 1>(d, p, st);
+    if (d->act == FV_ACT_SILU_TANH) return launch_mrf<32, kActSiluTanh, 16, 1>(d, p, st);
+    return launch_mrf<32, kActLeaky, 16, 1>(d, p, st);
+  }
+  if (d->act == FV_ACT_SILU) return launch_mrf<32, kActSilu, 8, 2>(d, p, st);
+  if (d->act == FV_ACT_SILU_TANH) return launch_mrf<32, kActSiluTanh, 8, 2>(d, p, st);
+  return launch_mrf<32, kActLeaky, 8, 2>(d, p, st);
 }

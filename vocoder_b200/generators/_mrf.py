@@ -212,7 +212,8 @@ class MRFGeneratorBase(nn.Module):
                 h_next = ws.f16(f"h_{i}", B, Lo, C, dev)
                 out_act, out_act_p = self._stage_out_act(last_stage)
                 cabi.mrf_fused(x0, fused, acc, out16=h_next if out_act is not None else None,
-                               act=cabi.ACT_SILU, out_act=out_act or cabi.ACT_NONE, out_act_param=out_act_p)
+                               act=cabi.ACT_SILU_TANH if self.mrf_silu_tanh else cabi.ACT_SILU,
+                               out_act=out_act or cabi.ACT_NONE, out_act_param=out_act_p)
                 if last_stage:
                     self._final_activation(acc, h_next, C)
                 h16, L = h_next, Lo
@@ -274,6 +275,9 @@ class MRFGeneratorBase(nn.Module):
 
     #: C <= 64 SiLU stages as one on-chip kernel per stage (fv_mrf_fused); False = layer-wise fv_conv1d launches
     fuse_mrf = True
+    #: opt-in: SiLU inside the fused stages as x/2 + x/2 tanh(x/2) with tanh.approx (one SFU op instead of two;
+    #: |error| <= 2.4e-4 |x| before the fp16 rounding of the operand, see FV_ACT_SILU_TANH)
+    mrf_silu_tanh = False
 
     #: utterances per residual-block pass; None = whole batch; 0 = size the block working set for L2 (_micro_batch)
     micro_batch = None
