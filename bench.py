@@ -273,7 +273,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-fuse-mrf", action="store_true", help="layer-wise fv_conv1d launches instead of fv_mrf_fused")
-    ap.add_argument("--mrf-silu-tanh", action="store_true", help="opt-in tanh.approx SiLU inside fv_mrf_fused")
+    ap.add_argument("--tc-tuning", default="", help="block_n,m_sub,epilogue,mainloop overrides for fv_conv1d (0 = auto)")
+    ap.add_argument("--mrf-silu-exact", action="store_true", help="ex2+rcp SiLU inside fv_mrf_fused instead of tanh.approx")
     ap.add_argument("--cpu-sample", type=int, default=0, help="utterances in the CPU baseline sample (0 = auto)")
     ap.add_argument("--dump-launches", default=None, help="write the per-launch conv timing table (json) here")
     ap.add_argument("--micro-batch", type=int, default=0,
@@ -330,6 +331,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     from vocoder_b200 import cabi
 
+    if args.tc_tuning:
+        cabi.set_tc_tuning(*[int(v) for v in args.tc_tuning.split(",")])
     model = build_model(kind).eval().to(dev)
     for m in model.modules():
         if hasattr(m, "use_cuda_graph"):
@@ -338,8 +341,8 @@ def main():
             m.micro_batch = args.micro_batch
         if args.no_fuse_mrf and hasattr(m, "fuse_mrf"):
             m.fuse_mrf = False
-        if args.mrf_silu_tanh and hasattr(m, "mrf_silu_tanh"):
-            m.mrf_silu_tanh = True
+        if args.mrf_silu_exact and hasattr(m, "mrf_silu_tanh"):
+            m.mrf_silu_tanh = False
     mel_host = synthetic_mel(B, n_mels, T, 1234 + rank).pin_memory()
     mel = mel_host.to(dev)
     wav_host = torch.empty(B, 1, T * hop).pin_memory()
@@ -423,7 +426,7 @@ def main():
                         f"working set {sum(m._ws.nbytes() for m in model.modules() if hasattr(m, '_ws')) / 1e9:.2f} GB > 126 MB L2")
         config["cuda_graph"] = not args.no_graph
         config["fuse_mrf"] = not args.no_fuse_mrf
-        config["mrf_silu"] = "tanh.approx" if args.mrf_silu_tanh else "ex2+rcp"
+        config["mrf_silu"] = "ex2+rcp" if args.mrf_silu_exact else "tanh.approx"
         config["micro_batch"] = args.micro_batch if args.micro_batch > 0 else "whole batch"
         line = {"metric": "audio samples/sec, mel->wav generator forward", "value": value, "unit": "samples/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,

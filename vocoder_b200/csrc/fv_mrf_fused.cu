@@ -112,9 +112,13 @@ __device__ __forceinline__ float fr_act(float v, float param) {
   }
 }
 
-template <int C, int ACT, int EW, int NCTA>
+// PIPE = true (needs EW = C / 4): every conv is issued as two half-tile passes (128-row blocks {0,1}, then {2,3}; the tap
+// tiles are streamed twice) with their own "accumulator complete" barriers, so the epilogue of the first half runs
+// under the MMAs of the second, and the next conv's first half starts as soon as blocks 0-2 of its operand exist.
+template <int C, int ACT, int EW, int NCTA, bool PIPE>
 __global__ void __launch_bounds__(FrCfg<C, EW, NCTA>::THREADS, NCTA) mrf_fused_kernel(const __grid_constant__ MrfParams p) {
   using Cfg = FrCfg<C, EW, NCTA>;
+  static_assert(!PIPE || EW * 4 == C, "the half-tile pipeline maps one 32x32 / 32x16 accumulator patch to each warp");
   constexpr int ROWB = Cfg::ROWB;
   constexpr int NCH = C / 32;  // 32-column chunks per row
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -125,9 +129,10 @@ __global__ void __launch_bounds__(FrCfg<C, EW, NCTA>::THREADS, NCTA) mrf_fused_k
   uint8_t* tail = smem + Cfg::RING_OFF + Cfg::NS * Cfg::W_TILE;
   uint64_t* w_full = reinterpret_cast<uint64_t*>(tail);
   uint64_t* w_empty = w_full + Cfg::NS;
-  uint64_t* a_ready = w_empty + Cfg::NS;   // epilogue warps -> MMA: operand of the next conv is in smem / X is in TMEM
-  uint64_t* acc_full = a_ready + 1;        // MMA -> epilogue: accumulators of the current conv are complete
-  uint64_t* stg_bar = acc_full + 1;        // one per epilogue warp: TMA loads into its staging patch
+  uint64_t* a_ready = w_empty + Cfg::NS;   // [2] epilogue warps -> MMA: operand of the next conv is in smem / X is in TMEM
+  uint64_t* acc_full = a_ready + 2;        // [2] MMA -> epilogue: accumulators of the current conv are complete
+  uint64_t* stg_bar = acc_full + 2;        // one per epilogue warp: TMA loads into its staging patch
+  // (PIPE: index = tile half; a_ready[0] also covers 128-row block 2, whose first rows the first half's taps reach)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stg_bar + EW);
   float* s_bias = reinterpret_cast<float*>(tail + 1024);  // [block][pair][2][C]: b1, cumulative b2
 
@@ -143,8 +148,10 @@ __global__ void __launch_bounds__(FrCfg<C, EW, NCTA>::THREADS, NCTA) mrf_fused_k
       mbar_init(&w_full[i], 1);
       mbar_init(&w_empty[i], 1);
     }
-    mbar_init(a_ready, EW);
-    mbar_init(acc_full, 1);
+    mbar_init(&a_ready[0], EW);
+    mbar_init(&a_ready[1], EW);
+    mbar_init(&acc_full[0], 1);
+    mbar_init(&acc_full[1], 1);
     for (int i = 0; i < EW; ++i) mbar_init(&stg_bar[i], 1);
     fence_barrier_init();
   } else if (warp == 1) {
@@ -184,14 +191,15 @@ __global__ void __launch_bounds__(FrCfg<C, EW, NCTA>::THREADS, NCTA) mrf_fused_k
         for (int pi = 0; pi < p.n_pairs; ++pi)
           for (int cv = 0; cv < 2; ++cv) {
             const int row0 = p.w_row0[j][pi][cv];
-            for (int tap = 0; tap < p.ksize[j]; ++tap, ++it) {
-              const int s = it % Cfg::NS;
-              mbar_wait(&w_empty[s], ((it / Cfg::NS) & 1) ^ 1);
-              if (leader) {
-                mbar_arrive_expect_tx(&w_full[s], Cfg::W_TILE);
-                tma_load_2d(smem + Cfg::RING_OFF + s * Cfg::W_TILE, &p.tmW, &w_full[s], 0, row0 + tap * C);
+            for (int h = 0; h < (PIPE ? 2 : 1); ++h)
+              for (int tap = 0; tap < p.ksize[j]; ++tap, ++it) {
+                const int s = it % Cfg::NS;
+                mbar_wait(&w_empty[s], ((it / Cfg::NS) & 1) ^ 1);
+                if (leader) {
+                  mbar_arrive_expect_tx(&w_full[s], Cfg::W_TILE);
+                  tma_load_2d(smem + Cfg::RING_OFF + s * Cfg::W_TILE, &p.tmW, &w_full[s], 0, row0 + tap * C);
+                }
               }
-            }
           }
     }
   } else if (warp == 1) {
@@ -204,31 +212,34 @@ __global__ void __launch_bounds__(FrCfg<C, EW, NCTA>::THREADS, NCTA) mrf_fused_k
         const int k = p.ksize[j], half_k = (k - 1) / 2;
         for (int pi = 0; pi < p.n_pairs; ++pi)
           for (int cv = 0; cv < 2; ++cv, ++n) {
-            mbar_wait(a_ready, n & 1);
-            tc_fence_after();
             const uint32_t slab = smem_u32(smem + (cv == 0 ? Cfg::XA_OFF : Cfg::TA_OFF)) + kFrGuard * ROWB;
             const uint32_t d_col = tmem_base + (cv == 0 ? T_COL : X_COL);
             const int dil = p.dil[j][pi][cv];
-            for (int tap = 0; tap < k; ++tap, ++it) {
-              const int s = it % Cfg::NS;
-              mbar_wait(&w_full[s], (it / Cfg::NS) & 1);
+            constexpr int MB = PIPE ? kFrMBlocks / 2 : kFrMBlocks;  // 128-row blocks per pass
+            for (int h = 0; h < (PIPE ? 2 : 1); ++h) {
+              mbar_wait(&a_ready[h], n & 1);
               tc_fence_after();
-              if (leader) {
-                const uint64_t da0 = make_kmajor_desc(slab + (tap - half_k) * dil * ROWB, ROWB);
-                const uint64_t db0 = make_kmajor_desc(smem_u32(smem + Cfg::RING_OFF + s * Cfg::W_TILE), ROWB);
+              for (int tap = 0; tap < k; ++tap, ++it) {
+                const int s = it % Cfg::NS;
+                mbar_wait(&w_full[s], (it / Cfg::NS) & 1);
+                tc_fence_after();
+                if (leader) {
+                  const uint64_t da0 = make_kmajor_desc(slab + ((tap - half_k) * dil + h * MB * 128) * ROWB, ROWB);
+                  const uint64_t db0 = make_kmajor_desc(smem_u32(smem + Cfg::RING_OFF + s * Cfg::W_TILE), ROWB);
 #pragma unroll
-                for (int m = 0; m < kFrMBlocks; ++m) {
+                  for (int m = 0; m < MB; ++m) {
 #pragma unroll
-                  for (int kk = 0; kk < C / 16; ++kk)
-                    umma_f16_ss(d_col + m * C, desc_advance(da0, m * 128 * ROWB + kk * 32), desc_advance(db0, kk * 32),
-                                idesc, (cv == 1 || tap > 0 || kk > 0) ? 1u : 0u);
+                    for (int kk = 0; kk < C / 16; ++kk)
+                      umma_f16_ss(d_col + (h * MB + m) * C, desc_advance(da0, m * 128 * ROWB + kk * 32),
+                                  desc_advance(db0, kk * 32), idesc, (cv == 1 || tap > 0 || kk > 0) ? 1u : 0u);
+                  }
+                  umma_commit(&w_empty[s]);
                 }
-                umma_commit(&w_empty[s]);
+                __syncwarp();
               }
+              if (leader) umma_commit(&acc_full[h]);
               __syncwarp();
             }
-            if (leader) umma_commit(acc_full);
-            __syncwarp();
           }
       }
     }
@@ -274,170 +285,222 @@ __global__ void __launch_bounds__(FrCfg<C, EW, NCTA>::THREADS, NCTA) mrf_fused_k
         v[4 * qq + 3] = __uint_as_float(r[4 * qq + 3]) + bb.w;
       }
     };
-    auto publish = [&]() {  // operand rows / TMEM stores of this warp are done -> MMA warp
+    // one 32-row x 32-column accumulator patch (128-row block m, column chunk cc): + bias -> activation -> operand slab
+    auto acc_item32 = [&](uint32_t col, int m, int cc, const float* bias, uint32_t slab_base, int g0) {
+      const int row_l = m * 128 + q * 32 + lane;
+      const int gr = g0 + row_l;
+      const bool in_seq = gr >= 0 && gr < p.L;
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(t_lane + col + m * C + cc * 32, r);
+      tmem_ld_wait();
+      float v[32];
+      add_bias(v, r, bias + cc * 32);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = in_seq ? fr_act<ACT>(v[i], p.act_param) : 0.f;
+      put_operand(slab_base, kFrGuard + row_l, cc, v);
+    };
+    // the same for a 32-row x 16-column patch (column group c16): the half-tile pipeline's unit for blocks 2 and 3
+    auto acc_item16 = [&](uint32_t col, int m, int c16, const float* bias, uint32_t slab_base, int g0) {
+      const int row_l = m * 128 + q * 32 + lane;
+      const int gr = g0 + row_l;
+      const bool in_seq = gr >= 0 && gr < p.L;
+      uint32_t r[32];
+      tmem_ld_32x32b_x16(t_lane + col + m * C + c16 * 16, r);
+      tmem_ld_wait();
+      const float4* b4 = reinterpret_cast<const float4*>(bias + c16 * 16);
+      float v[16];
+#pragma unroll
+      for (int qq = 0; qq < 4; ++qq) {
+        const float4 bb = b4[qq];
+        v[4 * qq] = __uint_as_float(r[4 * qq]) + bb.x;
+        v[4 * qq + 1] = __uint_as_float(r[4 * qq + 1]) + bb.y;
+        v[4 * qq + 2] = __uint_as_float(r[4 * qq + 2]) + bb.z;
+        v[4 * qq + 3] = __uint_as_float(r[4 * qq + 3]) + bb.w;
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = in_seq ? fr_act<ACT>(v[i], p.act_param) : 0.f;
+#pragma unroll
+      for (int qq = 0; qq < 2; ++qq) {
+        const uint32_t w0 = pack_half2_sat(v[8 * qq + 0], v[8 * qq + 1]);
+        const uint32_t w1 = pack_half2_sat(v[8 * qq + 2], v[8 * qq + 3]);
+        const uint32_t w2 = pack_half2_sat(v[8 * qq + 4], v[8 * qq + 5]);
+        const uint32_t w3 = pack_half2_sat(v[8 * qq + 6], v[8 * qq + 7]);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(
+                         slab_base + swz_off<ROWB>(kFrGuard + row_l, c16 * 2 + qq)),
+                     "r"(w0), "r"(w1), "r"(w2), "r"(w3)
+                     : "memory");
+      }
+    };
+    // tile entry of one patch: x -> X (TMEM, fp32) and act(x) -> XA (fp16); rows outside the sequence arrive as zeros
+    auto entry_item = [&](int m, int cc, int b, int g0) {
+      const int blk0 = m * 128 + q * 32;  // first tile row of this warp's 32-row group
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_wait_read();
+        mbar_arrive_expect_tx(my_bar, 4096);
+        tma_load_3d(patch32, &p.tmX, my_bar, cc * 32, g0 + blk0, b);
+      }
+      __syncwarp();
+      mbar_wait(my_bar, stg_phase);
+      stg_phase ^= 1;
+      uint32_t r[32];
+#pragma unroll
+      for (int qq = 0; qq < 8; ++qq)
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(r[4 * qq]), "=r"(r[4 * qq + 1]), "=r"(r[4 * qq + 2]), "=r"(r[4 * qq + 3])
+                     : "r"(p32_row + ((static_cast<uint32_t>(qq) ^ r_xor) << 4)));
+      tmem_st_32x32b_x32(t_lane + X_COL + m * C + cc * 32, r);
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = fr_act<ACT>(__uint_as_float(r[i]), p.act_param);
+      put_operand(xa_base, kFrGuard + blk0 + lane, cc, v);
+    };
+    // tile exit of one patch: block output -> running mean in out32 (-> activated fp16 after the last block)
+    auto exit_item = [&](int m, int cc, int b, int g0, int j, const float* b2c) {
+      const bool last = j == p.n_blocks - 1;
+      const int blk0 = m * 128 + q * 32;
+      const int grow = g0 + blk0;
+      if (!(blk0 >= p.h0 && blk0 < p.h0 + p.V && grow < p.L)) return;  // halo rows / past the sequence
+      __syncwarp();
+      if (lane == 0) {
+        if (j > 0) {
+          tma_store_wait_all();  // the partial sums this warp stored for block j-1 are visible
+          mbar_arrive_expect_tx(my_bar, 4096);
+          tma_load_3d(patch32, &p.tmO32, my_bar, cc * 32, grow, b);
+        } else {
+          tma_store_wait_read();
+        }
+      }
+      __syncwarp();
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(t_lane + X_COL + m * C + cc * 32, r);
+      tmem_ld_wait();
+      float v[32];
+      add_bias(v, r, b2c + cc * 32);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] *= p.out_scale;
+      if (j > 0) {
+        mbar_wait(my_bar, stg_phase);
+        stg_phase ^= 1;
+#pragma unroll
+        for (int qq = 0; qq < 8; ++qq) {
+          float4 a;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w)
+                       : "r"(p32_row + ((static_cast<uint32_t>(qq) ^ r_xor) << 4)));
+          v[4 * qq] += a.x;
+          v[4 * qq + 1] += a.y;
+          v[4 * qq + 2] += a.z;
+          v[4 * qq + 3] += a.w;
+        }
+      }
+#pragma unroll
+      for (int qq = 0; qq < 8; ++qq)
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(p32_row +
+                                                                      ((static_cast<uint32_t>(qq) ^ r_xor) << 4)),
+                     "f"(v[4 * qq]), "f"(v[4 * qq + 1]), "f"(v[4 * qq + 2]), "f"(v[4 * qq + 3])
+                     : "memory");
+      if (last && p.has_o16) {
+        if (p.out_act == FV_ACT_SILU) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fr_act<kActSilu>(v[i], 0.f);
+        } else if (p.out_act == FV_ACT_LEAKY) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fr_act<kActLeaky>(v[i], p.out_act_param);
+        } else if (p.out_act == FV_ACT_TANH) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = tanhf(v[i]);
+        } else if (p.out_act == FV_ACT_GELU) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = gelu_erf_fast(v[i]);
+        }
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) {
+          uint32_t w[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) w[u] = pack_half2_sat(v[8 * qq + 2 * u], v[8 * qq + 2 * u + 1]);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p16_row +
+                                                                        ((static_cast<uint32_t>(qq) ^ h_xor) << 4)),
+                       "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
+                       : "memory");
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_3d(&p.tmO32, patch32, cc * 32, grow, b);
+        if (last && p.has_o16) tma_store_3d(&p.tmO16, patch16, cc * 32, grow, b);
+        tma_store_commit();
+      }
+    };
+    auto publish = [&](uint64_t* bar) {  // operand rows / TMEM stores of this warp are done -> MMA warp
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(a_ready);
+      if (lane == 0) mbar_arrive(bar);
     };
-    // accumulator (TMEM column base `col`) + bias -> activation -> operand slab, for every row this thread owns
-    auto acc_to_operand = [&](uint32_t col, const float* bias, uint32_t slab_base, int g0) {
-#pragma unroll 1
-      for (int rr = 0; rr < Cfg::RR; ++rr) {
-        const int m = g + rr * Cfg::GROUPS;
-        const int row_l = m * 128 + q * 32 + lane;
-        const int gr = g0 + row_l;
-        const bool in_seq = gr >= 0 && gr < p.L;
-#pragma unroll 1
-        for (int cc = 0; cc < NCH; ++cc) {
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(t_lane + col + m * C + cc * 32, r);
-          tmem_ld_wait();
-          float v[32];
-          add_bias(v, r, bias + cc * 32);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = in_seq ? fr_act<ACT>(v[i], p.act_param) : 0.f;
-          put_operand(slab_base, kFrGuard + row_l, cc, v);
-        }
-      }
-    };
+    // PIPE: this warp's patch inside a tile half (blocks {0,1} / {2,3}) and its 16-column group inside one block
+    const int pm = g / NCH, pcc = g % NCH;
 
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int b = tile / p.tiles_per_b;
       const int g0 = (tile % p.tiles_per_b) * p.V - p.h0;  // global row of tile row 0
       for (int j = 0; j < p.n_blocks; ++j) {
-        // ---- tile entry: x -> X (TMEM, fp32) and act(x) -> XA (fp16); rows outside the sequence arrive as zeros
+        if constexpr (PIPE) {
+          entry_item(pm, pcc, b, g0);
+          entry_item(pm + 2, pcc, b, g0);
+        } else {
 #pragma unroll 1
-        for (int rr = 0; rr < Cfg::RR; ++rr) {
-          const int m = g + rr * Cfg::GROUPS;
-          const int blk0 = m * 128 + q * 32;  // first tile row of this warp's 32-row group
+          for (int rr = 0; rr < Cfg::RR; ++rr)
 #pragma unroll 1
-          for (int cc = 0; cc < NCH; ++cc) {
-            __syncwarp();
-            if (lane == 0) {
-              tma_store_wait_read();
-              mbar_arrive_expect_tx(my_bar, 4096);
-              tma_load_3d(patch32, &p.tmX, my_bar, cc * 32, g0 + blk0, b);
-            }
-            __syncwarp();
-            mbar_wait(my_bar, stg_phase);
-            stg_phase ^= 1;
-            uint32_t r[32];
-#pragma unroll
-            for (int qq = 0; qq < 8; ++qq)
-              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                           : "=r"(r[4 * qq]), "=r"(r[4 * qq + 1]), "=r"(r[4 * qq + 2]), "=r"(r[4 * qq + 3])
-                           : "r"(p32_row + ((static_cast<uint32_t>(qq) ^ r_xor) << 4)));
-            tmem_st_32x32b_x32(t_lane + X_COL + m * C + cc * 32, r);
-            float v[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fr_act<ACT>(__uint_as_float(r[i]), p.act_param);
-            put_operand(xa_base, kFrGuard + blk0 + lane, cc, v);
-          }
+            for (int cc = 0; cc < NCH; ++cc) entry_item(g + rr * Cfg::GROUPS, cc, b, g0);
         }
         tmem_st_wait();
-        publish();
+        publish(&a_ready[0]);
+        if constexpr (PIPE) publish(&a_ready[1]);
         for (int pi = 0; pi < p.n_pairs; ++pi) {
           const float* b1 = s_bias + ((j * p.n_pairs + pi) * 2) * C;
           const float* b2c = b1 + C;
-          // ---- conv1 done: T + b1 -> act -> TA
-          mbar_wait(acc_full, n & 1);
-          ++n;
-          tc_fence_after();
-          acc_to_operand(T_COL, b1, ta_base, g0);
-          publish();
-          // ---- conv2 done: X (+ cumulative b2) is the residual stream after this pair
-          mbar_wait(acc_full, n & 1);
-          ++n;
-          tc_fence_after();
-          if (pi + 1 < p.n_pairs) {
-            acc_to_operand(X_COL, b2c, xa_base, g0);
-            publish();
-          } else {
-            // ---- tile exit: block output -> running mean in out32 (-> activated fp16 after the last block)
-            const bool last = j == p.n_blocks - 1;
 #pragma unroll 1
-            for (int rr = 0; rr < Cfg::RR; ++rr) {
-              const int m = g + rr * Cfg::GROUPS;
-              const int blk0 = m * 128 + q * 32;
-              const int grow = g0 + blk0;
-              if (!(blk0 >= p.h0 && blk0 < p.h0 + p.V && grow < p.L)) continue;  // halo rows / past the sequence
+          for (int cv = 0; cv < 2; ++cv, ++n) {
+            // cv = 0: conv1 done, T + b1 -> act -> TA;  cv = 1: conv2 done, X (+ cumulative b2) -> act -> XA, or exit
+            const uint32_t col = cv == 0 ? T_COL : X_COL;
+            const float* bias = cv == 0 ? b1 : b2c;
+            const uint32_t dst = cv == 0 ? ta_base : xa_base;
+            const bool is_exit = cv == 1 && pi + 1 == p.n_pairs;
+            mbar_wait(&acc_full[0], n & 1);
+            tc_fence_after();
+            if constexpr (PIPE) {
+              if (!is_exit) {
+                acc_item32(col, pm, pcc, bias, dst, g0);       // first half under the MMAs of the second
+                mbar_wait(&acc_full[1], n & 1);
+                tc_fence_after();
+                acc_item16(col, 2, g, bias, dst, g0);
+                publish(&a_ready[0]);                          // blocks 0-2 written: next conv's first half may go
+                acc_item16(col, 3, g, bias, dst, g0);
+                publish(&a_ready[1]);
+              } else {
+                // the staging patches alias the slabs the second half's MMAs still read: exit after both halves
+                mbar_wait(&acc_full[1], n & 1);
+                tc_fence_after();
+                exit_item(pm, pcc, b, g0, j, b2c);
+                exit_item(pm + 2, pcc, b, g0, j, b2c);
+              }
+            } else {
+              if (!is_exit) {
 #pragma unroll 1
-              for (int cc = 0; cc < NCH; ++cc) {
-                __syncwarp();
-                if (lane == 0) {
-                  if (j > 0) {
-                    tma_store_wait_all();  // the partial sums this warp stored for block j-1 are visible
-                    mbar_arrive_expect_tx(my_bar, 4096);
-                    tma_load_3d(patch32, &p.tmO32, my_bar, cc * 32, grow, b);
-                  } else {
-                    tma_store_wait_read();
-                  }
-                }
-                __syncwarp();
-                uint32_t r[32];
-                tmem_ld_32x32b_x32(t_lane + X_COL + m * C + cc * 32, r);
-                tmem_ld_wait();
-                float v[32];
-                add_bias(v, r, b2c + cc * 32);
-#pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] *= p.out_scale;
-                if (j > 0) {
-                  mbar_wait(my_bar, stg_phase);
-                  stg_phase ^= 1;
-#pragma unroll
-                  for (int qq = 0; qq < 8; ++qq) {
-                    float4 a;
-                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w)
-                                 : "r"(p32_row + ((static_cast<uint32_t>(qq) ^ r_xor) << 4)));
-                    v[4 * qq] += a.x;
-                    v[4 * qq + 1] += a.y;
-                    v[4 * qq + 2] += a.z;
-                    v[4 * qq + 3] += a.w;
-                  }
-                }
-#pragma unroll
-                for (int qq = 0; qq < 8; ++qq)
-                  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(
-                                   p32_row + ((static_cast<uint32_t>(qq) ^ r_xor) << 4)),
-                               "f"(v[4 * qq]), "f"(v[4 * qq + 1]), "f"(v[4 * qq + 2]), "f"(v[4 * qq + 3])
-                               : "memory");
-                if (last && p.has_o16) {
-                  if (p.out_act == FV_ACT_SILU) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = fr_act<kActSilu>(v[i], 0.f);
-                  } else if (p.out_act == FV_ACT_LEAKY) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = fr_act<kActLeaky>(v[i], p.out_act_param);
-                  } else if (p.out_act == FV_ACT_TANH) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = tanhf(v[i]);
-                  } else if (p.out_act == FV_ACT_GELU) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = gelu_erf_fast(v[i]);
-                  }
-#pragma unroll
-                  for (int qq = 0; qq < 4; ++qq) {
-                    uint32_t w[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) w[u] = pack_half2_sat(v[8 * qq + 2 * u], v[8 * qq + 2 * u + 1]);
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(
-                                     p16_row + ((static_cast<uint32_t>(qq) ^ h_xor) << 4)),
-                                 "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
-                                 : "memory");
-                  }
-                }
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) {
-                  tma_store_3d(&p.tmO32, patch32, cc * 32, grow, b);
-                  if (last && p.has_o16) tma_store_3d(&p.tmO16, patch16, cc * 32, grow, b);
-                  tma_store_commit();
-                }
+                for (int rr = 0; rr < Cfg::RR; ++rr)
+#pragma unroll 1
+                  for (int cc = 0; cc < NCH; ++cc) acc_item32(col, g + rr * Cfg::GROUPS, cc, bias, dst, g0);
+                publish(&a_ready[0]);
+              } else {
+#pragma unroll 1
+                for (int rr = 0; rr < Cfg::RR; ++rr)
+#pragma unroll 1
+                  for (int cc = 0; cc < NCH; ++cc) exit_item(g + rr * Cfg::GROUPS, cc, b, g0, j, b2c);
               }
             }
-            if (Cfg::ALIAS && last && p.has_o16) {
+            if (is_exit && Cfg::ALIAS && j == p.n_blocks - 1 && p.has_o16) {
               // the fp16 exit patches alias XA: nobody may start the next tile's entry before every store has read them
               if (lane == 0) tma_store_wait_read();
               __syncwarp();
@@ -481,7 +544,17 @@ static const int g_mrf_c32_ctas = [] {
   return (e && e[0] == '1') ? 1 : 2;
 }();
 
-template <int C, int ACT, int EW, int NCTA>
+// FV_MRF_PIPE=1 selects the half-tile pipelined schedule.  Measured on B200 (HiFiGAN cfg B stages): it helps the
+// ex2+rcp SiLU by 5% (C=64: 1.79 -> 1.71 ms) and costs 2% with the tanh SiLU (1.54 -> 1.57 ms): the MMA phase of an
+// N <= 64 tile is bound by the shared-memory reads of the A operand (4 KB + 32 N bytes per 128xNx16 UMMA against 128 B/clk),
+// so the concurrent epilogue competes for the same port and every conv pays two barrier round trips instead of one.
+// Default: serial schedule.
+static const bool g_mrf_pipe = [] {
+  const char* e = getenv("FV_MRF_PIPE");
+  return e && e[0] == '1';
+}();
+
+template <int C, int ACT, int EW, int NCTA, bool PIPE>
 static int launch_mrf(const fv_mrf_desc* d, MrfParams& p, cudaStream_t stream) {
   using Cfg = FrCfg<C, EW, NCTA>;
   EncodeTiledFn enc = get_encode_fn();
@@ -504,13 +577,13 @@ static int launch_mrf(const fv_mrf_desc* d, MrfParams& p, cudaStream_t stream) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(mrf_fused_kernel<C, ACT, EW, NCTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    attr_err = cudaFuncSetAttribute(mrf_fused_kernel<C, ACT, EW, NCTA, PIPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
   });
   rc = check_cuda(attr_err, "cudaFuncSetAttribute(mrf_fused_kernel)");
   if (rc) return rc;
   const int slots = num_sms() * NCTA;
   const int grid = p.total_tiles < slots ? p.total_tiles : slots;
-  mrf_fused_kernel<C, ACT, EW, NCTA><<<grid, Cfg::THREADS, Cfg::SMEM, stream>>>(p);
+  mrf_fused_kernel<C, ACT, EW, NCTA, PIPE><<<grid, Cfg::THREADS, Cfg::SMEM, stream>>>(p);
   FV_CHECK_LAUNCH("mrf_fused_kernel");
   return 0;
 }
@@ -580,17 +653,18 @@ extern "C" int fv_mrf_fused(const fv_mrf_desc* d, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   // C = 64: the residual stream + conv1 accumulator of a 512-row tile fill TMEM -> one CTA per SM, 16 epilogue warps;
   // C = 32: two co-resident CTAs with 8 epilogue warps each (MMA of one overlaps the epilogue of the other)
+#define FV_MRF_DISPATCH(CC, EW, NCTA, PIPE)                                                          \
+  do {                                                                                                \
+    if (d->act == FV_ACT_SILU) return launch_mrf<CC, kActSilu, EW, NCTA, PIPE>(d, p, st);            \
+    if (d->act == FV_ACT_SILU_TANH) return launch_mrf<CC, kActSiluTanh, EW, NCTA, PIPE>(d, p, st);   \
+    return launch_mrf<CC, kActLeaky, EW, NCTA, PIPE>(d, p, st);                                      \
+  } while (0)
   if (d->C == 64) {
-    if (d->act == FV_ACT_SILU) return launch_mrf<64, kActSilu, 16, 1>(d, p, st);
-    if (d->act == FV_ACT_SILU_TANH) return launch_mrf<64, kActSiluTanh, 16, 1>(d, p, st);
-    return launch_mrf<64, kActLeaky, 16, 1>(d, p, st);
+    if (g_mrf_pipe) FV_MRF_DISPATCH(64, 16, 1, true);
+    FV_MRF_DISPATCH(64, 16, 1, false);
   }
-  if (g_mrf_c32_ctas == 1) {
-    if (d->act == FV_ACT_SILU) return launch_mrf<32, kActSilu, 16, 1>(d, p, st);
-    if (d->act == FV_ACT_SILU_TANH) return launch_mrf<32, kActSiluTanh, 16, 1>(d, p, st);
-    return launch_mrf<32, kActLeaky, 16, 1>(d, p, st);
-  }
-  if (d->act == FV_ACT_SILU) return launch_mrf<32, kActSilu, 8, 2>(d, p, st);
-  if (d->act == FV_ACT_SILU_TANH) return launch_mrf<32, kActSiluTanh, 8, 2>(d, p, st);
-  return launch_mrf<32, kActLeaky, 8, 2>(d, p, st);
+  if (g_mrf_c32_ctas == 1) FV_MRF_DISPATCH(32, 16, 1, false);
+  if (g_mrf_pipe) FV_MRF_DISPATCH(32, 8, 2, true);
+  FV_MRF_DISPATCH(32, 8, 2, false);
+#undef FV_MRF_DISPATCH
 }

@@ -217,17 +217,12 @@ struct SnakeFilt {
   float dn[12];
 };
 
-// sin with a two-constant Cody-Waite reduction to [-pi, pi] followed by the SFU sine: absolute error ~1e-6 for
-// |t| up to ~1e4 (the reduced argument is exact to ~1e-7), against ~30 instructions for sinf().
-__device__ __forceinline__ float fast_sin(float t) {
-  const float k = rintf(t * 0.15915494309189535f);
-  float r = fmaf(k, -6.2831854820251465f, t);      // 2pi hi (fp32)
-  r = fmaf(k, 1.7484556000744883e-07f, r);          // 2pi hi - 2pi
-  return __sinf(r);
-}
-
+// sin(t) on the SFU.  sin.approx = one multiply by 1/(2 pi) + MUFU.SIN, which reduces the argument itself: absolute
+// error ~2^-21 inside [-2 pi, 2 pi] and ~1.2e-7 |t| beyond (rounding of the product), i.e. <= 2.5e-5 for the
+// |alpha * u| <= 200 a Snake sees - two orders below the parity budget and below the fp16 rounding of the kernel's output.
+// (A Cody-Waite pre-reduction costs 4 more instructions per sine = 8 of the ~50 per sample; ncu: kernel is issue-bound.)
 __device__ __forceinline__ float snake_fn(float u, float a, float inv_b) {
-  const float s = fast_sin(u * a);
+  const float s = __sinf(u * a);
   return fmaf(inv_b * s, s, u);
 }
 
@@ -239,7 +234,7 @@ __device__ __forceinline__ float snake_fn(float u, float a, float inv_b) {
 // one 4-byte load, 24 FMA, 2 SFU sines and one 2-byte store per sample; six "pre-roll" steps fill the rings.
 // EDGE = false is the interior fast path (no index clamps, no replicate logic, pointer increments only): ncu showed
 // the kernel issue-bound with a third of its instructions being integer/predicate work of the edge handling.
-template <bool EDGE>
+template <bool EDGE, bool SPLIT>
 __device__ __forceinline__ void snake_segment(const float* __restrict__ xc, __half* __restrict__ orow,
                                               const SnakeFilt& f, float a, float inv_b, int t0, int t_end, int L,
                                               int pitch, int opitch, int split) {
@@ -251,13 +246,26 @@ __device__ __forceinline__ void snake_segment(const float* __restrict__ xc, __ha
   float X[6];   // ring: x~[t+6-q] lives in X[(k - q) mod 6] at unrolled position k
   float V[12];  // ring: v~[2t-5+j] lives in V[(2k + j) mod 12]
   float vlast = 0.f;
-  // window before the first pre-roll step (t = t0 - 6): x~[t+1 .. t+5] = x~[t0-5 .. t0-1] in X[1..5]
+  // every load of the pre-roll is issued before the first use (11 independent requests in flight per thread):
+  // window before the first pre-roll step (t = t0 - 6): x~[t+1 .. t+5] = x~[t0-5 .. t0-1] in X[1..5], then x~[t0 .. t0+5]
+  float xp[6];
 #pragma unroll
   for (int i = 1; i < 6; ++i) X[i] = ldx(t0 - 6 + i);
 #pragma unroll
+  for (int k = 0; k < 6; ++k) xp[k] = ldx(t0 + k);
+  // ... and so is the first main-loop window x~[t0+6 .. t0+11] (software pipeline: window i+1 loads under the math of i)
+  float xn[6];
+  const float* px = xc + (size_t)(t0 + 6) * pitch;  // interior path: running pointers instead of index math
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    if (EDGE) xn[k] = ldx(t0 + k + 6);
+    else xn[k] = px[(size_t)k * pitch];
+  }
+  px += (size_t)6 * pitch;
+#pragma unroll
   for (int k = 0; k < 6; ++k) {  // pre-roll: t = t0 - 6 + k produces v[2t0-5+2k], v[2t0-4+2k]
     const int t = t0 - 6 + k;
-    X[k] = ldx(t + 6);
+    X[k] = xp[k];
     float uo = 0.f, ue = 0.f;
 #pragma unroll
     for (int q = 0; q < 6; ++q) {
@@ -277,24 +285,27 @@ __device__ __forceinline__ void snake_segment(const float* __restrict__ xc, __ha
 #pragma unroll
     for (int j = 0; j < 5; ++j) V[j] = V[5];
   }
-  const float* px = xc + (size_t)(t0 + 6) * pitch;  // interior path: running pointers instead of index math
   __half* po = orow + (size_t)t0 * opitch;
   for (int tb = t0; tb < t_end; tb += 6) {
-    float xn[6];
+    float xw[6];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) {  // six independent loads in flight
-      if (EDGE) xn[k] = ldx(tb + k + 6);
-      else xn[k] = px[(size_t)k * pitch];
+    for (int k = 0; k < 6; ++k) xw[k] = xn[k];
+    if (tb + 6 < t_end) {  // next window: six independent loads in flight under this window's 200 instructions
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        if (EDGE) xn[k] = ldx(tb + k + 12);
+        else xn[k] = px[(size_t)k * pitch];
+      }
+      px += (size_t)6 * pitch;
     }
-    px += (size_t)6 * pitch;
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
       const int t = tb + k;
       float o = 0.f;
 #pragma unroll
       for (int j = 0; j < 12; ++j) o = fmaf(f.dn[j], V[(2 * k + j) % 12], o);
-      if (!EDGE || t < t_end) store_half_split(po + (size_t)k * opitch, o, split);
-      X[k] = xn[k];
+      if (!EDGE || t < t_end) store_half_split(po + (size_t)k * opitch, o, SPLIT ? split : 0);
+      X[k] = xw[k];
       float uo = 0.f, ue = 0.f;
 #pragma unroll
       for (int q = 0; q < 6; ++q) {
@@ -314,6 +325,7 @@ __device__ __forceinline__ void snake_segment(const float* __restrict__ xc, __ha
   }
 }
 
+template <bool SPLIT>
 __global__ void __launch_bounds__(256, 3) snake_aa_kernel(const float* __restrict__ x, __half* __restrict__ out,
                                                           const float* __restrict__ alpha,
                                                           const float* __restrict__ beta, const SnakeFilt f,
@@ -343,8 +355,8 @@ __global__ void __launch_bounds__(256, 3) snake_aa_kernel(const float* __restric
   const float* xc = x + ((size_t)b * L) * pitch + c;
   // interior segment: every x index in [t0-5, t0+SN_SEG+5] and every v index up to 2(t0+SN_SEG)+6 is in range
   const bool interior = (t0 >= 6) && (t0 + SN_SEG + 6 <= L - 1);
-  if (interior) snake_segment<false>(xc, orow, f, a, inv_b, t0, t_end, L, pitch, opitch, split);
-  else snake_segment<true>(xc, orow, f, a, inv_b, t0, t_end, L, pitch, opitch, split);
+  if (interior) snake_segment<false, SPLIT>(xc, orow, f, a, inv_b, t0, t_end, L, pitch, opitch, split);
+  else snake_segment<true, SPLIT>(xc, orow, f, a, inv_b, t0, t_end, L, pitch, opitch, split);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -671,8 +683,12 @@ extern "C" int fv_snake_aa(const float* x32, void* out16, const float* alpha, co
   }
   const int n_seg = ceil_div(L, SN_SEG);
   const long long total = (long long)B * n_seg * pitch;
-  snake_aa_kernel<<<grid1d(total, 256), 256, 0, (cudaStream_t)stream>>>(x32, (__half*)out16, alpha, beta, f, logscale,
-                                                                       B, L, C, pitch, n_seg, split);
+  if (split)  // strict precision: [hi | lo] fp16 pairs (the extra stores stay out of the default instantiation)
+    snake_aa_kernel<true><<<grid1d(total, 256), 256, 0, (cudaStream_t)stream>>>(x32, (__half*)out16, alpha, beta, f,
+                                                                               logscale, B, L, C, pitch, n_seg, split);
+  else
+    snake_aa_kernel<false><<<grid1d(total, 256), 256, 0, (cudaStream_t)stream>>>(x32, (__half*)out16, alpha, beta, f,
+                                                                                logscale, B, L, C, pitch, n_seg, split);
   FV_CHECK_LAUNCH("snake_aa_kernel");
   return 0;
 }
