@@ -313,6 +313,14 @@ def conv1d(a16: torch.Tensor, pc: PackedConv, L_out: Optional[int] = None, *, ga
     B, L_in, a_pitch = a16.shape
     if L_out is None:
         L_out = L_in
+    for name, t in (("residual", residual), ("out32", out32), ("out16", out16)):
+        if t is not None and (t.shape[0] != B or t.shape[1] != L_out):
+            raise FvError(f"{name} has shape {tuple(t.shape)}, expected [{B}, {L_out}, pitch]")
+    if (pc.n_phase == 1 and pc.n_taps == 1 and int(pc.tap_off[0]) == 0 and L_out == L_in and B > 1
+            and all(t is None or t.is_contiguous() for t in (a16, residual, out32, out16))):
+        # pointwise conv / linear layer: rows of different utterances never mix, so [B][L] is one GEMM M axis of B*L rows
+        # (tiles of 128/256 rows then fill completely: Vocos has L = 94 rows per utterance, 73% of a 128-row tile)
+        B, L_in, L_out = 1, B * L_in, B * L_in
     d = ConvDesc()
     d.a, d.B, d.L_in, d.a_pitch = _ptr(a16, torch.float16), B, L_in, a_pitch
     d.w, d.n_phase, d.n_taps = _ptr(pc.w, torch.float16), pc.n_phase, pc.n_taps
@@ -321,9 +329,6 @@ def conv1d(a16: torch.Tensor, pc: PackedConv, L_out: Optional[int] = None, *, ga
     d.L_out = L_out
     d.bias = _ptr(pc.bias, torch.float32) if (use_bias and pc.bias is not None) else None
     d.gamma = _ptr(gamma, torch.float32)
-    for name, t in (("residual", residual), ("out32", out32), ("out16", out16)):
-        if t is not None and (t.shape[0] != B or t.shape[1] != L_out):
-            raise FvError(f"{name} has shape {tuple(t.shape)}, expected [{B}, {L_out}, pitch]")
     d.residual, d.res_pitch = _ptr(residual, torch.float32), (0 if residual is None else residual.shape[2])
     d.out32, d.out32_pitch = _ptr(out32, torch.float32), (0 if out32 is None else out32.shape[2])
     d.accumulate, d.out_scale = int(bool(accumulate)), float(out_scale)

@@ -82,7 +82,7 @@ extern "C" int fv_conv1d(const fv_conv_desc* d, int engine, void* stream) {
     FV_REQUIRE(d->out16 && d->out16_split % 8 == 0 && d->out16_split >= r8 && d->out16_pitch >= d->out16_split + r8,
                FV_E_BADARG, "fv_conv1d: strict output layout needs out16_pitch >= out16_split + C_out (split=%d pitch=%d)",
                d->out16_split, d->out16_pitch);
-  FV_REQUIRE(d->act >= FV_ACT_NONE && d->act <= FV_ACT_POLAR, FV_E_BADARG, "fv_conv1d: bad activation %d", d->act);
+  FV_REQUIRE(d->act >= FV_ACT_NONE && d->act <= FV_ACT_SILU_TANH, FV_E_BADARG, "fv_conv1d: bad activation %d", d->act);
   FV_REQUIRE(!(d->accumulate && !d->out32), FV_E_BADARG, "fv_conv1d: accumulate needs out32");
   for (int i = 0; i < d->n_phase * d->n_taps; ++i)
     FV_REQUIRE(d->tap_off[i] > -30000 && d->tap_off[i] < 30000, FV_E_BADARG, "fv_conv1d: tap offset out of range");

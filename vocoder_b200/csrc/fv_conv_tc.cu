@@ -447,7 +447,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
           if (has_o16) {
             if (p.act == FV_ACT_SILU) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) o[i] = __fdividef(o[i], 1.0f + __expf(-o[i]));
+              for (int i = 0; i < 32; ++i) o[i] = silu_fast(o[i]);
+            } else if (p.act == FV_ACT_SILU_TANH) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] = silu_tanh(o[i]);
             } else if (p.act == FV_ACT_GELU) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) o[i] = gelu_erf_fast(o[i]);
@@ -626,7 +629,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
             if (p.out16 != nullptr) {
               if (p.act == FV_ACT_SILU) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) o[e] = __fdividef(o[e], 1.0f + __expf(-o[e]));
+                for (int e = 0; e < 4; ++e) o[e] = silu_fast(o[e]);
+              } else if (p.act == FV_ACT_SILU_TANH) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) o[e] = silu_tanh(o[e]);
               } else if (p.act == FV_ACT_GELU) {
 #pragma unroll
                 for (int e = 0; e < 4; ++e) o[e] = gelu_erf_fast(o[e]);

@@ -98,15 +98,9 @@ constexpr int kActSilu = 0, kActSiluTanh = 1, kActLeaky = 2;
 template <int ACT>
 __device__ __forceinline__ float fr_act(float v, float param) {
   if constexpr (ACT == kActSilu) {
-    float e, r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * -1.4426950408889634f));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
-    return v * r;
+    return silu_fast(v);
   } else if constexpr (ACT == kActSiluTanh) {
-    const float h = 0.5f * v;
-    float t;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
-    return fmaf(h, t, h);
+    return silu_tanh(v);
   } else {
     return v > 0.f ? v : v * param;
   }
@@ -404,6 +398,9 @@ __global__ void __launch_bounds__(FrCfg<C, EW, NCTA>::THREADS, NCTA) mrf_fused_k
         if (p.out_act == FV_ACT_SILU) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = fr_act<kActSilu>(v[i], 0.f);
+        } else if (p.out_act == FV_ACT_SILU_TANH) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fr_act<kActSiluTanh>(v[i], 0.f);
         } else if (p.out_act == FV_ACT_LEAKY) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = fr_act<kActLeaky>(v[i], p.out_act_param);
@@ -601,7 +598,8 @@ extern "C" int fv_mrf_fused(const fv_mrf_desc* d, void* stream) {
              FV_E_BADARG, "fv_mrf_fused: n_blocks=%d n_pairs=%d out of range", d->n_blocks, d->n_pairs);
   FV_REQUIRE(d->act == FV_ACT_SILU || d->act == FV_ACT_LEAKY || d->act == FV_ACT_SILU_TANH, FV_E_UNSUPPORTED,
              "fv_mrf_fused: inner activation must be SiLU or leaky ReLU");
-  FV_REQUIRE(d->out_act >= FV_ACT_NONE && d->out_act <= FV_ACT_TANH, FV_E_BADARG, "fv_mrf_fused: bad out_act");
+  FV_REQUIRE((d->out_act >= FV_ACT_NONE && d->out_act <= FV_ACT_TANH) || d->out_act == FV_ACT_SILU_TANH, FV_E_BADARG,
+             "fv_mrf_fused: bad out_act");
   FV_REQUIRE(d->x_pitch >= d->C && d->x_pitch % 4 == 0 && d->out32_pitch >= d->C && d->out32_pitch % 4 == 0 &&
                  (!d->out16 || (d->out16_pitch >= d->C && d->out16_pitch % 8 == 0)),
              FV_E_ALIGN, "fv_mrf_fused: bad pitches");

@@ -217,63 +217,98 @@ struct SnakeFilt {
   float dn[12];
 };
 
-// sin(t) on the SFU.  sin.approx = one multiply by 1/(2 pi) + MUFU.SIN, which reduces the argument itself: absolute
-// error ~2^-21 inside [-2 pi, 2 pi] and ~1.2e-7 |t| beyond (rounding of the product), i.e. <= 2.5e-5 for the
-// |alpha * u| <= 200 a Snake sees - two orders below the parity budget and below the fp16 rounding of the kernel's output.
-// (A Cody-Waite pre-reduction costs 4 more instructions per sine = 8 of the ~50 per sample; ncu: kernel is issue-bound.)
-__device__ __forceinline__ float snake_fn(float u, float a, float inv_b) {
-  const float s = __sinf(u * a);
-  return fmaf(inv_b * s, s, u);
+// Packed fp32x2 arithmetic (sm_100 FFMA2 / FMUL2): one issue slot for two channels.  ptxas encodes a {f, f} pair built
+// from a kernel parameter as a scalar-broadcast uniform-register operand (FFMA2 R, R.F32x2, UR.F32, R.F32x2), so the 24
+// filter taps cost no vector registers.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long ra, rb, rc, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  unsigned long long ra, rb, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+__device__ __forceinline__ float2 bc2(float f) { return make_float2(f, f); }
+
+// x + sin^2(a x) / b for two channels.  sin.approx = one multiply by 1/(2 pi) + MUFU.SIN, which reduces the argument
+// itself: absolute error ~2^-21 inside [-2 pi, 2 pi] and ~1.2e-7 |t| beyond (rounding of the product), i.e. <= 2.5e-5 for
+// the |alpha * u| <= 200 a Snake sees - two orders below the parity budget and below the fp16 rounding of the output.
+__device__ __forceinline__ float2 snake_fn2(float2 u, float2 a, float2 inv_b) {
+  const float2 t = fmul2(u, a);
+  const float2 sn = make_float2(__sinf(t.x), __sinf(t.y));
+  return ffma2(fmul2(inv_b, sn), sn, u);
+}
+
+// fp16 pair store; in strict mode (split > 0) also the residual pair fp16(v - hi) `split` halfs further on
+__device__ __forceinline__ void store_half2_split(__half* dst, float2 v, int split) {
+  const uint32_t h = pack_half2_sat(v.x, v.y);
+  *reinterpret_cast<uint32_t*>(dst) = h;
+  if (split > 0) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h));
+    *reinterpret_cast<uint32_t*>(dst + split) = pack_half2_sat(v.x - f.x, v.y - f.y);
+  }
 }
 
 // Streaming formulation (Appendix B4 of SURVEY.md).  With x~ the edge-replicated input and v~ the edge-replicated
 // activated 2x signal:   out[t] = sum_j f[j] * v~[2t - 5 + j],  and both new values a step needs,
 //   v[2t+7] = act(2 * sum_q f[2q]   * x~[t+6-q]),   v[2t+8] = act(2 * sum_q f[2q+1] * x~[t+6-q]),
-// read the same 6-sample window.  A thread owns one channel and marches over SN_SEG steps keeping x~[t+1..t+6] in a
-// 6-register ring and v~[2t-5..2t+6] in a 12-register ring (unrolled by 6 so ring slots are compile-time registers):
-// one 4-byte load, 24 FMA, 2 SFU sines and one 2-byte store per sample; six "pre-roll" steps fill the rings.
-// EDGE = false is the interior fast path (no index clamps, no replicate logic, pointer increments only): ncu showed
-// the kernel issue-bound with a third of its instructions being integer/predicate work of the edge handling.
+// read the same 6-sample window.  A thread owns TWO adjacent channels (packed fp32x2 math) and marches over SN_SEG steps
+// keeping x~[t+1..t+6] in a 6-slot ring and v~[2t-5..2t+6] in a 12-slot ring (unrolled by 6 so ring slots are
+// compile-time registers): per sample pair one 8-byte load, 24 FFMA2, 4 SFU sines and one 4-byte store; six "pre-roll"
+// steps fill the rings.  Loads run one 6-step window ahead of the math (software pipeline).
+// EDGE = false is the interior fast path (no index clamps, no replicate logic, pointer increments only).
 template <bool EDGE, bool SPLIT>
 __device__ __forceinline__ void snake_segment(const float* __restrict__ xc, __half* __restrict__ orow,
-                                              const SnakeFilt& f, float a, float inv_b, int t0, int t_end, int L,
+                                              const SnakeFilt& f, float2 a, float2 inv_b, int t0, int t_end, int L,
                                               int pitch, int opitch, int split) {
   const int nl = 2 * L - 1;
   auto ldx = [&](int t) {
     if (EDGE) t = t < 0 ? 0 : (t > L - 1 ? L - 1 : t);  // replicate edge of the INPUT (first filter pads its own input)
-    return xc[(size_t)t * pitch];
+    return *reinterpret_cast<const float2*>(xc + (size_t)t * pitch);
   };
-  float X[6];   // ring: x~[t+6-q] lives in X[(k - q) mod 6] at unrolled position k
-  float V[12];  // ring: v~[2t-5+j] lives in V[(2k + j) mod 12]
-  float vlast = 0.f;
-  // every load of the pre-roll is issued before the first use (11 independent requests in flight per thread):
+  const float2 zero2 = make_float2(0.f, 0.f);
+  float2 X[6];   // ring: x~[t+6-q] lives in X[(k - q) mod 6] at unrolled position k
+  float2 V[12];  // ring: v~[2t-5+j] lives in V[(2k + j) mod 12]
+  float2 vlast = zero2;
+  // every load of the pre-roll is issued before the first use:
   // window before the first pre-roll step (t = t0 - 6): x~[t+1 .. t+5] = x~[t0-5 .. t0-1] in X[1..5], then x~[t0 .. t0+5]
-  float xp[6];
+  float2 xp[6];
 #pragma unroll
   for (int i = 1; i < 6; ++i) X[i] = ldx(t0 - 6 + i);
 #pragma unroll
   for (int k = 0; k < 6; ++k) xp[k] = ldx(t0 + k);
-  // ... and so is the first main-loop window x~[t0+6 .. t0+11] (software pipeline: window i+1 loads under the math of i)
-  float xn[6];
+  // ... and so is the first main-loop window x~[t0+6 .. t0+11]
+  float2 xn[6];
   const float* px = xc + (size_t)(t0 + 6) * pitch;  // interior path: running pointers instead of index math
 #pragma unroll
   for (int k = 0; k < 6; ++k) {
     if (EDGE) xn[k] = ldx(t0 + k + 6);
-    else xn[k] = px[(size_t)k * pitch];
+    else xn[k] = *reinterpret_cast<const float2*>(px + (size_t)k * pitch);
   }
   px += (size_t)6 * pitch;
 #pragma unroll
   for (int k = 0; k < 6; ++k) {  // pre-roll: t = t0 - 6 + k produces v[2t0-5+2k], v[2t0-4+2k]
     const int t = t0 - 6 + k;
     X[k] = xp[k];
-    float uo = 0.f, ue = 0.f;
+    float2 uo = zero2, ue = zero2;
 #pragma unroll
     for (int q = 0; q < 6; ++q) {
-      const float xv = X[(k - q + 6) % 6];
-      uo = fmaf(f.up[2 * q], xv, uo);
-      ue = fmaf(f.up[2 * q + 1], xv, ue);
+      const float2 xv = X[(k - q + 6) % 6];
+      uo = ffma2(xv, bc2(f.up[2 * q]), uo);
+      ue = ffma2(xv, bc2(f.up[2 * q + 1]), ue);
     }
-    float va = snake_fn(uo, a, inv_b), vb = snake_fn(ue, a, inv_b);  // f.up carries the 2x gain
+    float2 va = snake_fn2(uo, a, inv_b), vb = snake_fn2(ue, a, inv_b);  // f.up carries the 2x gain
     if (EDGE) {
       if (2 * t + 7 <= nl) vlast = va; else va = vlast;
       if (2 * t + 8 <= nl) vlast = vb; else vb = vlast;
@@ -287,33 +322,33 @@ __device__ __forceinline__ void snake_segment(const float* __restrict__ xc, __ha
   }
   __half* po = orow + (size_t)t0 * opitch;
   for (int tb = t0; tb < t_end; tb += 6) {
-    float xw[6];
+    float2 xw[6];
 #pragma unroll
     for (int k = 0; k < 6; ++k) xw[k] = xn[k];
-    if (tb + 6 < t_end) {  // next window: six independent loads in flight under this window's 200 instructions
+    if (tb + 6 < t_end) {  // next window: six independent loads in flight under this window's math
 #pragma unroll
       for (int k = 0; k < 6; ++k) {
         if (EDGE) xn[k] = ldx(tb + k + 12);
-        else xn[k] = px[(size_t)k * pitch];
+        else xn[k] = *reinterpret_cast<const float2*>(px + (size_t)k * pitch);
       }
       px += (size_t)6 * pitch;
     }
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
       const int t = tb + k;
-      float o = 0.f;
+      float2 o = zero2;
 #pragma unroll
-      for (int j = 0; j < 12; ++j) o = fmaf(f.dn[j], V[(2 * k + j) % 12], o);
-      if (!EDGE || t < t_end) store_half_split(po + (size_t)k * opitch, o, SPLIT ? split : 0);
+      for (int j = 0; j < 12; ++j) o = ffma2(V[(2 * k + j) % 12], bc2(f.dn[j]), o);
+      if (!EDGE || t < t_end) store_half2_split(po + (size_t)k * opitch, o, SPLIT ? split : 0);
       X[k] = xw[k];
-      float uo = 0.f, ue = 0.f;
+      float2 uo = zero2, ue = zero2;
 #pragma unroll
       for (int q = 0; q < 6; ++q) {
-        const float xv = X[(k - q + 6) % 6];
-        uo = fmaf(f.up[2 * q], xv, uo);
-        ue = fmaf(f.up[2 * q + 1], xv, ue);
+        const float2 xv = X[(k - q + 6) % 6];
+        uo = ffma2(xv, bc2(f.up[2 * q]), uo);
+        ue = ffma2(xv, bc2(f.up[2 * q + 1]), ue);
       }
-      float va = snake_fn(uo, a, inv_b), vb = snake_fn(ue, a, inv_b);  // f.up carries the 2x gain
+      float2 va = snake_fn2(uo, a, inv_b), vb = snake_fn2(ue, a, inv_b);  // f.up carries the 2x gain
       if (EDGE) {
         if (2 * t + 7 <= nl) vlast = va; else va = vlast;
         if (2 * t + 8 <= nl) vlast = vb; else vb = vlast;
@@ -325,33 +360,37 @@ __device__ __forceinline__ void snake_segment(const float* __restrict__ xc, __ha
   }
 }
 
+// one thread = one channel PAIR x SN_SEG time steps (pitch is a multiple of 8, so pairs never straddle a row)
 template <bool SPLIT>
-__global__ void __launch_bounds__(256, 3) snake_aa_kernel(const float* __restrict__ x, __half* __restrict__ out,
+__global__ void __launch_bounds__(256, 2) snake_aa_kernel(const float* __restrict__ x, __half* __restrict__ out,
                                                           const float* __restrict__ alpha,
                                                           const float* __restrict__ beta, const SnakeFilt f,
                                                           int logscale, int B, int L, int C, int pitch, int n_seg,
                                                           int split) {
-  const long long total = (long long)B * n_seg * pitch;
+  const int hp = pitch >> 1;
+  const long long total = (long long)B * n_seg * hp;
   const long long item = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (item >= total) return;
-  const int c = (int)(item % pitch);
-  const int seg = (int)((item / pitch) % n_seg);
-  const int b = (int)(item / ((long long)pitch * n_seg));
+  const int c = 2 * (int)(item % hp);
+  const int seg = (int)((item / hp) % n_seg);
+  const int b = (int)(item / ((long long)hp * n_seg));
   const int t0 = seg * SN_SEG;
   const int t_end = min(t0 + SN_SEG, L);
   const int opitch = pitch + split;
   __half* orow = out + ((size_t)b * L) * opitch + c;
   if (c >= C) {  // padded channels stay zero
-    for (int t = t0; t < t_end; ++t) store_half_split(orow + (size_t)t * opitch, 0.f, split);
+    for (int t = t0; t < t_end; ++t) store_half2_split(orow + (size_t)t * opitch, make_float2(0.f, 0.f), split);
     return;
   }
-  float a = alpha[c];
-  float bb = beta ? beta[c] : a;
+  // a padded odd channel (c + 1 == C) reads x = 0 and therefore writes 0 whatever its parameters
+  const int c1 = c + 1 < C ? c + 1 : c;
+  float2 a = make_float2(alpha[c], alpha[c1]);
+  float2 bb = beta ? make_float2(beta[c], beta[c1]) : a;
   if (logscale) {
-    a = expf(a);
-    bb = expf(bb);
+    a = make_float2(expf(a.x), expf(a.y));
+    bb = make_float2(expf(bb.x), expf(bb.y));
   }
-  const float inv_b = 1.0f / (bb + 1e-9f);
+  const float2 inv_b = make_float2(1.0f / (bb.x + 1e-9f), 1.0f / (bb.y + 1e-9f));
   const float* xc = x + ((size_t)b * L) * pitch + c;
   // interior segment: every x index in [t0-5, t0+SN_SEG+5] and every v index up to 2(t0+SN_SEG)+6 is in range
   const bool interior = (t0 >= 6) && (t0 + SN_SEG + 6 <= L - 1);
@@ -671,7 +710,8 @@ extern "C" int fv_conv_post_tanh(const void* a16, const float* w32, const float*
 extern "C" int fv_snake_aa(const float* x32, void* out16, const float* alpha, const float* beta, const float* filt_up,
                            const float* filt_down, int logscale, int B, int L, int C, int pitch, int split,
                            void* stream) {
-  FV_REQUIRE(x32 && out16 && alpha && filt_up && filt_down && B > 0 && L > 0 && C > 0 && pitch >= C &&
+  FV_REQUIRE(x32 && out16 && alpha && filt_up && filt_down && B > 0 && L > 0 && C > 0 && pitch >= C && pitch % 2 == 0 &&
+                 (reinterpret_cast<uintptr_t>(x32) & 7) == 0 && (reinterpret_cast<uintptr_t>(out16) & 3) == 0 &&
                  (split == 0 || split == pitch),
              FV_E_BADARG, "fv_snake_aa: bad arguments");
   SnakeFilt f;
@@ -682,7 +722,7 @@ extern "C" int fv_snake_aa(const float* x32, void* out16, const float* alpha, co
     f.dn[i] = filt_down[i];
   }
   const int n_seg = ceil_div(L, SN_SEG);
-  const long long total = (long long)B * n_seg * pitch;
+  const long long total = (long long)B * n_seg * (pitch / 2);
   if (split)  // strict precision: [hi | lo] fp16 pairs (the extra stores stay out of the default instantiation)
     snake_aa_kernel<true><<<grid1d(total, 256), 256, 0, (cudaStream_t)stream>>>(x32, (__half*)out16, alpha, beta, f,
                                                                                logscale, B, L, C, pitch, n_seg, split);

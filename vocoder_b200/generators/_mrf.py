@@ -212,7 +212,7 @@ class MRFGeneratorBase(nn.Module):
                 h_next = ws.f16(f"h_{i}", B, Lo, C, dev)
                 out_act, out_act_p = self._stage_out_act(last_stage)
                 cabi.mrf_fused(x0, fused, acc, out16=h_next if out_act is not None else None,
-                               act=cabi.ACT_SILU_TANH if self.mrf_silu_tanh else cabi.ACT_SILU,
+                               act=self._silu(),
                                out_act=out_act or cabi.ACT_NONE, out_act_param=out_act_p)
                 if last_stage:
                     self._final_activation(acc, h_next, C)
@@ -223,7 +223,7 @@ class MRFGeneratorBase(nn.Module):
                 xa0 = None
             else:
                 xa0 = ws.f16(f"xa0_{i}", B, Lo, C, dev)
-                cabi.conv1d(h16, up, Lo, residual=nz, out32=x0, out16=xa0, act=cabi.ACT_SILU, engine=eng)
+                cabi.conv1d(h16, up, Lo, residual=nz, out32=x0, out16=xa0, act=self._silu(), engine=eng)
             acc = ws.f32(f"acc_{i}", B, Lo, C, dev)
             h_next = ws.f16(f"h_{i}", B, Lo, C, dev)
             # The residual blocks can run per micro-batch of utterances (working set resident in the 126 MB L2).
@@ -254,10 +254,10 @@ class MRFGeneratorBase(nn.Module):
                             cabi.conv1d(xa_m, c1s[p_i], out32=t32_m, engine=eng)
                             self._snake(blk.activations[2 * p_i + 1], t32_m, ta_m, C)
                         else:
-                            cabi.conv1d(xa, c1s[p_i], out16=ta_m, act=cabi.ACT_SILU, engine=eng)
+                            cabi.conv1d(xa, c1s[p_i], out16=ta_m, act=self._silu(), engine=eng)
                         if not last_pair:
                             cabi.conv1d(ta_m, c2s[p_i], residual=xr, out32=xr_m,
-                                        out16=None if self.snake_blocks else xa_m, act=cabi.ACT_SILU, engine=eng)
+                                        out16=None if self.snake_blocks else xa_m, act=self._silu(), engine=eng)
                             xr, xa = xr_m, xa_m
                         else:
                             want16 = (j == nk - 1) and out_act is not None
@@ -275,7 +275,10 @@ class MRFGeneratorBase(nn.Module):
 
     #: C <= 64 SiLU stages as one on-chip kernel per stage (fv_mrf_fused); False = layer-wise fv_conv1d launches
     fuse_mrf = True
-    #: SiLU inside the fused stages as x/2 + x/2 tanh(x/2) with tanh.approx (one SFU op instead of two; |error| <=
+    def _silu(self) -> int:
+        return cabi.ACT_SILU_TANH if self.mrf_silu_tanh else cabi.ACT_SILU
+
+    #: SiLU epilogues (fused stages and layer-wise convs) as x/2 + x/2 tanh(x/2) with tanh.approx (one SFU op instead of two; |error| <=
     #: 2.4e-4 |x| before the fp16 rounding of the operand, see FV_ACT_SILU_TANH).  Measured on B200: stage-level error
     #: 5.8e-5 vs 4.3e-5 (ex2 + rcp) against the fp64 contract, waveform error of the full-width stress model unchanged
     #: (8.1e-5 both); False selects the ex2 + rcp form.

@@ -69,9 +69,10 @@ class HiFiGANGenerator(MRFGeneratorBase):
         return list(self.resblocks[stage].blocks)
 
     def _pre_act(self):  # F.silu before ups[0] (hifigan.py:230)
-        return cabi.ACT_SILU, 0.0
+        return self._silu(), 0.0
 
     def _stage_out_act(self, last_stage):
         if last_stage:  # activation_post (hifigan.py:245)
-            return act_of_module(self.activation_post)
-        return cabi.ACT_SILU, 0.0  # F.silu before the next ups (hifigan.py:230)
+            act, param = act_of_module(self.activation_post)
+            return (self._silu() if act == cabi.ACT_SILU else act), param
+        return self._silu(), 0.0  # F.silu before the next ups (hifigan.py:230)
