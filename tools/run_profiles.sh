@@ -1,18 +1,26 @@
 #!/usr/bin/env bash
-# Round-end evidence run on the B200 box: benches for every workload + ncu launch lists + full captures.
+# Round-end evidence run on the B200 box: benches for every workload (with the CPU baseline and the reference arm) + ncu
+# launch lists + full captures of the dominant kernels.  Outputs land in gpurun_out/; tools/ncu_summary.py turns them
+# into the tables under profiles/.
 set -uo pipefail
 mkdir -p gpurun_out
 python bench.py --steps 20 --warmup 3 > gpurun_out/final_bench_hifigan_b64.log 2>&1
 python bench.py --steps 10 --warmup 3 --workload bigvgan_b32 > gpurun_out/final_bench_bigvgan_b32.log 2>&1
 python bench.py --steps 10 --warmup 3 --workload vocos_huge_b128 > gpurun_out/final_bench_vocos_huge_b128.log 2>&1
-python bench.py --steps 20 --warmup 3 --workload hifigan_b1 > gpurun_out/final_bench_hifigan_b1.log 2>&1
+python bench.py --steps 20 --warmup 3 --workload hifigan_b1 --no-cpu-baseline > gpurun_out/final_bench_hifigan_b1.log 2>&1
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/final_bench_reference.log 2>&1
-ncu --metrics gpu__time_duration.sum --clock-control none -s 380 -c 420 --csv --log-file gpurun_out/launches_r01.csv \
+# launch lists: skip the one-time weight packing (torch kernels of the first forward), keep ~5 forwards
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 420 -c 260 --csv --log-file gpurun_out/launches_hifigan_b64.csv \
     python bench.py --steps 2 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
-ncu --metrics gpu__time_duration.sum --clock-control none -s 560 -c 760 --csv --log-file gpurun_out/launches_bigvgan_r01.csv \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 900 -c 800 --csv --log-file gpurun_out/launches_bigvgan_b32.csv \
     python bench.py --steps 2 --warmup 3 --no-graph --no-cpu-baseline --workload bigvgan_b32 > gpurun_out/ncu_bench_bigvgan.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:conv_tc -s 28 -c 3 -f -o gpurun_out/prof_conv_r01 \
-    python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:snake_aa -s 30 -c 2 -f -o gpurun_out/prof_snake_r01 \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 700 -c 600 --csv --log-file gpurun_out/launches_vocos_huge_b128.csv \
+    python bench.py --steps 2 --warmup 3 --no-graph --no-cpu-baseline --workload vocos_huge_b128 > gpurun_out/ncu_bench_vocos.log 2>&1
+# full captures: conv_tc in the C=128 stage of HiFiGAN (convs1, convs2, convs1), both fused MRF stages, one snake launch
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_tc -s 105 -c 3 -f -o gpurun_out/prof_conv_tc \
+    python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/ncu_full_conv.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:mrf_fused -s 4 -c 2 -f -o gpurun_out/prof_mrf_fused \
+    python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/ncu_full_mrf.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:snake_aa -s 40 -c 1 -f -o gpurun_out/prof_snake \
     python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline --workload bigvgan_b32 > gpurun_out/ncu_full_snake.log 2>&1
-tail -c 300 gpurun_out/final_bench_hifigan_b64.log
+for f in gpurun_out/final_bench_*.log; do echo "== $f"; tail -c 400 "$f"; echo; done

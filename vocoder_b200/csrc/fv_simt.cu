@@ -211,7 +211,7 @@ __global__ void conv_post_kernel(const __half* __restrict__ a, const float* __re
 // anti-aliased Snake: up 2x (polyphase 6+6 taps) -> x + sin^2(a x)/(b+1e-9) -> down 2x (12 taps), one pass.
 // One thread = one channel x SN_T consecutive time steps; the activated 2x signal lives only in registers.
 // ------------------------------------------------------------------------------------------------
-constexpr int SN_SEG = 48;  // time steps per thread (a multiple of 6, the period of the register rings)
+constexpr int SN_SEG_MIN = 36, SN_SEG_MAX = 96;  // time steps per thread: a multiple of 6 (period of the register rings)
 struct SnakeFilt {
   float up[12];
   float dn[12];
@@ -263,7 +263,7 @@ __device__ __forceinline__ void store_half2_split(__half* dst, float2 v, int spl
 // Streaming formulation (Appendix B4 of SURVEY.md).  With x~ the edge-replicated input and v~ the edge-replicated
 // activated 2x signal:   out[t] = sum_j f[j] * v~[2t - 5 + j],  and both new values a step needs,
 //   v[2t+7] = act(2 * sum_q f[2q]   * x~[t+6-q]),   v[2t+8] = act(2 * sum_q f[2q+1] * x~[t+6-q]),
-// read the same 6-sample window.  A thread owns TWO adjacent channels (packed fp32x2 math) and marches over SN_SEG steps
+// read the same 6-sample window.  A thread owns TWO adjacent channels (packed fp32x2 math) and marches over seg_len steps
 // keeping x~[t+1..t+6] in a 6-slot ring and v~[2t-5..2t+6] in a 12-slot ring (unrolled by 6 so ring slots are
 // compile-time registers): per sample pair one 8-byte load, 24 FFMA2, 4 SFU sines and one 4-byte store; six "pre-roll"
 // steps fill the rings.  Loads run one 6-step window ahead of the math (software pipeline).
@@ -360,13 +360,13 @@ __device__ __forceinline__ void snake_segment(const float* __restrict__ xc, __ha
   }
 }
 
-// one thread = one channel PAIR x SN_SEG time steps (pitch is a multiple of 8, so pairs never straddle a row)
+// one thread = one channel PAIR x seg_len time steps (pitch is a multiple of 8, so pairs never straddle a row)
 template <bool SPLIT>
 __global__ void __launch_bounds__(256, 2) snake_aa_kernel(const float* __restrict__ x, __half* __restrict__ out,
                                                           const float* __restrict__ alpha,
                                                           const float* __restrict__ beta, const SnakeFilt f,
                                                           int logscale, int B, int L, int C, int pitch, int n_seg,
-                                                          int split) {
+                                                          int seg_len, int split) {
   const int hp = pitch >> 1;
   const long long total = (long long)B * n_seg * hp;
   const long long item = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -374,8 +374,8 @@ __global__ void __launch_bounds__(256, 2) snake_aa_kernel(const float* __restric
   const int c = 2 * (int)(item % hp);
   const int seg = (int)((item / hp) % n_seg);
   const int b = (int)(item / ((long long)hp * n_seg));
-  const int t0 = seg * SN_SEG;
-  const int t_end = min(t0 + SN_SEG, L);
+  const int t0 = seg * seg_len;
+  const int t_end = min(t0 + seg_len, L);
   const int opitch = pitch + split;
   __half* orow = out + ((size_t)b * L) * opitch + c;
   if (c >= C) {  // padded channels stay zero
@@ -392,8 +392,8 @@ __global__ void __launch_bounds__(256, 2) snake_aa_kernel(const float* __restric
   }
   const float2 inv_b = make_float2(1.0f / (bb.x + 1e-9f), 1.0f / (bb.y + 1e-9f));
   const float* xc = x + ((size_t)b * L) * pitch + c;
-  // interior segment: every x index in [t0-5, t0+SN_SEG+5] and every v index up to 2(t0+SN_SEG)+6 is in range
-  const bool interior = (t0 >= 6) && (t0 + SN_SEG + 6 <= L - 1);
+  // interior segment: every x index in [t0-5, t0+seg_len+5] and every v index up to 2(t0+seg_len)+6 is in range
+  const bool interior = (t0 >= 6) && (t0 + seg_len + 6 <= L - 1);
   if (interior) snake_segment<false, SPLIT>(xc, orow, f, a, inv_b, t0, t_end, L, pitch, opitch, split);
   else snake_segment<true, SPLIT>(xc, orow, f, a, inv_b, t0, t_end, L, pitch, opitch, split);
 }
@@ -721,14 +721,33 @@ extern "C" int fv_snake_aa(const float* x32, void* out16, const float* alpha, co
     f.up[i] = 2.0f * filt_up[i];  // the up-sampler's gain of `ratio` (= 2) is folded into its taps
     f.dn[i] = filt_down[i];
   }
-  const int n_seg = ceil_div(L, SN_SEG);
+  // Segment length: every thread does the same amount of work, so the grid runs in whole waves of 2 x 256 threads per
+  // SM and a launch of 3.1 waves costs 4.  Pick the multiple of 6 in [36, 96] with the best (work / waves) ratio,
+  // counting the 6 pre-roll steps every segment pays.
+  int seg_len = 48;
+  {
+    const long long per_wave = (long long)num_sms() * 2 * 256;
+    double best = -1.0;
+    for (int sl = SN_SEG_MIN; sl <= SN_SEG_MAX; sl += 6) {
+      const long long thr = (long long)B * ceil_div(L, sl) * (pitch / 2);
+      const long long waves = (thr + per_wave - 1) / per_wave;
+      const double score = (double)B * L * (pitch / 2) / ((double)waves * per_wave * (sl + 6));  // useful steps per slot-step
+      if (score > best) {
+        best = score;
+        seg_len = sl;
+      }
+    }
+  }
+  const int n_seg = ceil_div(L, seg_len);
   const long long total = (long long)B * n_seg * (pitch / 2);
   if (split)  // strict precision: [hi | lo] fp16 pairs (the extra stores stay out of the default instantiation)
     snake_aa_kernel<true><<<grid1d(total, 256), 256, 0, (cudaStream_t)stream>>>(x32, (__half*)out16, alpha, beta, f,
-                                                                               logscale, B, L, C, pitch, n_seg, split);
+                                                                               logscale, B, L, C, pitch, n_seg, seg_len,
+                                                                               split);
   else
     snake_aa_kernel<false><<<grid1d(total, 256), 256, 0, (cudaStream_t)stream>>>(x32, (__half*)out16, alpha, beta, f,
-                                                                                logscale, B, L, C, pitch, n_seg, split);
+                                                                                logscale, B, L, C, pitch, n_seg, seg_len,
+                                                                                split);
   FV_CHECK_LAUNCH("snake_aa_kernel");
   return 0;
 }
