@@ -174,6 +174,20 @@ FV_API int fv_resample_linear(const float* x32, float* out32, void* out16, int p
                               float act_param, int B, int L_in, int L_out, int C, int in_pitch, int out_pitch,
                               int out_coff, float scale, int split, void* stream);
 
+/* Mel front-end, the step immediately before the path (LinearSpectrogram / LogMelSpectrogram,
+ * fish_vocoder/data/transforms/spectrogram.py:6-104; used at test.py:71, models/gan.py:284):
+ * fv_frame_audio: y [B][L] fp32 -> out16 [B][R][pitch] fp16, row r = samples r*hop .. r*hop+hop-1 of
+ *                 F.pad(y, (pad_left, pad_right), "reflect") (spectrogram.py:29-37); with the signal laid out like this the
+ *                 framed, windowed DFT (torch.stft, center=False) is an fv_conv1d with n_fft/hop taps (offsets 0..k-1) whose
+ *                 weights are window * {cos, -sin}: output columns [re_0..re_{F-1} | im_0..im_{F-1}], F = n_fft/2 + 1.
+ * fv_spec_mag:    sqrt(re^2 + im^2 + eps) (spectrogram.py:54-55) -> fp16 operand of the mel matmul and/or fp32.
+ * fv_log_mel_out: log(max(x, floor)) (spectrogram.py:93-94), channels-last [B][T][pitch] -> channels-first [B][C][T]. */
+FV_API int fv_frame_audio(const float* y, void* out16, int B, int L, int hop, int pad_left, int pad_right, int R,
+                          int pitch, int split, void* stream);
+FV_API int fv_spec_mag(const float* spec, void* out16, float* out32, int B, int T, int F, int spec_pitch, int pitch,
+                       int split, int out32_pitch, float eps, void* stream);
+FV_API int fv_log_mel_out(const float* x32, float* out, int B, int C, int T, int pitch, float floor_v, void* stream);
+
 /*
  * Fused MRF stage: mean over `n_blocks` residual blocks, each a chain of `n_pairs` pairs
  *     xt = act(x); xt = conv_{k, dil1}(xt) + b1; xt = act(xt); xt = conv_{k, dil2}(xt) + b2; x = x + xt

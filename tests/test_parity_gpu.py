@@ -411,3 +411,47 @@ def test_cli_end_to_end(tmp_path):
         import numpy as np
         pcm = np.frombuffer(f.readframes(f.getnframes()), dtype=np.int16).reshape(-1, 2).T / 32767.0
     assert float(np.abs(pcm - out[:, 0].numpy()).max()) < 1e-3 + 1.0 / 32767
+
+
+# ------------------------------------------------------------------------------------------------
+# mel front-end: audio -> log-mel on the GPU, strict operand mode, vs the reference goldens
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["frontend_24k", "frontend_44k"])
+def test_mel_front_end_matches_reference_golden(name):
+    """Tolerances: log-mel within 1e-3 absolute (the generator's input tolerance), linear magnitudes within 1e-4 of the
+    spectrum's peak, against the UNMODIFIED reference LogMelSpectrogram (torch.stft + torchaudio MelScale, CPU fp32)."""
+    from vocoder_b200.transforms import LogMelSpectrogram
+    kw, sd, ins, out, extra = load_golden(name)
+    m = LogMelSpectrogram(**kw)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda()
+    y = ins["audio"].cuda()
+    with torch.no_grad():
+        cabi.reset_launch_count()
+        mel = m(y).cpu()
+        n_launch = cabi.launch_count()
+        lin = m.spectrogram(y.unsqueeze(1)).cpu()          # [B, 1, L] accepted like the reference (spectrogram.py:26-27)
+    want_lin = torch.from_numpy(extra["out_linear"])
+    assert mel.shape == out.shape and lin.shape == want_lin.shape
+    e_mel = float((mel - out).abs().max())
+    e_lin = float((lin - want_lin).abs().max()) / float(want_lin.abs().max())
+    print(f"{name}: log-mel max|delta| {e_mel:.3e} (range [{float(out.min()):.2f}, {float(out.max()):.2f}]), "
+          f"linear rel. to peak {e_lin:.3e}, {n_launch} launches")
+    assert n_launch == 5                                    # frame, DFT conv, magnitude, mel GEMM, log + layout exit
+    assert e_mel <= 1e-3 and e_lin <= 1e-4
+
+
+def test_mel_front_end_feeds_generator_end_to_end():
+    """wav -> mel -> wav entirely through libfv_b200.so: shapes and finiteness of the composed path (test.py:71,88-90)."""
+    from vocoder_b200.generators import HiFiGANGenerator
+    from vocoder_b200.transforms import LogMelSpectrogram
+    torch.manual_seed(0)
+    fe = LogMelSpectrogram(sample_rate=24000, n_fft=1024, win_length=1024, hop_length=256, n_mels=80).cuda()
+    gen = HiFiGANGenerator(hop_length=256, upsample_rates=(8, 8, 2, 2), upsample_kernel_sizes=(16, 16, 4, 4),
+                           num_mels=80, upsample_initial_channel=128, use_template=False).eval().cuda()
+    y = (0.5 * torch.sin(torch.arange(2 * 256 * 40).float() * 0.05)).reshape(2, -1).cuda()
+    with torch.no_grad():
+        mel = fe(y)
+        wav = gen(mel)
+    assert mel.shape == (2, 80, 40) and wav.shape == (2, 1, 40 * 256)
+    assert bool(torch.isfinite(mel).all()) and bool(torch.isfinite(wav).all())

@@ -27,7 +27,7 @@ EXPORTS = [
     "fv_last_error", "fv_abi_version", "fv_launch_count", "fv_reset_launch_count", "fv_conv1d",
     "fv_set_tc_tuning", "fv_pack_input", "fv_unpack_output", "fv_conv_post_tanh", "fv_snake_aa",
     "fv_dwconv_layernorm", "fv_istft_ola", "fv_noise_conv", "fv_act_cast", "fv_resample_linear",
-    "fv_mrf_fused", "fv_debug_rowshift_probe",
+    "fv_mrf_fused", "fv_frame_audio", "fv_spec_mag", "fv_log_mel_out", "fv_debug_rowshift_probe",
 ]
 MRF_MAX_BLOCKS, MRF_MAX_PAIRS, MRF_MAX_REACH = 4, 4, 32
 
@@ -103,6 +103,9 @@ def lib() -> ctypes.CDLL:
     L.fv_act_cast.argtypes = [vp, vp, vp, vp, vp, ci, cf, ci, cf, cf, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp]
     L.fv_resample_linear.argtypes = [vp, vp, vp, ci, cf, ci, cf, ci, ci, ci, ci, ci, ci, ci, cf, ci, vp]
     L.fv_mrf_fused.argtypes = [ctypes.POINTER(MrfDesc), vp]
+    L.fv_frame_audio.argtypes = [vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, vp]
+    L.fv_spec_mag.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, cf, vp]
+    L.fv_log_mel_out.argtypes = [vp, vp, ci, ci, ci, ci, cf, vp]
     L.fv_debug_rowshift_probe.argtypes = [vp, vp, vp, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
@@ -259,6 +262,17 @@ def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], dilation: int 
     offs = [(j - (k - 1) // 2) * dilation for j in range(k)]
     b = None if bias is None else bias.detach().float().contiguous()
     return PackedConv(w.contiguous(), b, offs, 1, k, c_in, c_out, cp, w.shape[-1], split)
+
+
+def pack_taps(mats: Sequence[torch.Tensor], offsets: Sequence[int], bias: Optional[torch.Tensor] = None) -> PackedConv:
+    """General single-phase packer: out[q] = sum_i mats[i] @ a[q + offsets[i]], mats[i] = [C_out, C_in]."""
+    c_out, c_in = mats[0].shape
+    cp, wp = c_out_pad_of(c_out), pitch_of(c_in)
+    w, put, split = _alloc_w(1, len(mats), cp, wp, mats[0].device)
+    for i, m in enumerate(mats):
+        put(0, i, m.detach().float())
+    b = None if bias is None else bias.detach().float().contiguous()
+    return PackedConv(w.contiguous(), b, [int(o) for o in offsets], 1, len(mats), c_in, c_out, cp, w.shape[-1], split)
 
 
 def pack_linear(weight: torch.Tensor, bias: Optional[torch.Tensor]) -> PackedConv:
@@ -436,6 +450,39 @@ def resample_linear(x32: torch.Tensor, C: int, L_out: int, scale: float, *, pre_
                                     _ptr(out16, torch.float16), int(pre_act), float(pre_param), int(act),
                                     float(act_param), B, L_in, L_out, C, in_pitch, o.shape[2], out_coff, float(scale),
                                     split_of(out16), _stream()), "fv_resample_linear")
+
+
+# ----------------------------------------------------------------------------------------------
+# mel front-end helpers (fv_frontend.cu)
+# ----------------------------------------------------------------------------------------------
+def frame_audio(y: torch.Tensor, hop: int, pad_left: int, pad_right: int, rows: int) -> torch.Tensor:
+    """y [B, L] fp32 -> fp16 operand [B, rows, pitch(hop)] of the reflect-padded signal, `hop` samples per row."""
+    B, L = y.shape
+    pitch = pitch_of(hop)
+    split = pitch if is_strict() else 0
+    out = torch.empty(B, rows, pitch + split, dtype=torch.float16, device=y.device)
+    _check(lib().fv_frame_audio(_ptr(y, torch.float32), _ptr(out), B, L, hop, pad_left, pad_right, rows, pitch, split,
+                                _stream()), "fv_frame_audio")
+    return out
+
+
+def spec_mag(spec: torch.Tensor, F: int, eps: float, *, out16: Optional[torch.Tensor] = None,
+             out32: Optional[torch.Tensor] = None) -> None:
+    """spec [B, T, >=2F] fp32 ([re | im]) -> sqrt(re^2 + im^2 + eps) as fp16 operand and/or fp32 [B, T, >=F]."""
+    B, T, sp = spec.shape
+    pitch = (out16.shape[2] // (2 if is_strict() else 1)) if out16 is not None else out32.shape[2]
+    _check(lib().fv_spec_mag(_ptr(spec, torch.float32), _ptr(out16, torch.float16), _ptr(out32, torch.float32), B, T, F,
+                             sp, pitch, split_of(out16), 0 if out32 is None else out32.shape[2], float(eps),
+                             _stream()), "fv_spec_mag")
+
+
+def log_mel_out(x32: torch.Tensor, C: int, floor: float) -> torch.Tensor:
+    """x32 [B, T, pitch] fp32 channels-last -> log(max(x, floor)) as [B, C, T] fp32."""
+    B, T, pitch = x32.shape
+    out = torch.empty(B, C, T, dtype=torch.float32, device=x32.device)
+    _check(lib().fv_log_mel_out(_ptr(x32, torch.float32), _ptr(out), B, C, T, pitch, float(floor), _stream()),
+           "fv_log_mel_out")
+    return out
 
 
 # ----------------------------------------------------------------------------------------------

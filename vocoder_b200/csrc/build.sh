@@ -8,7 +8,7 @@ FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 --shared
        -Xcompiler -fvisibility=hidden --expt-relaxed-constexpr -Xptxas -v)
 mkdir -p "${HERE}/_obj"
 pids=()
-for f in fv_api fv_simt fv_conv_tc fv_mrf_fused fv_debug; do
+for f in fv_api fv_simt fv_conv_tc fv_mrf_fused fv_frontend fv_debug; do
   ( "${NVCC}" "${FLAGS[@]}" -dc -c "${HERE}/${f}.cu" -o "${HERE}/_obj/${f}.o" > "${HERE}/_obj/${f}.log" 2>&1 ) &
   pids+=($!)
 done
@@ -16,5 +16,5 @@ rc=0
 for p in "${pids[@]}"; do wait "$p" || rc=1; done
 if [ $rc -ne 0 ]; then cat "${HERE}"/_obj/*.log; exit 1; fi
 "${NVCC}" -gencode arch=compute_100a,code=sm_100a --shared -Xcompiler -fPIC -o "${OUT}" \
-  "${HERE}/_obj/fv_api.o" "${HERE}/_obj/fv_simt.o" "${HERE}/_obj/fv_conv_tc.o" "${HERE}/_obj/fv_mrf_fused.o" "${HERE}/_obj/fv_debug.o"
+  "${HERE}/_obj/fv_api.o" "${HERE}/_obj/fv_simt.o" "${HERE}/_obj/fv_conv_tc.o" "${HERE}/_obj/fv_mrf_fused.o" "${HERE}/_obj/fv_frontend.o" "${HERE}/_obj/fv_debug.o"
 echo "built ${OUT}"
