@@ -16,6 +16,7 @@
 // Replaces the cuDNN/cuBLAS calls behind nn.Conv1d / nn.ConvTranspose1d / nn.Linear in
 // fish_vocoder/modules/generators/hifigan.py:29-98,158-187,214-222, bigvgan.py:149-218,
 // encoders/convnext.py:104-116,160-177 and generators/vocos.py:41,55.
+#include <cstdlib>
 #include <mutex>
 
 #include "fv_common.cuh"
@@ -39,6 +40,7 @@ struct ConvTcParams {
   int B, n_phase, n_taps, k_chunks, C_out, C_out_r8, C_out_pad, q_rows, L_out;
   int m_tiles, n_tiles, total_tiles;
   int a_split, out16_split;  // strict precision: [hi | lo] operand / output layout (0 = plain fp16), see fv_conv_desc
+  int use_pair;  // host only: launch the cta_group::2 variant when the tile shape has one
   int use_slab, off_min, slab_boxes, w_resident;  // slab mainloop: smallest tap offset, 64-row boxes per slab, weights stay in smem
   const float* bias;
   const float* gamma;
@@ -50,14 +52,14 @@ struct ConvTcParams {
   int16_t tap_off[FV_MAX_TAPS];
 };
 
-template <int BLOCK_N, int M_SUB, int BLOCK_K, bool EPI_TMA, bool SLAB = false>
+template <int BLOCK_N, int M_SUB, int BLOCK_K, bool EPI_TMA, bool SLAB = false, bool PAIR = false>
 struct TcCfg {
   static constexpr int ROW_BYTES = BLOCK_K * 2;
   static constexpr int A_SUB_BYTES = 128 * ROW_BYTES;
   static constexpr int A_STAGE = M_SUB * A_SUB_BYTES;
   static constexpr int A_BOX_ROWS = (M_SUB * 128 <= 256) ? M_SUB * 128 : 256;
   static constexpr int N_A_BOX = M_SUB * 128 / A_BOX_ROWS;
-  static constexpr int B_STAGE = BLOCK_N * ROW_BYTES;
+  static constexpr int B_STAGE = (BLOCK_N / (PAIR ? 2 : 1)) * ROW_BYTES;  // CTA pair: each CTA stages half of the N rows
   static constexpr int STAGE = A_STAGE + B_STAGE;
   static constexpr int ACC_COLS = M_SUB * BLOCK_N;
   static constexpr int ACC_BUFS = (2 * ACC_COLS <= 512) ? 2 : 1;
@@ -94,9 +96,18 @@ struct TcCfg {
 // HEAVY_ACT = false keeps only the cheap activations (none / SiLU / leaky / GELU) in the epilogue body; tanh and the
 // polar map (expf + sincosf with its Payne-Hanek slow path) live in the HEAVY_ACT = true instantiations, so the hot
 // kernels stay small enough for the instruction cache.
-template <int BLOCK_N, int M_SUB, int BLOCK_K, bool EPI_TMA, bool HEAVY_ACT, bool SLAB>
+// PAIR = true: the kernel is launched in clusters of two CTAs (the two SMs of a TPC) that share every tile: 2 x M_SUB x 128
+// rows by BLOCK_N columns, `tcgen05.mma.cta_group::2` (M = 256) issued by the leader CTA.  Each CTA stages its own rows
+// of A and HALF of the weight tile, so a 128x256x16 step reads 4 + 4 KB of shared memory per SM instead of 4 + 8 KB
+// (a 256-wide SS-mode UMMA on one SM sits at 96 B/clk of the 128 B/clk port before the TMA writes are counted).
+template <int BLOCK_N, int M_SUB, int BLOCK_K, bool EPI_TMA, bool HEAVY_ACT, bool SLAB, bool PAIR = false>
 __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
-  using Cfg = TcCfg<BLOCK_N, M_SUB, BLOCK_K, EPI_TMA, SLAB>;
+  using Cfg = TcCfg<BLOCK_N, M_SUB, BLOCK_K, EPI_TMA, SLAB, PAIR>;
+  static_assert(!PAIR || (!SLAB && EPI_TMA), "the CTA-pair variant exists for the per-tap mainloop with the TMA epilogue");
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
+  const int n_workers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;   // tiles are dealt to CTAs, or to CTA pairs
+  const int worker = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  constexpr int TILE_ROWS = (PAIR ? 2 : 1) * M_SUB * 128;                 // rows of one tile (of the pair)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   if ((smem_u32(smem) & 1023u) != 0) {  // swizzled TMA/UMMA tiles need a 1024-byte aligned window
@@ -129,7 +140,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], kEpiThreads);
+      mbar_init(&tempty_bar[i], (PAIR ? 2 : 1) * kEpiThreads);  // pair: both CTAs' epilogues release the leader
       mbar_init(&afull_bar[i], 1);
       mbar_init(&aempty_bar[i], 1);
     }
@@ -142,10 +153,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     }
     fence_barrier_init();
   } else if (warp == 1) {
-    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    if constexpr (PAIR) tmem_alloc_pair(tmem_slot, Cfg::TMEM_COLS);
+    else tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();  // barrier inits of BOTH CTAs are visible before any remote arrive / TMA
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -164,13 +177,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
         const int col = kc * BLOCK_K;
         return (p.a_split > 0 && col >= 2 * p.a_split) ? col - 2 * p.a_split : col;
       };
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int tile = worker; tile < p.total_tiles; tile += n_workers) {
         int r = tile;
         const int n_t = r % p.n_tiles; r /= p.n_tiles;
         const int m_t = r % p.m_tiles; r /= p.m_tiles;
         const int b = r % p.B;
         const int phase = r / p.B;
-        const int q0 = m_t * (M_SUB * 128);
+        const int q0 = m_t * TILE_ROWS + (int)cta_rank * (M_SUB * 128);
         const int n0 = n_t * BLOCK_N;
         if constexpr (SLAB) {
           uint8_t* b_ring = smem + 2 * Cfg::A_SLAB;
@@ -204,13 +217,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
               const int s = it % Cfg::STAGES;
               mbar_wait(&empty_bar[s], ((it / Cfg::STAGES) & 1) ^ 1);
               if (leader) {
-                mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE);
                 uint8_t* sa = smem + s * Cfg::STAGE;
+                if constexpr (PAIR) {
+                  // both CTAs' bytes complete on the leader's barrier; the leader arms it for the sum
+                  if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * Cfg::STAGE);
 #pragma unroll
-                for (int bx = 0; bx < Cfg::N_A_BOX; ++bx)
-                  tma_load_3d(sa + bx * Cfg::A_BOX_ROWS * Cfg::ROW_BYTES, &p.tmA, &full_bar[s], a_col(kc),
-                              row0 + bx * Cfg::A_BOX_ROWS, b);
-                tma_load_2d(sa + Cfg::A_STAGE, &p.tmW, &full_bar[s], kc * BLOCK_K, wrow);
+                  for (int bx = 0; bx < Cfg::N_A_BOX; ++bx)
+                    tma_load_3d_pair(sa + bx * Cfg::A_BOX_ROWS * Cfg::ROW_BYTES, &p.tmA, &full_bar[s], a_col(kc),
+                                     row0 + bx * Cfg::A_BOX_ROWS, b);
+                  tma_load_2d_pair(sa + Cfg::A_STAGE, &p.tmW, &full_bar[s], kc * BLOCK_K,
+                                   wrow + (int)cta_rank * (BLOCK_N / 2));
+                } else {
+                  mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE);
+#pragma unroll
+                  for (int bx = 0; bx < Cfg::N_A_BOX; ++bx)
+                    tma_load_3d(sa + bx * Cfg::A_BOX_ROWS * Cfg::ROW_BYTES, &p.tmA, &full_bar[s], a_col(kc),
+                                row0 + bx * Cfg::A_BOX_ROWS, b);
+                  tma_load_2d(sa + Cfg::A_STAGE, &p.tmW, &full_bar[s], kc * BLOCK_K, wrow);
+                }
               }
             }
           }
@@ -219,12 +243,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    // (whole warp runs the loops and the barrier waits; one elected lane issues tcgen05.mma / tcgen05.commit)
-    {
+    // (whole warp runs the loops and the barrier waits; one elected lane issues tcgen05.mma / tcgen05.commit;
+    //  CTA pair: only the leader CTA issues, its commits arrive on both CTAs' barriers)
+    if (!PAIR || cta_rank == 0) {
       const bool leader = elect_one();
-      constexpr uint32_t idesc = make_idesc_f16(128, BLOCK_N);
+      constexpr uint32_t idesc = make_idesc_f16(PAIR ? 256 : 128, BLOCK_N);
       uint32_t it = 0, ita = 0, tile_i = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tile_i) {
+      for (int tile = worker; tile < p.total_tiles; tile += n_workers, ++tile_i) {
         const uint32_t buf = tile_i % Cfg::ACC_BUFS;
         mbar_wait(&tempty_bar[buf], ((tile_i / Cfg::ACC_BUFS) & 1) ^ 1);
         tc_fence_after();
@@ -287,17 +312,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
               for (int sub = 0; sub < M_SUB; ++sub) {
 #pragma unroll
                 for (int kk = 0; kk < BLOCK_K / 16; ++kk) {
-                  umma_f16_ss(tmem_base + (buf * M_SUB + sub) * BLOCK_N,
-                              desc_advance(da0, sub * Cfg::A_SUB_BYTES + kk * 32), desc_advance(db0, kk * 32), idesc,
-                              (st > 0 || kk > 0) ? 1u : 0u);
+                  if constexpr (PAIR)
+                    umma_f16_ss_pair(tmem_base + (buf * M_SUB + sub) * BLOCK_N,
+                                     desc_advance(da0, sub * Cfg::A_SUB_BYTES + kk * 32), desc_advance(db0, kk * 32),
+                                     idesc, (st > 0 || kk > 0) ? 1u : 0u);
+                  else
+                    umma_f16_ss(tmem_base + (buf * M_SUB + sub) * BLOCK_N,
+                                desc_advance(da0, sub * Cfg::A_SUB_BYTES + kk * 32), desc_advance(db0, kk * 32), idesc,
+                                (st > 0 || kk > 0) ? 1u : 0u);
                 }
               }
-              umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
+              // frees the smem stage (of both CTAs) once these MMAs have read it
+              if constexpr (PAIR) umma_commit_pair(&empty_bar[s]);
+              else umma_commit(&empty_bar[s]);
             }
             __syncwarp();
           }
         }
-        if (leader) umma_commit(&tfull_bar[buf]);  // accumulator complete -> epilogue
+        if (leader) {  // accumulator complete -> epilogue (of both CTAs)
+          if constexpr (PAIR) umma_commit_pair(&tfull_bar[buf]);
+          else umma_commit(&tfull_bar[buf]);
+        }
         __syncwarp();
       }
     }
@@ -323,13 +358,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
       const uint32_t h_xor = static_cast<uint32_t>((lane >> 1) & 3);
       const bool has_res = p.residual != nullptr, has_o32 = p.out32 != nullptr, has_o16 = p.out16 != nullptr;
       uint32_t tile_i = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tile_i) {
+      for (int tile = worker; tile < p.total_tiles; tile += n_workers, ++tile_i) {
         int r = tile;
         const int n_t = r % p.n_tiles; r /= p.n_tiles;
         const int m_t = r % p.m_tiles; r /= p.m_tiles;
         const int b = r % p.B;
         const int phase = r / p.B;
-        const int q0 = m_t * (M_SUB * 128);
+        const int q0 = m_t * TILE_ROWS + (int)cta_rank * (M_SUB * 128);
         const int n0 = n_t * BLOCK_N;
         const uint32_t buf = tile_i % Cfg::ACC_BUFS;
 
@@ -371,7 +406,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
           tmem_ld_wait();
           if (item + kEpiStride >= n_items) {
             tc_fence_before();
-            mbar_arrive(&tempty_bar[buf]);
+            if constexpr (PAIR) mbar_arrive_leader(&tempty_bar[buf]); else mbar_arrive(&tempty_bar[buf]);
           }
           float o[32];
           const float4* bp = reinterpret_cast<const float4*>(s_bias + ch * 32);
@@ -520,7 +555,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
         }
         if (cgrp >= n_items) {
           tc_fence_before();
-          mbar_arrive(&tempty_bar[buf]);
+          if constexpr (PAIR) mbar_arrive_leader(&tempty_bar[buf]); else mbar_arrive(&tempty_bar[buf]);
         }
       }
       if (lane == 0) tma_store_wait_all();  // global writes complete before the CTA retires
@@ -534,13 +569,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     const int c4 = (lane % Cfg::LPR) * 4;    // first of this lane's 4 consecutive columns within the chunk
     constexpr int N_ITEMS = M_SUB * Cfg::NCH;
     uint32_t tile_i = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tile_i) {
+    for (int tile = worker; tile < p.total_tiles; tile += n_workers, ++tile_i) {
       int r = tile;
       const int n_t = r % p.n_tiles; r /= p.n_tiles;
       const int m_t = r % p.m_tiles; r /= p.m_tiles;
       const int b = r % p.B;
       const int phase = r / p.B;
-      const int q0 = m_t * (M_SUB * 128);
+      const int q0 = m_t * TILE_ROWS + (int)cta_rank * (M_SUB * 128);
       const int n0 = n_t * BLOCK_N;
       const uint32_t buf = tile_i % Cfg::ACC_BUFS;
       const size_t brow0 = static_cast<size_t>(b) * p.L_out;
@@ -584,7 +619,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
         tmem_ld_wait();
         if (item + kEpiStride >= N_ITEMS) {  // this warp's last TMEM read of the tile: hand the accumulator back
           tc_fence_before();
-          mbar_arrive(&tempty_bar[buf]);
+          if constexpr (PAIR) mbar_arrive_leader(&tempty_bar[buf]); else mbar_arrive(&tempty_bar[buf]);
         }
         // transpose through this warp's private smem patch: thread = row  ->  lanes along the channel axis
         __syncwarp();
@@ -677,17 +712,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
       }
       if (cgrp >= N_ITEMS) {  // idle warp of this tile shape still owes its TMEM-release arrivals
         tc_fence_before();
-        mbar_arrive(&tempty_bar[buf]);
+        if constexpr (PAIR) mbar_arrive_leader(&tempty_bar[buf]); else mbar_arrive(&tempty_bar[buf]);
       }
     }
     }  // LSU epilogue
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();  // neither CTA may leave (or free TMEM) while the pair's MMAs / arrivals are in flight
+  else __syncthreads();
   if (warp == 1) {
     __syncwarp();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if constexpr (PAIR) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
+    else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -742,9 +779,9 @@ static int encode_epi_map(EncodeTiledFn enc, CUtensorMap* tm, const void* base, 
   return 0;
 }
 
-template <int BLOCK_N, int M_SUB, int BLOCK_K, bool EPI_TMA, bool HEAVY_ACT, bool SLAB>
+template <int BLOCK_N, int M_SUB, int BLOCK_K, bool EPI_TMA, bool HEAVY_ACT, bool SLAB, bool PAIR = false>
 static int launch_tc_impl(const fv_conv_desc* d, ConvTcParams& p, cudaStream_t stream) {
-  using Cfg = TcCfg<BLOCK_N, M_SUB, BLOCK_K, EPI_TMA, SLAB>;
+  using Cfg = TcCfg<BLOCK_N, M_SUB, BLOCK_K, EPI_TMA, SLAB, PAIR>;
   if constexpr (!Cfg::VALID) {
     return set_error(FV_E_UNSUPPORTED, "tile configuration N=%d M_SUB=%d K=%d does not fit in shared memory", BLOCK_N,
                      M_SUB, BLOCK_K);
@@ -782,7 +819,7 @@ static int launch_tc_impl(const fv_conv_desc* d, ConvTcParams& p, cudaStream_t s
   {  // weights: {w_pitch, n_phase*n_taps*C_out_pad}
     cuuint64_t dims[2] = {(cuuint64_t)d->w_pitch, (cuuint64_t)d->n_phase * d->n_taps * d->C_out_pad};
     cuuint64_t strides[1] = {(cuuint64_t)d->w_pitch * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)BLOCK_N};
+    cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)(BLOCK_N / (PAIR ? 2 : 1))};  // pair: half the N rows per CTA
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(&p.tmW, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(d->w), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(Cfg::ROW_BYTES), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -797,7 +834,7 @@ static int launch_tc_impl(const fv_conv_desc* d, ConvTcParams& p, cudaStream_t s
     if (rc) return rc;
   }
   p.k_chunks = d->a_split > 0 ? (3 * d->a_split) / BLOCK_K : ceil_div(d->a_pitch, BLOCK_K);
-  p.m_tiles = ceil_div(p.q_rows, M_SUB * 128);
+  p.m_tiles = ceil_div(p.q_rows, (PAIR ? 2 : 1) * M_SUB * 128);
   p.n_tiles = ceil_div(d->C_out, BLOCK_N);
   FV_REQUIRE(p.n_tiles * BLOCK_N <= d->C_out_pad, FV_E_BADARG, "C_out_pad %d too small for %d tiles of %d",
              d->C_out_pad, p.n_tiles, BLOCK_N);
@@ -812,13 +849,34 @@ static int launch_tc_impl(const fv_conv_desc* d, ConvTcParams& p, cudaStream_t s
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, M_SUB, BLOCK_K, EPI_TMA, HEAVY_ACT, SLAB>,
+    attr_err = cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, M_SUB, BLOCK_K, EPI_TMA, HEAVY_ACT, SLAB, PAIR>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
   });
   int rc = check_cuda(attr_err, "cudaFuncSetAttribute(conv_tc_kernel)");
   if (rc) return rc;
-  const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  conv_tc_kernel<BLOCK_N, M_SUB, BLOCK_K, EPI_TMA, HEAVY_ACT, SLAB><<<grid, kTcThreads, Cfg::SMEM_BYTES, stream>>>(p);
+  if constexpr (PAIR) {
+    // clusters of two CTAs = the two SMs of a TPC; one tile per cluster at a time
+    const int pairs = num_sms() / 2;
+    const int n_clusters = p.total_tiles < pairs ? p.total_tiles : pairs;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * n_clusters, 1, 1);
+    cfg.blockDim = dim3(kTcThreads, 1, 1);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    rc = check_cuda(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, M_SUB, BLOCK_K, EPI_TMA, HEAVY_ACT, SLAB, PAIR>, p),
+                    "cudaLaunchKernelEx(conv_tc_kernel pair)");
+    if (rc) return rc;
+  } else {
+    const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+    conv_tc_kernel<BLOCK_N, M_SUB, BLOCK_K, EPI_TMA, HEAVY_ACT, SLAB><<<grid, kTcThreads, Cfg::SMEM_BYTES, stream>>>(p);
+  }
   FV_CHECK_LAUNCH("conv_tc_kernel");
   return 0;
   }
@@ -839,6 +897,10 @@ static int launch_tc(const fv_conv_desc* d, ConvTcParams& p, cudaStream_t stream
     if constexpr (TcCfg<BLOCK_N, M_SUB, BLOCK_K, true, true>::VALID) {
       if (slab_ok && p.use_slab) return launch_tc_impl<BLOCK_N, M_SUB, BLOCK_K, true, false, true>(d, p, stream);
     }
+  }
+  if constexpr (EPI_TMA && BLOCK_N == 256 && M_SUB == 1 && BLOCK_K == 64) {
+    // CTA pair (cta_group::2) for the wide GEMM-like layers: 256 x 256 tiles over two SMs
+    if (p.use_pair && p.q_rows >= 256) return launch_tc_impl<BLOCK_N, M_SUB, BLOCK_K, true, false, false, true>(d, p, stream);
   }
   return launch_tc_impl<BLOCK_N, M_SUB, BLOCK_K, EPI_TMA, false, false>(d, p, stream);
 }
@@ -913,6 +975,13 @@ int conv1d_tc(const fv_conv_desc* d, cudaStream_t stream, int block_n_override, 
   // per tile instead of one small TMA stage per tap: 96.7 -> 76.2 us for C = 16, k = 11).  Auto picks accordingly.
   p.use_slab = mainloop == 2 || (mainloop == 0 && d->a_pitch <= 32 && d->n_taps >= 5 && d->n_phase == 1);
   for (int i = 0; i < d->n_phase * d->n_taps; ++i) p.tap_off[i] = (int16_t)d->tap_off[i];
+  {
+    static const bool pair_on = [] {
+      const char* e = getenv("FV_TC_PAIR");  // FV_TC_PAIR=0 keeps every launch on single-CTA tiles (A/B measurements)
+      return !(e && e[0] == '0');
+    }();
+    p.use_pair = pair_on && d->a_split == 0 && !p.use_slab;
+  }
 
   const int bn = block_n_override ? block_n_override : pick_block_n(d->C_out, d->C_out_pad);
   // two 128-row accumulators per CTA share every weight tile; a single one when the sequence is short

@@ -207,6 +207,81 @@ __global__ void conv_post_kernel(const __half* __restrict__ a, const float* __re
   }
 }
 
+// Sliding-window variant for the common shapes (k <= 7 taps, plain fp16 rows): a group of G lanes (one 16-byte chunk of 8
+// channels each) produces PT consecutive samples from PT + K - 1 rows read ONCE (the per-sample kernel above re-reads every
+// row K times through L1), with the lane's K x 8 weights held in registers.
+constexpr int POST_T = 8;
+template <int G, int K>
+__global__ void __launch_bounds__(256) conv_post_sliding_kernel(const __half* __restrict__ a, const float* __restrict__ w,
+                                                                const float* bias, float* __restrict__ wav, int B, int L,
+                                                                int C, int pitch, int apply_tanh) {
+  constexpr int HALF = (K - 1) / 2;
+  const int g = threadIdx.x % G;
+  float wr[K][8];
+#pragma unroll
+  for (int j = 0; j < K; ++j)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = g * 8 + e;
+      wr[j][e] = c < C ? w[j * C + c] : 0.f;
+    }
+  const int segs_per_b = (L + POST_T - 1) / POST_T;
+  const long long total = (long long)B * segs_per_b;
+  const int groups = blockDim.x / G;
+  const long long per_iter = (long long)gridDim.x * groups;
+  const long long n_iter = (total + per_iter - 1) / per_iter;
+  const float b0 = bias ? bias[0] : 0.f;
+  for (long long it = 0; it < n_iter; ++it) {  // uniform trip count: every lane reaches the shuffles
+    const long long sidx = (it * gridDim.x + blockIdx.x) * groups + threadIdx.x / G;
+    const bool live = sidx < total;
+    float acc[POST_T];
+#pragma unroll
+    for (int i = 0; i < POST_T; ++i) acc[i] = 0.f;
+    int b = 0, t0 = 0;
+    if (live) {
+      b = (int)(sidx / segs_per_b);
+      t0 = (int)(sidx % segs_per_b) * POST_T;
+      const __half* base = a + (size_t)b * L * pitch + g * 8;
+#pragma unroll
+      for (int i = 0; i < POST_T + K - 1; ++i) {
+        const int r = t0 - HALF + i;
+        if (r < 0 || r >= L) continue;
+        const uint4 pk = *reinterpret_cast<const uint4*>(base + (size_t)r * pitch);
+        const __half2* h2 = reinterpret_cast<const __half2*>(&pk);
+        float x[8];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __half22float2(h2[e]);
+          x[2 * e] = f.x;
+          x[2 * e + 1] = f.y;
+        }
+#pragma unroll
+        for (int j = 0; j < K; ++j) {   // row r is tap j of output t = r - j + HALF, i.e. local output i - j
+          const int o = i - j;
+          if (o >= 0 && o < POST_T) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[o] = fmaf(x[e], wr[j][e], acc[o]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < POST_T; ++i) {
+#pragma unroll
+      for (int off = G / 2; off > 0; off >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], off);
+    }
+    if (live && g == 0) {
+#pragma unroll
+      for (int i = 0; i < POST_T; ++i) {
+        if (t0 + i < L) {
+          const float v = acc[i] + b0;
+          wav[(size_t)b * L + t0 + i] = apply_tanh ? tanhf(v) : v;
+        }
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // anti-aliased Snake: up 2x (polyphase 6+6 taps) -> x + sin^2(a x)/(b+1e-9) -> down 2x (12 taps), one pass.
 // One thread = one channel x SN_T consecutive time steps; the activated 2x signal lives only in registers.
@@ -689,6 +764,23 @@ extern "C" int fv_conv_post_tanh(const void* a16, const float* w32, const float*
   const int chunks = pitch / 8;
   const int threads = 256;
   const long long total = (long long)B * L;
+  if (split == 0 && k == 7 && (chunks == 1 || chunks == 2 || chunks == 4 || chunks == 8)) {
+    const long long groups_total = (long long)B * ceil_div(L, POST_T);
+#define FV_POST_S(G)                                                                                        \
+  {                                                                                                         \
+    long long blocks = (groups_total + (threads / G) - 1) / (threads / G);                                  \
+    if (blocks > 148 * 8) blocks = 148 * 8;                                                                 \
+    conv_post_sliding_kernel<G, 7><<<(int)blocks, threads, 0, (cudaStream_t)stream>>>(                      \
+        (const __half*)a16, w32, bias, wav, B, L, C, pitch, apply_tanh);                                    \
+  }
+    if (chunks == 1) FV_POST_S(1)
+    else if (chunks == 2) FV_POST_S(2)
+    else if (chunks == 4) FV_POST_S(4)
+    else FV_POST_S(8)
+#undef FV_POST_S
+    FV_CHECK_LAUNCH("conv_post_sliding_kernel");
+    return 0;
+  }
 #define FV_POST(G)                                                                                          \
   {                                                                                                         \
     long long blocks = (total + (threads / G) - 1) / (threads / G);                                         \
