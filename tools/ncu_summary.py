@@ -65,7 +65,10 @@ def launches(path: str, title: str) -> None:
 
 
 def full(path: str, title: str) -> None:
-    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if path.endswith(".csv"):   # raw page already exported on the GPU box (tools/run_profiles.sh)
+        out = open(path, errors="replace").read()
+    else:
+        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units = rows[0], rows[1]
     print(f"# {title}\n")

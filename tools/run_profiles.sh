@@ -17,10 +17,17 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 900 -c 
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 700 -c 600 --csv --log-file gpurun_out/launches_vocos_huge_b128.csv \
     python bench.py --steps 2 --warmup 3 --no-graph --no-cpu-baseline --workload vocos_huge_b128 > gpurun_out/ncu_bench_vocos.log 2>&1
 # full captures: conv_tc in the C=128 stage of HiFiGAN (convs1, convs2, convs1), both fused MRF stages, one snake launch
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_tc -s 105 -c 3 -f -o gpurun_out/prof_conv_tc \
-    python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/ncu_full_conv.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:mrf_fused -s 4 -c 2 -f -o gpurun_out/prof_mrf_fused \
-    python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/ncu_full_mrf.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:snake_aa -s 40 -c 1 -f -o gpurun_out/prof_snake \
-    python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline --workload bigvgan_b32 > gpurun_out/ncu_full_snake.log 2>&1
+# (a --set full report is ~35 MB and gpurun_out/ may carry 64 MiB: the raw page is exported on the box, the report dropped)
+capture() {  # capture NAME KERNEL_REGEX SKIP COUNT BENCH_ARGS...
+  local name="$1" rx="$2" skip="$3" cnt="$4"; shift 4
+  timeout 600 ncu --set full --clock-control none --import-source on -k "regex:${rx}" -s "${skip}" -c "${cnt}" -f \
+      -o "gpurun_out/prof_${name}" python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline "$@" \
+      > "gpurun_out/ncu_full_${name}.log" 2>&1
+  ncu -i "gpurun_out/prof_${name}.ncu-rep" --page raw --csv > "gpurun_out/prof_${name}_raw.csv" 2>/dev/null
+  rm -f "gpurun_out/prof_${name}.ncu-rep"
+}
+capture conv_tc conv_tc 105 3
+capture mrf_fused mrf_fused 4 2
+capture snake snake_aa 40 1 --workload bigvgan_b32
+capture vocos_gemm conv_tc 171 2 --workload vocos_huge_b128
 for f in gpurun_out/final_bench_*.log; do echo "== $f"; tail -c 400 "$f"; echo; done

@@ -898,9 +898,11 @@ static int launch_tc(const fv_conv_desc* d, ConvTcParams& p, cudaStream_t stream
       if (slab_ok && p.use_slab) return launch_tc_impl<BLOCK_N, M_SUB, BLOCK_K, true, false, true>(d, p, stream);
     }
   }
-  if constexpr (EPI_TMA && BLOCK_N == 256 && M_SUB == 1 && BLOCK_K == 64) {
-    // CTA pair (cta_group::2) for the wide GEMM-like layers: 256 x 256 tiles over two SMs
-    if (p.use_pair && p.q_rows >= 256) return launch_tc_impl<BLOCK_N, M_SUB, BLOCK_K, true, false, false, true>(d, p, stream);
+  if constexpr (EPI_TMA && BLOCK_K == 64 && ((BLOCK_N == 256 && M_SUB == 1) || (BLOCK_N == 128 && M_SUB == 2))) {
+    // CTA pair (cta_group::2) for the wide layers: 256 x 256 (GEMMs, C = 256 convs) or 512 x 128 (C = 128 convs) tiles
+    // over two SMs; FV_TC_PAIR bit 0 enables the N = 256 shape, bit 1 the N = 128 shape
+    if ((p.use_pair & (BLOCK_N == 256 ? 1 : 2)) && p.q_rows >= 2 * M_SUB * 128)
+      return launch_tc_impl<BLOCK_N, M_SUB, BLOCK_K, true, false, false, true>(d, p, stream);
   }
   return launch_tc_impl<BLOCK_N, M_SUB, BLOCK_K, EPI_TMA, false, false>(d, p, stream);
 }
@@ -976,11 +978,11 @@ int conv1d_tc(const fv_conv_desc* d, cudaStream_t stream, int block_n_override, 
   p.use_slab = mainloop == 2 || (mainloop == 0 && d->a_pitch <= 32 && d->n_taps >= 5 && d->n_phase == 1);
   for (int i = 0; i < d->n_phase * d->n_taps; ++i) p.tap_off[i] = (int16_t)d->tap_off[i];
   {
-    static const bool pair_on = [] {
+    static const int pair_mask = [] {
       const char* e = getenv("FV_TC_PAIR");  // FV_TC_PAIR=0 keeps every launch on single-CTA tiles (A/B measurements)
-      return !(e && e[0] == '0');
+      return e ? atoi(e) : 1;
     }();
-    p.use_pair = pair_on && d->a_split == 0 && !p.use_slab;
+    p.use_pair = (d->a_split == 0 && !p.use_slab) ? pair_mask : 0;
   }
 
   const int bn = block_n_override ? block_n_override : pick_block_n(d->C_out, d->C_out_pad);

@@ -4,6 +4,9 @@
 // cross-check engine).  All HBM-bound: coalesced along the channel axis of the channels-last layout, 16-byte
 // vector accesses where the layout allows, grids sized from the problem (>= several waves of 148 SMs at the
 // BASELINE shapes).
+#include <cstdlib>
+#include <mutex>
+
 #include "fv_common.cuh"
 
 namespace fv {
@@ -628,6 +631,146 @@ __global__ void __launch_bounds__(256) dwconv_ln_tiled_kernel(const float* __res
   }
 }
 
+// Vectorised variant: one CTA = DW8_R consecutive time steps x all channels, a thread owns groups of FOUR adjacent channels
+// (16-byte loads / stores: a warp moves 512 contiguous bytes per instruction), 14 input rows per 8 outputs (1.75 loads per
+// output).  The depthwise results stay in shared memory for the two LayerNorm reductions (mean, then centred variance).
+constexpr int DW8_R = 8;
+
+template <int K>
+__global__ void __launch_bounds__(256, 2) dwconv_ln_vec_kernel(const float* __restrict__ x, __half* __restrict__ out16,
+                                                            float* __restrict__ out32, const float* __restrict__ dw_wT,
+                                                            const float* __restrict__ dw_b,
+                                                            const float* __restrict__ ln_w,
+                                                            const float* __restrict__ ln_b, float eps, int T, int C,
+                                                            int pitch, int tiles_per_b, int split) {
+  extern __shared__ float s_h[];  // [DW8_R][pitch]
+  __shared__ float s_red[8][DW8_R];
+  __shared__ float s_mean[DW8_R], s_rstd[DW8_R];
+  const int b = blockIdx.x / tiles_per_b;
+  const int t0 = (blockIdx.x % tiles_per_b) * DW8_R;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nthr = blockDim.x, nwarp = nthr >> 5;
+  const float* xb = x + (size_t)b * T * pitch;
+  constexpr int HALF = K > 0 ? (K - 1) / 2 : 0;
+  constexpr int WIN = DW8_R + (K > 0 ? K - 1 : 0);
+  const int C4 = C >> 2;  // C % 4 == 0 (checked by the launcher)
+  float sum[DW8_R];
+#pragma unroll
+  for (int r = 0; r < DW8_R; ++r) sum[r] = 0.f;
+  for (int g = tid; g < C4; g += nthr) {
+    const int c = g * 4;
+    float4 acc[DW8_R];
+    if constexpr (K > 0) {
+      const float4 bias = *reinterpret_cast<const float4*>(dw_b + c);
+#pragma unroll
+      for (int r = 0; r < DW8_R; ++r) acc[r] = bias;
+      float4 w[K];
+#pragma unroll
+      for (int j = 0; j < K; ++j) w[j] = *reinterpret_cast<const float4*>(dw_wT + (size_t)j * C + c);
+#pragma unroll
+      for (int i = 0; i < WIN; ++i) {
+        const int t = t0 - HALF + i;
+        float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t >= 0 && t < T) xv = *reinterpret_cast<const float4*>(xb + (size_t)t * pitch + c);
+#pragma unroll
+        for (int j = 0; j < K; ++j) {  // input row i is tap j of output row r = i - j
+          const int r = i - j;
+          if (r >= 0 && r < DW8_R) {
+            acc[r].x = fmaf(w[j].x, xv.x, acc[r].x);
+            acc[r].y = fmaf(w[j].y, xv.y, acc[r].y);
+            acc[r].z = fmaf(w[j].z, xv.z, acc[r].z);
+            acc[r].w = fmaf(w[j].w, xv.w, acc[r].w);
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < DW8_R; ++r) {
+        const int t = t0 + r;
+        acc[r] = (t < T) ? *reinterpret_cast<const float4*>(xb + (size_t)t * pitch + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < DW8_R; ++r) {
+      *reinterpret_cast<float4*>(s_h + r * pitch + c) = acc[r];
+      sum[r] += (acc[r].x + acc[r].y) + (acc[r].z + acc[r].w);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < DW8_R; ++r) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], off);
+    if (lane == 0) s_red[warp][r] = sum[r];
+  }
+  __syncthreads();
+  if (tid < DW8_R) {
+    float m = 0.f;
+    for (int w = 0; w < nwarp; ++w) m += s_red[w][tid];
+    s_mean[tid] = m / C;
+  }
+  __syncthreads();
+  float var[DW8_R];
+#pragma unroll
+  for (int r = 0; r < DW8_R; ++r) var[r] = 0.f;
+  for (int g = tid; g < C4; g += nthr) {
+#pragma unroll
+    for (int r = 0; r < DW8_R; ++r) {
+      const float4 h = *reinterpret_cast<const float4*>(s_h + r * pitch + g * 4);
+      const float m = s_mean[r];
+      const float d0 = h.x - m, d1 = h.y - m, d2 = h.z - m, d3 = h.w - m;
+      var[r] = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, var[r]))));
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < DW8_R; ++r) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) var[r] += __shfl_xor_sync(0xffffffffu, var[r], off);
+    if (lane == 0) s_red[warp][r] = var[r];
+  }
+  __syncthreads();
+  if (tid < DW8_R) {
+    float v = 0.f;
+    for (int w = 0; w < nwarp; ++w) v += s_red[w][tid];
+    s_rstd[tid] = 1.0f / sqrtf(v / C + eps);
+  }
+  __syncthreads();
+  const int P4 = pitch >> 2;
+  for (int g = tid; g < P4; g += nthr) {
+    const int c = g * 4;
+    float4 gw = make_float4(0.f, 0.f, 0.f, 0.f), gb = gw;
+    if (c < C) {
+      gw = *reinterpret_cast<const float4*>(ln_w + c);
+      gb = *reinterpret_cast<const float4*>(ln_b + c);
+    }
+#pragma unroll
+    for (int r = 0; r < DW8_R; ++r) {
+      const int t = t0 + r;
+      if (t >= T) break;
+      float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < C) {
+        const float4 h = *reinterpret_cast<const float4*>(s_h + r * pitch + c);
+        const float m = s_mean[r], rs = s_rstd[r];
+        y.x = fmaf((h.x - m) * rs, gw.x, gb.x);
+        y.y = fmaf((h.y - m) * rs, gw.y, gb.y);
+        y.z = fmaf((h.z - m) * rs, gw.z, gb.z);
+        y.w = fmaf((h.w - m) * rs, gw.w, gb.w);
+      }
+      const size_t row = (size_t)b * T + t;
+      if (out16) {
+        __half* dst = out16 + row * (pitch + split) + c;
+        const uint32_t h0 = pack_half2_sat(y.x, y.y), h1 = pack_half2_sat(y.z, y.w);
+        *reinterpret_cast<uint2*>(dst) = make_uint2(h0, h1);
+        if (split > 0) {
+          const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&h0));
+          const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&h1));
+          *reinterpret_cast<uint2*>(dst + split) =
+              make_uint2(pack_half2_sat(y.x - f0.x, y.y - f0.y), pack_half2_sat(y.z - f1.x, y.w - f1.y));
+        }
+      }
+      if (out32) *reinterpret_cast<float4*>(out32 + row * pitch + c) = y;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // ISTFT("same") overlap-add + envelope normalisation
 // ------------------------------------------------------------------------------------------------
@@ -851,6 +994,38 @@ extern "C" int fv_dwconv_layernorm(const float* x32, void* out16, float* out32, 
                  (split == 0 || split == pitch),
              FV_E_BADARG, "fv_dwconv_layernorm: bad arguments");
   FV_REQUIRE(k <= 0 || (dw_w && dw_b && (k & 1)), FV_E_BADARG, "fv_dwconv_layernorm: bad depthwise kernel");
+  const int vec_smem = DW8_R * pitch * (int)sizeof(float);
+  const bool aligned16 = ((reinterpret_cast<uintptr_t>(x32) | reinterpret_cast<uintptr_t>(out16) |
+                           reinterpret_cast<uintptr_t>(out32) | reinterpret_cast<uintptr_t>(dw_w) |
+                           reinterpret_cast<uintptr_t>(dw_b) | reinterpret_cast<uintptr_t>(ln_w) |
+                           reinterpret_cast<uintptr_t>(ln_b)) & 15) == 0;
+  static const bool vec_on = [] {
+    const char* e = getenv("FV_DWLN_VEC");  // FV_DWLN_VEC=0: the scalar 4-row kernel (A/B measurements)
+    return !(e && e[0] == '0');
+  }();
+  if (vec_on && (k <= 0 || k == 7) && C % 4 == 0 && pitch % 4 == 0 && aligned16 && vec_smem <= 200 * 1024) {
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] {
+      attr_err = cudaFuncSetAttribute(dwconv_ln_vec_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (attr_err == cudaSuccess)
+        attr_err = cudaFuncSetAttribute(dwconv_ln_vec_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    });
+    int rc = check_cuda(attr_err, "cudaFuncSetAttribute(dwconv_ln_vec_kernel)");
+    if (rc) return rc;
+    const int tiles_per_b = ceil_div(T, DW8_R);
+    const int grid = B * tiles_per_b;
+    int threads = round_up(C / 4, 32);
+    threads = threads < 64 ? 64 : (threads > 256 ? 256 : threads);
+    if (k == 7)
+      dwconv_ln_vec_kernel<7><<<grid, threads, vec_smem, (cudaStream_t)stream>>>(
+          x32, (__half*)out16, out32, dw_w, dw_b, ln_w, ln_b, eps, T, C, pitch, tiles_per_b, split);
+    else
+      dwconv_ln_vec_kernel<0><<<grid, threads, vec_smem, (cudaStream_t)stream>>>(
+          x32, (__half*)out16, out32, dw_w, dw_b, ln_w, ln_b, eps, T, C, pitch, tiles_per_b, split);
+    FV_CHECK_LAUNCH("dwconv_ln_vec_kernel");
+    return 0;
+  }
   const int tiled_smem = DW_R * pitch * (int)sizeof(float);
   if ((k <= 0 || k == 7) && tiled_smem <= 48 * 1024) {
     const int tiles_per_b = ceil_div(T, DW_R);
