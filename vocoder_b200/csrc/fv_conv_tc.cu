@@ -941,8 +941,13 @@ int pick_block_n(int C_out, int C_out_pad) {
   if (C_out <= 32) return 32;                    // N = 32 keeps the TMA epilogue (32-column boxes) even for C <= 16
   if (C_out <= 64) return 64;
   if (C_out <= 128) return 128;
+  // 256-wide tiles (the CTA-pair kernel) unless they would pad C_out by more than 10%
   const int pad128 = round_up(C_out, 128), pad256 = round_up(C_out, 256);
-  return pad256 <= pad128 ? 256 : 128;
+  static const bool wide = [] {
+    const char* e = getenv("FV_TC_WIDE");  // FV_TC_WIDE=0: 256-wide tiles only when they pad no more than 128-wide ones
+    return !(e && e[0] == '0');
+  }();
+  return (pad256 <= pad128 || (wide && pad256 * 10 <= pad128 * 11)) ? 256 : 128;
 }
 
 // Called by fv_conv1d (fv_api.cu) after argument validation.  m_sub_override / block_n_override: 0 = heuristic.
