@@ -252,7 +252,7 @@ def roofline_of(recs, peaks, step_ms):
     else:
         roof = {"bound": "tensor", "achieved": f["flops"] / t / 1e12, "peak": peaks["tensor_tflops"], "unit": "TFLOP/s"}
     roof["frac"] = roof["achieved"] / roof["peak"]
-    roof["traffic"] = None
+    roof["traffic"] = None  # filled by main() from profiles/r01_traffic.json (ncu --set full capture of a launch of this family)
     roof.update({"kernel": f"{top} (all {f['launches']} launches of one step)", "launches": f["launches"],
                  "kernel_ms_per_step": f["ms"], "share_of_step": f["ms"] / step_ms,
                  "alg_tflop_per_step": f["flops"] / 1e12, "alg_gbytes_per_step": f["bytes"] / 1e9,
@@ -413,6 +413,13 @@ def main():
             with open(args.dump_launches, "w") as f:
                 json.dump(recs, f)
         roofline = roofline_of(recs, peaks, dev_ms / args.steps)
+        try:  # DRAM bytes of a profiled launch of the dominant family (ncu --set full, committed under profiles/)
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(args.workload)
+            if tr and tr.get("traffic_bytes") and roofline["kernel"].startswith(tr["kernel"]):
+                roofline["traffic"] = tr["traffic_bytes"]
+                roofline["traffic_ref"] = {k: tr[k] for k in ("launch", "algorithmic_bytes", "source")}
+        except (OSError, ValueError):
+            pass
 
         cpu_baseline = None
         if not args.no_cpu_baseline and world == 1:
