@@ -177,6 +177,13 @@ def group_gemm():
         dict(name="lin_1032_1024", B=2, L=50, c_in=1026, c_out=1024, k=1, act=A.ACT_NONE),
         dict(name="lin_2816_11264_gelu", B=1, L=300, c_in=2816, c_out=11264, k=1, act=A.ACT_GELU,
              engines=("tc",)),
+        # 256-wide tiles = the CTA-pair (cta_group::2) kernel: ragged row counts (second CTA of the last pair partly or
+        # fully past the end), every epilogue input, 10%-padded C_out, dilated taps crossing utterance boundaries
+        dict(name="pair_lin_704_1408_res_gamma_acc", B=7, L=111, c_in=704, c_out=1408, k=1, act=A.ACT_NONE, use_res=True,
+             use_gamma=True, accumulate=True, scale=0.5),
+        dict(name="pair_lin_256_512_silu_rows257", B=1, L=257, c_in=256, c_out=512, k=1, act=A.ACT_SILU),
+        dict(name="pair_conv_256_256_k7_d3_res", B=3, L=700, c_in=256, c_out=256, k=7, d=3, act=A.ACT_SILU, use_res=True),
+        dict(name="pair_conv_512_256_k3_L384", B=2, L=384, c_in=512, c_out=256, k=3, d=1, act=A.ACT_LEAKY),
     ]
     return [run_conv_case(**c) for c in cases]
 
