@@ -52,8 +52,9 @@ struct ConvTcParams {
   int16_t tap_off[FV_MAX_TAPS];
 };
 
-template <int BLOCK_N, int M_SUB, int BLOCK_K, bool EPI_TMA, bool SLAB = false, bool PAIR = false>
+template <int BLOCK_N, int M_SUB, int BLOCK_K, bool EPI_TMA, bool SLAB = false, bool PAIR = false, bool FAT = false>
 struct TcCfg {
+  static constexpr int EW = FAT ? 16 : kEpiWarps;  // epilogue warps (FAT: the fp16-only epilogue with 4 warps per scheduler)
   static constexpr int ROW_BYTES = BLOCK_K * 2;
   static constexpr int A_SUB_BYTES = 128 * ROW_BYTES;
   static constexpr int A_STAGE = M_SUB * A_SUB_BYTES;
@@ -71,8 +72,9 @@ struct TcCfg {
   // epilogue staging.  LSU flavour: per-warp padded transpose patch.  TMA flavour: per-warp swizzled boxes, two
   // 32x32 fp32 patches (4 KB each, SWIZZLE_128B: residual-in / out32, or ping-pong outputs when there is no
   // residual) and a 32x32 fp16 patch (2 KB, SWIZZLE_64B).
-  static constexpr int EPI_WARP_BYTES = EPI_TMA ? (2 * 4096 + 2048) : (32 * STG_STRIDE * 4);
-  static constexpr int STG_BYTES = ((kEpiWarps * EPI_WARP_BYTES + 1023) / 1024) * 1024;
+  // FAT: two ping-pong 32x32 fp16 patches (2 KB each, SWIZZLE_64B) per warp
+  static constexpr int EPI_WARP_BYTES = FAT ? 4096 : (EPI_TMA ? (2 * 4096 + 2048) : (32 * STG_STRIDE * 4));
+  static constexpr int STG_BYTES = ((EW * EPI_WARP_BYTES + 1023) / 1024) * 1024;
   static constexpr int TAIL_BYTES = 1024 + 2 * BLOCK_N * 4;  // barriers, tmem ptr, bias/gamma
   // per-tap mainloop: ring of (operand tile, weight tile) stages.  Slab mainloop: two operand slabs of
   // M_SUB*128 + 64 rows (one per K chunk, every tap is a row-shifted UMMA descriptor into it) + a ring of weight tiles.
@@ -100,9 +102,16 @@ struct TcCfg {
 // rows by BLOCK_N columns, `tcgen05.mma.cta_group::2` (M = 256) issued by the leader CTA.  Each CTA stages its own rows
 // of A and HALF of the weight tile, so a 128x256x16 step reads 4 + 4 KB of shared memory per SM instead of 4 + 8 KB
 // (a 256-wide SS-mode UMMA on one SM sits at 96 B/clk of the 128 B/clk port before the TMA writes are counted).
-template <int BLOCK_N, int M_SUB, int BLOCK_K, bool EPI_TMA, bool HEAVY_ACT, bool SLAB, bool PAIR = false>
-__global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
-  using Cfg = TcCfg<BLOCK_N, M_SUB, BLOCK_K, EPI_TMA, SLAB, PAIR>;
+// FAT = true: launches whose only output is the activated fp16 operand (convs1, conv_pre, ConvNeXt pwconv1: no residual, no
+// fp32 output, no layer scale) are bound by the epilogue when it runs on 8 warps = 2 per scheduler (ncu: ~5 stall cycles per
+// issued instruction, a 12032 x 5632 GELU GEMM tile takes 18k cycles against 11k of MMA).  This variant runs 16 epilogue
+// warps (576 threads) over a lean fp16-only path with two ping-pong 2 KB staging patches per warp.
+template <int BLOCK_N, int M_SUB, int BLOCK_K, bool EPI_TMA, bool HEAVY_ACT, bool SLAB, bool PAIR = false, bool FAT = false>
+__global__ void __launch_bounds__(64 + (FAT ? 16 : kEpiWarps) * 32, 1)
+    conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
+  using Cfg = TcCfg<BLOCK_N, M_SUB, BLOCK_K, EPI_TMA, SLAB, PAIR, FAT>;
+  static_assert(!FAT || (EPI_TMA && !HEAVY_ACT), "the 16-warp epilogue is the fp16-only TMA flavour");
+  constexpr int EW = Cfg::EW, ESTRIDE = EW / 4, ETHREADS = EW * 32;
   static_assert(!PAIR || (!SLAB && EPI_TMA), "the CTA-pair variant exists for the per-tap mainloop with the TMA epilogue");
   const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
   const int n_workers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;   // tiles are dealt to CTAs, or to CTA pairs
@@ -123,7 +132,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
   uint64_t* tfull_bar = aempty_bar + 2;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* epi_bar = tempty_bar + 2;  // two per epilogue warp (TMA epilogue: residual prefetch, running-sum load)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(epi_bar + 2 * kEpiWarps);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(epi_bar + 2 * EW);
   float* s_bias = reinterpret_cast<float*>(tail + 1024);
   float* s_gamma = s_bias + BLOCK_N;
   float* s_stage = reinterpret_cast<float*>(s_stage_raw);
@@ -140,12 +149,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], (PAIR ? 2 : 1) * kEpiThreads);  // pair: both CTAs' epilogues release the leader
+      mbar_init(&tempty_bar[i], (PAIR ? 2 : 1) * ETHREADS);  // pair: both CTAs' epilogues release the leader
       mbar_init(&afull_bar[i], 1);
       mbar_init(&aempty_bar[i], 1);
     }
     if (SLAB) tma_prefetch_desc(&p.tmA2);
-    for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&epi_bar[i], 1);
+    for (int i = 0; i < 2 * EW; ++i) mbar_init(&epi_bar[i], 1);
     if (EPI_TMA) {
       if (p.residual) tma_prefetch_desc(&p.tmR);
       if (p.out32) tma_prefetch_desc(&p.tmO32);
@@ -338,7 +347,105 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps
-    if constexpr (EPI_TMA) {
+    if constexpr (FAT) {
+      // fp16-only epilogue on 16 warps: accumulator + bias -> * out_scale -> activation -> fp16 -> swizzled 32x32 patch ->
+      // bulk store; thread = accumulator row, items (128-row block, 32-column chunk) dealt to the 4 warps of a lane quarter
+      const int ew = warp - 2;
+      const int quarter = warp & 3;
+      const int cgrp = ew >> 2;
+      const int tid_e = threadIdx.x - 64;
+      uint8_t* H0 = s_stage_raw + ew * 4096;  // 32 rows x 64 B, SWIZZLE_64B, two of them
+      uint32_t parity = 0;
+      int staged_n_t = -1;
+      const uint32_t h_xor = static_cast<uint32_t>((lane >> 1) & 3);
+      uint32_t tile_i = 0;
+      for (int tile = worker; tile < p.total_tiles; tile += n_workers, ++tile_i) {
+        int r = tile;
+        const int n_t = r % p.n_tiles; r /= p.n_tiles;
+        const int m_t = r % p.m_tiles; r /= p.m_tiles;
+        const int b = r % p.B;
+        const int phase = r / p.B;
+        const int q0 = m_t * TILE_ROWS + (int)cta_rank * (M_SUB * 128);
+        const int n0 = n_t * BLOCK_N;
+        const uint32_t buf = tile_i % Cfg::ACC_BUFS;
+        if (n_t != staged_n_t) {  // bias of this N tile -> smem
+          named_bar_sync(1, ETHREADS);
+          for (int i = tid_e; i < BLOCK_N; i += ETHREADS) {
+            const int col = n0 + i;
+            s_bias[i] = (p.bias != nullptr && col < p.C_out) ? p.bias[col] : 0.f;
+          }
+          named_bar_sync(1, ETHREADS);
+          staged_n_t = n_t;
+        }
+        int n_ch = (p.C_out_r8 - n0 + 31) / 32;  // column chunks of this tile that hold real channels
+        n_ch = n_ch < Cfg::NCH ? n_ch : Cfg::NCH;
+        const int n_items = M_SUB * n_ch;
+        mbar_wait(&tfull_bar[buf], (tile_i / Cfg::ACC_BUFS) & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int item = cgrp; item < n_items; item += ESTRIDE) {
+          const int sub = item / n_ch, ch = item % n_ch;
+          const int qb = q0 + sub * 128 + quarter * 32;
+          uint32_t acc[32];
+          tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + (buf * M_SUB + sub) * BLOCK_N +
+                                 ch * 32, acc);
+          tmem_ld_wait();
+          if (item + ESTRIDE >= n_items) {  // this warp's last TMEM read of the tile: hand the accumulator back
+            tc_fence_before();
+            if constexpr (PAIR) mbar_arrive_leader(&tempty_bar[buf]); else mbar_arrive(&tempty_bar[buf]);
+          }
+          float o[32];
+          const float4* bp = reinterpret_cast<const float4*>(s_bias + ch * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 bb = bp[j];
+            o[4 * j + 0] = (__uint_as_float(acc[4 * j + 0]) + bb.x) * p.out_scale;
+            o[4 * j + 1] = (__uint_as_float(acc[4 * j + 1]) + bb.y) * p.out_scale;
+            o[4 * j + 2] = (__uint_as_float(acc[4 * j + 2]) + bb.z) * p.out_scale;
+            o[4 * j + 3] = (__uint_as_float(acc[4 * j + 3]) + bb.w) * p.out_scale;
+          }
+          if (p.act == FV_ACT_SILU) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = silu_fast(o[i]);
+          } else if (p.act == FV_ACT_SILU_TANH) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = silu_tanh(o[i]);
+          } else if (p.act == FV_ACT_GELU) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = gelu_erf_fast(o[i]);
+          } else if (p.act == FV_ACT_LEAKY) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = o[i] > 0.f ? o[i] : o[i] * p.act_param;
+          }
+          uint8_t* Hout = H0 + parity * 2048;
+          parity ^= 1;
+          if (lane == 0) tma_store_wait_read_keep1();  // the store issued two items ago has drained this patch
+          __syncwarp();
+          const uint32_t h_row = smem_u32(Hout) + lane * 64;
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const uint32_t w0 = pack_half2_sat(o[8 * jj + 0], o[8 * jj + 1]);
+            const uint32_t w1 = pack_half2_sat(o[8 * jj + 2], o[8 * jj + 3]);
+            const uint32_t w2 = pack_half2_sat(o[8 * jj + 4], o[8 * jj + 5]);
+            const uint32_t w3 = pack_half2_sat(o[8 * jj + 6], o[8 * jj + 7]);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(h_row + ((static_cast<uint32_t>(jj) ^ h_xor) << 4)),
+                         "r"(w0), "r"(w1), "r"(w2), "r"(w3)
+                         : "memory");
+          }
+          fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the bulk-copy engine
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_4d(&p.tmO16, Hout, n0 + ch * 32, phase, qb, b);
+            tma_store_commit();
+          }
+        }
+        if (cgrp >= n_items) {  // idle warp of this tile shape still owes its TMEM-release arrivals
+          tc_fence_before();
+          if constexpr (PAIR) mbar_arrive_leader(&tempty_bar[buf]); else mbar_arrive(&tempty_bar[buf]);
+        }
+      }
+      if (lane == 0) tma_store_wait_all();
+    } else if constexpr (EPI_TMA) {
       // thread = accumulator row throughout (the native TMEM layout); all global traffic of the epilogue is TMA:
       // the residual patch is bulk-loaded into a swizzled smem box, combined in place, and bulk-stored as out32;
       // the activated fp16 patch goes out through a second box.  No per-element address math, no LSU global ops.
@@ -779,9 +886,10 @@ static int encode_epi_map(EncodeTiledFn enc, CUtensorMap* tm, const void* base, 
   return 0;
 }
 
-template <int BLOCK_N, int M_SUB, int BLOCK_K, bool EPI_TMA, bool HEAVY_ACT, bool SLAB, bool PAIR = false>
+template <int BLOCK_N, int M_SUB, int BLOCK_K, bool EPI_TMA, bool HEAVY_ACT, bool SLAB, bool PAIR = false, bool FAT = false>
 static int launch_tc_impl(const fv_conv_desc* d, ConvTcParams& p, cudaStream_t stream) {
-  using Cfg = TcCfg<BLOCK_N, M_SUB, BLOCK_K, EPI_TMA, SLAB, PAIR>;
+  using Cfg = TcCfg<BLOCK_N, M_SUB, BLOCK_K, EPI_TMA, SLAB, PAIR, FAT>;
+  constexpr int THREADS = 64 + Cfg::EW * 32;
   if constexpr (!Cfg::VALID) {
     return set_error(FV_E_UNSUPPORTED, "tile configuration N=%d M_SUB=%d K=%d does not fit in shared memory", BLOCK_N,
                      M_SUB, BLOCK_K);
@@ -849,7 +957,7 @@ static int launch_tc_impl(const fv_conv_desc* d, ConvTcParams& p, cudaStream_t s
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, M_SUB, BLOCK_K, EPI_TMA, HEAVY_ACT, SLAB, PAIR>,
+    attr_err = cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, M_SUB, BLOCK_K, EPI_TMA, HEAVY_ACT, SLAB, PAIR, FAT>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
   });
   int rc = check_cuda(attr_err, "cudaFuncSetAttribute(conv_tc_kernel)");
@@ -860,7 +968,7 @@ static int launch_tc_impl(const fv_conv_desc* d, ConvTcParams& p, cudaStream_t s
     const int n_clusters = p.total_tiles < pairs ? p.total_tiles : pairs;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * n_clusters, 1, 1);
-    cfg.blockDim = dim3(kTcThreads, 1, 1);
+    cfg.blockDim = dim3(THREADS, 1, 1);
     cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -870,12 +978,13 @@ static int launch_tc_impl(const fv_conv_desc* d, ConvTcParams& p, cudaStream_t s
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    rc = check_cuda(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, M_SUB, BLOCK_K, EPI_TMA, HEAVY_ACT, SLAB, PAIR>, p),
+    rc = check_cuda(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, M_SUB, BLOCK_K, EPI_TMA, HEAVY_ACT, SLAB, PAIR, FAT>, p),
                     "cudaLaunchKernelEx(conv_tc_kernel pair)");
     if (rc) return rc;
   } else {
     const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-    conv_tc_kernel<BLOCK_N, M_SUB, BLOCK_K, EPI_TMA, HEAVY_ACT, SLAB><<<grid, kTcThreads, Cfg::SMEM_BYTES, stream>>>(p);
+    conv_tc_kernel<BLOCK_N, M_SUB, BLOCK_K, EPI_TMA, HEAVY_ACT, SLAB, false, FAT>
+        <<<grid, THREADS, Cfg::SMEM_BYTES, stream>>>(p);
   }
   FV_CHECK_LAUNCH("conv_tc_kernel");
   return 0;
@@ -899,6 +1008,20 @@ static int launch_tc(const fv_conv_desc* d, ConvTcParams& p, cudaStream_t stream
     }
   }
   if constexpr (EPI_TMA && BLOCK_K == 64 && ((BLOCK_N == 256 && M_SUB == 1) || (BLOCK_N == 128 && M_SUB == 2))) {
+    // fp16-only output (convs1, conv_pre, pwconv1): the 16-warp epilogue (FV_TC_FAT=0 disables)
+    static const bool fat_on = [] {
+      const char* e = getenv("FV_TC_FAT");
+      return !(e && e[0] == '0');
+    }();
+    const bool o16_only = fat_on && d->out16 && !d->out32 && !d->residual && !d->gamma && !d->accumulate &&
+                          d->out16_split == 0 && d->a_split == 0 && !p.use_slab;
+    if (o16_only) {
+      if constexpr (BLOCK_N == 256) {
+        if ((p.use_pair & 1) && p.q_rows >= 256)
+          return launch_tc_impl<BLOCK_N, M_SUB, BLOCK_K, true, false, false, true, true>(d, p, stream);
+      }
+      return launch_tc_impl<BLOCK_N, M_SUB, BLOCK_K, true, false, false, false, true>(d, p, stream);
+    }
     // CTA pair (cta_group::2) for the wide layers: 256 x 256 (GEMMs, C = 256 convs) or 512 x 128 (C = 128 convs) tiles
     // over two SMs; FV_TC_PAIR bit 0 enables the N = 256 shape, bit 1 the N = 128 shape
     if ((p.use_pair & (BLOCK_N == 256 ? 1 : 2)) && p.q_rows >= 2 * M_SUB * 128)
