@@ -30,6 +30,9 @@ WORKLOADS = {
     "hifigan_b1": ("hifigan", 1, 80, 94, 256, 24000, "hifigan baseline generator, batch 1 x 1 s @ 24 kHz"),
     "bigvgan_b32": ("bigvgan", 32, 100, 87, 512, 44100,
                     "bigvgan generator with anti-aliased Snake (100 mel, hop 512), batch 32 x 1 s @ 44.1 kHz"),
+    "firefly_b32": ("firefly", 32, 128, 87, 512, 44100,
+                    "firefly-gan-base (ConvNeXt [3,3,9,3]x[128,256,384,512] + HiFiGAN head, rates 8-8-2-2-2, k13 pre/post), "
+                    "batch 32 x 1 s @ 44.1 kHz"),
     "vocos_huge_b128": ("vocos", 128, 100, 94, 256, 24000,
                         "vocos_huge ConvNeXt [3,3,27,3]x[352,704,1408,2816] + ISTFT(1024/256), batch 128 x 1 s @ 24 kHz"),
 }
@@ -46,6 +49,14 @@ def build_model(kind: str):
                                 pre_conv_kernel_size=7, post_conv_kernel_size=7)
     if kind == "bigvgan":
         return BigVGANGenerator(hop_length=512, num_mels=100, use_template=False)
+    if kind == "firefly":  # configs/model/generator/firefly-gan-base.yaml + resolution/44100_512_2048.yaml
+        return UnifyGenerator(
+            backbone=ConvNeXtEncoder(input_channels=128, depths=[3, 3, 9, 3], dims=[128, 256, 384, 512],
+                                     drop_path_rate=0.2, kernel_size=7),
+            head=HiFiGANGenerator(hop_length=512, upsample_rates=(8, 8, 2, 2, 2), upsample_kernel_sizes=(16, 16, 4, 4, 4),
+                                  resblock_kernel_sizes=(3, 7, 11), resblock_dilation_sizes=((1, 3, 5),) * 3,
+                                  num_mels=512, upsample_initial_channel=512, use_template=False,
+                                  pre_conv_kernel_size=13, post_conv_kernel_size=13))
     if kind == "vocos":
         return UnifyGenerator(
             backbone=ConvNeXtEncoder(input_channels=100, depths=[3, 3, 27, 3], dims=[352, 704, 1408, 2816],
@@ -65,6 +76,8 @@ def oracle_forward(kind, sd, mel, model):
         return G.hifigan_forward(sd, mel, model.upsample_rates)
     if kind == "bigvgan":
         return G.bigvgan_forward(sd, mel, model.upsample_rates)
+    if kind == "firefly":
+        return G.unify_hifigan_forward(sd, mel, model.head.upsample_rates)
     return G.unify_vocos_forward(sd, mel, 1024, 256, 1024)
 
 

@@ -286,6 +286,15 @@ def unify_vocos_forward(sd: SD, mel: Tensor, n_fft: int, hop: int, win: int) -> 
     return x[:, None, :]
 
 
+def unify_hifigan_forward(sd: SD, mel: Tensor, upsample_rates: Sequence[int],
+                          resblock_dilation_sizes: Sequence[Sequence[int]] = ((1, 3, 5),) * 3) -> Tensor:
+    """unify.py:18-33 with ConvNeXtEncoder backbone + HiFiGANGenerator head = configs/model/generator/firefly-gan-base.yaml
+    (the head consumes the backbone's [B, dims[-1], T] output as its "mel", pre/post kernels 13)."""
+    x = convnext_forward(sd, mel, "backbone.")
+    head = {k[len("head."):]: v for k, v in sd.items() if k.startswith("head.")}
+    return hifigan_forward(head, x, upsample_rates, resblock_dilation_sizes)
+
+
 # --------------------------------------------------------------------------------------------
 # RefineGAN  (fish_vocoder/modules/generators/refinegan.py)
 # --------------------------------------------------------------------------------------------

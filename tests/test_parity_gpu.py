@@ -37,6 +37,8 @@ def _build(name, kwargs):
         return BigVGANGenerator(**kwargs)
     if name.startswith("vocos"):
         return UnifyGenerator(backbone=ConvNeXtEncoder(**kwargs["backbone"]), head=ISTFTHead(**kwargs["head"]))
+    if name.startswith("firefly"):  # configs/model/generator/firefly-gan-base.yaml: ConvNeXt backbone + HiFiGAN head
+        return UnifyGenerator(backbone=ConvNeXtEncoder(**kwargs["backbone"]), head=HiFiGANGenerator(**kwargs["head"]))
     if name.startswith("refinegan"):
         from vocoder_b200.generators.refinegan import RefineGANGenerator
         return RefineGANGenerator(**kwargs)
@@ -83,6 +85,9 @@ def test_generator_matches_reference_golden(name):
     else:
         assert err <= TOL * peak, f"{name}: max|delta|={err:.3e} (peak {peak:.3f})"
         assert err_emu <= max(5e-4 * peak, gap), f"{name}: vs rounded oracle {err_emu:.3e}"
+    if name.startswith("firefly"):  # quiet output (|y| <= 0.045): the absolute bar alone would be lax, also bound the
+        true_peak = float(out.abs().max())            # error relative to the waveform's own peak
+        assert err <= max(5e-3 * true_peak, 1.5 * gap), f"{name}: {err:.3e} vs waveform peak {true_peak:.3e}"
 
 
 def _set_precision(m, mode):

@@ -35,6 +35,9 @@ def oracle_forward(name, kwargs, sd, ins, extra=None):
     if name.startswith("vocos"):
         h = kwargs["head"]
         return G.unify_vocos_forward(sd, ins["mel"], h["n_fft"], h["hop_length"], h["win_length"])
+    if name.startswith("firefly"):
+        return G.unify_hifigan_forward(sd, ins["mel"], kwargs["head"]["upsample_rates"],
+                                       kwargs["head"]["resblock_dilation_sizes"])
     if name.startswith("refinegan"):
         return G.refinegan_forward(sd, ins["mel"], ins["template"], numpy_noise_fn(extra["noise_seed"][0]),
                                    kwargs["downsample_rates"], kwargs["upsample_rates"], kwargs["leaky_relu_slope"])
@@ -42,7 +45,7 @@ def oracle_forward(name, kwargs, sd, ins, extra=None):
 
 
 ALL_GOLDEN = ["hifigan_small_ref", "hifigan_small_stress", "hifigan_template_stress", "bigvgan_small_ref",
-              "bigvgan_small_stress", "vocos_small_ref", "vocos_small_stress", "refinegan_small_stress"]
+              "bigvgan_small_stress", "vocos_small_ref", "vocos_small_stress", "refinegan_small_stress", "firefly_small_stress"]
 
 
 def channels_last_noise(seed):
