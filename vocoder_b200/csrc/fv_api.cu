@@ -4,6 +4,8 @@
 #include <cstdarg>
 #include <cstdio>
 
+#include <cstdlib>
+
 #include "fv_common.cuh"
 
 namespace fv {
@@ -35,6 +37,18 @@ int conv1d_tc(const fv_conv_desc* d, cudaStream_t stream, int block_n_override, 
               int mainloop);
 int conv1d_simt(const fv_conv_desc* d, cudaStream_t stream);
 
+}  // namespace fv
+
+namespace fv {
+bool pdl_enabled() {
+  static const bool on = [] {
+    // Measured on B200 under CUDA-graph replay (HiFiGAN b64 / b1, BigVGAN b32, Vocos b128): within run-to-run noise
+    // (b1: 0.873 -> 0.852 ms), so the attribute is opt-in: FV_PDL=1
+    const char* e = getenv("FV_PDL");
+    return e && e[0] == '1';
+  }();
+  return on;
+}
 }  // namespace fv
 
 using namespace fv;

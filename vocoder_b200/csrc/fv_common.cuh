@@ -43,6 +43,44 @@ static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 static inline int ceil_div(int x, int m) { return (x + m - 1) / m; }
 
 // ------------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL): the hot kernels are launched with cudaLaunchAttributeProgrammaticStreamSerialization,
+// signal `launch_dependents` at entry and execute `griddepcontrol.wait` before their first global access, so the next
+// kernel's launch latency and prologue (barrier init, TMEM allocation, tensor-map prefetch) overlap this kernel's tail.
+// Both instructions are no-ops in a kernel launched without the attribute.  Opt-in (FV_PDL=1): measured neutral.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+bool pdl_enabled();  // fv_api.cu
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                        int cluster_x, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster_x;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
+// ------------------------------------------------------------------------------------------------
 // activation math shared by the tensor-core epilogue and the CUDA-core kernels
 // ------------------------------------------------------------------------------------------------
 // exact-erf GELU (nn.GELU default) with erf from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7): one SFU reciprocal,

@@ -139,6 +139,7 @@ __global__ void __launch_bounds__(64 + (FAT ? 16 : kEpiWarps) * 32, 1)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();  // the next kernel may start its prologue under this kernel's tail
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
@@ -170,6 +171,7 @@ __global__ void __launch_bounds__(64 + (FAT ? 16 : kEpiWarps) * 32, 1)
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above touched only this CTA's smem / TMEM; global memory of the previous kernel from here on
 
   const int k_steps = p.n_taps * p.k_chunks;
 
@@ -962,29 +964,14 @@ static int launch_tc_impl(const fv_conv_desc* d, ConvTcParams& p, cudaStream_t s
   });
   int rc = check_cuda(attr_err, "cudaFuncSetAttribute(conv_tc_kernel)");
   if (rc) return rc;
-  if constexpr (PAIR) {
-    // clusters of two CTAs = the two SMs of a TPC; one tile per cluster at a time
-    const int pairs = num_sms() / 2;
-    const int n_clusters = p.total_tiles < pairs ? p.total_tiles : pairs;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * n_clusters, 1, 1);
-    cfg.blockDim = dim3(THREADS, 1, 1);
-    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    rc = check_cuda(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, M_SUB, BLOCK_K, EPI_TMA, HEAVY_ACT, SLAB, PAIR, FAT>, p),
-                    "cudaLaunchKernelEx(conv_tc_kernel pair)");
+  {
+    // PAIR: clusters of two CTAs = the two SMs of a TPC, one tile per cluster at a time
+    const int workers = PAIR ? num_sms() / 2 : num_sms();
+    const int n_work = p.total_tiles < workers ? p.total_tiles : workers;
+    rc = check_cuda(launch_kernel(conv_tc_kernel<BLOCK_N, M_SUB, BLOCK_K, EPI_TMA, HEAVY_ACT, SLAB, PAIR, FAT>,
+                                  dim3((PAIR ? 2 : 1) * n_work), dim3(THREADS), Cfg::SMEM_BYTES, stream, PAIR ? 2 : 1, p),
+                    "cudaLaunchKernelEx(conv_tc_kernel)");
     if (rc) return rc;
-  } else {
-    const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-    conv_tc_kernel<BLOCK_N, M_SUB, BLOCK_K, EPI_TMA, HEAVY_ACT, SLAB, false, FAT>
-        <<<grid, THREADS, Cfg::SMEM_BYTES, stream>>>(p);
   }
   FV_CHECK_LAUNCH("conv_tc_kernel");
   return 0;

@@ -132,6 +132,7 @@ __global__ void __launch_bounds__(FrCfg<C, EW, NCTA>::THREADS, NCTA) mrf_fused_k
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmX);
@@ -151,6 +152,7 @@ __global__ void __launch_bounds__(FrCfg<C, EW, NCTA>::THREADS, NCTA) mrf_fused_k
   } else if (warp == 1) {
     tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
   }
+  pdl_wait();  // global memory written by the previous kernel is read from here on
   // biases -> smem (conv2 biases as running sums over the pairs: the TMEM residual stream never sees them)
   for (int i = threadIdx.x; i < p.n_blocks * C; i += blockDim.x) {
     const int j = i / C, c = i % C;
@@ -580,7 +582,10 @@ static int launch_mrf(const fv_mrf_desc* d, MrfParams& p, cudaStream_t stream) {
   if (rc) return rc;
   const int slots = num_sms() * NCTA;
   const int grid = p.total_tiles < slots ? p.total_tiles : slots;
-  mrf_fused_kernel<C, ACT, EW, NCTA, PIPE><<<grid, Cfg::THREADS, Cfg::SMEM, stream>>>(p);
+  rc = check_cuda(launch_kernel(mrf_fused_kernel<C, ACT, EW, NCTA, PIPE>, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM, stream,
+                                1, p),
+                  "cudaLaunchKernelEx(mrf_fused_kernel)");
+  if (rc) return rc;
   FV_CHECK_LAUNCH("mrf_fused_kernel");
   return 0;
 }

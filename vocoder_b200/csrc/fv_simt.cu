@@ -445,6 +445,8 @@ __global__ void __launch_bounds__(256, 2) snake_aa_kernel(const float* __restric
                                                           const float* __restrict__ beta, const SnakeFilt f,
                                                           int logscale, int B, int L, int C, int pitch, int n_seg,
                                                           int seg_len, int split) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int hp = pitch >> 1;
   const long long total = (long long)B * n_seg * hp;
   const long long item = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -643,6 +645,8 @@ __global__ void __launch_bounds__(256, 2) dwconv_ln_vec_kernel(const float* __re
                                                             const float* __restrict__ ln_w,
                                                             const float* __restrict__ ln_b, float eps, int T, int C,
                                                             int pitch, int tiles_per_b, int split) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float s_h[];  // [DW8_R][pitch]
   __shared__ float s_red[8][DW8_R];
   __shared__ float s_mean[DW8_R], s_rstd[DW8_R];
@@ -976,13 +980,15 @@ extern "C" int fv_snake_aa(const float* x32, void* out16, const float* alpha, co
   const int n_seg = ceil_div(L, seg_len);
   const long long total = (long long)B * n_seg * (pitch / 2);
   if (split)  // strict precision: [hi | lo] fp16 pairs (the extra stores stay out of the default instantiation)
-    snake_aa_kernel<true><<<grid1d(total, 256), 256, 0, (cudaStream_t)stream>>>(x32, (__half*)out16, alpha, beta, f,
-                                                                               logscale, B, L, C, pitch, n_seg, seg_len,
-                                                                               split);
+    FV_REQUIRE(launch_kernel(snake_aa_kernel<true>, dim3(grid1d(total, 256)), dim3(256), 0, (cudaStream_t)stream, 1, x32,
+                             (__half*)out16, alpha, beta, f, logscale, B, L, C, pitch, n_seg, seg_len,
+                             split) == cudaSuccess,
+               FV_E_DRIVER, "launch of snake_aa_kernel failed");
   else
-    snake_aa_kernel<false><<<grid1d(total, 256), 256, 0, (cudaStream_t)stream>>>(x32, (__half*)out16, alpha, beta, f,
-                                                                                logscale, B, L, C, pitch, n_seg, seg_len,
-                                                                                split);
+    FV_REQUIRE(launch_kernel(snake_aa_kernel<false>, dim3(grid1d(total, 256)), dim3(256), 0, (cudaStream_t)stream, 1, x32,
+                             (__half*)out16, alpha, beta, f, logscale, B, L, C, pitch, n_seg, seg_len,
+                             split) == cudaSuccess,
+               FV_E_DRIVER, "launch of snake_aa_kernel failed");
   FV_CHECK_LAUNCH("snake_aa_kernel");
   return 0;
 }
@@ -1017,12 +1023,14 @@ extern "C" int fv_dwconv_layernorm(const float* x32, void* out16, float* out32, 
     const int grid = B * tiles_per_b;
     int threads = round_up(C / 4, 32);
     threads = threads < 64 ? 64 : (threads > 256 ? 256 : threads);
+    cudaError_t le;
     if (k == 7)
-      dwconv_ln_vec_kernel<7><<<grid, threads, vec_smem, (cudaStream_t)stream>>>(
-          x32, (__half*)out16, out32, dw_w, dw_b, ln_w, ln_b, eps, T, C, pitch, tiles_per_b, split);
+      le = launch_kernel(dwconv_ln_vec_kernel<7>, dim3(grid), dim3(threads), vec_smem, (cudaStream_t)stream, 1, x32,
+                         (__half*)out16, out32, dw_w, dw_b, ln_w, ln_b, eps, T, C, pitch, tiles_per_b, split);
     else
-      dwconv_ln_vec_kernel<0><<<grid, threads, vec_smem, (cudaStream_t)stream>>>(
-          x32, (__half*)out16, out32, dw_w, dw_b, ln_w, ln_b, eps, T, C, pitch, tiles_per_b, split);
+      le = launch_kernel(dwconv_ln_vec_kernel<0>, dim3(grid), dim3(threads), vec_smem, (cudaStream_t)stream, 1, x32,
+                         (__half*)out16, out32, dw_w, dw_b, ln_w, ln_b, eps, T, C, pitch, tiles_per_b, split);
+    FV_REQUIRE(le == cudaSuccess, FV_E_DRIVER, "launch of dwconv_ln_vec_kernel failed: %s", cudaGetErrorString(le));
     FV_CHECK_LAUNCH("dwconv_ln_vec_kernel");
     return 0;
   }
