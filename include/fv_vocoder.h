@@ -198,7 +198,7 @@ FV_API int fv_log_mel_out(const float* x32, float* out, int B, int C, int T, int
  *     out32[b, t, c] = (1/n_blocks) * sum_j block_j(x)[b, t, c]        (also the running-sum scratch: required)
  *     out16          = fp16(out_act(out32))                            (optional)
  * Replaces ParralelBlock.forward / ResBlock1.forward (hifigan.py:101-108,117-133): the stack([...]).mean(0) over
- * kernel sizes (3,7,11) of 3 x {silu, conv(k,d), silu, conv(k,1), +x}.  C in {32, 64}; tap reach (k-1)/2*dil <= 32.
+ * kernel sizes (3,7,11) of 3 x {silu, conv(k,d), silu, conv(k,1), +x}.  C in {16, 32, 64}; tap reach (k-1)/2*dil <= 32.
  */
 #define FV_MRF_MAX_BLOCKS 4
 #define FV_MRF_MAX_PAIRS 4

@@ -262,7 +262,8 @@ def _mrf_reference(x, blocks, out_act):
     return mean.permute(0, 2, 1), act.permute(0, 2, 1)
 
 
-@pytest.mark.parametrize("C,L,B,ks", [(32, 52, 2, (3, 7, 11)), (64, 1000, 2, (3, 7, 11)), (32, 1537, 3, (3, 7, 11)),
+@pytest.mark.parametrize("C,L,B,ks", [(16, 45, 2, (3, 7, 11)), (16, 3000, 3, (3, 7, 11)), (16, 777, 1, (5,)),
+                                        (32, 52, 2, (3, 7, 11)), (64, 1000, 2, (3, 7, 11)), (32, 1537, 3, (3, 7, 11)),
                                         (64, 384, 1, (11,)), (64, 4000, 5, (3, 5)), (32, 6016, 40, (3, 7, 11))])
 def test_mrf_fused_kernel(C, L, B, ks):
     torch.manual_seed(C + L)

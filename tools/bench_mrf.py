@@ -46,7 +46,7 @@ def reference(x, blocks):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--acts", default="silu,tanh")
-    ap.add_argument("--shapes", default="64x12032x64,32x24064x64")
+    ap.add_argument("--shapes", default="64x12032x64,32x24064x64,16x44544x32")
     ap.add_argument("--iters", type=int, default=10)
     args = ap.parse_args()
     acts = {"silu": cabi.ACT_SILU, "tanh": cabi.ACT_SILU_TANH, "leaky": cabi.ACT_LEAKY}

@@ -502,7 +502,7 @@ class PackedMrf:
 
 def mrf_fusable(C: int, blocks) -> bool:
     """blocks: [(convs1, convs2)] of nn.Conv1d-like modules.  True when fv_mrf_fused covers the stage."""
-    if is_strict() or C not in (32, 64) or not 1 <= len(blocks) <= MRF_MAX_BLOCKS:
+    if is_strict() or C not in (16, 32, 64) or not 1 <= len(blocks) <= MRF_MAX_BLOCKS:
         return False
     n_pairs = len(blocks[0][0])
     halo = 0

@@ -57,9 +57,13 @@ struct FrCfg {
   static constexpr int ROWB = C * 2;                          // bytes per operand row = swizzle span
   static constexpr int SLAB_ROWS = kFrTile + 2 * kFrGuard;
   static constexpr int SLAB = SLAB_ROWS * ROWB;               // multiple of 1024
-  static constexpr int W_TILE = C * ROWB;
-  static constexpr int STG32 = EW * 4096;                     // per-warp 32 x 32 fp32 patch, SWIZZLE_128B
-  static constexpr int STG16 = EW * 2048;                     // per-warp 32 x 32 fp16 patch, SWIZZLE_64B
+  static constexpr int W_BYTES = C * ROWB;                    // one [C_out x C_in] tap tile
+  static constexpr int W_TILE = W_BYTES < 1024 ? 1024 : W_BYTES;  // ring slot (swizzled tiles stay 1024-byte aligned)
+  static constexpr int CW = C < 32 ? C : 32;                  // columns per epilogue patch (one TMEM load / TMA box)
+  static constexpr int P32 = 32 * CW * 4;                     // per-warp 32 x CW fp32 patch, swizzle span = CW * 4 bytes
+  static constexpr int P16 = 32 * CW * 2;                     // per-warp 32 x CW fp16 patch, swizzle span = CW * 2 bytes
+  static constexpr int STG32 = EW * P32;
+  static constexpr int STG16 = EW * P16;
   // when the staging patches do not fit next to the slabs they alias them (slabs are dead at tile entry / exit)
   static constexpr bool ALIAS = 2 * SLAB + STG32 + STG16 + 8 * W_TILE + 16384 > SMEM_LIMIT;
   static constexpr int XA_OFF = 0;
@@ -79,14 +83,38 @@ struct FrCfg {
   static_assert(TMEM_COLS * NCTA <= 512, "co-resident CTAs exceed TMEM");
   static_assert(!ALIAS || (STG32 <= SLAB && STG16 <= SLAB), "staging does not fit in the slabs it aliases");
   static_assert(NS >= 4, "weight ring too shallow");
-  static_assert(SLAB % 1024 == 0 && W_TILE % 1024 == 0, "swizzled tiles must stay 1024-byte aligned");
+  static_assert(SLAB % 1024 == 0 && W_TILE % 1024 == 0 && (STG32 % 1024 == 0) && (STG16 % 1024 == 0),
+                "swizzled tiles must stay 1024-byte aligned");
+  static_assert(C == 16 || C == 32 || C == 64, "supported channel counts");
 };
 
-// byte offset of 16-byte chunk `chunk` of operand row `row` inside a K-major swizzled slab (base 1024-aligned)
+// byte offset of 16-byte chunk `chunk` of row `row` inside a swizzled tile whose rows are ROWB bytes = the swizzle span
+// (base 1024-aligned): K-major operand slabs and the TMA staging patches use the same function
 template <int ROWB>
 __device__ __forceinline__ uint32_t swz_off(int row, int chunk) {
   if constexpr (ROWB == 128) return row * 128 + ((chunk ^ (row & 7)) << 4);
-  else return row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4);
+  else if constexpr (ROWB == 64) return row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4);
+  else return row * 32 + ((chunk ^ ((row >> 2) & 1)) << 4);
+}
+
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+// CW = 32 or 16 accumulator columns of this thread's TMEM lane <-> registers
+template <int CW>
+__device__ __forceinline__ void tmem_ld_cw(uint32_t taddr, uint32_t (&r)[32]) {
+  if constexpr (CW == 32) tmem_ld_32x32b_x32(taddr, r);
+  else tmem_ld_32x32b_x16(taddr, r);
+}
+template <int CW>
+__device__ __forceinline__ void tmem_st_cw(uint32_t taddr, const uint32_t (&r)[32]) {
+  if constexpr (CW == 32) tmem_st_32x32b_x32(taddr, r);
+  else tmem_st_32x32b_x16(taddr, r);
 }
 
 // Inner activation of the residual blocks, resolved at compile time: the epilogue body must be straight-line code
@@ -114,7 +142,9 @@ __global__ void __launch_bounds__(FrCfg<C, EW, NCTA>::THREADS, NCTA) mrf_fused_k
   using Cfg = FrCfg<C, EW, NCTA>;
   static_assert(!PIPE || EW * 4 == C, "the half-tile pipeline maps one 32x32 / 32x16 accumulator patch to each warp");
   constexpr int ROWB = Cfg::ROWB;
-  constexpr int NCH = C / 32;  // 32-column chunks per row
+  constexpr int CW = Cfg::CW;      // columns per epilogue patch
+  constexpr int NCH = C / CW;      // patches per row
+  constexpr int R32 = CW * 4, R16 = CW * 2;  // row bytes of the fp32 / fp16 staging patches
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) {
     if (threadIdx.x == 0) printf("fv: dynamic shared memory is not 1024-byte aligned\n");
@@ -192,7 +222,7 @@ __global__ void __launch_bounds__(FrCfg<C, EW, NCTA>::THREADS, NCTA) mrf_fused_k
                 const int s = it % Cfg::NS;
                 mbar_wait(&w_empty[s], ((it / Cfg::NS) & 1) ^ 1);
                 if (leader) {
-                  mbar_arrive_expect_tx(&w_full[s], Cfg::W_TILE);
+                  mbar_arrive_expect_tx(&w_full[s], Cfg::W_BYTES);
                   tma_load_2d(smem + Cfg::RING_OFF + s * Cfg::W_TILE, &p.tmW, &w_full[s], 0, row0 + tap * C);
                 }
               }
@@ -247,33 +277,31 @@ __global__ void __launch_bounds__(FrCfg<C, EW, NCTA>::THREADS, NCTA) mrf_fused_k
     const int q = warp & 3;
     const int g = e >> 2;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    uint8_t* patch32 = smem + Cfg::STG32_OFF + e * 4096;
-    uint8_t* patch16 = smem + Cfg::STG16_OFF + e * 2048;
-    const uint32_t p32_row = smem_u32(patch32) + lane * 128;
-    const uint32_t p16_row = smem_u32(patch16) + lane * 64;
-    const uint32_t r_xor = lane & 7, h_xor = (lane >> 1) & 3;
+    uint8_t* patch32 = smem + Cfg::STG32_OFF + e * Cfg::P32;
+    uint8_t* patch16 = smem + Cfg::STG16_OFF + e * Cfg::P16;
+    const uint32_t p32_base = smem_u32(patch32), p16_base = smem_u32(patch16);  // this thread's row = lane
     const uint32_t xa_base = smem_u32(smem + Cfg::XA_OFF), ta_base = smem_u32(smem + Cfg::TA_OFF);
     uint64_t* my_bar = &stg_bar[e];
     uint32_t stg_phase = 0, n = 0;
 
-    // activation -> fp16 -> this thread's 64 bytes (32 columns) of operand row `srow`
+    // activation -> fp16 -> this thread's CW columns (CW / 8 16-byte chunks) of operand row `srow`
     auto put_operand = [&](uint32_t slab_base, int srow, int cc, const float (&v)[32]) {
 #pragma unroll
-      for (int qq = 0; qq < 4; ++qq) {
+      for (int qq = 0; qq < CW / 8; ++qq) {
         const uint32_t w0 = pack_half2_sat(v[8 * qq + 0], v[8 * qq + 1]);
         const uint32_t w1 = pack_half2_sat(v[8 * qq + 2], v[8 * qq + 3]);
         const uint32_t w2 = pack_half2_sat(v[8 * qq + 4], v[8 * qq + 5]);
         const uint32_t w3 = pack_half2_sat(v[8 * qq + 6], v[8 * qq + 7]);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(slab_base + swz_off<ROWB>(srow, cc * 4 + qq)),
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(slab_base + swz_off<ROWB>(srow, cc * (CW / 8) + qq)),
                      "r"(w0), "r"(w1), "r"(w2), "r"(w3)
                      : "memory");
       }
     };
-    // v = accumulator + bias (32 consecutive channels; the bias row is 16-byte aligned: broadcast LDS.128)
+    // v = accumulator + bias (CW consecutive channels; the bias row is 16-byte aligned: broadcast LDS.128)
     auto add_bias = [&](float (&v)[32], const uint32_t (&r)[32], const float* bias) {
       const float4* b4 = reinterpret_cast<const float4*>(bias);
 #pragma unroll
-      for (int qq = 0; qq < 8; ++qq) {
+      for (int qq = 0; qq < CW / 4; ++qq) {
         const float4 bb = b4[qq];
         v[4 * qq] = __uint_as_float(r[4 * qq]) + bb.x;
         v[4 * qq + 1] = __uint_as_float(r[4 * qq + 1]) + bb.y;
@@ -287,12 +315,12 @@ __global__ void __launch_bounds__(FrCfg<C, EW, NCTA>::THREADS, NCTA) mrf_fused_k
       const int gr = g0 + row_l;
       const bool in_seq = gr >= 0 && gr < p.L;
       uint32_t r[32];
-      tmem_ld_32x32b_x32(t_lane + col + m * C + cc * 32, r);
+      tmem_ld_cw<CW>(t_lane + col + m * C + cc * CW, r);
       tmem_ld_wait();
       float v[32];
-      add_bias(v, r, bias + cc * 32);
+      add_bias(v, r, bias + cc * CW);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = in_seq ? fr_act<ACT>(v[i], p.act_param) : 0.f;
+      for (int i = 0; i < CW; ++i) v[i] = in_seq ? fr_act<ACT>(v[i], p.act_param) : 0.f;
       put_operand(slab_base, kFrGuard + row_l, cc, v);
     };
     // the same for a 32-row x 16-column patch (column group c16): the half-tile pipeline's unit for blocks 2 and 3
@@ -333,22 +361,22 @@ __global__ void __launch_bounds__(FrCfg<C, EW, NCTA>::THREADS, NCTA) mrf_fused_k
       __syncwarp();
       if (lane == 0) {
         tma_store_wait_read();
-        mbar_arrive_expect_tx(my_bar, 4096);
-        tma_load_3d(patch32, &p.tmX, my_bar, cc * 32, g0 + blk0, b);
+        mbar_arrive_expect_tx(my_bar, Cfg::P32);
+        tma_load_3d(patch32, &p.tmX, my_bar, cc * CW, g0 + blk0, b);
       }
       __syncwarp();
       mbar_wait(my_bar, stg_phase);
       stg_phase ^= 1;
       uint32_t r[32];
 #pragma unroll
-      for (int qq = 0; qq < 8; ++qq)
+      for (int qq = 0; qq < CW / 4; ++qq)
         asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
                      : "=r"(r[4 * qq]), "=r"(r[4 * qq + 1]), "=r"(r[4 * qq + 2]), "=r"(r[4 * qq + 3])
-                     : "r"(p32_row + ((static_cast<uint32_t>(qq) ^ r_xor) << 4)));
-      tmem_st_32x32b_x32(t_lane + X_COL + m * C + cc * 32, r);
+                     : "r"(p32_base + swz_off<R32>(lane, qq)));
+      tmem_st_cw<CW>(t_lane + X_COL + m * C + cc * CW, r);
       float v[32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = fr_act<ACT>(__uint_as_float(r[i]), p.act_param);
+      for (int i = 0; i < CW; ++i) v[i] = fr_act<ACT>(__uint_as_float(r[i]), p.act_param);
       put_operand(xa_base, kFrGuard + blk0 + lane, cc, v);
     };
     // tile exit of one patch: block output -> running mean in out32 (-> activated fp16 after the last block)
@@ -361,29 +389,29 @@ __global__ void __launch_bounds__(FrCfg<C, EW, NCTA>::THREADS, NCTA) mrf_fused_k
       if (lane == 0) {
         if (j > 0) {
           tma_store_wait_all();  // the partial sums this warp stored for block j-1 are visible
-          mbar_arrive_expect_tx(my_bar, 4096);
-          tma_load_3d(patch32, &p.tmO32, my_bar, cc * 32, grow, b);
+          mbar_arrive_expect_tx(my_bar, Cfg::P32);
+          tma_load_3d(patch32, &p.tmO32, my_bar, cc * CW, grow, b);
         } else {
           tma_store_wait_read();
         }
       }
       __syncwarp();
       uint32_t r[32];
-      tmem_ld_32x32b_x32(t_lane + X_COL + m * C + cc * 32, r);
+      tmem_ld_cw<CW>(t_lane + X_COL + m * C + cc * CW, r);
       tmem_ld_wait();
       float v[32];
-      add_bias(v, r, b2c + cc * 32);
+      add_bias(v, r, b2c + cc * CW);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] *= p.out_scale;
+      for (int i = 0; i < CW; ++i) v[i] *= p.out_scale;
       if (j > 0) {
         mbar_wait(my_bar, stg_phase);
         stg_phase ^= 1;
 #pragma unroll
-        for (int qq = 0; qq < 8; ++qq) {
+        for (int qq = 0; qq < CW / 4; ++qq) {
           float4 a;
           asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                        : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w)
-                       : "r"(p32_row + ((static_cast<uint32_t>(qq) ^ r_xor) << 4)));
+                       : "r"(p32_base + swz_off<R32>(lane, qq)));
           v[4 * qq] += a.x;
           v[4 * qq + 1] += a.y;
           v[4 * qq + 2] += a.z;
@@ -391,44 +419,42 @@ __global__ void __launch_bounds__(FrCfg<C, EW, NCTA>::THREADS, NCTA) mrf_fused_k
         }
       }
 #pragma unroll
-      for (int qq = 0; qq < 8; ++qq)
-        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(p32_row +
-                                                                      ((static_cast<uint32_t>(qq) ^ r_xor) << 4)),
+      for (int qq = 0; qq < CW / 4; ++qq)
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(p32_base + swz_off<R32>(lane, qq)),
                      "f"(v[4 * qq]), "f"(v[4 * qq + 1]), "f"(v[4 * qq + 2]), "f"(v[4 * qq + 3])
                      : "memory");
       if (last && p.has_o16) {
         if (p.out_act == FV_ACT_SILU) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = fr_act<kActSilu>(v[i], 0.f);
+          for (int i = 0; i < CW; ++i) v[i] = fr_act<kActSilu>(v[i], 0.f);
         } else if (p.out_act == FV_ACT_SILU_TANH) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = fr_act<kActSiluTanh>(v[i], 0.f);
+          for (int i = 0; i < CW; ++i) v[i] = fr_act<kActSiluTanh>(v[i], 0.f);
         } else if (p.out_act == FV_ACT_LEAKY) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = fr_act<kActLeaky>(v[i], p.out_act_param);
+          for (int i = 0; i < CW; ++i) v[i] = fr_act<kActLeaky>(v[i], p.out_act_param);
         } else if (p.out_act == FV_ACT_TANH) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = tanhf(v[i]);
+          for (int i = 0; i < CW; ++i) v[i] = tanhf(v[i]);
         } else if (p.out_act == FV_ACT_GELU) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = gelu_erf_fast(v[i]);
+          for (int i = 0; i < CW; ++i) v[i] = gelu_erf_fast(v[i]);
         }
 #pragma unroll
-        for (int qq = 0; qq < 4; ++qq) {
+        for (int qq = 0; qq < CW / 8; ++qq) {
           uint32_t w[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) w[u] = pack_half2_sat(v[8 * qq + 2 * u], v[8 * qq + 2 * u + 1]);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p16_row +
-                                                                        ((static_cast<uint32_t>(qq) ^ h_xor) << 4)),
-                       "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p16_base + swz_off<R16>(lane, qq)), "r"(w[0]),
+                       "r"(w[1]), "r"(w[2]), "r"(w[3])
                        : "memory");
         }
       }
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        tma_store_3d(&p.tmO32, patch32, cc * 32, grow, b);
-        if (last && p.has_o16) tma_store_3d(&p.tmO16, patch16, cc * 32, grow, b);
+        tma_store_3d(&p.tmO32, patch32, cc * CW, grow, b);
+        if (last && p.has_o16) tma_store_3d(&p.tmO16, patch16, cc * CW, grow, b);
         tma_store_commit();
       }
     };
@@ -523,16 +549,18 @@ __global__ void __launch_bounds__(FrCfg<C, EW, NCTA>::THREADS, NCTA) mrf_fused_k
 // host side
 // ------------------------------------------------------------------------------------------------
 static int encode_rows_map(EncodeTiledFn enc, CUtensorMap* tm, const void* base, bool fp16, int C, int pitch, int L,
-                           int B) {
+                           int B, int cw) {
   const cuuint64_t es = fp16 ? 2 : 4;
   cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)L, (cuuint64_t)B};
   cuuint64_t strides[2] = {(cuuint64_t)pitch * es, (cuuint64_t)pitch * es * (cuuint64_t)L};
-  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t box[3] = {(cuuint32_t)cw, 32, 1};  // one epilogue patch: 32 rows x cw columns, swizzle span = row bytes
+  const int row_bytes = cw * (int)es;
+  const CUtensorMapSwizzle swz = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                 : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(tm, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   fp16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   FV_REQUIRE(r == CUDA_SUCCESS, FV_E_DRIVER, "cuTensorMapEncodeTiled(mrf rows) failed: %d", (int)r);
   return 0;
 }
@@ -558,9 +586,9 @@ static int launch_mrf(const fv_mrf_desc* d, MrfParams& p, cudaStream_t stream) {
   using Cfg = FrCfg<C, EW, NCTA>;
   EncodeTiledFn enc = get_encode_fn();
   FV_REQUIRE(enc != nullptr, FV_E_DRIVER, "cuTensorMapEncodeTiled not available from the driver");
-  int rc = encode_rows_map(enc, &p.tmX, d->x, false, C, d->x_pitch, d->L, d->B);
-  if (!rc) rc = encode_rows_map(enc, &p.tmO32, d->out32, false, C, d->out32_pitch, d->L, d->B);
-  if (!rc && d->out16) rc = encode_rows_map(enc, &p.tmO16, d->out16, true, C, d->out16_pitch, d->L, d->B);
+  int rc = encode_rows_map(enc, &p.tmX, d->x, false, C, d->x_pitch, d->L, d->B, Cfg::CW);
+  if (!rc) rc = encode_rows_map(enc, &p.tmO32, d->out32, false, C, d->out32_pitch, d->L, d->B, Cfg::CW);
+  if (!rc && d->out16) rc = encode_rows_map(enc, &p.tmO16, d->out16, true, C, d->out16_pitch, d->L, d->B, Cfg::CW);
   if (rc) return rc;
   {
     cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)d->w_rows};
@@ -569,7 +597,8 @@ static int launch_mrf(const fv_mrf_desc* d, MrfParams& p, cudaStream_t stream) {
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(&p.tmW, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(d->w), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     Cfg::ROWB == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                     Cfg::ROWB == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                      : (Cfg::ROWB == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B),
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     FV_REQUIRE(r == CUDA_SUCCESS, FV_E_DRIVER, "cuTensorMapEncodeTiled(mrf W) failed: %d", (int)r);
   }
@@ -598,7 +627,7 @@ extern "C" int fv_mrf_fused(const fv_mrf_desc* d, void* stream) {
   FV_REQUIRE(d != nullptr, FV_E_BADARG, "fv_mrf_fused: null descriptor");
   FV_REQUIRE(d->x && d->w && d->bias && d->out32, FV_E_BADARG, "fv_mrf_fused: null pointer (x, w, bias, out32 required)");
   FV_REQUIRE(d->B > 0 && d->L > 0, FV_E_BADARG, "fv_mrf_fused: bad sizes B=%d L=%d", d->B, d->L);
-  FV_REQUIRE(d->C == 32 || d->C == 64, FV_E_UNSUPPORTED, "fv_mrf_fused: C must be 32 or 64 (got %d)", d->C);
+  FV_REQUIRE(d->C == 16 || d->C == 32 || d->C == 64, FV_E_UNSUPPORTED, "fv_mrf_fused: C must be 16, 32 or 64 (got %d)", d->C);
   FV_REQUIRE(d->n_blocks >= 1 && d->n_blocks <= FV_MRF_MAX_BLOCKS && d->n_pairs >= 1 && d->n_pairs <= FV_MRF_MAX_PAIRS,
              FV_E_BADARG, "fv_mrf_fused: n_blocks=%d n_pairs=%d out of range", d->n_blocks, d->n_pairs);
   FV_REQUIRE(d->act == FV_ACT_SILU || d->act == FV_ACT_LEAKY || d->act == FV_ACT_SILU_TANH, FV_E_UNSUPPORTED,
@@ -666,6 +695,7 @@ extern "C" int fv_mrf_fused(const fv_mrf_desc* d, void* stream) {
     if (g_mrf_pipe) FV_MRF_DISPATCH(64, 16, 1, true);
     FV_MRF_DISPATCH(64, 16, 1, false);
   }
+  if (d->C == 16) FV_MRF_DISPATCH(16, 8, 2, false);  // 32-byte operand rows, 16-column patches, two CTAs per SM
   if (g_mrf_c32_ctas == 1) FV_MRF_DISPATCH(32, 16, 1, false);
   if (g_mrf_pipe) FV_MRF_DISPATCH(32, 8, 2, true);
   FV_MRF_DISPATCH(32, 8, 2, false);
