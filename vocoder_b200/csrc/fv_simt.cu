@@ -289,6 +289,7 @@ __global__ void __launch_bounds__(256) conv_post_sliding_kernel(const __half* __
 // anti-aliased Snake: up 2x (polyphase 6+6 taps) -> x + sin^2(a x)/(b+1e-9) -> down 2x (12 taps), one pass.
 // One thread = one channel x SN_T consecutive time steps; the activated 2x signal lives only in registers.
 // ------------------------------------------------------------------------------------------------
+constexpr int SN_BLOCKS = 2;  // resident 256-thread blocks per SM (118 registers; 3 blocks = 80 registers spill: 3.9 -> 4.7 ms)
 constexpr int SN_SEG_MIN = 36, SN_SEG_MAX = 96;  // time steps per thread: a multiple of 6 (period of the register rings)
 struct SnakeFilt {
   float up[12];
@@ -440,7 +441,7 @@ __device__ __forceinline__ void snake_segment(const float* __restrict__ xc, __ha
 
 // one thread = one channel PAIR x seg_len time steps (pitch is a multiple of 8, so pairs never straddle a row)
 template <bool SPLIT>
-__global__ void __launch_bounds__(256, 2) snake_aa_kernel(const float* __restrict__ x, __half* __restrict__ out,
+__global__ void __launch_bounds__(256, SN_BLOCKS) snake_aa_kernel(const float* __restrict__ x, __half* __restrict__ out,
                                                           const float* __restrict__ alpha,
                                                           const float* __restrict__ beta, const SnakeFilt f,
                                                           int logscale, int B, int L, int C, int pitch, int n_seg,
@@ -960,12 +961,12 @@ extern "C" int fv_snake_aa(const float* x32, void* out16, const float* alpha, co
     f.up[i] = 2.0f * filt_up[i];  // the up-sampler's gain of `ratio` (= 2) is folded into its taps
     f.dn[i] = filt_down[i];
   }
-  // Segment length: every thread does the same amount of work, so the grid runs in whole waves of 2 x 256 threads per
+  // Segment length: every thread does the same amount of work, so the grid runs in whole waves of SN_BLOCKS x 256 threads per
   // SM and a launch of 3.1 waves costs 4.  Pick the multiple of 6 in [36, 96] with the best (work / waves) ratio,
   // counting the 6 pre-roll steps every segment pays.
   int seg_len = 48;
   {
-    const long long per_wave = (long long)num_sms() * 2 * 256;
+    const long long per_wave = (long long)num_sms() * SN_BLOCKS * 256;
     double best = -1.0;
     for (int sl = SN_SEG_MIN; sl <= SN_SEG_MAX; sl += 6) {
       const long long thr = (long long)B * ceil_div(L, sl) * (pitch / 2);
