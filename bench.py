@@ -30,6 +30,8 @@ WORKLOADS = {
     "hifigan_b1": ("hifigan", 1, 80, 94, 256, 24000, "hifigan baseline generator, batch 1 x 1 s @ 24 kHz"),
     "bigvgan_b32": ("bigvgan", 32, 100, 87, 512, 44100,
                     "bigvgan generator with anti-aliased Snake (100 mel, hop 512), batch 32 x 1 s @ 44.1 kHz"),
+    "hifigan_yaml_b32": ("hifigan5", 32, 128, 87, 512, 44100,
+                         "hifigan.yaml as written (128 mel, hop 512, rates 8-8-2-2-2, ch 512), batch 32 x 1 s @ 44.1 kHz"),
     "firefly_b32": ("firefly", 32, 128, 87, 512, 44100,
                     "firefly-gan-base (ConvNeXt [3,3,9,3]x[128,256,384,512] + HiFiGAN head, rates 8-8-2-2-2, k13 pre/post), "
                     "batch 32 x 1 s @ 44.1 kHz"),
@@ -46,6 +48,11 @@ def build_model(kind: str):
         return HiFiGANGenerator(hop_length=256, upsample_rates=(8, 8, 2, 2), upsample_kernel_sizes=(16, 16, 4, 4),
                                 resblock_kernel_sizes=(3, 7, 11), resblock_dilation_sizes=((1, 3, 5),) * 3,
                                 num_mels=80, upsample_initial_channel=512, use_template=False,
+                                pre_conv_kernel_size=7, post_conv_kernel_size=7)
+    if kind == "hifigan5":  # configs/model/generator/hifigan.yaml + resolution/44100_512_2048.yaml (SURVEY 8d variant A')
+        return HiFiGANGenerator(hop_length=512, upsample_rates=(8, 8, 2, 2, 2), upsample_kernel_sizes=(16, 16, 8, 2, 2),
+                                resblock_kernel_sizes=(3, 7, 11), resblock_dilation_sizes=((1, 3, 5),) * 3,
+                                num_mels=128, upsample_initial_channel=512, use_template=False,
                                 pre_conv_kernel_size=7, post_conv_kernel_size=7)
     if kind == "bigvgan":
         return BigVGANGenerator(hop_length=512, num_mels=100, use_template=False)
@@ -72,7 +79,7 @@ def synthetic_mel(B, n_mels, T, seed):
 
 def oracle_forward(kind, sd, mel, model):
     from oracle import generators as G
-    if kind == "hifigan":
+    if kind in ("hifigan", "hifigan5"):
         return G.hifigan_forward(sd, mel, model.upsample_rates)
     if kind == "bigvgan":
         return G.bigvgan_forward(sd, mel, model.upsample_rates)

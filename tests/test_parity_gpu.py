@@ -315,6 +315,39 @@ def test_full_width_stress_hifigan_vs_oracle(variant):
     assert err <= TOL * peak, f"{variant}: max|delta|={err:.3e}"
 
 
+def test_five_stage_hifigan_fused_c16_vs_oracle_and_layerwise():
+    """The literal hifigan.yaml layout (rates 8-8-2-2-2, hop 512: stages C = 256, 128, 64, 32, 16) with stress weights: the
+    three fused stages (C = 64, 32, 16) against the fp32 oracle and against the layer-wise path."""
+    from tests.util import stress_init
+    from vocoder_b200.generators import HiFiGANGenerator
+    torch.manual_seed(0)
+    m = HiFiGANGenerator(hop_length=512, upsample_rates=(8, 8, 2, 2, 2), upsample_kernel_sizes=(16, 16, 8, 2, 2),
+                         num_mels=128, use_template=False)    # hifigan.yaml:3-4
+    stress_init(m, seed=5)
+    m = m.eval()
+    torch.manual_seed(99)
+    mel = torch.empty(2, 128, 11).uniform_(-11.5129, 2.0)
+    from oracle import generators as G
+    with torch.no_grad():
+        want = G.hifigan_forward({k: v.detach() for k, v in m.state_dict().items()}, mel, m.upsample_rates)
+    m = m.cuda()
+    with torch.no_grad():
+        cabi.reset_launch_count()
+        fused = m(mel.cuda()).cpu()
+        n_fused = cabi.launch_count()
+        m.fuse_mrf = False
+        cabi.reset_launch_count()
+        layer = m(mel.cuda()).cpu()
+        n_layer = cabi.launch_count()
+    assert fused.shape == want.shape == (2, 1, 11 * 512)
+    assert n_layer - n_fused == 3 * (18 - 1)          # three stages collapse from 18 conv launches to one each
+    peak = max(1.0, float(want.abs().max()))
+    e_f, e_l = float((fused - want).abs().max()), float((layer - want).abs().max())
+    print(f"5-stage stress hifigan: fused {e_f:.3e}, layer-wise {e_l:.3e} vs fp32 oracle (peak {peak:.3f})")
+    assert e_f <= TOL * peak and e_l <= TOL * peak
+    assert float((fused - layer).abs().max()) <= 3e-4
+
+
 def test_mrf_fused_generator_matches_layerwise():
     m, n_mels, hop = _full("hifigan")
     m = m.eval().cuda()
