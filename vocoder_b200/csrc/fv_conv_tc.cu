@@ -1038,6 +1038,9 @@ static int dispatch_m(const fv_conv_desc* d, ConvTcParams& p, cudaStream_t s, in
       if (m_sub == 1) return dispatch_k<BLOCK_N, 1, true>(d, p, s);
       if constexpr (BLOCK_N <= 64) {  // four 128-row accumulators: 512-row tiles amortise the per-tile cost at small C
         if (m_sub == 4) return dispatch_k<BLOCK_N, 4, true>(d, p, s);
+        if constexpr (BLOCK_N == 32) {  // eight accumulators (1024-row tiles, 2 x 256 TMEM columns) for the narrowest layers
+          if (m_sub == 8) return dispatch_k<BLOCK_N, 8, true>(d, p, s);
+        }
       }
       return dispatch_k<BLOCK_N, 2, true>(d, p, s);
     }
@@ -1105,6 +1108,15 @@ int conv1d_tc(const fv_conv_desc* d, cudaStream_t stream, int block_n_override, 
   int m_sub = m_sub_override ? m_sub_override : ((p.q_rows > 128 && bn < 256) ? 2 : 1);
   if (bn == 256) m_sub = 1;  // two 256-column accumulators do not leave room for a pipelined smem ring
   if (!m_sub_override && bn <= 64 && p.q_rows >= 2048) m_sub = 4;
+  {
+    static const bool m8 = [] {
+      // 1024-row tiles (eight accumulators) for N = 32, K <= 32 layers with long sequences: twice the epilogue items per
+      // tile (all 8 epilogue warps busy) and half the per-tile latencies; BigVGAN cfg C 8.01 -> 7.83 ms.  FV_TC_M8=0 disables.
+      const char* e = getenv("FV_TC_M8");
+      return !(e && e[0] == '0');
+    }();
+    if (m8 && !m_sub_override && bn == 32 && d->a_pitch <= 32 && d->a_split == 0 && p.q_rows >= 8192 && (d->L_out % d->n_phase) == 0 && epilogue != 1) m_sub = 8;
+  }
   if (d->a_pitch <= 32 && m_sub < 2) m_sub = 2;
   if (d->a_split > 0 && d->a_split % 64 != 0 && m_sub < 2) m_sub = 2;
   // TMA epilogue needs a rectangular {phase, q} view of the output rows; epilogue: 0 = auto, 1 = LSU, 2 = TMA
