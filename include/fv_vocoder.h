@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define FV_ABI_VERSION 2
+#define FV_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define FV_API __attribute__((visibility("default")))
@@ -50,6 +50,14 @@ enum fv_act {
                        generators/vocos.py:57-67                                                  */
   FV_ACT_SILU_TANH = 6 /* F.silu as x/2 + x/2 tanh(x/2) with tanh.approx (one SFU op, |err| <= 2.4e-4 |x|):
                           opt-in inner activation of fv_mrf_fused only                             */
+};
+
+/* how the two anti-alias filters of fv_snake_aa pad their inputs (the BigVGAN-flavoured Activation1d
+ * replicates the edge sample; other releases of alias_free_torch may reflect or zero-pad - unverifiable offline) */
+enum fv_edge_mode {
+  FV_EDGE_REPLICATE = 0, /* F.pad(mode="replicate"): default, streaming kernel */
+  FV_EDGE_REFLECT = 1,   /* F.pad(mode="reflect"): mirror without repeating the edge sample */
+  FV_EDGE_ZERO = 2       /* F.pad(mode="constant", value=0) */
 };
 
 /* which kernel family executes fv_conv1d */
@@ -138,9 +146,11 @@ FV_API int fv_conv_post_tanh(const void* a16, const float* w32, const float* bia
  * SURVEY B4): 2x Kaiser-sinc up (12 taps, replicate edges) -> x + sin^2(a x)/(b+1e-9) -> 2x down, ONE kernel.
  * x32 [B][L][pitch] fp32 -> out16 [B][L][pitch] fp16.  alpha/beta are the raw (log-scale) parameters [C];
  * beta == NULL selects Snake (beta := alpha).  filt_up / filt_down = HOST pointers to the 12 fp32 taps (the
- * module's `upsample.filter` / `downsample.lowpass.filter` buffers; passed by value to the kernel). */
+ * module's `upsample.filter` / `downsample.lowpass.filter` buffers; passed by value to the kernel).
+ * edge_mode: enum fv_edge_mode, applied to the padding of both filters. */
 FV_API int fv_snake_aa(const float* x32, void* out16, const float* alpha, const float* beta, const float* filt_up,
-                const float* filt_down, int logscale, int B, int L, int C, int pitch, int split, void* stream);
+                const float* filt_down, int logscale, int B, int L, int C, int pitch, int split, int edge_mode,
+                void* stream);
 
 /* ConvNeXt block front half (convnext.py:127-129): depthwise conv k (zero pad) + LayerNorm over C (eps) -> fp16.
  * x32 [B][T][pitch] -> out16 [B][T][pitch].  dw_w [k][C] (tap-major, i.e. the module's [C,1,k] weight transposed so
@@ -150,11 +160,14 @@ FV_API int fv_dwconv_layernorm(const float* x32, void* out16, float* out32, cons
                         const float* ln_w, const float* ln_b, float eps, int B, int T, int C, int pitch, int k,
                         int split, void* stream);
 
-/* ISTFT("same") tail (vocos==0.0.2 spectral_ops.ISTFT): windowed frames [B][T][n_fft] fp32 (window
- * already folded into the inverse-DFT basis) -> overlap-add, trim (win-hop)/2, divide by the hann^2 envelope.
- * wav [B][T*hop]. */
+/* ISTFT tail (vocos==0.0.2 spectral_ops.ISTFT): windowed frames [B][T][n_fft] fp32 (window already
+ * folded into the inverse-DFT basis; `window` [n_fft] is only used for the squared-window envelope) -> overlap-add,
+ * trim, divide by the envelope.
+ *   center == 0: padding="same"   (generators/vocos.py:33-38): trim (win-hop)/2 either side, wav [B][T*hop]
+ *   center != 0: padding="center" (torch.istft(center=True), the upstream-Vocos head of scripts/vocos_gen.py:5-16):
+ *                trim n_fft/2 either side, wav [B][(T-1)*hop] */
 FV_API int fv_istft_ola(const float* frames, const float* window, float* wav, int B, int T, int n_fft, int hop,
-                 int frame_pitch, void* stream);
+                 int frame_pitch, int center, void* stream);
 
 /* template path (hifigan.py:191-204,233-234): noise_convs[i](template) as fp32 [B][L_i][pitch]; C_in == 1.
  * template [B][L_audio], w [C][k], bias [C]; out row t = sum_j w[c][j] * template[t*stride - pad + j]. */

@@ -84,23 +84,26 @@ def kaiser_sinc_taps(cutoff: float = 0.25, half_width: float = 0.3, k: int = 12)
     return f / f.sum()
 
 
-def aa_activation(x: Tensor, act, f_up: Tensor, f_down: Tensor) -> Tensor:
+def aa_activation(x: Tensor, act, f_up: Tensor, f_down: Tensor, edge_mode: str = "replicate") -> Tensor:
     """alias_free_torch.Activation1d (up 2x -> act -> down 2x), replicate edges.
 
     up  : pad 5|5 replicate, 2 * conv_transpose1d(stride 2, depthwise f), crop 15|15
     down: pad 5|6 replicate, conv1d(stride 2, depthwise f)
+    edge_mode: "replicate" (BigVGAN-flavoured copy, default) | "reflect" | "zero" - the padding mode of BOTH filters
+    (SURVEY 8c unresolved ambiguity: the PyPI 0.0.6 wheel may differ and cannot be inspected offline).
     """
     C = x.shape[1]
     k = f_up.numel()
     pad = k // 2 - 1
     crop_l = pad * 2 + (k - 2) // 2
     crop_r = pad * 2 + (k - 2 + 1) // 2
-    u = F.pad(x, (pad, pad), mode="replicate")
+    pmode = {"replicate": "replicate", "reflect": "reflect", "zero": "constant"}[edge_mode]
+    u = F.pad(x, (pad, pad), mode=pmode)
     u = 2.0 * F.conv_transpose1d(u, f_up.reshape(1, 1, -1).expand(C, 1, -1), stride=2, groups=C)
     u = u[..., crop_l:-crop_r]
     u = act(u)
     kd = f_down.numel()
-    u = F.pad(u, (kd // 2 - 1, kd // 2), mode="replicate")
+    u = F.pad(u, (kd // 2 - 1, kd // 2), mode=pmode)
     return F.conv1d(u, f_down.reshape(1, 1, -1).expand(C, 1, -1), stride=2, groups=C)
 
 
@@ -167,22 +170,28 @@ def noise_conv(sd: SD, i: int, template: Tensor, upsample_rates: Sequence[int]) 
 # --------------------------------------------------------------------------------------------
 # BigVGAN  (fish_vocoder/modules/generators/bigvgan.py)
 # --------------------------------------------------------------------------------------------
-def _act1d(sd: SD, prefix: str, x: Tensor, kind: str = "snakebeta") -> Tensor:
+def _act1d(sd: SD, prefix: str, x: Tensor, kind: str | None = None, edge_mode: str = "replicate",
+           logscale: bool = True) -> Tensor:
+    """Activation1d(SnakeBeta | Snake) (bigvgan.py:226-233).  kind None = by the keys present (SnakeBeta has `act.beta`);
+    `logscale` is a constructor flag of the activation (bigvgan.py:34,90), not visible in the state dict."""
     f_up = sd[prefix + ".upsample.filter"].reshape(-1)
     f_dn = sd[prefix + ".downsample.lowpass.filter"].reshape(-1)
+    if kind is None:
+        kind = "snakebeta" if (prefix + ".act.beta") in sd else "snake"
     if kind == "snakebeta":
-        fn = lambda v: snake_beta(v, sd[prefix + ".act.alpha"], sd[prefix + ".act.beta"])
+        fn = lambda v: snake_beta(v, sd[prefix + ".act.alpha"], sd[prefix + ".act.beta"], logscale)
     else:
-        fn = lambda v: snake(v, sd[prefix + ".act.alpha"])
-    return aa_activation(x, fn, f_up, f_dn)
+        fn = lambda v: snake(v, sd[prefix + ".act.alpha"], logscale)
+    return aa_activation(x, fn, f_up, f_dn, edge_mode)
 
 
-def bigvgan_ampblock(sd: SD, prefix: str, x: Tensor, dilations: Sequence[int]) -> Tensor:
+def bigvgan_ampblock(sd: SD, prefix: str, x: Tensor, dilations: Sequence[int], edge_mode: str = "replicate",
+                     logscale: bool = True) -> Tensor:
     """bigvgan.py:235-245 AMPBlock.forward (activations[::2] before convs1, [1::2] before convs2)."""
     for i, d in enumerate(dilations):
-        xt = _act1d(sd, f"{prefix}.activations.{2 * i}", x)
+        xt = _act1d(sd, f"{prefix}.activations.{2 * i}", x, edge_mode=edge_mode, logscale=logscale)
         xt = conv_same(sd, f"{prefix}.convs1.{i}", xt, d)
-        xt = _act1d(sd, f"{prefix}.activations.{2 * i + 1}", xt)
+        xt = _act1d(sd, f"{prefix}.activations.{2 * i + 1}", xt, edge_mode=edge_mode, logscale=logscale)
         xt = conv_same(sd, f"{prefix}.convs2.{i}", xt, 1)
         x = xt + x
     return x
@@ -190,8 +199,10 @@ def bigvgan_ampblock(sd: SD, prefix: str, x: Tensor, dilations: Sequence[int]) -
 
 def bigvgan_forward(sd: SD, mel: Tensor, upsample_rates: Sequence[int],
                     resblock_dilation_sizes: Sequence[Sequence[int]] = ((1, 3, 5),) * 3,
-                    template: Tensor | None = None, post_kind: str | None = None) -> Tensor:
-    """bigvgan.py:352-371 BigVGANGenerator.forward (no activation before ups, bigvgan.py:355-356)."""
+                    template: Tensor | None = None, post_kind: str | None = None,
+                    edge_mode: str = "replicate", block_logscale=None) -> Tensor:
+    """bigvgan.py:352-371 BigVGANGenerator.forward (no activation before ups, bigvgan.py:355-356).
+    block_logscale: optional {resblock index: bool} for AMPBlocks built with snake_logscale=False (bigvgan.py:145)."""
     x = conv_same(sd, "conv_pre", mel)
     nk = len(resblock_dilation_sizes)
     use_template = any(k.startswith("noise_convs.") for k in sd)
@@ -199,12 +210,11 @@ def bigvgan_forward(sd: SD, mel: Tensor, upsample_rates: Sequence[int],
         x = conv_transpose(sd, f"ups.{i}", x, u)
         if use_template:
             x = x + noise_conv(sd, i, template, upsample_rates)
-        ys = [bigvgan_ampblock(sd, f"resblocks.{i * nk + j}", x, resblock_dilation_sizes[j])
+        ys = [bigvgan_ampblock(sd, f"resblocks.{i * nk + j}", x, resblock_dilation_sizes[j], edge_mode,
+                               (block_logscale or {}).get(i * nk + j, True))
               for j in range(nk)]
         x = torch.stack(ys, 0).mean(0)
-    if post_kind is None:
-        post_kind = "snakebeta" if "activation_post.act.beta" in sd else "snake"
-    x = _act1d(sd, "activation_post", x, post_kind)
+    x = _act1d(sd, "activation_post", x, post_kind, edge_mode)
     x = conv_same(sd, "conv_post", x)
     return torch.tanh(x)
 
@@ -270,19 +280,73 @@ def istft_same(spec: Tensor, n_fft: int, hop: int, win: int, window: Tensor) -> 
     return y / env
 
 
-def istft_head_forward(sd: SD, x: Tensor, n_fft: int, hop: int, win: int, prefix: str = "") -> Tensor:
-    """vocos.py:43-69 ISTFTHead.forward."""
-    x = F.conv1d(x, sd[prefix + "out.weight"], sd[prefix + "out.bias"])
+def istft_center(spec: Tensor, n_fft: int, hop: int, win: int, window: Tensor) -> Tensor:
+    """vocos==0.0.2 ISTFT(padding="center") = torch.istft(spec, n_fft, hop, win, window, center=True), restated:
+    the window is zero-padded (centred) to n_fft; a two-sided spectrum (n_fft rows - what the reference head produces
+    with its 2*n_fft outputs, vocos.py:40-41,57-69) is cut to its first n_fft/2+1 rows (ATen istft with a real output:
+    `input.slice(-1, 0, n_fft/2+1)` before the c2r transform), then irfft; overlap-add, divide by the squared-window
+    envelope, trim n_fft/2 either side -> (T-1)*hop samples.  Checked against torch.istft in tests/test_oracle_cpu.py."""
+    B, N, T = spec.shape
+    if win < n_fft:
+        left = (n_fft - win) // 2
+        window = F.pad(window, (left, n_fft - win - left))
+    frames = torch.fft.irfft(spec[:, :n_fft // 2 + 1], n_fft, dim=1, norm="backward")
+    frames = frames * window[None, :, None]
+    out_len = (T - 1) * hop + n_fft
+    y = frames.new_zeros(B, out_len)
+    env = torch.zeros(out_len)
+    wsq = window.square()
+    for t in range(T):
+        y[:, t * hop:t * hop + n_fft] += frames[:, :, t]
+        env[t * hop:t * hop + n_fft] += wsq
+    lo, hi = n_fft // 2, out_len - n_fft // 2
+    y, env = y[:, lo:hi], env[lo:hi]
+    assert (env.abs() > 1e-11).all()
+    return y / env
+
+
+def istft_head_forward(sd: SD, x: Tensor, n_fft: int, hop: int, win: int, prefix: str = "",
+                       padding: str = "same") -> Tensor:
+    """vocos.py:43-69 ISTFTHead.forward.  `out.weight` [2*n_fft, dim, 1] = the reference layout; [n_fft+2, dim] = the
+    upstream-Vocos layout (vocos==0.0.2 heads.ISTFTHead: nn.Linear(dim, n_fft + 2), scripts/vocos_gen.py:5-16)."""
+    w = sd[prefix + "out.weight"]
+    if w.ndim == 2:
+        w = w[:, :, None]
+    x = F.conv1d(x, w, sd[prefix + "out.bias"])
     mag, p = x.chunk(2, dim=1)
     mag = torch.clip(torch.exp(mag), max=1e2)
     S = mag * (torch.cos(p) + 1j * torch.sin(p))
+    if padding == "center":
+        return istft_center(S, n_fft, hop, win, sd[prefix + "istft.window"])
     return istft_same(S, n_fft, hop, win, sd[prefix + "istft.window"])
 
 
-def unify_vocos_forward(sd: SD, mel: Tensor, n_fft: int, hop: int, win: int) -> Tensor:
+def vocos_backbone_forward(sd: SD, x: Tensor, prefix: str = "") -> Tensor:
+    """Upstream vocos==0.0.2 models.VocosBackbone.forward (third-party, NOT in /root/reference; restated from its
+    published source - parity unpinned): embed Conv1d(k=7, pad 3) -> LayerNorm over C -> n x ConvNeXtBlock (dwconv k7,
+    LayerNorm, Linear, GELU, Linear, gamma, residual) -> final LayerNorm.  Returns [B, dim, T] (channels-first; upstream
+    hands [B, T, dim] to the head, whose Linear is the same contraction)."""
+    x = F.conv1d(x, sd[prefix + "embed.weight"], sd[prefix + "embed.bias"], padding=sd[prefix + "embed.weight"].shape[-1] // 2)
+    x = F.layer_norm(x.transpose(1, 2), (x.shape[1],), sd[prefix + "norm.weight"], sd[prefix + "norm.bias"], 1e-6)
+    x = x.transpose(1, 2)
+    n = _count(sd, prefix + "convnext.{}.")
+    for j in range(n):
+        x = convnext_block(sd, f"{prefix}convnext.{j}", x)
+    x = F.layer_norm(x.transpose(1, 2), (x.shape[1],), sd[prefix + "final_layer_norm.weight"],
+                     sd[prefix + "final_layer_norm.bias"], 1e-6)
+    return x.transpose(1, 2)
+
+
+def upstream_vocos_forward(sd: SD, mel: Tensor, n_fft: int, hop: int, padding: str = "center") -> Tensor:
+    """vocos.Vocos.decode (scripts/vocos_gen.py:12-16): VocosBackbone -> ISTFTHead(out_dim = n_fft + 2, win = n_fft)."""
+    x = vocos_backbone_forward(sd, mel, "backbone.")
+    return istft_head_forward(sd, x, n_fft, hop, n_fft, "head.", padding)[:, None, :]
+
+
+def unify_vocos_forward(sd: SD, mel: Tensor, n_fft: int, hop: int, win: int, padding: str = "same") -> Tensor:
     """unify.py:18-33 UnifyGenerator.forward with ConvNeXtEncoder backbone + ISTFTHead (no vq)."""
     x = convnext_forward(sd, mel, "backbone.")
-    x = istft_head_forward(sd, x, n_fft, hop, win, "head.")
+    x = istft_head_forward(sd, x, n_fft, hop, win, "head.", padding)
     return x[:, None, :]
 
 

@@ -110,7 +110,7 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(cabi.LIB_PATH)
     for name in declared:
         assert hasattr(lib, name), f"{name} not exported"
-    assert cabi.lib().fv_abi_version() == 2
+    assert cabi.lib().fv_abi_version() == 3
 
 
 def test_conv_desc_struct_matches_header_layout():

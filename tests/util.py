@@ -30,11 +30,14 @@ def oracle_forward(name, kwargs, sd, ins, extra=None):
         return G.hifigan_forward(sd, ins["mel"], kwargs["upsample_rates"], kwargs["resblock_dilation_sizes"],
                                  template=ins.get("template"))
     if name.startswith("bigvgan"):
+        # bigvgan_snake_mix_stress: the four AMPBlocks of the first two stages were built with snake_logscale=False
+        block_logscale = {i: False for i in range(4)} if name.startswith("bigvgan_snake_mix") else None
         return G.bigvgan_forward(sd, ins["mel"], kwargs["upsample_rates"], kwargs["resblock_dilation_sizes"],
-                                 template=ins.get("template"))
+                                 template=ins.get("template"), block_logscale=block_logscale)
     if name.startswith("vocos"):
         h = kwargs["head"]
-        return G.unify_vocos_forward(sd, ins["mel"], h["n_fft"], h["hop_length"], h["win_length"])
+        return G.unify_vocos_forward(sd, ins["mel"], h["n_fft"], h["hop_length"], h["win_length"],
+                                     h.get("padding", "same"))
     if name.startswith("firefly"):
         return G.unify_hifigan_forward(sd, ins["mel"], kwargs["head"]["upsample_rates"],
                                        kwargs["head"]["resblock_dilation_sizes"])
@@ -45,7 +48,34 @@ def oracle_forward(name, kwargs, sd, ins, extra=None):
 
 
 ALL_GOLDEN = ["hifigan_small_ref", "hifigan_small_stress", "hifigan_template_stress", "bigvgan_small_ref",
-              "bigvgan_small_stress", "vocos_small_ref", "vocos_small_stress", "refinegan_small_stress", "firefly_small_stress"]
+              "bigvgan_small_stress", "vocos_small_ref", "vocos_small_stress", "refinegan_small_stress", "firefly_small_stress",
+              "vocos_center_stress", "bigvgan_snake_mix_stress"]
+
+
+def build_module(name, kwargs):
+    """Our module for a golden fixture (same constructor calls oracle/make_golden*.py made on the reference classes)."""
+    from vocoder_b200.encoders import ConvNeXtEncoder
+    from vocoder_b200.generators import BigVGANGenerator, HiFiGANGenerator, ISTFTHead, UnifyGenerator
+    if name.startswith("hifigan"):
+        return HiFiGANGenerator(**kwargs)
+    if name.startswith("bigvgan_snake_mix"):
+        from vocoder_b200.generators.bigvgan import AMPBlock, Snake, SnakeBeta
+        m = BigVGANGenerator(activation=Snake, **kwargs)
+        nk = len(kwargs["resblock_kernel_sizes"])
+        for j, (k, d) in enumerate(zip(kwargs["resblock_kernel_sizes"], kwargs["resblock_dilation_sizes"])):
+            m.resblocks[j] = AMPBlock(m.stage_channels[0], k, tuple(d), activation=Snake, snake_logscale=False)
+            m.resblocks[nk + j] = AMPBlock(m.stage_channels[1], k, tuple(d), activation=SnakeBeta, snake_logscale=False)
+        return m
+    if name.startswith("bigvgan"):
+        return BigVGANGenerator(**kwargs)
+    if name.startswith("vocos"):
+        return UnifyGenerator(backbone=ConvNeXtEncoder(**kwargs["backbone"]), head=ISTFTHead(**kwargs["head"]))
+    if name.startswith("firefly"):  # configs/model/generator/firefly-gan-base.yaml: ConvNeXt backbone + HiFiGAN head
+        return UnifyGenerator(backbone=ConvNeXtEncoder(**kwargs["backbone"]), head=HiFiGANGenerator(**kwargs["head"]))
+    if name.startswith("refinegan"):
+        from vocoder_b200.generators.refinegan import RefineGANGenerator
+        return RefineGANGenerator(**kwargs)
+    raise KeyError(name)
 
 
 def channels_last_noise(seed):

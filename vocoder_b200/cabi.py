@@ -20,6 +20,7 @@ LIB_PATH = os.path.join(_HERE, "libfv_b200.so")
 
 ACT_NONE, ACT_SILU, ACT_LEAKY, ACT_GELU, ACT_TANH, ACT_POLAR, ACT_SILU_TANH = range(7)
 ENGINE_TC, ENGINE_SIMT = 0, 1
+EDGE_MODES = {"replicate": 0, "reflect": 1, "zero": 2}  # enum fv_edge_mode
 MAX_TAPS = 64
 
 # every symbol include/fv_vocoder.h declares (tests check the library exports exactly these)
@@ -96,9 +97,9 @@ def lib() -> ctypes.CDLL:
     L.fv_pack_input.argtypes = [vp, vp, ci, ci, ci, ci, ci, vp]
     L.fv_unpack_output.argtypes = [vp, vp, ci, ci, ci, ci, vp]
     L.fv_conv_post_tanh.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, vp]
-    L.fv_snake_aa.argtypes = [vp, vp, vp, vp, ctypes.POINTER(cf), ctypes.POINTER(cf), ci, ci, ci, ci, ci, ci, vp]
+    L.fv_snake_aa.argtypes = [vp, vp, vp, vp, ctypes.POINTER(cf), ctypes.POINTER(cf), ci, ci, ci, ci, ci, ci, ci, vp]
     L.fv_dwconv_layernorm.argtypes = [vp, vp, vp, vp, vp, vp, vp, cf, ci, ci, ci, ci, ci, ci, vp]
-    L.fv_istft_ola.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, vp]
+    L.fv_istft_ola.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, ci, vp]
     L.fv_noise_conv.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, vp]
     L.fv_act_cast.argtypes = [vp, vp, vp, vp, vp, ci, cf, ci, cf, cf, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp]
     L.fv_resample_linear.argtypes = [vp, vp, vp, ci, cf, ci, cf, ci, ci, ci, ci, ci, ci, ci, cf, ci, vp]
@@ -111,7 +112,7 @@ def lib() -> ctypes.CDLL:
         fn = getattr(L, name)
         if name not in ("fv_last_error", "fv_launch_count", "fv_reset_launch_count", "fv_set_tc_tuning"):
             fn.restype = ctypes.c_int
-    if L.fv_abi_version() != 2:
+    if L.fv_abi_version() != 3:
         raise FvError("libfv_b200.so ABI version mismatch")
     _lib = L
     return L
@@ -131,6 +132,11 @@ def _ptr(t: Optional[torch.Tensor], dtype=None) -> Optional[int]:
         return None
     if not t.is_cuda:
         raise FvError("vocoder_b200 kernels need CUDA tensors (no CPU fallback)")
+    if t.device.index != torch.cuda.current_device():
+        # launches go to the CURRENT device's stream, tensor maps and kernel attributes are per device: a pointer of
+        # another GPU would fault or silently use peer access.  Module forwards enter torch.cuda.device(x.device).
+        raise FvError(f"tensor lives on cuda:{t.device.index} but the current device is cuda:{torch.cuda.current_device()}: "
+                      "wrap the call in torch.cuda.device(tensor.device)")
     if not t.is_contiguous():
         raise FvError("tensor must be contiguous")
     if dtype is not None and t.dtype != dtype:
@@ -151,20 +157,45 @@ def round_up(x: int, m: int) -> int:
 #            at 3x the tensor work and 2x the operand bytes.  Activation buffers are then [B][L][2*pitch] = [hi | lo].
 # The mode is thread-local state entered by the module's forward (``module.precision``).
 # ----------------------------------------------------------------------------------------------
-PRECISIONS = ("fp16", "strict")
+#   "mixed"  fp16 operands, except on the few contractions that dominate the waveform error (measured per layer on the
+#            reference goldens, tools/precision_probe.py): the trunk of BigVGAN (conv_pre, ups, conv_post) and the stem /
+#            downsample / head / inverse-DFT contractions of the Vocos path, which run strict.  The residual-block convs
+#            and the ConvNeXt pointwise GEMMs (>= 95% of the tensor work) stay single fp16.
+PRECISIONS = ("fp16", "mixed", "strict")
+DEFAULT_PRECISION = "mixed"  # what a module without an explicit ``precision`` attribute runs in
 _tls = threading.local()
 
 
 def is_strict() -> bool:
+    """True while the CURRENT layer carries [hi | lo] operands (whole forward in "strict", selected layers in "mixed")."""
     return getattr(_tls, "strict", False)
 
 
+def mode() -> str:
+    return getattr(_tls, "mode", "fp16")
+
+
+def is_mixed() -> bool:
+    return mode() == "mixed"
+
+
 @contextlib.contextmanager
-def precision(mode: str):
-    if mode not in PRECISIONS:
-        raise ValueError(f"precision must be one of {PRECISIONS}, got {mode!r}")
+def precision(mode_: str):
+    if mode_ not in PRECISIONS:
+        raise ValueError(f"precision must be one of {PRECISIONS}, got {mode_!r}")
+    old = (is_strict(), mode())
+    _tls.strict, _tls.mode = mode_ == "strict", mode_
+    try:
+        yield
+    finally:
+        _tls.strict, _tls.mode = old
+
+
+@contextlib.contextmanager
+def strict_layer(on: bool = True):
+    """Operand layout of the enclosed pack / launch calls: [hi | lo] when `on` (a "mixed"-mode strict layer)."""
     old = is_strict()
-    _tls.strict = mode == "strict"
+    _tls.strict = bool(on) or old
     try:
         yield
     finally:
@@ -322,7 +353,7 @@ def conv_transpose_out_len(L: int, k: int, u: int) -> int:
 # ----------------------------------------------------------------------------------------------
 def conv1d(a16: torch.Tensor, pc: PackedConv, L_out: Optional[int] = None, *, gamma=None, residual=None,
            out32=None, accumulate=False, out_scale=1.0, out16=None, act=ACT_NONE, act_param=0.0,
-           engine=ENGINE_TC, use_bias=True) -> None:
+           engine=ENGINE_TC, use_bias=True, out16_split: Optional[int] = None) -> None:
     """a16 [B, L_in, a_pitch] fp16 -> out32 [B, L_out, >=C_out] fp32 and/or out16 fp16 (see fv_conv_desc)."""
     B, L_in, a_pitch = a16.shape
     if L_out is None:
@@ -353,7 +384,9 @@ def conv1d(a16: torch.Tensor, pc: PackedConv, L_out: Optional[int] = None, *, ga
                       f"{2 * pc.split} halfs per row, got {a_pitch}")
     if not pc.split and is_strict():
         raise FvError("weights were packed in fp16 mode but the call runs in strict mode: repack")
-    d.a_split, d.out16_split = pc.split, split_of(out16)
+    # out16_split: None = layout of the current layer context; an int = the consumer's layout ("mixed": a plain layer
+    # feeding a strict one writes [hi | lo], a strict layer feeding a plain one writes plain fp16)
+    d.a_split, d.out16_split = pc.split, (split_of(out16) if out16_split is None else int(out16_split))
     _check(lib().fv_conv1d(ctypes.byref(d), int(engine), _stream()), "fv_conv1d")
 
 
@@ -377,10 +410,11 @@ def unpack_output(x32: torch.Tensor, C: int) -> torch.Tensor:
 
 
 def conv_post_tanh(a16: torch.Tensor, w32: torch.Tensor, bias: Optional[torch.Tensor], C: int,
-                   apply_tanh: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """a16 [B, L, pitch] fp16, w32 [k, C] fp32 -> wav [B, 1, L] fp32."""
+                   apply_tanh: bool = True, out: Optional[torch.Tensor] = None,
+                   split: Optional[int] = None) -> torch.Tensor:
+    """a16 [B, L, pitch] fp16 ([hi | lo] when split > 0), w32 [k, C] fp32 -> wav [B, 1, L] fp32."""
     B, L, width = a16.shape
-    split = split_of(a16)
+    split = split_of(a16) if split is None else int(split)
     k = w32.shape[0]
     if out is None:
         out = torch.empty(B, 1, L, dtype=torch.float32, device=a16.device)
@@ -391,34 +425,41 @@ def conv_post_tanh(a16: torch.Tensor, w32: torch.Tensor, bias: Optional[torch.Te
 
 
 def snake_aa(x32: torch.Tensor, out16: torch.Tensor, alpha: torch.Tensor, beta: Optional[torch.Tensor],
-             filt_up: Sequence[float], filt_down: Sequence[float], C: int, logscale: bool = True) -> None:
+             filt_up: Sequence[float], filt_down: Sequence[float], C: int, logscale: bool = True,
+             split: Optional[int] = None, edge_mode: str = "replicate") -> None:
+    if edge_mode not in EDGE_MODES:
+        raise ValueError(f"edge_mode must be one of {tuple(EDGE_MODES)}, got {edge_mode!r}")
     B, L, pitch = x32.shape
     fu = (ctypes.c_float * 12)(*[float(v) for v in filt_up])
     fd = (ctypes.c_float * 12)(*[float(v) for v in filt_down])
+    split = split_of(out16) if split is None else int(split)
     _check(lib().fv_snake_aa(_ptr(x32, torch.float32), _ptr(out16, torch.float16), _ptr(alpha, torch.float32),
-                             _ptr(beta, torch.float32), fu, fd, int(logscale), B, L, C, pitch, split_of(out16),
-                             _stream()),
+                             _ptr(beta, torch.float32), fu, fd, int(logscale), B, L, C, pitch, split,
+                             EDGE_MODES[edge_mode], _stream()),
            "fv_snake_aa")
 
 
 def dwconv_layernorm(x32: torch.Tensor, C: int, dw_w, dw_b, ln_w, ln_b, eps: float, k: int,
-                     out16: Optional[torch.Tensor] = None, out32: Optional[torch.Tensor] = None) -> None:
+                     out16: Optional[torch.Tensor] = None, out32: Optional[torch.Tensor] = None,
+                     split: Optional[int] = None) -> None:
     B, T, pitch = x32.shape
+    split = split_of(out16) if split is None else int(split)
     _check(lib().fv_dwconv_layernorm(_ptr(x32, torch.float32), _ptr(out16, torch.float16),
                                      _ptr(out32, torch.float32), _ptr(dw_w, torch.float32),
                                      _ptr(dw_b, torch.float32), _ptr(ln_w, torch.float32),
                                      _ptr(ln_b, torch.float32), float(eps), B, T, C, pitch, int(k),
-                                     split_of(out16), _stream()),
+                                     split, _stream()),
            "fv_dwconv_layernorm")
 
 
 def istft_ola(frames: torch.Tensor, window: torch.Tensor, n_fft: int, hop: int,
-              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+              out: Optional[torch.Tensor] = None, center: bool = False) -> torch.Tensor:
+    """frames [B, T, >=n_fft] fp32 -> wav [B, T*hop] (padding="same") or [B, (T-1)*hop] (padding="center")."""
     B, T, fp = frames.shape
     if out is None:
-        out = torch.empty(B, T * hop, dtype=torch.float32, device=frames.device)
+        out = torch.empty(B, (T - 1) * hop if center else T * hop, dtype=torch.float32, device=frames.device)
     _check(lib().fv_istft_ola(_ptr(frames, torch.float32), _ptr(window, torch.float32), _ptr(out), B, T, n_fft,
-                              hop, fp, _stream()), "fv_istft_ola")
+                              hop, fp, int(bool(center)), _stream()), "fv_istft_ola")
     return out
 
 

@@ -9,6 +9,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "../../include/fv_vocoder.h"
 
 namespace fv {
@@ -37,7 +39,21 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn get_encode_fn();
-int num_sms();
+int num_sms();  // of the CURRENT device (cached per device ordinal)
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-device property of a kernel: set it once per (kernel, device).
+// `done` is a per-instantiation bit mask of device ordinals (function-local static of the caller).
+template <typename Kern>
+static inline cudaError_t ensure_dyn_smem(Kern kern, int bytes, std::atomic<unsigned long long>& done) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
+  return e;
+}
 
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 static inline int ceil_div(int x, int m) { return (x + m - 1) / m; }

@@ -854,12 +854,14 @@ EncodeTiledFn get_encode_fn() {
 }
 
 int num_sms() {
-  static int n = 0;
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int n = cache[dev & 63].load(std::memory_order_relaxed);
   if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
+    cache[dev & 63].store(n, std::memory_order_relaxed);
   }
   return n;
 }
@@ -956,13 +958,10 @@ static int launch_tc_impl(const fv_conv_desc* d, ConvTcParams& p, cudaStream_t s
     p.w_resident = (d->n_taps * p.k_chunks <= Cfg::NB && p.n_tiles == 1 && d->n_phase == 1) ? 1 : 0;
   }
 
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, M_SUB, BLOCK_K, EPI_TMA, HEAVY_ACT, SLAB, PAIR, FAT>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-  });
-  int rc = check_cuda(attr_err, "cudaFuncSetAttribute(conv_tc_kernel)");
+  static std::atomic<unsigned long long> attr_done{0};
+  int rc = check_cuda(ensure_dyn_smem(conv_tc_kernel<BLOCK_N, M_SUB, BLOCK_K, EPI_TMA, HEAVY_ACT, SLAB, PAIR, FAT>,
+                                      Cfg::SMEM_BYTES, attr_done),
+                      "cudaFuncSetAttribute(conv_tc_kernel)");
   if (rc) return rc;
   {
     // PAIR: clusters of two CTAs = the two SMs of a TPC, one tile per cluster at a time

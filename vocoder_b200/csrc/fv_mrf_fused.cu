@@ -602,12 +602,9 @@ static int launch_mrf(const fv_mrf_desc* d, MrfParams& p, cudaStream_t stream) {
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     FV_REQUIRE(r == CUDA_SUCCESS, FV_E_DRIVER, "cuTensorMapEncodeTiled(mrf W) failed: %d", (int)r);
   }
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(mrf_fused_kernel<C, ACT, EW, NCTA, PIPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
-  });
-  rc = check_cuda(attr_err, "cudaFuncSetAttribute(mrf_fused_kernel)");
+  static std::atomic<unsigned long long> attr_done{0};
+  rc = check_cuda(ensure_dyn_smem(mrf_fused_kernel<C, ACT, EW, NCTA, PIPE>, Cfg::SMEM, attr_done),
+                  "cudaFuncSetAttribute(mrf_fused_kernel)");
   if (rc) return rc;
   const int slots = num_sms() * NCTA;
   const int grid = p.total_tiles < slots ? p.total_tiles : slots;

@@ -479,6 +479,77 @@ __global__ void __launch_bounds__(256, SN_BLOCKS) snake_aa_kernel(const float* _
   else snake_segment<true, SPLIT>(xc, orow, f, a, inv_b, t0, t_end, L, pitch, opitch, split);
 }
 
+// Edge modes other than `replicate` (FV_EDGE_REFLECT / FV_EDGE_ZERO: what another release of alias_free_torch may pad
+// its two filters with, SURVEY 8c "unresolved ambiguity"): a direct, non-streaming evaluation, one thread per output
+// sample pair.  3x the arithmetic of the streaming kernel; never on the default path.
+//   out[t] = sum_j dn[j] * v~[2t - 5 + j],   v~ = v padded by the edge mode over [-5, 2L + 5]
+//   v[n]   = act(sum_q up[2q + (n even)] * x~[(n + 5 - (n even)) / 2 - q]),   x~ = x padded over [-5, L + 4]
+__device__ __forceinline__ int edge_index(int i, int n, int mode, bool& zero) {
+  zero = false;
+  if (i >= 0 && i < n) return i;
+  if (mode == FV_EDGE_ZERO) {
+    zero = true;
+    return 0;
+  }
+  if (mode == FV_EDGE_REFLECT) {  // F.pad(mode="reflect"): the edge sample itself is not repeated
+    i = i < 0 ? -i : 2 * (n - 1) - i;
+    return i < 0 ? 0 : (i > n - 1 ? n - 1 : i);
+  }
+  return i < 0 ? 0 : n - 1;
+}
+
+__global__ void __launch_bounds__(256) snake_aa_direct_kernel(const float* __restrict__ x, __half* __restrict__ out,
+                                                              const float* __restrict__ alpha,
+                                                              const float* __restrict__ beta, const SnakeFilt f,
+                                                              int logscale, int B, int L, int C, int pitch, int split,
+                                                              int mode) {
+  const int hp = pitch >> 1;
+  const long long total = (long long)B * L * hp;
+  const long long item = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (item >= total) return;
+  const int c = 2 * (int)(item % hp);
+  const int t = (int)((item / hp) % L);
+  const int b = (int)(item / ((long long)hp * L));
+  const int opitch = pitch + split;
+  __half* o = out + ((size_t)b * L + t) * opitch + c;
+  if (c >= C) {
+    store_half2_split(o, make_float2(0.f, 0.f), split);
+    return;
+  }
+  const int c1 = c + 1 < C ? c + 1 : c;
+  float2 a = make_float2(alpha[c], alpha[c1]);
+  float2 bb = beta ? make_float2(beta[c], beta[c1]) : a;
+  if (logscale) {
+    a = make_float2(expf(a.x), expf(a.y));
+    bb = make_float2(expf(bb.x), expf(bb.y));
+  }
+  const float2 inv_b = make_float2(1.0f / (bb.x + 1e-9f), 1.0f / (bb.y + 1e-9f));
+  const float* xc = x + ((size_t)b * L) * pitch + c;
+  const int nl = 2 * L;
+  float2 acc = make_float2(0.f, 0.f);
+  for (int j = 0; j < 12; ++j) {
+    bool vz;
+    const int n = edge_index(2 * t - 5 + j, nl, mode, vz);
+    if (vz) continue;
+    const int even = (n & 1) ? 0 : 1;
+    const int base = (n + 5 - even) / 2;
+    float2 u = make_float2(0.f, 0.f);
+    for (int q = 0; q < 6; ++q) {
+      bool xz;
+      const int xi = edge_index(base - q, L, mode, xz);
+      if (xz) continue;
+      const float2 xv = *reinterpret_cast<const float2*>(xc + (size_t)xi * pitch);
+      const float w = f.up[2 * q + even];
+      u.x = fmaf(xv.x, w, u.x);
+      u.y = fmaf(xv.y, w, u.y);
+    }
+    const float2 v = snake_fn2(u, a, inv_b);
+    acc.x = fmaf(v.x, f.dn[j], acc.x);
+    acc.y = fmaf(v.y, f.dn[j], acc.y);
+  }
+  store_half2_split(o, acc, split);
+}
+
 // ------------------------------------------------------------------------------------------------
 // depthwise conv (k taps, zero pad) + LayerNorm over C, one warp per (b, t) row.
 // ------------------------------------------------------------------------------------------------
@@ -780,14 +851,13 @@ __global__ void __launch_bounds__(256, 2) dwconv_ln_vec_kernel(const float* __re
 // ISTFT("same") overlap-add + envelope normalisation
 // ------------------------------------------------------------------------------------------------
 __global__ void istft_ola_kernel(const float* __restrict__ frames, const float* __restrict__ window,
-                                 float* __restrict__ wav, int B, int T, int n_fft, int hop, int frame_pitch) {
-  const long long total = (long long)B * T * hop;
+                                 float* __restrict__ wav, int B, int T, int n_fft, int hop, int frame_pitch, int trim,
+                                 int Lw) {
+  const long long total = (long long)B * Lw;
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (idx >= total) return;
-  const int Lw = T * hop;
   const int b = (int)(idx / Lw), s = (int)(idx % Lw);
-  const int pad = (n_fft - hop) / 2;
-  const int pos = s + pad;
+  const int pos = s + trim;
   int f_hi = pos / hop;
   if (f_hi > T - 1) f_hi = T - 1;
   int f_lo = (pos - n_fft + hop) / hop;  // ceil((pos - n_fft + 1) / hop) for pos - n_fft + 1 > 0
@@ -949,17 +1019,28 @@ extern "C" int fv_conv_post_tanh(const void* a16, const float* w32, const float*
 
 extern "C" int fv_snake_aa(const float* x32, void* out16, const float* alpha, const float* beta, const float* filt_up,
                            const float* filt_down, int logscale, int B, int L, int C, int pitch, int split,
-                           void* stream) {
+                           int edge_mode, void* stream) {
   FV_REQUIRE(x32 && out16 && alpha && filt_up && filt_down && B > 0 && L > 0 && C > 0 && pitch >= C && pitch % 2 == 0 &&
                  (reinterpret_cast<uintptr_t>(x32) & 7) == 0 && (reinterpret_cast<uintptr_t>(out16) & 3) == 0 &&
                  (split == 0 || split == pitch),
              FV_E_BADARG, "fv_snake_aa: bad arguments");
+  FV_REQUIRE(edge_mode == FV_EDGE_REPLICATE || edge_mode == FV_EDGE_REFLECT || edge_mode == FV_EDGE_ZERO, FV_E_BADARG,
+             "fv_snake_aa: unknown edge mode %d", edge_mode);
+  FV_REQUIRE(edge_mode != FV_EDGE_REFLECT || L >= 6, FV_E_UNSUPPORTED,
+             "fv_snake_aa: reflect padding of 5 samples needs L >= 6 (got %d)", L);
   SnakeFilt f;
   // the 12 taps are tiny, deterministic buffers of the module; fetch them once per call (async, stream ordered
   // copies would need a staging buffer - the module passes HOST copies of the taps instead, see python side)
   for (int i = 0; i < 12; ++i) {
     f.up[i] = 2.0f * filt_up[i];  // the up-sampler's gain of `ratio` (= 2) is folded into its taps
     f.dn[i] = filt_down[i];
+  }
+  if (edge_mode != FV_EDGE_REPLICATE) {
+    const long long items = (long long)B * L * (pitch / 2);
+    snake_aa_direct_kernel<<<grid1d(items, 256), 256, 0, (cudaStream_t)stream>>>(x32, (__half*)out16, alpha, beta, f,
+                                                                                logscale, B, L, C, pitch, split, edge_mode);
+    FV_CHECK_LAUNCH("snake_aa_direct_kernel");
+    return 0;
   }
   // Segment length: every thread does the same amount of work, so the grid runs in whole waves of SN_BLOCKS x 256 threads per
   // SM and a launch of 3.1 waves costs 4.  Pick the multiple of 6 in [36, 96] with the best (work / waves) ratio,
@@ -1011,14 +1092,11 @@ extern "C" int fv_dwconv_layernorm(const float* x32, void* out16, float* out32, 
     return !(e && e[0] == '0');
   }();
   if (vec_on && (k <= 0 || k == 7) && C % 4 == 0 && pitch % 4 == 0 && aligned16 && vec_smem <= 200 * 1024) {
-    static std::once_flag once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [] {
-      attr_err = cudaFuncSetAttribute(dwconv_ln_vec_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      if (attr_err == cudaSuccess)
-        attr_err = cudaFuncSetAttribute(dwconv_ln_vec_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    });
-    int rc = check_cuda(attr_err, "cudaFuncSetAttribute(dwconv_ln_vec_kernel)");
+    static std::atomic<unsigned long long> attr_done7{0}, attr_done0{0};
+    int rc = check_cuda(ensure_dyn_smem(dwconv_ln_vec_kernel<7>, 200 * 1024, attr_done7),
+                        "cudaFuncSetAttribute(dwconv_ln_vec_kernel)");
+    if (!rc) rc = check_cuda(ensure_dyn_smem(dwconv_ln_vec_kernel<0>, 200 * 1024, attr_done0),
+                             "cudaFuncSetAttribute(dwconv_ln_vec_kernel)");
     if (rc) return rc;
     const int tiles_per_b = ceil_div(T, DW8_R);
     const int grid = B * tiles_per_b;
@@ -1063,13 +1141,18 @@ extern "C" int fv_dwconv_layernorm(const float* x32, void* out16, float* out32, 
 }
 
 extern "C" int fv_istft_ola(const float* frames, const float* window, float* wav, int B, int T, int n_fft, int hop,
-                            int frame_pitch, void* stream) {
-  FV_REQUIRE(frames && window && wav && B > 0 && T > 0 && n_fft > 0 && hop > 0 && hop <= n_fft &&
-                 frame_pitch >= n_fft && (n_fft - hop) % 2 == 0,
+                            int frame_pitch, int center, void* stream) {
+  FV_REQUIRE(frames && window && wav && B > 0 && T > 0 && n_fft > 0 && hop > 0 && hop <= n_fft && frame_pitch >= n_fft,
              FV_E_BADARG, "fv_istft_ola: bad arguments");
-  const long long total = (long long)B * T * hop;
+  // "same" (vocos.spectral_ops.ISTFT): trim (win - hop) / 2 either side of the (T-1) hop + win long overlap-add -> T hop
+  // "center" (torch.istft(center=True)): trim n_fft / 2 either side -> (T - 1) hop samples
+  FV_REQUIRE(center || (n_fft - hop) % 2 == 0, FV_E_BADARG, "fv_istft_ola: padding='same' needs an even (win - hop)");
+  FV_REQUIRE(!center || T >= 2, FV_E_BADARG, "fv_istft_ola: padding='center' needs at least two frames");
+  const int trim = center ? n_fft / 2 : (n_fft - hop) / 2;
+  const int Lw = center ? (T - 1) * hop : T * hop;
+  const long long total = (long long)B * Lw;
   istft_ola_kernel<<<grid1d(total, 256), 256, 0, (cudaStream_t)stream>>>(frames, window, wav, B, T, n_fft, hop,
-                                                                        frame_pitch);
+                                                                        frame_pitch, trim, Lw);
   FV_CHECK_LAUNCH("istft_ola_kernel");
   return 0;
 }

@@ -1,1 +1,2 @@
 from .convnext import ConvNeXtEncoder  # noqa: F401
+from .vocos_backbone import VocosBackbone  # noqa: F401

@@ -15,7 +15,8 @@ import torch
 from torch import nn
 
 from .. import cabi
-from ..runtime import GraphedForward, Workspace, params_key, require_cuda, with_precision
+from ..runtime import (GraphedForward, Workspace, forward_signature, params_key, require_channels, require_cuda,
+                       with_precision)
 
 
 class LayerNorm(nn.Module):
@@ -95,9 +96,22 @@ class ConvNeXtEncoder(nn.Module):
         self._ws = Workspace()
         self._packed = None
         self._packed_key = None
+        self._pack_gen = 0
         self._graphed: Optional[GraphedForward] = None
+        self._ws.add_listener(self._drop_graphs)
         self.use_cuda_graph = False
+        self.clone_graph_output = True
         self.engine = cabi.ENGINE_TC
+
+    def _drop_graphs(self):
+        if self._graphed is not None:
+            self._graphed.invalidate()
+
+    @staticmethod
+    def _sens_ctx():
+        """ "mixed" precision: the stem conv and the three 1x1 downsample convs (~1% of the tensor work, but every later
+        block sees their error) carry [hi | lo] operands."""
+        return cabi.strict_layer(cabi.is_mixed())
 
     def _init_weights(self, m):
         if isinstance(m, (nn.Conv1d, nn.Linear)):  # convnext.py:201-204
@@ -113,13 +127,14 @@ class ConvNeXtEncoder(nn.Module):
         with torch.no_grad():
             P = {"down": [], "stages": []}
             for i, layer in enumerate(self.downsample_layers):
-                if i == 0:
-                    conv, ln = layer[0], layer[1]
-                    P["down"].append((cabi.pack_conv(conv.weight, conv.bias), f32(ln.weight), f32(ln.bias), ln.eps))
-                else:
-                    ln, conv = layer[0], layer[1]
-                    P["down"].append((cabi.pack_linear(conv.weight[:, :, 0], conv.bias), f32(ln.weight),
-                                      f32(ln.bias), ln.eps))
+                with self._sens_ctx():
+                    if i == 0:
+                        conv, ln = layer[0], layer[1]
+                        P["down"].append((cabi.pack_conv(conv.weight, conv.bias), f32(ln.weight), f32(ln.bias), ln.eps))
+                    else:
+                        ln, conv = layer[0], layer[1]
+                        P["down"].append((cabi.pack_linear(conv.weight[:, :, 0], conv.bias), f32(ln.weight),
+                                          f32(ln.bias), ln.eps))
             for stage in self.stages:
                 blocks = []
                 for blk in stage:
@@ -133,33 +148,53 @@ class ConvNeXtEncoder(nn.Module):
                 P["stages"].append(blocks)
             P["norm"] = (f32(self.norm.weight), f32(self.norm.bias), self.norm.eps)
         self._packed, self._packed_key = P, key
-        if self._graphed is not None:
-            self._graphed.invalidate()
+        self._pack_gen += 1
+        self._drop_graphs()
         return P
 
     # ---- launch sequence ----------------------------------------------------------------------------
-    def _encode_cl(self, a0: torch.Tensor, want32: bool = False):
-        """a0 fp16 [B,T,pitch(input_channels)] -> final-LayerNorm output as fp16 operand (and fp32 if asked)."""
+    def _pack_input(self, x: torch.Tensor) -> torch.Tensor:
+        with self._sens_ctx():
+            return cabi.pack_input(x)
+
+    def _encode_cl(self, a0: torch.Tensor, want32: bool = False, out_strict: bool = False):
+        """a0 fp16 [B,T,pitch(input_channels)] (from _pack_input) -> final-LayerNorm output as fp16 operand (and fp32 if
+        asked).  out_strict: the consumer of the operand is a strict layer of a "mixed" forward (ISTFT head)."""
         P = self._ensure_packed(a0.device)
         ws, dev, eng = self._ws, a0.device, self.engine
+        ws.enter(forward_signature(a0) + (want32, out_strict))
         B, T, _ = a0.shape
+        mixed = cabi.is_mixed()
+
+        def pit(C_):  # channel pitch of every buffer of this forward: the strict-layer pitch in "mixed" mode, so the plain
+            with cabi.strict_layer(mixed):  # and the [hi | lo] operand rows derived from one fp32 stream share it
+                return cabi.pitch_of(C_)
+
+        def f32(name, C_):
+            return ws.get(name, (B, T, pit(C_)), torch.float32, dev)
+
+        def f16(name, C_, hilo=False):
+            return ws.get(name, (B, T, pit(C_) * (2 if (hilo or cabi.is_strict()) else 1)), torch.float16, dev)
+
         x = None
         for i, blocks in enumerate(P["stages"]):
             pc, ln_w, ln_b, eps = P["down"][i]
             C = pc.c_out
-            xn = ws.f32(f"x_{i}", B, T, C, dev)
+            xn = f32(f"x_{i}", C)
             if i == 0:   # stem: conv k + LayerNorm(channels_first)            convnext.py:160-169
-                y = ws.f32("stem", B, T, C, dev)
-                cabi.conv1d(a0, pc, out32=y, engine=eng)
+                y = f32("stem", C)
+                with self._sens_ctx():
+                    cabi.conv1d(a0, pc, out32=y, engine=eng)
                 cabi.dwconv_layernorm(y, C, None, None, ln_w, ln_b, eps, 0, out32=xn)
             else:        # LayerNorm(channels_first) + 1x1 conv                 convnext.py:172-177
                 Cp = self.dims[i - 1]
-                h = ws.f16(f"dn_{i}", B, T, Cp, dev)
-                cabi.dwconv_layernorm(x, Cp, None, None, ln_w, ln_b, eps, 0, out16=h)
-                cabi.conv1d(h, pc, out32=xn, engine=eng)
+                h = f16(f"dn_{i}", Cp, hilo=mixed)
+                with self._sens_ctx():
+                    cabi.dwconv_layernorm(x, Cp, None, None, ln_w, ln_b, eps, 0, out16=h)
+                    cabi.conv1d(h, pc, out32=xn, engine=eng)
             x = xn
-            h16 = ws.f16(f"h_{i}", B, T, C, dev)
-            z16 = ws.f16(f"z_{i}", B, T, blocks[0]["pw1"].c_out if blocks else C, dev)
+            h16 = f16(f"h_{i}", C)
+            z16 = f16(f"z_{i}", blocks[0]["pw1"].c_out if blocks else C)
             for blk in blocks:
                 cabi.dwconv_layernorm(x, C, blk["dw_w"], blk["dw_b"], blk["ln_w"], blk["ln_b"], blk["eps"], blk["k"],
                                       out16=h16)
@@ -167,13 +202,14 @@ class ConvNeXtEncoder(nn.Module):
                 cabi.conv1d(z16, blk["pw2"], gamma=blk["gamma"], residual=x, out32=x, engine=eng)
         ln_w, ln_b, eps = P["norm"]
         C = self.dims[-1]
-        out16 = ws.f16("enc_out16", B, T, C, dev)
-        out32 = ws.f32("enc_out32", B, T, C, dev) if want32 else None
-        cabi.dwconv_layernorm(x, C, None, None, ln_w, ln_b, eps, 0, out16=out16, out32=out32)
+        out16 = f16("enc_out16", C, hilo=out_strict)
+        out32 = f32("enc_out32", C) if want32 else None
+        with cabi.strict_layer(out_strict):
+            cabi.dwconv_layernorm(x, C, None, None, ln_w, ln_b, eps, 0, out16=out16, out32=out32)
         return out16, out32
 
     def _forward_eager(self, x):
-        a0 = cabi.pack_input(x)
+        a0 = self._pack_input(x)
         _, out32 = self._encode_cl(a0, want32=True)
         return cabi.unpack_output(out32, self.dims[-1])
 
@@ -181,10 +217,12 @@ class ConvNeXtEncoder(nn.Module):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         """[B, input_channels, T] -> [B, dims[-1], T] fp32 (convnext.py:206-214)."""
         require_cuda(x, "ConvNeXtEncoder")
+        require_channels(x, self.input_channels, "ConvNeXtEncoder")
         x = x.contiguous().float()
         if self.use_cuda_graph and not torch.is_grad_enabled():
             self._ensure_packed(x.device)
             if self._graphed is None:
                 self._graphed = GraphedForward(self._forward_eager)
-            return self._graphed(x).clone()
+            y = self._graphed(x, tag=self._pack_gen)
+            return y.clone() if self.clone_graph_output else y
         return self._forward_eager(x)

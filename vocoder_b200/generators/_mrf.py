@@ -23,7 +23,10 @@ from torch.nn.utils.parametrizations import weight_norm
 from torch.nn.utils.parametrize import remove_parametrizations as _torch_remove_parametrizations
 
 from .. import cabi
-from ..runtime import GraphedForward, Workspace, params_key, require_cuda, with_precision
+import contextlib
+
+from ..runtime import (GraphedForward, Workspace, forward_signature, params_key, require_channels, require_cuda,
+                       with_precision)
 
 
 def same_padding(kernel_size: int, dilation: int = 1) -> int:
@@ -95,9 +98,16 @@ class MRFGeneratorBase(nn.Module):
         self._ws = Workspace()
         self._packed = None
         self._packed_key = None
+        self._pack_gen = 0  # bumped by every re-pack: part of the key of every CUDA graph that replays packed pointers
         self._graphed: Optional[GraphedForward] = None
+        self._ws.add_listener(self._drop_graphs)
         self.use_cuda_graph = False
+        self.clone_graph_output = True  # False: forward returns the graph's static output buffer (valid until the next call)
         self.engine = cabi.ENGINE_TC
+
+    def _drop_graphs(self):
+        if self._graphed is not None:
+            self._graphed.invalidate()
 
     def _finish_trunk(self):
         self.conv_post = wn_conv(self.stage_channels[-1], 1, self._post_k)
@@ -114,21 +124,36 @@ class MRFGeneratorBase(nn.Module):
     @with_precision
     def forward(self, x: torch.Tensor, template: Optional[torch.Tensor] = None) -> torch.Tensor:
         require_cuda(x, type(self).__name__)
+        require_channels(x, self.num_mels, type(self).__name__)
         if self.use_template and template is None:
             raise ValueError("use_template=True requires a template [B, 1, T*hop]")
         x = x.contiguous().float()
         tpl = None
         if self.use_template:
             tpl = template.contiguous().float()
+            if tpl.shape[0] != x.shape[0] or tpl.shape[-1] != x.shape[-1] * self.hop_length:
+                raise ValueError(f"template must be [B, 1, T*hop] = [{x.shape[0]}, 1, {x.shape[-1] * self.hop_length}], "
+                                 f"got {tuple(tpl.shape)}")
         if self.use_cuda_graph and not torch.is_grad_enabled():
             self._ensure_packed(x.device)
             if self._graphed is None:
                 self._graphed = GraphedForward(self._forward_eager)
-            return self._graphed(x, tpl).clone()
+            y = self._graphed(x, tpl, tag=self._pack_gen)
+            return y.clone() if self.clone_graph_output else y
         return self._forward_eager(x, tpl)
 
+    def _trunk_strict(self) -> bool:
+        """ "mixed" precision: conv_pre / ups / conv_post of the Snake generators carry [hi | lo] operands.  Measured on the
+        reference goldens (tools/precision_probe.py): the trunk alone is ~90% of the fp16-operand waveform error, at
+        < 5% of the tensor work."""
+        return cabi.is_mixed() and self.snake_blocks
+
+    def _trunk_ctx(self):
+        return cabi.strict_layer() if self._trunk_strict() else contextlib.nullcontext()
+
     def _forward_eager(self, x, tpl):
-        a0 = cabi.pack_input(x)
+        with self._trunk_ctx():
+            a0 = cabi.pack_input(x)
         return self._forward_cl(a0, tpl)
 
     # ---- weight packing ------------------------------------------------------------------------
@@ -140,10 +165,12 @@ class MRFGeneratorBase(nn.Module):
         if self._packed is not None and self._packed_key == key:
             return self._packed
         with torch.no_grad():
-            P = {"pre": cabi.pack_conv(self.conv_pre.weight, self.conv_pre.bias), "ups": [], "blocks": [],
-                 "noise": [], "fused": []}
+            with self._trunk_ctx():
+                P = {"pre": cabi.pack_conv(self.conv_pre.weight, self.conv_pre.bias), "ups": [], "blocks": [],
+                     "noise": [], "fused": []}
             for i, up in enumerate(self.ups):
-                P["ups"].append(cabi.pack_conv_transpose(up.weight, up.bias, self.upsample_rates[i]))
+                with self._trunk_ctx():
+                    P["ups"].append(cabi.pack_conv_transpose(up.weight, up.bias, self.upsample_rates[i]))
                 blocks = []
                 mods = self._block_modules(i)
                 pairs = [(list(blk.convs1), list(blk.convs2)) for blk in mods]
@@ -166,8 +193,8 @@ class MRFGeneratorBase(nn.Module):
             P["post_w"] = wp[0].t().contiguous()          # [k, C]
             P["post_b"] = self.conv_post.bias.detach().float().contiguous()
         self._packed, self._packed_key = P, key
-        if self._graphed is not None:
-            self._graphed.invalidate()
+        self._pack_gen += 1
+        self._drop_graphs()
         return P
 
     # ---- hooks for the activation flavour -------------------------------------------------------
@@ -177,19 +204,28 @@ class MRFGeneratorBase(nn.Module):
     def _stage_out_act(self, last_stage: bool):   # activation fused into the stage's final epilogue
         raise NotImplementedError
 
-    def _final_activation(self, acc, h16, C):     # un-fusable activation_post (BigVGAN AA-Snake) else no-op
+    def _final_activation(self, acc, h16, C, split):     # un-fusable activation_post (BigVGAN AA-Snake) else no-op
         return None
 
     # ---- the launch sequence ----------------------------------------------------------------------
     def _forward_cl(self, a0: torch.Tensor, tpl: Optional[torch.Tensor]) -> torch.Tensor:
-        """a0: fp16 [B, T, pitch(num_mels)] channels-last.  Returns wav fp32 [B, 1, T*hop]."""
+        """a0: fp16 [B, T, pitch(num_mels)] channels-last ([hi | lo] when the trunk is strict).  Returns wav fp32 [B, 1, T*hop]."""
         P = self._ensure_packed(a0.device)
         ws, dev, eng = self._ws, a0.device, self.engine
+        ws.enter(forward_signature(a0, tpl))
         B, T, _ = a0.shape
         pre = P["pre"]
+        trunk = self._trunk_strict()   # "mixed": h16 (what ups / conv_post consume) is [hi | lo] between stages
+
+        def h_buf(name, L_, C_):       # operand of a trunk layer + the `split` its producer must write
+            with self._trunk_ctx():
+                t = ws.f16(name, B, L_, C_, dev)
+            return t, ((t.shape[-1] // 2) if (trunk or cabi.is_strict()) else 0)
+
         act_pre, act_pre_p = self._pre_act()
-        h16 = ws.f16("h_pre", B, T, pre.c_out, dev)
-        cabi.conv1d(a0, pre, out16=h16, act=act_pre, act_param=act_pre_p, engine=eng)
+        h16, h_split = h_buf("h_pre", T, pre.c_out)
+        with self._trunk_ctx():
+            cabi.conv1d(a0, pre, out16=h16, act=act_pre, act_param=act_pre_p, engine=eng)
         L = T
         n_stage = self.num_upsamples
         for i in range(n_stage):
@@ -215,17 +251,18 @@ class MRFGeneratorBase(nn.Module):
                                act=self._silu(),
                                out_act=out_act or cabi.ACT_NONE, out_act_param=out_act_p)
                 if last_stage:
-                    self._final_activation(acc, h_next, C)
+                    self._final_activation(acc, h_next, C, 0)
                 h16, L = h_next, Lo
                 continue
-            if self.snake_blocks:
-                cabi.conv1d(h16, up, Lo, residual=nz, out32=x0, engine=eng)
-                xa0 = None
-            else:
-                xa0 = ws.f16(f"xa0_{i}", B, Lo, C, dev)
-                cabi.conv1d(h16, up, Lo, residual=nz, out32=x0, out16=xa0, act=self._silu(), engine=eng)
+            with self._trunk_ctx():
+                if self.snake_blocks:
+                    cabi.conv1d(h16, up, Lo, residual=nz, out32=x0, engine=eng)
+                    xa0 = None
+                else:
+                    xa0 = ws.f16(f"xa0_{i}", B, Lo, C, dev)
+                    cabi.conv1d(h16, up, Lo, residual=nz, out32=x0, out16=xa0, act=self._silu(), engine=eng)
             acc = ws.f32(f"acc_{i}", B, Lo, C, dev)
-            h_next = ws.f16(f"h_{i}", B, Lo, C, dev)
+            h_next, h_split = h_buf(f"h_{i}", Lo, C)
             # The residual blocks can run per micro-batch of utterances (working set resident in the 126 MB L2).
             # Measured on B200 (HiFiGAN cfg B): 64 -> 8.6 ms, 32 -> 9.4 ms, 16 -> 10.6 ms, 8 -> 13.7 ms per forward:
             # tail and launch effects outweigh the L2 hits, so the default is the whole batch.
@@ -263,14 +300,16 @@ class MRFGeneratorBase(nn.Module):
                             want16 = (j == nk - 1) and out_act is not None
                             cabi.conv1d(ta_m, c2s[p_i], residual=xr, out32=acc_m, accumulate=j > 0,
                                         out_scale=1.0 / nk, out16=h_m if want16 else None,
-                                        act=out_act if want16 else cabi.ACT_NONE, act_param=out_act_p, engine=eng)
+                                        act=out_act if want16 else cabi.ACT_NONE, act_param=out_act_p, engine=eng,
+                                        out16_split=h_split if want16 else None)
             if last_stage:
-                self._final_activation(acc, h_next, C)
+                self._final_activation(acc, h_next, C, h_split)
             h16, L = h_next, Lo
-        wav = cabi.conv_post_tanh(h16, P["post_w"], P["post_b"], self.stage_channels[-1], apply_tanh=True)
+        wav = cabi.conv_post_tanh(h16, P["post_w"], P["post_b"], self.stage_channels[-1], apply_tanh=True,
+                                  split=h_split if (trunk or cabi.is_strict()) else 0)
         return wav
 
-    def _snake(self, act_module, x32, out16, C):
+    def _snake(self, act_module, x32, out16, C, split=None):
         raise NotImplementedError
 
     #: C <= 64 SiLU stages as one on-chip kernel per stage (fv_mrf_fused); False = layer-wise fv_conv1d launches

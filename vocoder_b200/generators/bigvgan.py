@@ -75,6 +75,10 @@ class Activation1d(_ParamOnly):
     """State-dict compatible holder for alias_free_torch.Activation1d (up 2x / act / down 2x, 12 taps):
     buffers ``upsample.filter`` and ``downsample.lowpass.filter`` [1,1,12], submodule ``act``."""
 
+    #: how both anti-alias filters pad their input: "replicate" (the BigVGAN-flavoured alias_free_torch the state_dict
+    #: layout matches), "reflect" or "zero" (SURVEY 8c: the PyPI 0.0.6 wheel could not be inspected offline)
+    edge_mode = "replicate"
+
     def __init__(self, activation, up_ratio=2, down_ratio=2, up_kernel_size=12, down_kernel_size=12):
         super().__init__()
         if (up_ratio, down_ratio, up_kernel_size, down_kernel_size) != (2, 2, 12, 12):
@@ -103,6 +107,8 @@ class AMPBlock(nn.Module):
 
 class BigVGANGenerator(MRFGeneratorBase):
     snake_blocks = True
+    #: overrides Activation1d.edge_mode of every anti-aliased activation when set ("replicate" | "reflect" | "zero")
+    aa_edge_mode = None
 
     def __init__(
         self,
@@ -157,11 +163,12 @@ class BigVGANGenerator(MRFGeneratorBase):
             self._filt_cache[key] = v
         return v[1], v[2]
 
-    def _snake(self, a1d: Activation1d, x32, out16, C):
+    def _snake(self, a1d: Activation1d, x32, out16, C, split=None):
         act = a1d.act
         up, dn = self._taps(a1d)
         beta = act.beta.detach() if isinstance(act, SnakeBeta) else None
-        cabi.snake_aa(x32, out16, act.alpha.detach(), beta, up, dn, C, logscale=bool(act.alpha_logscale))
+        cabi.snake_aa(x32, out16, act.alpha.detach(), beta, up, dn, C, logscale=bool(act.alpha_logscale), split=split,
+                      edge_mode=self.aa_edge_mode or a1d.edge_mode)
 
-    def _final_activation(self, acc, h16, C):
-        self._snake(self.activation_post, acc, h16, C)
+    def _final_activation(self, acc, h16, C, split):
+        self._snake(self.activation_post, acc, h16, C, split)

@@ -22,7 +22,8 @@ from torch import nn
 from torch.nn.utils.parametrizations import weight_norm
 
 from .. import cabi
-from ..runtime import GraphedForward, Workspace, params_key, require_cuda, with_precision
+from ..runtime import (GraphedForward, Workspace, forward_signature, params_key, require_channels, require_cuda,
+                       with_precision)
 from ._mrf import same_padding, strip_weight_norm
 
 
@@ -171,6 +172,7 @@ class RefineGANGenerator(nn.Module):
     def _forward_eager(self, mel, tpl):
         P = self._ensure_packed(mel.device)
         ws, dev, eng, sl = self._ws, mel.device, self.engine, self.leaky_relu_slope
+        ws.enter(forward_signature(mel, tpl))
         LK = cabi.ACT_LEAKY
         B, _, T = mel.shape
         L = tpl.shape[-1]

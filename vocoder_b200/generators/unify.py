@@ -20,15 +20,28 @@ class UnifyGenerator(nn.Module):
         self.head = head
         self.vq = vq
         self.use_cuda_graph = False
+        self.clone_graph_output = True
         self._graphed: Optional[GraphedForward] = None
+        # the sub-modules' workspaces hold the buffers a graph captured here replays: dropping them drops the graph
+        for m in (backbone, head):
+            ws = getattr(m, "_ws", None)
+            if ws is not None:
+                ws.add_listener(self._drop_graphs)
+
+    def _drop_graphs(self):
+        if self._graphed is not None:
+            self._graphed.invalidate()
 
     def _fused_ok(self) -> bool:
         return self.vq is None and hasattr(self.backbone, "_encode_cl") and hasattr(self.head, "_forward_cl")
 
     def _forward_fused(self, x, template):
-        a0 = cabi.pack_input(x)
-        h16, _ = self.backbone._encode_cl(a0)
-        if getattr(self.head, "use_template", None) is not None:   # MRF head (firefly-gan-base.yaml)
+        a0 = self.backbone._pack_input(x)
+        mrf_head = getattr(self.head, "use_template", None) is not None   # MRF head (firefly-gan-base.yaml)
+        # "mixed" precision: the ISTFT head's contractions are strict layers, so the encoder hands over [hi | lo]
+        out_strict = cabi.is_mixed() and (self.head._trunk_strict() if mrf_head else True)
+        h16, _ = self.backbone._encode_cl(a0, out_strict=out_strict)
+        if mrf_head:
             y = self.head._forward_cl(h16, template)
         else:
             y = self.head._forward_cl(h16)
@@ -46,7 +59,12 @@ class UnifyGenerator(nn.Module):
                 self.head._ensure_packed(x.device)
                 if self._graphed is None:
                     self._graphed = GraphedForward(self._forward_fused)
-                return self._graphed(x, template).clone()
+                # the graph replays pointers into the sub-modules' packed weights: key it on their pack generations, so
+                # load_state_dict / remove_parametrizations / an in-place weight edit / a precision or engine change
+                # after a graphed forward re-captures instead of replaying freed memory
+                tag = (self.backbone._pack_gen, self.head._pack_gen)
+                y = self._graphed(x, template, tag=tag)
+                return y.clone() if self.clone_graph_output else y
             return self._forward_fused(x, template)
         x = self.backbone(x)
         vq_result = None

@@ -19,7 +19,11 @@ from typing import Dict, Iterable, Optional
 import numpy as np
 import torch
 
+import functools
+import importlib
+
 _TARGETS = {
+    "VocosBackbone": ("vocoder_b200.encoders.vocos_backbone", "VocosBackbone"),
     "HiFiGANGenerator": ("vocoder_b200.generators.hifigan", "HiFiGANGenerator"),
     "BigVGANGenerator": ("vocoder_b200.generators.bigvgan", "BigVGANGenerator"),
     "RefineGANGenerator": ("vocoder_b200.generators.refinegan", "RefineGANGenerator"),
@@ -33,12 +37,22 @@ def instantiate(cfg):
     """Minimal stand-in for hydra.utils.instantiate (fish_vocoder/test.py:31): builds the object a `_target_` names,
     recursively, mapping the reference's dotted paths onto the vocoder_b200 classes."""
     if isinstance(cfg, dict) and "_target_" in cfg:
-        cls_name = cfg["_target_"].split(".")[-1]
-        if cls_name not in _TARGETS:
-            raise KeyError(f"no B200 implementation for _target_ {cfg['_target_']}")
-        mod, name = _TARGETS[cls_name]
-        cls = getattr(__import__(mod, fromlist=[name]), name)
-        kwargs = {k: instantiate(v) for k, v in cfg.items() if k != "_target_"}
+        target = cfg["_target_"]
+        cls_name = target.split(".")[-1]
+        if cls_name in _TARGETS:
+            mod, name = _TARGETS[cls_name]
+            cls = getattr(importlib.import_module(mod), name)
+        elif target.startswith(("torch.nn.", "functools.")):
+            # plain torch callables the reference yamls pass by name, e.g.
+            # post_activation: {_target_: torch.nn.SiLU, _partial_: true}
+            mod, name = target.rsplit(".", 1)
+            cls = getattr(importlib.import_module(mod), name)
+        else:
+            raise KeyError(f"no B200 implementation for _target_ {target}")
+        kwargs = {k: instantiate(v) for k, v in cfg.items() if k not in ("_target_", "_partial_", "_recursive_",
+                                                                           "_convert_")}
+        if cfg.get("_partial_", False):   # hydra: functools.partial(target, **kwargs)
+            return functools.partial(cls, **kwargs)
         return cls(**kwargs)
     if isinstance(cfg, dict):
         return {k: instantiate(v) for k, v in cfg.items()}
@@ -59,7 +73,10 @@ def generator_state_dict(ckpt: Dict, prefix: str = "generator.") -> Dict[str, to
 def load_generator(cfg, ckpt_path: Optional[str], device="cuda") -> torch.nn.Module:
     gen = instantiate(cfg)
     if ckpt_path:
-        ckpt = torch.load(ckpt_path, map_location="cpu", weights_only=False)
+        try:  # tensors-only first; a Lightning checkpoint with pickled hyper-parameters needs the full loader
+            ckpt = torch.load(ckpt_path, map_location="cpu", weights_only=True)
+        except Exception:  # noqa: BLE001
+            ckpt = torch.load(ckpt_path, map_location="cpu", weights_only=False)
         gen.load_state_dict(generator_state_dict(ckpt), strict=True)
     return gen.eval().to(device)
 
@@ -71,6 +88,7 @@ def context_frames(gen) -> int:
     """Conservative one-sided receptive field of the generator in mel frames (input context a chunk needs so that its
     interior equals the un-chunked forward)."""
     from .encoders.convnext import ConvNeXtEncoder
+    from .encoders.vocos_backbone import VocosBackbone
     from .generators._mrf import MRFGeneratorBase
     from .generators.unify import UnifyGenerator
     from .generators.vocos import ISTFTHead
@@ -97,9 +115,12 @@ def context_frames(gen) -> int:
         return sum(gen.depths) * (gen.kernel_size // 2) + gen.kernel_size // 2 + 1
     if isinstance(gen, ISTFTHead):
         return gen.win_length // gen.hop_length + 1
+    if isinstance(gen, VocosBackbone):
+        return (len(gen.convnext) + 1) * 3 + 1
     if isinstance(gen, UnifyGenerator):
         return context_frames(gen.backbone) + context_frames(gen.head)
-    raise TypeError(f"no receptive-field model for {type(gen).__name__}")
+    raise TypeError(f"no receptive-field model for {type(gen).__name__}: synthesise it with a single forward "
+                    "(RefineGAN's U-Net mixes time scales; chunk it upstream of the mel if memory is short)")
 
 
 def hop_of(gen) -> int:
@@ -108,20 +129,34 @@ def hop_of(gen) -> int:
     return hop_of(gen.head)
 
 
+def _call(gen, mel, template):
+    return gen(mel) if template is None else gen(mel, template)
+
+
 @torch.no_grad()
-def chunked_forward(gen, mel: torch.Tensor, chunk_frames: int = 2048, context: Optional[int] = None) -> torch.Tensor:
+def chunked_forward(gen, mel: torch.Tensor, chunk_frames: int = 2048, context: Optional[int] = None,
+                    template: Optional[torch.Tensor] = None) -> torch.Tensor:
     """mel [B, n_mels, T] -> wav [B, 1, T*hop] in chunks of `chunk_frames` frames (+ `context` frames of overlap on each
-    side, recomputed and discarded), so device memory is bounded by the chunk, not by the utterance length."""
+    side, recomputed and discarded), so device memory is bounded by the chunk, not by the utterance length: the
+    generators keep workspace buffers and CUDA graphs for the few most recent input shapes only (runtime.Workspace), and
+    a long file presents at most three (first / interior / last chunk).  `template` [B, 1, T*hop] (generators built with
+    use_template=True, hifigan.py:233-234) is sliced alongside the mel."""
     B, _, T = mel.shape
-    ctx = context_frames(gen) if context is None else int(context)
     hop = hop_of(gen)
+    if template is not None and template.shape[-1] != T * hop:
+        raise ValueError(f"template must hold T*hop = {T * hop} samples, got {template.shape[-1]}")
+    try:
+        ctx = context_frames(gen) if context is None else int(context)
+    except TypeError:
+        return _call(gen, mel, template)  # no receptive-field model (RefineGAN): one forward
     if T <= chunk_frames + 2 * ctx:
-        return gen(mel)
+        return _call(gen, mel, template)
     out = torch.empty(B, 1, T * hop, dtype=torch.float32, device=mel.device)
     for start in range(0, T, chunk_frames):
         end = min(T, start + chunk_frames)
         lo, hi = max(0, start - ctx), min(T, end + ctx)
-        y = gen(mel[:, :, lo:hi].contiguous())
+        tpl = None if template is None else template[:, :, lo * hop:hi * hop].contiguous()
+        y = _call(gen, mel[:, :, lo:hi].contiguous(), tpl)
         out[:, :, start * hop:end * hop] = y[:, :, (start - lo) * hop:(end - lo) * hop]
     return out
 
@@ -130,8 +165,9 @@ def chunked_forward(gen, mel: torch.Tensor, chunk_frames: int = 2048, context: O
 # I/O + CLI
 # ------------------------------------------------------------------------------------------------
 def load_mel(path: str, n_mels: Optional[int] = None) -> torch.Tensor:
-    x = torch.from_numpy(np.load(path)) if path.endswith(".npy") else torch.load(path, map_location="cpu",
-                                                                                 weights_only=False)
+    # mel inputs are plain tensors: never unpickle arbitrary objects from a data directory
+    x = torch.from_numpy(np.load(path, allow_pickle=False)) if path.endswith(".npy") else torch.load(
+        path, map_location="cpu", weights_only=True)
     x = x.to(torch.float32)
     if x.ndim == 2:
         x = x[None]
@@ -171,7 +207,12 @@ def main(argv=None) -> int:
     ap.add_argument("--sample-rate", type=int, default=44100)
     ap.add_argument("--chunk-frames", type=int, default=4096)
     ap.add_argument("--device", default="cuda")
+    ap.add_argument("--template-dir", default=None,
+                    help="directory of <name>.pt/.npy templates [1, T*hop] for generators built with use_template=True")
     args = ap.parse_args(argv)
+    dev = torch.device(args.device)
+    if dev.type == "cuda":
+        torch.cuda.set_device(dev)  # kernels launch on the current device's stream
     with open(args.config) as f:
         cfg = yaml.safe_load(f)
     gen = load_generator(cfg, args.ckpt, args.device)
@@ -179,7 +220,17 @@ def main(argv=None) -> int:
     os.makedirs(args.output_dir, exist_ok=True)
     for path in iter_inputs(args.input):
         mel = load_mel(path, n_mels).to(args.device)
-        wav = chunked_forward(gen, mel, args.chunk_frames)
+        tpl = None
+        if args.template_dir:
+            stem = os.path.splitext(os.path.basename(path))[0]
+            for ext in (".pt", ".pth", ".npy"):
+                cand = os.path.join(args.template_dir, stem + ext)
+                if os.path.exists(cand):
+                    tpl = load_mel(cand).reshape(mel.shape[0], 1, -1).to(args.device)
+                    break
+            if tpl is None:
+                raise FileNotFoundError(f"no template for {path} in {args.template_dir}")
+        wav = chunked_forward(gen, mel, args.chunk_frames, template=tpl)
         out = os.path.join(args.output_dir, os.path.splitext(os.path.basename(path))[0] + ".wav")
         write_wav(out, wav[:, 0], args.sample_rate)
         print(f"{path} -> {out}  ({wav.shape[-1] / args.sample_rate:.2f} s)")

@@ -5,7 +5,8 @@ Nothing here computes: torch is used for device memory, streams and graph captur
 from __future__ import annotations
 
 import functools
-from typing import Callable, Dict, Iterable, Tuple
+from collections import OrderedDict
+from typing import Callable, Dict, Iterable, List, Tuple
 
 import torch
 
@@ -13,37 +14,77 @@ from . import cabi
 
 
 class Workspace:
-    """Named device buffers reused across forward calls (stable addresses => CUDA-graph friendly)."""
+    """Named device buffers reused across forward calls (stable addresses => CUDA-graph friendly).
 
-    def __init__(self):
-        self._bufs: Dict[Tuple, torch.Tensor] = {}
+    Buffers are grouped by the *signature* of the forward that asked for them (``enter(sig)``: input shape, precision
+    mode, device).  At most ``max_signatures`` signatures stay resident; the least recently used group is dropped when a
+    new one arrives, so synthesising a directory of files with ever-changing lengths does not grow device memory
+    without bound.  Dropping buffers invalidates every CUDA graph that captured their addresses: listeners
+    (``GraphedForward.invalidate``) are called on eviction.
+    """
+
+    def __init__(self, max_signatures: int = 4):
+        self.max_signatures = max_signatures
+        self._groups: "OrderedDict[Tuple, Dict[Tuple, torch.Tensor]]" = OrderedDict()
+        self._sig: Tuple = ()
+        self._listeners: List[Callable[[], None]] = []
+
+    def add_listener(self, fn: Callable[[], None]) -> None:
+        self._listeners.append(fn)
+
+    def enter(self, sig: Tuple) -> None:
+        """Declare the signature of the forward that is about to request buffers."""
+        self._sig = sig
+        if sig in self._groups:
+            self._groups.move_to_end(sig)
+            return
+        self._groups[sig] = {}
+        evicted = False
+        while len(self._groups) > self.max_signatures:
+            self._groups.popitem(last=False)
+            evicted = True
+        if evicted:
+            for fn in self._listeners:
+                fn()
 
     def get(self, name: str, shape: Tuple[int, ...], dtype: torch.dtype, device, zero: bool = False) -> torch.Tensor:
+        group = self._groups.setdefault(self._sig, {})
         key = (name, tuple(shape), dtype, str(device))
-        t = self._bufs.get(key)
+        t = group.get(key)
         if t is None:
             # always zero-filled at creation: kernels that write only c < C (act_cast, resample_linear, snake_aa) rely
             # on the channel padding of operand buffers being zero (0-weights x NaN garbage would still be NaN)
             t = torch.zeros(shape, dtype=dtype, device=device)
-            self._bufs[key] = t
+            group[key] = t
         return t
 
     def f32(self, name, B, L, C, device):
         return self.get(name, (B, L, cabi.pitch_of(C)), torch.float32, device)
 
     def f16(self, name, B, L, C, device):
-        return self.get(name, (B, L, cabi.f16_width(C)), torch.float16, device)  # strict mode: [hi | lo]
+        return self.get(name, (B, L, cabi.f16_width(C)), torch.float16, device)  # strict layer: [hi | lo]
 
     def clear(self):
-        self._bufs.clear()
+        self._groups.clear()
+        for fn in self._listeners:
+            fn()
 
     def nbytes(self) -> int:
-        return sum(t.numel() * t.element_size() for t in self._bufs.values())
+        return sum(t.numel() * t.element_size() for g in self._groups.values() for t in g.values())
+
+    def n_signatures(self) -> int:
+        return len(self._groups)
+
+
+def forward_signature(*tensors) -> Tuple:
+    """Workspace / graph signature of a forward: precision mode + shape, dtype and device of every input."""
+    return (cabi.mode(), cabi.is_strict()) + tuple(
+        (tuple(t.shape), t.dtype, t.device.index) if t is not None else None for t in tensors)
 
 
 def params_key(tensors: Iterable[torch.Tensor]) -> Tuple:
     """Cheap fingerprint of a parameter set: changes when any tensor is updated in place, replaced or moved."""
-    return (cabi.is_strict(),) + tuple((t.data_ptr(), t._version, t.device.index) for t in tensors)
+    return (cabi.mode(), cabi.is_strict()) + tuple((t.data_ptr(), t._version, t.device.index) for t in tensors)
 
 
 def require_cuda(x: torch.Tensor, who: str) -> None:
@@ -54,12 +95,23 @@ def require_cuda(x: torch.Tensor, who: str) -> None:
     cabi.lib()  # raises loudly when the extension has not been built
 
 
+def require_channels(x: torch.Tensor, channels: int, who: str) -> None:
+    """A mismatched channel count would run silently (TMA zero-fills the missing weight columns): refuse it."""
+    if x.ndim != 3 or x.shape[1] != channels:
+        raise ValueError(f"{who}: expected input [B, {channels}, T], got {tuple(x.shape)}")
+
+
 def with_precision(fn):
-    """Run a module's forward under its ``precision`` attribute ("fp16" default | "strict", see cabi.precision)."""
+    """Run a module's forward under its ``precision`` attribute (see cabi.precision) and on the device of its input:
+    launches use the CURRENT device's stream, so a module living on cuda:1 must make cuda:1 current for the call."""
 
     @functools.wraps(fn)
     def wrapper(self, *args, **kwargs):
-        with cabi.precision(getattr(self, "precision", "fp16")):
+        x = args[0] if args else None
+        with cabi.precision(getattr(self, "precision", None) or cabi.DEFAULT_PRECISION):
+            if isinstance(x, torch.Tensor) and x.is_cuda:
+                with torch.cuda.device(x.device):
+                    return fn(self, *args, **kwargs)
             return fn(self, *args, **kwargs)
 
     return wrapper
@@ -69,20 +121,27 @@ class GraphedForward:
     """Capture ``fn(static_inputs...) -> static_output`` once per input signature and replay it.
 
     The captured region contains only kernels of libfv_b200.so (launched on torch's capturing stream);
-    replay removes the per-launch host cost of the ~80-150 kernels of one generator forward.
+    replay removes the per-launch host cost of the ~80-150 kernels of one generator forward.  At most ``max_graphs``
+    signatures are kept (least recently used first out).  ``tag`` is an extra key component: callers pass the pack
+    generation of the weights the graph was captured with, so a re-pack (load_state_dict, remove_parametrizations,
+    precision / engine change) can never replay pointers of freed packed weights.
     """
 
-    def __init__(self, fn: Callable[..., torch.Tensor], warmup: int = 2):
+    def __init__(self, fn: Callable[..., torch.Tensor], warmup: int = 2, max_graphs: int = 4):
         self.fn = fn
         self.warmup = warmup
-        self._graphs: Dict[Tuple, Tuple] = {}
+        self.max_graphs = max_graphs
+        self._graphs: "OrderedDict[Tuple, Tuple]" = OrderedDict()
+        self._tag = None
 
     def invalidate(self):
         self._graphs.clear()
 
-    def __call__(self, *inputs: torch.Tensor) -> torch.Tensor:
-        sig = (cabi.is_strict(),) + tuple((tuple(t.shape), t.dtype, t.device.index) if t is not None else None
-                                          for t in inputs)
+    def __call__(self, *inputs: torch.Tensor, tag=None) -> torch.Tensor:
+        if tag != self._tag:
+            self.invalidate()
+            self._tag = tag
+        sig = forward_signature(*inputs)
         entry = self._graphs.get(sig)
         if entry is None:
             static_in = [None if t is None else t.clone() for t in inputs]
@@ -97,7 +156,12 @@ class GraphedForward:
             with torch.cuda.graph(graph):
                 static_out = self.fn(*static_in)
             entry = (graph, static_in, static_out)
+            # the warm-up may have evicted a workspace group and with it every older graph: insert after it
             self._graphs[sig] = entry
+            while len(self._graphs) > self.max_graphs:
+                self._graphs.popitem(last=False)
+        else:
+            self._graphs.move_to_end(sig)
         graph, static_in, static_out = entry
         for s, t in zip(static_in, inputs):
             if s is not None:

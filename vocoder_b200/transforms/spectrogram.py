@@ -19,7 +19,7 @@ import torch
 from torch import nn
 
 from .. import cabi
-from ..runtime import Workspace, params_key, require_cuda
+from ..runtime import Workspace, forward_signature, params_key, require_cuda
 
 
 def slaney_mel_filterbank(n_freqs: int, f_min: float, f_max: float, n_mels: int, sample_rate: int) -> torch.Tensor:
@@ -106,13 +106,15 @@ class LinearSpectrogram(nn.Module):
         k = n_fft // hop
         pc = self._ensure_packed()
         rows = T + k - 1
+        self._ws.enter(forward_signature(y))
         a16 = cabi.frame_audio(y, hop, pad_l, pad_r, rows)
         spec = self._ws.f32("spec", B, T, pc.c_out, y.device)
         cabi.conv1d(a16, pc, T, out32=spec)
         return spec, T
 
     def forward(self, y: torch.Tensor) -> torch.Tensor:
-        with cabi.precision("strict"):
+        require_cuda(y, type(self).__name__)
+        with cabi.precision("strict"), torch.cuda.device(y.device):
             spec, T = self._spectrum_cl(y)
             B = spec.shape[0]
             mag = self._ws.f32("mag", B, T, self.n_freqs, spec.device)
@@ -161,10 +163,12 @@ class LogMelSpectrogram(nn.Module):
         return self._packed
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        with cabi.precision("strict"):
+        require_cuda(x, type(self).__name__)
+        with cabi.precision("strict"), torch.cuda.device(x.device):
             spec, T = self.spectrogram._spectrum_cl(x)
             B, F, dev = spec.shape[0], self.spectrogram.n_freqs, spec.device
             pc = self._ensure_packed()
+            self._ws.enter(forward_signature(x))
             mag16 = self._ws.f16("mag16", B, T, F, dev)
             cabi.spec_mag(spec, F, 1e-6, out16=mag16)
             mel = self._ws.f32("mel", B, T, self.n_mels, dev)
