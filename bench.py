@@ -7,6 +7,13 @@ One process per GPU (torchrun for N > 1: RANK/LOCAL_RANK/WORLD_SIZE/MASTER_* fro
 forward of the generator over one batch of synthetic mel.  Rank 0 prints ONE JSON line (see README / DESIGN.md).
 Multi-GPU = embarrassingly parallel batch split (weak scaling, no data-path collective; NCCL only for the
 barrier and the max-over-ranks reduction of the device time).
+
+The headline (`value`, `e2e`, `roofline`, `parity`, `cpu_baseline`) is BASELINE.json configs[1] (HiFiGAN, batch 64 x 1 s @
+24 kHz).  The other BASELINE configs are measured in the same run and reported under `workloads`:
+configs[2] bigvgan_b32, configs[3] vocos_huge_b128, configs[0]'s shape on the GPU (hifigan_b1) at N = 1, and configs[4]
+(BigVGAN, 32 utterances per GPU, batch-sharded) at every N.  Every timed number carries a `parity` object next to it:
+max |delta| of the GPU waveform against the CPU oracle on the first utterances of the same batch, for the timed
+("ref-init") weights and for SURVEY-8d stress weights, in the precision mode that was timed.
 """
 from __future__ import annotations
 
@@ -38,6 +45,7 @@ WORKLOADS = {
     "vocos_huge_b128": ("vocos", 128, 100, 94, 256, 24000,
                         "vocos_huge ConvNeXt [3,3,27,3]x[352,704,1408,2816] + ISTFT(1024/256), batch 128 x 1 s @ 24 kHz"),
 }
+METRIC = "audio samples/sec, mel->wav generator forward"
 
 
 def build_model(kind: str):
@@ -88,19 +96,51 @@ def oracle_forward(kind, sd, mel, model):
     return G.unify_vocos_forward(sd, mel, 1024, 256, 1024)
 
 
-def time_cpu_port(kind, model, n_mels, T, hop, sample_B, steps=1, warmup=1):
-    """The reference's CPU PyTorch path (oracle port: same torch ops the reference modules call) on host cores."""
-    sd = {k: v.detach().cpu().float() for k, v in model.state_dict().items()}
-    mel = synthetic_mel(sample_B, n_mels, T, 1234)
-    times = []
-    with torch.no_grad():
-        for i in range(warmup + steps):
-            t0 = time.perf_counter()
-            oracle_forward(kind, sd, mel, model)
-            dt = time.perf_counter() - t0
-            if i >= warmup:
-                times.append(dt)
-    return sample_B * T * hop / min(times), sum(times) / len(times), min(times)
+def cpu_state_dict(model):
+    return {k: v.detach().cpu().float() for k, v in model.state_dict().items()}
+
+
+def time_cpu_port(kind, model, mel, steps=1, warmup=1, threads=None):
+    """The reference's CPU PyTorch path (oracle port: same torch ops the reference modules call) on host cores.
+    Returns (best seconds per forward, last output)."""
+    sd = cpu_state_dict(model)
+    old = torch.get_num_threads()
+    if threads:
+        torch.set_num_threads(threads)
+    times, y = [], None
+    try:
+        with torch.no_grad():
+            for i in range(warmup + steps):
+                t0 = time.perf_counter()
+                y = oracle_forward(kind, sd, mel, model)
+                dt = time.perf_counter() - t0
+                if i >= warmup:
+                    times.append(dt)
+    finally:
+        torch.set_num_threads(old)
+    return min(times), y
+
+
+def model_precision(model) -> str:
+    from vocoder_b200 import cabi
+    return getattr(model, "precision", None) or cabi.DEFAULT_PRECISION
+
+
+def set_precision(model, mode):
+    if not mode:
+        return
+    for sub in model.modules():
+        if hasattr(sub, "_ws"):
+            sub.precision = mode
+    model.precision = mode
+
+
+def parity_of(y_gpu, want, mode, weights, n):
+    peak = float(want.abs().max())
+    err = float((y_gpu - want).abs().max())
+    return {"max_abs_err": err, "peak": peak, "rel_to_peak": err / max(peak, 1e-30), "mode": mode, "weights": weights,
+            "utterances": n, "oracle": "oracle/generators.py (fp32 CPU restatement pinned on reference goldens)",
+            "tolerance": 1e-3, "pass": err <= 1e-3 * max(1.0, peak)}
 
 
 class ClockSampler:
@@ -122,6 +162,7 @@ class ClockSampler:
             self.thread.start()
         except Exception:  # noqa: BLE001
             self.proc = None
+        return self
 
     def _read(self):
         for line in self.proc.stdout:
@@ -160,11 +201,14 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "tensor_tflops": 1590.0, "tensor_tflops_sustained": 1400.0, "source": "fallback"}
 
 
+# ----------------------------------------------------------------------------------------------------------------------
+# algorithmic work per launch: what the roofline fractions are computed from
+# ----------------------------------------------------------------------------------------------------------------------
 def _alg_conv1d(a16, pc, L_out=None, **kw):
     B, L_in, _ = a16.shape
     rows = B * (L_in if L_out is None else L_out)
     flops = 2.0 * rows * pc.c_out * pc.c_in * pc.n_taps
-    byts = 2.0 * B * L_in * pc.c_in + 2.0 * pc.n_phase * pc.n_taps * pc.c_out * pc.c_in
+    byts = 2.0 * B * L_in * pc.c_in * (2 if pc.split else 1) + 2.0 * pc.n_phase * pc.n_taps * pc.c_out * pc.c_in
     if kw.get("residual") is not None:
         byts += 4.0 * rows * pc.c_out
     if kw.get("out32") is not None:
@@ -180,6 +224,20 @@ def _alg_mrf_fused(x32, pm, out32, **kw):
     taps = sum(k * 2 * len(pm.dil1[j]) for j, k in enumerate(pm.ksize))
     flops = 2.0 * B * L * pm.C * pm.C * taps
     byts = 8.0 * B * L * pm.C + 2.0 * taps * pm.C * pm.C + (2.0 * B * L * pm.C if kw.get("out16") is not None else 0.0)
+    return flops, byts
+
+
+def _alg_snake_conv(x32, sp, pc, **kw):
+    # anti-aliased Snake + conv in one launch: fp32 in, conv epilogue out
+    B, L, _ = x32.shape
+    flops = 2.0 * B * L * pc.c_out * pc.c_in * pc.n_taps
+    byts = 4.0 * B * L * pc.c_in + 2.0 * pc.n_taps * pc.c_out * pc.c_in
+    if kw.get("residual") is not None:
+        byts += 4.0 * B * L * pc.c_out
+    if kw.get("out32") is not None:
+        byts += 4.0 * B * L * pc.c_out * (2 if kw.get("accumulate") else 1)
+    if kw.get("out16") is not None:
+        byts += 2.0 * B * L * pc.c_out
     return flops, byts
 
 
@@ -209,6 +267,7 @@ def _alg_ola(frames, window, n_fft, hop, *a, **kw):
 
 # C-ABI wrapper -> (kernel family, algorithmic (flops, bytes) of one launch); formulas in DESIGN.md section 4
 FAMILIES = {"conv1d": ("conv_tc_kernel", _alg_conv1d), "mrf_fused": ("mrf_fused_kernel", _alg_mrf_fused),
+            "snake_conv": ("snake_conv_kernel", _alg_snake_conv),
             "snake_aa": ("snake_aa_kernel", _alg_snake), "dwconv_layernorm": ("dwconv_ln_kernel", _alg_dwln),
             "conv_post_tanh": ("conv_post_kernel", _alg_post), "pack_input": ("pack_input_kernel", _alg_pack),
             "istft_ola": ("istft_ola_kernel", _alg_ola)}
@@ -233,6 +292,8 @@ def profile_launches(model, mel):
         return wrapped
 
     for name, (fam, alg) in FAMILIES.items():
+        if not hasattr(cabi, name):
+            continue
         saved[name] = getattr(cabi, name)
         setattr(cabi, name, make(name, fam, alg, saved[name]))
     try:
@@ -272,124 +333,96 @@ def roofline_of(recs, peaks, step_ms):
     else:
         roof = {"bound": "tensor", "achieved": f["flops"] / t / 1e12, "peak": peaks["tensor_tflops"], "unit": "TFLOP/s"}
     roof["frac"] = roof["achieved"] / roof["peak"]
-    roof["traffic"] = None  # filled by main() from profiles/r01_traffic.json (ncu --set full capture of a launch of this family)
+    roof["traffic"] = None  # filled from profiles/r0N_traffic.json (ncu --set full capture of a launch of this family)
+    total_flops = sum(v["flops"] for v in fams.values())
+    total_bytes = sum(v["bytes"] for v in fams.values())
+    total_roof = sum(v["t_roof"] for v in fams.values())
     roof.update({"kernel": f"{top} (all {f['launches']} launches of one step)", "launches": f["launches"],
                  "kernel_ms_per_step": f["ms"], "share_of_step": f["ms"] / step_ms,
                  "alg_tflop_per_step": f["flops"] / 1e12, "alg_gbytes_per_step": f["bytes"] / 1e9,
                  "tensor_frac": f["flops"] / t / 1e12 / peaks["tensor_tflops"],
                  "hbm_frac": f["bytes"] / t / 1e9 / peaks["hbm_gbs"],
                  "per_launch_roofline_frac": f["t_roof"] / t, "peak_source": peaks["source"] + " (burst)",
+                 "whole_step": {"alg_tflop": total_flops / 1e12, "alg_gbytes_hbm": total_bytes / 1e9,
+                                "tflops": total_flops / (step_ms * 1e-3) / 1e12,
+                                "tensor_frac_burst": total_flops / (step_ms * 1e-3) / 1e12 / peaks["tensor_tflops"],
+                                "tensor_frac_sustained": total_flops / (step_ms * 1e-3) / 1e12 /
+                                peaks["tensor_tflops_sustained"],
+                                "sum_t_roof_over_t_step": total_roof / (step_ms * 1e-3)},
                  "families": table})
     return roof
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="hifigan_b64", choices=list(WORKLOADS))
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--no-fuse-mrf", action="store_true", help="layer-wise fv_conv1d launches instead of fv_mrf_fused")
-    ap.add_argument("--tc-tuning", default="", help="block_n,m_sub,epilogue,mainloop overrides for fv_conv1d (0 = auto)")
-    ap.add_argument("--mrf-silu-exact", action="store_true", help="ex2+rcp SiLU inside fv_mrf_fused instead of tanh.approx")
-    ap.add_argument("--cpu-sample", type=int, default=0, help="utterances in the CPU baseline sample (0 = auto)")
-    ap.add_argument("--dump-launches", default=None, help="write the per-launch conv timing table (json) here")
-    ap.add_argument("--micro-batch", type=int, default=0,
-                    help="utterances per residual-block pass (0 = whole batch, the measured optimum)")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3)
-
-    kind, B, n_mels, T, hop, sr, desc = WORKLOADS[args.workload]
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    samples_per_step = B * T * hop
-    config = {"workload": f"{args.workload}: {desc}", "batch_per_gpu": B, "mel_shape": [B, n_mels, T],
-              "samples_per_step_per_gpu": samples_per_step, "weights": "ref-init (seed 0), no checkpoint offline",
-              "parallelism": f"batch-shard x{world}" if world > 1 else "single GPU"}
-
-    # ------------------------------------------------------------------ reference arm (CPU, rank 0 only)
-    if args.impl == "reference":
-        if rank != 0:
+def attach_traffic(roofline, workload):
+    """DRAM bytes of a profiled launch of the dominant family (ncu --set full, committed under profiles/)."""
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", name))).get(workload)
+        except (OSError, ValueError):
+            continue
+        if tr and tr.get("traffic_bytes") and roofline["kernel"].startswith(tr["kernel"]):
+            roofline["traffic"] = tr["traffic_bytes"]
+            roofline["traffic_ref"] = {k: tr[k] for k in ("launch", "algorithmic_bytes", "source") if k in tr}
+            roofline["traffic_ref"]["file"] = "profiles/" + name
             return
-        torch.set_num_threads(max(1, os.cpu_count() or 1))
-        model = build_model(kind).eval()
-        sample_B = args.cpu_sample or max(1, min(B, 8))
-        sd = {k: v.detach().cpu().float() for k, v in model.state_dict().items()}
-        mel = synthetic_mel(sample_B, n_mels, T, 1234)
-        with torch.no_grad():
-            for _ in range(max(1, min(args.warmup, 1))):
-                oracle_forward(kind, sd, mel, model)
-            t0 = time.perf_counter()
-            for _ in range(args.steps):
-                oracle_forward(kind, sd, mel, model)
-            dt = time.perf_counter() - t0
-        val = sample_B * T * hop * args.steps / dt
-        cores = torch.get_num_threads()
-        line = {"impl": "reference", "metric": "audio samples/sec, mel->wav generator forward", "value": val,
-                "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-                "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": "port",
-                                 "sample": f"{sample_B} of {B} utterances per step (oracle port of the reference's "
-                                           f"CPU PyTorch path, {cores} threads)"},
-                "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "rtf": val / sr}
-        print(json.dumps(line), flush=True)
-        return
 
-    # ------------------------------------------------------------------ our arm
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py (impl=ours) needs a CUDA device: the product path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+
+# ----------------------------------------------------------------------------------------------------------------------
+# one workload on this rank's GPU
+# ----------------------------------------------------------------------------------------------------------------------
+def run_workload(name, args, dev, rank, world, barrier, all_max, *, full: bool):
+    """Times `name` on this rank (device-resident + end to end), and on rank 0 adds roofline / parity / CPU legs.
+    full = headline treatment (stress parity, sustained run, CPU baseline with warm-up)."""
     from vocoder_b200 import cabi
-
-    if args.tc_tuning:
-        cabi.set_tc_tuning(*[int(v) for v in args.tc_tuning.split(",")])
-    model = build_model(kind).eval().to(dev)
+    kind, B, n_mels, T, hop, sr, desc = WORKLOADS[name]
+    samples_per_step = B * T * hop
+    model = build_model(kind).eval()
+    set_precision(model, args.precision)
+    mode = model_precision(model)
     for m in model.modules():
-        if hasattr(m, "use_cuda_graph"):
-            m.use_cuda_graph = False
         if args.micro_batch > 0 and hasattr(m, "micro_batch"):
             m.micro_batch = args.micro_batch
         if args.no_fuse_mrf and hasattr(m, "fuse_mrf"):
             m.fuse_mrf = False
+        if args.no_fuse_snake and hasattr(m, "fuse_snake"):
+            m.fuse_snake = False
         if args.mrf_silu_exact and hasattr(m, "mrf_silu_tanh"):
             m.mrf_silu_tanh = False
+    model = model.to(dev)
     mel_host = synthetic_mel(B, n_mels, T, 1234 + rank).pin_memory()
     mel = mel_host.to(dev)
     wav_host = torch.empty(B, 1, T * hop).pin_memory()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    steps = args.steps
 
     with torch.no_grad():
+        # ---- weight pack (fold weight-norm, round, re-lay) timed separately (SURVEY 8d), then one eager forward
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for m in model.modules():
+            if hasattr(m, "_ensure_packed") and hasattr(m, "_ws"):
+                with cabi.precision(mode):
+                    m._ensure_packed(dev)
+        torch.cuda.synchronize()
+        pack_ms = (time.perf_counter() - t0) * 1e3
         cabi.reset_launch_count()
         y = model(mel)
         torch.cuda.synchronize()
         launches_per_step = cabi.launch_count()
         assert y.shape == (B, 1, T * hop) and bool(torch.isfinite(y).all())
+        y_first = y[:min(B, 8)].detach().cpu()
         if not args.no_graph:
+            for m in model.modules():
+                if hasattr(m, "clone_graph_output"):
+                    m.clone_graph_output = False   # the timed loop consumes the output before the next replay
             model.use_cuda_graph = True
-        for _ in range(args.warmup):
+        for _ in range(max(args.warmup, 3)):
             model(mel)
         torch.cuda.synchronize()
 
         flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
-        sampler = ClockSampler(local_rank)
-        if rank == 0:
-            sampler.start()
+        sampler = ClockSampler(dev.index).start() if rank == 0 else None
         # ---- device-resident timing: K steps, L2 flushed between steps, device time summed per step
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         barrier()
         wall0 = time.perf_counter()
         for e0, e1 in evs:
@@ -407,21 +440,46 @@ def main():
         barrier()
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s0.record()
-        for _ in range(args.steps):
+        for _ in range(steps):
             x = mel_host.to(dev, non_blocking=True)
             wav_host.copy_(model(x), non_blocking=True)
         s1.record()
         barrier()
         e2e_ms = s0.elapsed_time(s1)
-        clocks = sampler.stop() if rank == 0 else None
+        clocks = sampler.stop() if sampler else None
 
-    t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = float(t[0]), float(t[1])
-    total_samples = samples_per_step * args.steps * world
-    value = total_samples / (dev_ms * 1e-3)
-    e2e_value = total_samples / (e2e_ms * 1e-3)
+        # ---- sustained: back-to-back replays for >= 2 s (no L2 flush, clocks settle under the power cap)
+        sustained = None
+        if full and not args.no_sustained:
+            n_sus = max(steps, int(2.2e3 / max(dev_ms / steps, 1e-3)))
+            sampler2 = ClockSampler(dev.index).start() if rank == 0 else None
+            barrier()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for _ in range(n_sus):
+                model(mel)
+            s1.record()
+            barrier()
+            sus_ms = s0.elapsed_time(s1)
+            sus_clocks = sampler2.stop() if sampler2 else None
+            sustained = (sus_ms, n_sus, sus_clocks)
+
+    dev_ms, e2e_ms = all_max([dev_ms, e2e_ms])
+    total_samples = samples_per_step * steps * world
+    out = {"workload": f"{name}: {desc}", "batch_per_gpu": B, "mel_shape": [B, n_mels, T], "sample_rate": sr,
+           "samples_per_step_per_gpu": samples_per_step, "precision_mode": mode, "n_gpus": world,
+           "value": total_samples / (dev_ms * 1e-3), "unit": "samples/s", "ms_per_step": dev_ms / steps,
+           "rtf_per_gpu": total_samples / (dev_ms * 1e-3) / world / sr,
+           "e2e": {"value": total_samples / (e2e_ms * 1e-3), "unit": "samples/s",
+                   "h2d_bytes_per_step": mel_host.numel() * 4, "d2h_bytes_per_step": wav_host.numel() * 4,
+                   "ms_per_step": e2e_ms / steps},
+           "gpu_launches": launches_per_step * steps, "launches_per_step": launches_per_step,
+           "pack_ms": pack_ms, "wall_s_timed_region": wall, "clocks": clocks}
+    if sustained is not None:
+        sus_ms, n_sus = all_max([sustained[0]])[0], sustained[1]
+        out["sustained"] = {"seconds": sus_ms * 1e-3, "steps": n_sus, "ms_per_step": sus_ms / n_sus,
+                            "value": samples_per_step * n_sus * world / (sus_ms * 1e-3), "unit": "samples/s",
+                            "l2": "not flushed (back-to-back replays)", "clocks": sustained[2]}
 
     if rank == 0:
         peaks = load_peaks()
@@ -429,41 +487,194 @@ def main():
         with torch.no_grad():
             for _ in range(2):
                 recs = profile_launches(model, mel)
-        if args.dump_launches:
+        if args.dump_launches and full:
             with open(args.dump_launches, "w") as f:
                 json.dump(recs, f)
-        roofline = roofline_of(recs, peaks, dev_ms / args.steps)
-        try:  # DRAM bytes of a profiled launch of the dominant family (ncu --set full, committed under profiles/)
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(args.workload)
-            if tr and tr.get("traffic_bytes") and roofline["kernel"].startswith(tr["kernel"]):
-                roofline["traffic"] = tr["traffic_bytes"]
-                roofline["traffic_ref"] = {k: tr[k] for k in ("launch", "algorithmic_bytes", "source")}
-        except (OSError, ValueError):
-            pass
+        roofline = roofline_of(recs, peaks, dev_ms / steps)
+        attach_traffic(roofline, name)
+        out["roofline"] = roofline
+        out["workspace_gb"] = sum(m._ws.nbytes() for m in model.modules() if hasattr(m, "_ws")) / 1e9
 
-        cpu_baseline = None
-        if not args.no_cpu_baseline and world == 1:
-            torch.set_num_threads(max(1, os.cpu_count() or 1))
-            sample_B = args.cpu_sample or max(1, min(B, 8))
-            v, mean_s, best_s = time_cpu_port(kind, model, n_mels, T, hop, sample_B, steps=2, warmup=1)
-            cpu_baseline = {"value": v, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
-                            "sample": f"{sample_B} of {B} utterances, best of 2 after 1 warm-up "
-                                      f"({best_s:.2f} s per forward; oracle port of the reference CPU PyTorch path)"}
+        # ---- parity + CPU baseline: the oracle on the first utterances of the SAME batch (same seed => same mel)
+        torch.set_num_threads(max(1, os.cpu_count() or 1))
+        if not args.no_cpu_baseline:
+            sample_B = args.cpu_sample or max(1, min(B, 16 if full else 4))
+            best_s, want = time_cpu_port(kind, model, mel_host[:sample_B].clone(), steps=2 if full else 1,
+                                         warmup=1 if full else 0)
+            if world == 1:  # a reported baseline of the host cores: rank 0 at N = 1 only (parity is checked at every N)
+                out["cpu_baseline"] = {
+                    "value": sample_B * T * hop / best_s, "unit": "samples/s", "cores": torch.get_num_threads(),
+                    "kind": "port",
+                    "sample": f"{sample_B} of {B} utterances, best of {2 if full else 1} ({best_s:.2f} s per forward; oracle "
+                              f"port of the reference CPU PyTorch path)"}
+            n_par = min(sample_B, y_first.shape[0])
+            parity = {"ref_init": parity_of(y_first[:n_par], want[:n_par], mode, "ref-init (seed 0), the timed weights", n_par)}
+            if not args.no_stress_parity:
+                from tests.util import stress_init
+                sm = build_model(kind).eval()
+                stress_init(sm, seed=1)
+                set_precision(sm, args.precision)
+                n_s = 2
+                with torch.no_grad():
+                    want_s = oracle_forward(kind, cpu_state_dict(sm), mel_host[:n_s].clone(), sm)
+                    del model
+                    torch.cuda.empty_cache()
+                    ys = sm.to(dev)(mel_host[:n_s].to(dev)).cpu()
+                parity["stress"] = parity_of(ys, want_s, mode, "stress-init (SURVEY 8d, seed 1)", n_s)
+                del sm
+            parity["max_abs_err"] = max(p["max_abs_err"] for p in parity.values() if isinstance(p, dict))
+            parity["pass"] = all(p["pass"] for p in parity.values() if isinstance(p, dict))
+            out["parity"] = parity
+    torch.cuda.empty_cache()
+    return out
+
+
+def reference_arm(args, config, kind, B, n_mels, T, hop, sr):
+    """--impl reference: the reference's CPU implementation of the path (oracle port) on all host cores, rank 0 only."""
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    model = build_model(kind).eval()
+    sd = cpu_state_dict(model)
+    sample_B = args.cpu_sample or B          # the named batch; shrunk below only if K steps would not end in minutes
+    mel = synthetic_mel(B, n_mels, T, 1234)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        oracle_forward(kind, sd, mel[:min(sample_B, 8)], model)     # warm-up (oneDNN primitive caches) + speed probe
+        per_utt = (time.perf_counter() - t0) / min(sample_B, 8)
+        budget_s = 150.0
+        while sample_B > 1 and per_utt * sample_B * args.steps > budget_s:
+            sample_B = max(1, sample_B // 2)
+        x = mel[:sample_B]
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            oracle_forward(kind, sd, x, model)
+        dt = time.perf_counter() - t0
+    val = sample_B * T * hop * args.steps / dt
+    cores = torch.get_num_threads()
+    same = sample_B == B
+    return {"impl": "reference", "metric": METRIC, "value": val, "unit": "samples/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "same_config": same,
+            "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": "port",
+                             "sample": (f"the full batch of {B} utterances per step" if same else
+                                        f"{sample_B} of {B} utterances per step (bounded so {args.steps} steps end within minutes)")
+                             + f" (oracle port of the reference's CPU PyTorch path, {cores} threads)"},
+            "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "rtf": val / sr}
+
+
+def cfg_a_cpu_rows():
+    """BASELINE.md section 3 "required row": config A (HiFiGAN, B = 1) on the host cores, all threads and one thread."""
+    kind, _, n_mels, T, hop, sr, _ = WORKLOADS["hifigan_b1"]
+    model = build_model(kind).eval()
+    mel = synthetic_mel(1, n_mels, T, 1234)
+    rows = {}
+    for label, thr in (("all_threads", max(1, os.cpu_count() or 1)), ("one_thread", 1)):
+        best, _ = time_cpu_port(kind, model, mel, steps=3, warmup=1, threads=thr)
+        rows[label] = {"threads": thr, "ms_per_forward": best * 1e3, "samples_per_s": T * hop / best, "rtf": T * hop / best / sr}
+    rows["note"] = "configs[0]: hifigan baseline generator, batch 1 x 1 s @ 24 kHz, CPU PyTorch (oracle port), best of 3"
+    return rows
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="hifigan_b64", choices=list(WORKLOADS))
+    ap.add_argument("--extra", default=None,
+                    help="comma list of further workloads reported under `workloads` (default: the other BASELINE configs; "
+                         "'none' disables)")
+    ap.add_argument("--precision", default=None, choices=["fp16", "mixed", "strict"],
+                    help="operand precision of every module (default: each generator's own default)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-stress-parity", action="store_true")
+    ap.add_argument("--no-sustained", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-fuse-mrf", action="store_true", help="layer-wise fv_conv1d launches instead of fv_mrf_fused")
+    ap.add_argument("--no-fuse-snake", action="store_true", help="standalone fv_snake_aa launches instead of fv_snake_conv")
+    ap.add_argument("--tc-tuning", default="", help="block_n,m_sub,epilogue,mainloop overrides for fv_conv1d (0 = auto)")
+    ap.add_argument("--mrf-silu-exact", action="store_true", help="ex2+rcp SiLU inside fv_mrf_fused instead of tanh.approx")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="utterances in the CPU baseline sample (0 = auto)")
+    ap.add_argument("--dump-launches", default=None, help="write the per-launch conv timing table (json) here")
+    ap.add_argument("--micro-batch", type=int, default=0,
+                    help="utterances per residual-block pass (0 = whole batch, the measured optimum)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    kind, B, n_mels, T, hop, sr, desc = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    config = {"workload": f"{args.workload}: {desc}", "batch_per_gpu": B, "mel_shape": [B, n_mels, T],
+              "samples_per_step_per_gpu": B * T * hop, "weights": "ref-init (seed 0), no checkpoint offline",
+              "parallelism": f"batch-shard x{world}" if world > 1 else "single GPU"}
+
+    if args.impl == "reference":
+        if rank == 0:
+            print(json.dumps(reference_arm(args, config, kind, B, n_mels, T, hop, sr)), flush=True)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl=ours) needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from vocoder_b200 import cabi
+
+    if args.tc_tuning:
+        cabi.set_tc_tuning(*[int(v) for v in args.tc_tuning.split(",")])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def all_max(vals):
+        t = torch.tensor(vals, dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t]
+
+    t_start = time.perf_counter()
+    head = run_workload(args.workload, args, dev, rank, world, barrier, all_max, full=True)
+    if args.extra is None:
+        extra = [w for w in (("bigvgan_b32", "vocos_huge_b128", "hifigan_b1") if world == 1 else ("bigvgan_b32",))
+                 if w != args.workload]
+    else:
+        extra = [w for w in args.extra.split(",") if w and w != "none"]
+    others = {}
+    for w in extra:
+        others[w] = run_workload(w, args, dev, rank, world, barrier, all_max, full=False)
+        if w == "bigvgan_b32" and world > 1:
+            others[w]["baseline_config"] = ("configs[4]: bigvgan 44.1 kHz, 32 utterances per GPU, NCCL batch split "
+                                            f"({32 * world} utterances over {world} GPUs)")
+
+    if rank == 0:
         config["l2"] = ("L2 flushed between timed steps (256 MiB memset outside the per-step event pairs); per-step "
-                        f"working set {sum(m._ws.nbytes() for m in model.modules() if hasattr(m, '_ws')) / 1e9:.2f} GB > 126 MB L2")
+                        f"working set {head.get('workspace_gb', 0.0):.2f} GB > 126 MB L2")
         config["cuda_graph"] = not args.no_graph
         config["fuse_mrf"] = not args.no_fuse_mrf
         config["mrf_silu"] = "ex2+rcp" if args.mrf_silu_exact else "tanh.approx"
         config["micro_batch"] = args.micro_batch if args.micro_batch > 0 else "whole batch"
-        line = {"metric": "audio samples/sec, mel->wav generator forward", "value": value, "unit": "samples/s",
-                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f16 operands (TF32-grade mantissa), f32 accumulate/residual stream", "data": "synthetic",
-                "config": config, "rtf_per_gpu": value / world / sr,
-                "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": mel_host.numel() * 4,
-                        "d2h_bytes_per_step": wav_host.numel() * 4, "ms_per_step": e2e_ms / args.steps},
-                "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
-                "wall_s_timed_region": wall, "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks}
+        config["precision_mode"] = head["precision_mode"]
+        line = {"metric": METRIC, "value": head["value"], "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None,
+                "dtype": "f16 tensor-core operands (TF32-grade mantissa; [hi|lo] pairs on the layers the precision mode marks), "
+                         "f32 accumulate / residual stream",
+                "data": "synthetic", "config": config, "rtf_per_gpu": head["rtf_per_gpu"], "e2e": head["e2e"],
+                "gpu_launches": head["gpu_launches"], "launches_per_step": head["launches_per_step"],
+                "pack_ms": head["pack_ms"], "wall_s_timed_region": head["wall_s_timed_region"],
+                "sustained": head.get("sustained"), "parity": head.get("parity"), "roofline": head.get("roofline"),
+                "cpu_baseline": head.get("cpu_baseline"), "clocks": head["clocks"], "workloads": others}
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_config_a"] = cfg_a_cpu_rows()
+        line["bench_wall_s"] = time.perf_counter() - t_start
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

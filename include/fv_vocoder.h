@@ -241,6 +241,11 @@ FV_API int fv_mrf_fused(const fv_mrf_desc* d, void* stream);
  * A descriptor starts r rows into a TMA-written 144x64 fp16 slab.  a16 [144][64], w16 [64][64], out [12][2][128][64]. */
 FV_API int fv_debug_rowshift_probe(const void* a16, const void* w16, float* out, void* stream);
 
+/* bring-up probe (not on the product path): SM cycles per tcgen05.mma (M = 128 per CTA, K = 16, fp16) with resident
+ * operands.  mode 0 = SS cta_group::1, 1 = SS cta_group::2 (CTA pair, M = 256), 2 = A from TMEM; n = UMMA N; bg = background
+ * shared-memory traffic of 8 other warps (0 none, 1 stores, 2 loads).  out[cta] = cycles per UMMA x 1000. */
+FV_API int fv_debug_umma_rate(int mode, int n, int reps, int bg, int* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

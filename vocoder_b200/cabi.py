@@ -29,6 +29,7 @@ EXPORTS = [
     "fv_set_tc_tuning", "fv_pack_input", "fv_unpack_output", "fv_conv_post_tanh", "fv_snake_aa",
     "fv_dwconv_layernorm", "fv_istft_ola", "fv_noise_conv", "fv_act_cast", "fv_resample_linear",
     "fv_mrf_fused", "fv_frame_audio", "fv_spec_mag", "fv_log_mel_out", "fv_debug_rowshift_probe",
+    "fv_debug_umma_rate",
 ]
 MRF_MAX_BLOCKS, MRF_MAX_PAIRS, MRF_MAX_REACH = 4, 4, 32
 
@@ -108,6 +109,7 @@ def lib() -> ctypes.CDLL:
     L.fv_spec_mag.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, cf, vp]
     L.fv_log_mel_out.argtypes = [vp, vp, ci, ci, ci, ci, cf, vp]
     L.fv_debug_rowshift_probe.argtypes = [vp, vp, vp, vp]
+    L.fv_debug_umma_rate.argtypes = [ci, ci, ci, ci, vp, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("fv_last_error", "fv_launch_count", "fv_reset_launch_count", "fv_set_tc_tuning"):
@@ -252,15 +254,58 @@ class PackedConv:
     c_out_pad: int
     w_pitch: int
     split: int = 0  # strict mode: operand pitch P; the K axis of `w` is [Whi | Whi | Wlo] (w_pitch = 3P)
+    # fp16 range guard: rows of `w` whose magnitudes sit outside fp16's comfortable range were multiplied by a power of two
+    # s[o] at pack time (exact); w_scale = 1 / s is applied by the fp32 epilogue (through its layer-scale slot) and `bias`
+    # already holds bias * s, so (acc * s + bias * s) / s == acc + bias.  None = no row needed it (the usual case).
+    w_scale: Optional[torch.Tensor] = None
 
     def __post_init__(self):
         assert self.n_phase * self.n_taps <= MAX_TAPS, "too many taps for one call"
         self._tap_arr = (ctypes.c_int32 * len(self.tap_off))(*[int(v) for v in self.tap_off])
+        self._gamma_cache = {}
 
     def to(self, device) -> "PackedConv":
         return PackedConv(self.w.to(device), None if self.bias is None else self.bias.to(device),
                           list(self.tap_off), self.n_phase, self.n_taps, self.c_in, self.c_out,
-                          self.c_out_pad, self.w_pitch, self.split)
+                          self.c_out_pad, self.w_pitch, self.split,
+                          None if self.w_scale is None else self.w_scale.to(device))
+
+    def gamma_for(self, gamma: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+        """The per-channel factor the epilogue applies: the caller's layer scale times the weight de-scaling."""
+        if self.w_scale is None:
+            return gamma
+        if gamma is None:
+            return self.w_scale
+        key = (gamma.data_ptr(), gamma._version)
+        g = self._gamma_cache.get(key)
+        if g is None:
+            self._gamma_cache.clear()
+            g = (gamma.detach().float() * self.w_scale).contiguous()
+            self._gamma_cache[key] = g
+        return g
+
+
+# rows whose largest |w| falls outside [2^-9, 2^13] are rescaled: fp16 is normal down to 6.1e-5 (2^-14) and the row's small
+# entries need ~5 more bits below its maximum to keep the contraction's relative error at the 2^-11 of a well-scaled row
+W_SCALE_LO, W_SCALE_HI = 2.0 ** -9, 2.0 ** 13
+
+
+def weight_row_scale(amax: torch.Tensor) -> Optional[torch.Tensor]:
+    """amax [C_out] = max |w| of every output channel.  None when every (non-zero) row is inside the comfortable fp16
+    range; otherwise the power-of-two scale s[o] that brings the row maximum into [0.5, 1)."""
+    amax = amax.detach().float()
+    nz = amax > 0
+    if not bool(nz.any()) or not bool(((amax[nz] < W_SCALE_LO) | (amax[nz] > W_SCALE_HI)).any()):
+        return None
+    e = torch.ceil(torch.log2(torch.where(nz, amax, torch.ones_like(amax))))
+    return torch.where(nz, torch.exp2(-e), torch.ones_like(amax))
+
+
+def _scaled_bias(bias: Optional[torch.Tensor], s: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    if bias is None:
+        return None
+    b = bias.detach().float()
+    return (b if s is None else b * s).contiguous()
 
 
 def _alloc_w(n_phase: int, n_taps: int, cp: int, wp: int, device):
@@ -288,11 +333,14 @@ def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], dilation: int 
     cp, wp = c_out_pad_of(c_out), pitch_of(c_in)
     w, put, split = _alloc_w(1, k, cp, wp, weight.device)
     wf = weight.detach().float()
+    s = weight_row_scale(wf.abs().amax(dim=(1, 2)))
+    if s is not None:
+        wf = wf * s[:, None, None]
     for j in range(k):
         put(0, j, wf[:, :, j])
     offs = [(j - (k - 1) // 2) * dilation for j in range(k)]
-    b = None if bias is None else bias.detach().float().contiguous()
-    return PackedConv(w.contiguous(), b, offs, 1, k, c_in, c_out, cp, w.shape[-1], split)
+    return PackedConv(w.contiguous(), _scaled_bias(bias, s), offs, 1, k, c_in, c_out, cp, w.shape[-1], split,
+                      None if s is None else (1.0 / s).contiguous())
 
 
 def pack_taps(mats: Sequence[torch.Tensor], offsets: Sequence[int], bias: Optional[torch.Tensor] = None) -> PackedConv:
@@ -300,10 +348,12 @@ def pack_taps(mats: Sequence[torch.Tensor], offsets: Sequence[int], bias: Option
     c_out, c_in = mats[0].shape
     cp, wp = c_out_pad_of(c_out), pitch_of(c_in)
     w, put, split = _alloc_w(1, len(mats), cp, wp, mats[0].device)
+    s = weight_row_scale(torch.stack([m.detach().float().abs().amax(dim=1) for m in mats]).amax(dim=0))
     for i, m in enumerate(mats):
-        put(0, i, m.detach().float())
-    b = None if bias is None else bias.detach().float().contiguous()
-    return PackedConv(w.contiguous(), b, [int(o) for o in offsets], 1, len(mats), c_in, c_out, cp, w.shape[-1], split)
+        mf = m.detach().float()
+        put(0, i, mf if s is None else mf * s[:, None])
+    return PackedConv(w.contiguous(), _scaled_bias(bias, s), [int(o) for o in offsets], 1, len(mats), c_in, c_out, cp,
+                      w.shape[-1], split, None if s is None else (1.0 / s).contiguous())
 
 
 def pack_linear(weight: torch.Tensor, bias: Optional[torch.Tensor]) -> PackedConv:
@@ -332,6 +382,9 @@ def pack_conv_transpose(weight: torch.Tensor, bias: Optional[torch.Tensor], stri
     w, put, split = _alloc_w(u, n_taps, cp, wp, weight.device)
     offs = []
     wf = weight.detach().float()
+    s = weight_row_scale(wf.abs().amax(dim=(0, 2)))
+    if s is not None:
+        wf = wf * s[None, :, None]
     for r, taps in enumerate(phases):
         for i in range(n_taps):
             if i < len(taps):
@@ -340,8 +393,8 @@ def pack_conv_transpose(weight: torch.Tensor, bias: Optional[torch.Tensor], stri
                 offs.append(off)
             else:
                 offs.append(0)
-    b = None if bias is None else bias.detach().float().contiguous()
-    return PackedConv(w.contiguous(), b, offs, u, n_taps, c_in, c_out, cp, w.shape[-1], split)
+    return PackedConv(w.contiguous(), _scaled_bias(bias, s), offs, u, n_taps, c_in, c_out, cp, w.shape[-1], split,
+                      None if s is None else (1.0 / s).contiguous())
 
 
 def conv_transpose_out_len(L: int, k: int, u: int) -> int:
@@ -373,7 +426,7 @@ def conv1d(a16: torch.Tensor, pc: PackedConv, L_out: Optional[int] = None, *, ga
     d.tap_off = pc._tap_arr
     d.L_out = L_out
     d.bias = _ptr(pc.bias, torch.float32) if (use_bias and pc.bias is not None) else None
-    d.gamma = _ptr(gamma, torch.float32)
+    d.gamma = _ptr(pc.gamma_for(gamma), torch.float32)
     d.residual, d.res_pitch = _ptr(residual, torch.float32), (0 if residual is None else residual.shape[2])
     d.out32, d.out32_pitch = _ptr(out32, torch.float32), (0 if out32 is None else out32.shape[2])
     d.accumulate, d.out_scale = int(bool(accumulate)), float(out_scale)
@@ -555,6 +608,8 @@ def mrf_fusable(C: int, blocks) -> bool:
         for c in list(c1s) + list(c2s):
             if c.kernel_size[0] != k or k % 2 == 0 or c.in_channels != C or c.out_channels != C or c.bias is None:
                 return False
+            if weight_row_scale(c.weight.detach().abs().amax(dim=(1, 2))) is not None:
+                return False  # fp16 range guard: the layer-wise path rescales such rows, the fused kernel cannot
             reach = (k - 1) // 2 * c.dilation[0]
             if reach > MRF_MAX_REACH:
                 return False

@@ -78,9 +78,127 @@ __global__ void __launch_bounds__(128, 1) rowshift_probe_kernel(const __grid_con
   }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// ------------------------------------------------------------------------------------------------
+// fv_debug_umma_rate: how many SM cycles does one tcgen05.mma (M = 128 per CTA, K = 16, fp16) take for a given N and operand
+// source, with the operands already resident?  One CTA per SM (or one CTA pair per TPC) issues `reps` x 16 UMMAs
+// (4 accumulator blocks x 4 K steps, cycling through 4 A tiles and 2 B tiles so the shared-memory reads are real) and
+// times the span from the first issue to the completion of the last one with clock64.
+//   mode 0: SS, cta_group::1                      mode 1: SS, cta_group::2 (M = 256 over a CTA pair, B split)
+//   mode 2: A from TMEM (TS), cta_group::1
+//   bg    : 0 = idle epilogue warps; 1 = 8 warps stream st.shared.v4 into a scratch slab (an epilogue writing its
+//           operand rows); 2 = 8 warps stream ld.shared.v4
+// out[cta] = cycles per UMMA * 1000 (int).
+// ------------------------------------------------------------------------------------------------
+struct RateParams {
+  int* out;
+  int n, reps, mode, bg;
+};
+
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+template <bool PAIR>
+__global__ void __launch_bounds__(320, 1) umma_rate_kernel(const RateParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  // 4 A tiles of 128 x 64 fp16 (16 KB each), 2 B tiles of up to 256 x 64 (32 KB each), 32 KB scratch, barriers
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + 4 * 16384;
+  uint8_t* sS = sB + 2 * 32768;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sS + 32768);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 2);
+  volatile int* stop = reinterpret_cast<volatile int*>(tmem_slot + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  for (int i = threadIdx.x; i < (4 * 16384 + 2 * 32768 + 32768) / 4; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u | ((i * 2654435761u) & 0x03ff03ffu);  // fp16 values in [1, 2)
+  if (threadIdx.x == 0) {
+    mbar_init(&bar[0], 1);
+    *stop = 0;
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    if constexpr (PAIR) tmem_alloc_pair(tmem_slot, 512);
+    else tmem_alloc(tmem_slot, 512);
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  if constexpr (PAIR) cluster_sync_all();
+  else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int N = p.n;
+  const int blocks = (4 * N <= 448) ? 4 : (2 * N <= 448 ? 2 : 1);
+  if (warp == 1) {
+    if (p.mode == 2) {  // park two A tiles (128 lanes x 32 packed columns) at TMEM columns 448..511
+      uint32_t r[32];
+      for (int i = 0; i < 32; ++i) r[i] = 0x3c003c00u | ((lane * 40503u + i * 9973u) & 0x03ff03ffu);
+      // warp 1 owns lanes 32..63 only; the probe times the pipe, the values are irrelevant
+      tmem_st_32x32b_x32(tmem_base + (32u << 16) + 448, r);
+      tmem_st_32x32b_x32(tmem_base + (32u << 16) + 480, r);
+      tmem_st_wait();
+      tc_fence_before();
+    }
+    __syncwarp();
+    if ((!PAIR || rank == 0) && elect_one()) {
+      const uint32_t idesc = make_idesc_f16(PAIR ? 256 : 128, N);
+      const long long t0 = clock64();
+      for (int rep = 0; rep < p.reps; ++rep) {
+#pragma unroll 1
+        for (int m = 0; m < blocks; ++m) {
+          const uint64_t da0 = make_kmajor_desc(smem_u32(sA) + ((m + rep) & 3) * 16384, 128);
+          const uint64_t db0 = make_kmajor_desc(smem_u32(sB) + (rep & 1) * 32768, 128);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint32_t d = tmem_base + m * N;
+            if (p.mode == 2) umma_f16_ts(d, tmem_base + 448 + (rep & 1) * 32 + kk * 8, desc_advance(db0, kk * 32), idesc, 1u);
+            else if (PAIR) umma_f16_ss_pair(d, desc_advance(da0, kk * 32), desc_advance(db0, kk * 32), idesc, 1u);
+            else umma_f16_ss(d, desc_advance(da0, kk * 32), desc_advance(db0, kk * 32), idesc, 1u);
+          }
+        }
+      }
+      if constexpr (PAIR) umma_commit_pair(&bar[0]);
+      else umma_commit(&bar[0]);
+      while (!mbar_try_wait(&bar[0], 0)) {
+      }
+      const long long t1 = clock64();
+      p.out[blockIdx.x] = (int)((t1 - t0) * 1000 / ((long long)p.reps * blocks * 4));
+      *stop = 1;
+    }
+    __syncwarp();
+  } else if (warp >= 2 && p.bg != 0) {
+    // background shared-memory traffic from 8 "epilogue" warps until the MMA thread is done
+    const uint32_t base = smem_u32(sS) + (warp - 2) * 4096 + lane * 16;
+    uint32_t acc = 0;
+    while (!*stop) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (p.bg == 1) {
+          asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(base + i * 512), "r"(acc) : "memory");
+        } else {
+          uint32_t a, b, c, d;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(base + i * 512));
+          acc += a + b + c + d;
+        }
+      }
+    }
+    if (acc == 0x12345678u) p.out[0] = (int)acc;
+  }
+  tc_fence_before();
+  if constexpr (PAIR) cluster_sync_all();
+  else __syncthreads();
+  if (warp == 1) {
+    if constexpr (PAIR) tmem_dealloc_pair(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
+  }
+}
 
 }  // namespace fv
 
@@ -119,5 +237,29 @@ extern "C" int fv_debug_rowshift_probe(const void* a16, const void* w16, float* 
   const int smem = 1024 + 18432 + 8192 + 64;
   rowshift_probe_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(p);
   FV_CHECK_LAUNCH("rowshift_probe_kernel");
+  return 0;
+}
+
+extern "C" int fv_debug_umma_rate(int mode, int n, int reps, int bg, int* out, void* stream) {
+  FV_REQUIRE(out && (mode >= 0 && mode <= 2) && n >= 16 && n <= 256 && n % 16 == 0 && reps > 0 && bg >= 0 && bg <= 2,
+             FV_E_BADARG, "fv_debug_umma_rate: bad arguments");
+  RateParams p = {out, n, reps, mode, bg};
+  const int smem = 4 * 16384 + 2 * 32768 + 32768 + 64;
+  const int ctas = num_sms();
+  cudaError_t e;
+  if (mode == 1) {
+    static std::atomic<unsigned long long> done{0};
+    e = ensure_dyn_smem(umma_rate_kernel<true>, smem, done);
+    if (e == cudaSuccess)
+      e = launch_kernel(umma_rate_kernel<true>, dim3(ctas / 2 * 2), dim3(320), smem, (cudaStream_t)stream, 2, p);
+  } else {
+    static std::atomic<unsigned long long> done{0};
+    e = ensure_dyn_smem(umma_rate_kernel<false>, smem, done);
+    if (e == cudaSuccess)
+      e = launch_kernel(umma_rate_kernel<false>, dim3(ctas), dim3(320), smem, (cudaStream_t)stream, 1, p);
+  }
+  int rc = check_cuda(e, "umma_rate_kernel");
+  if (rc) return rc;
+  FV_CHECK_LAUNCH("umma_rate_kernel");
   return 0;
 }

@@ -114,6 +114,12 @@ class MRFGeneratorBase(nn.Module):
         init_normal(self.ups)
         init_normal(self.conv_post)
 
+    def saturation_report(self):
+        """fp16 operands clamp at +-65504 instead of overflowing: how many elements of the last forward's operand buffers
+        sit on the clamp (0 for any sane checkpoint).  Debugging aid (synchronises)."""
+        from ..runtime import saturation_report
+        return saturation_report(self)
+
     # ---- reference surface -------------------------------------------------------------------
     def remove_parametrizations(self):
         """Fold weight-norm into plain weights (hifigan.py:251-257).  The kernels always consume folded,
@@ -261,7 +267,8 @@ class MRFGeneratorBase(nn.Module):
                 else:
                     xa0 = ws.f16(f"xa0_{i}", B, Lo, C, dev)
                     cabi.conv1d(h16, up, Lo, residual=nz, out32=x0, out16=xa0, act=self._silu(), engine=eng)
-            acc = ws.f32(f"acc_{i}", B, Lo, C, dev)
+            with self._trunk_ctx():   # same channel pitch as the [hi | lo] operand the final activation derives from it
+                acc = ws.f32(f"acc_{i}", B, Lo, C, dev)
             h_next, h_split = h_buf(f"h_{i}", Lo, C)
             # The residual blocks can run per micro-batch of utterances (working set resident in the 126 MB L2).
             # Measured on B200 (HiFiGAN cfg B): 64 -> 8.6 ms, 32 -> 9.4 ms, 16 -> 10.6 ms, 8 -> 13.7 ms per forward:

@@ -69,6 +69,18 @@ class Workspace:
         for fn in self._listeners:
             fn()
 
+    def saturation_report(self) -> Dict[str, int]:
+        """fp16 operand buffers of the most recent forward -> number of elements clamped to +-65504 (operands saturate
+        instead of overflowing: cvt.rn.satfinite).  Synchronises; a debugging aid, not part of the forward."""
+        group = self._groups.get(self._sig, {})
+        rep = {}
+        for (name, _, dtype, _), t in group.items():
+            if dtype == torch.float16 and t.is_cuda:
+                n = int((t.abs() >= 65504.0).sum())
+                if n:
+                    rep[name] = n
+        return rep
+
     def nbytes(self) -> int:
         return sum(t.numel() * t.element_size() for g in self._groups.values() for t in g.values())
 
@@ -168,3 +180,15 @@ class GraphedForward:
                 s.copy_(t, non_blocking=True)
         graph.replay()
         return static_out
+
+
+def saturation_report(module: torch.nn.Module) -> Dict:
+    """{"saturated": total, "buffers": {name: count}} over every workspace below `module` (see Workspace.saturation_report).
+    Intermediates of the on-chip fused stages (fv_mrf_fused) never reach HBM and are not visible here."""
+    bufs = {}
+    for name, sub in module.named_modules():
+        ws = getattr(sub, "_ws", None)
+        if isinstance(ws, Workspace):
+            for k, v in ws.saturation_report().items():
+                bufs[f"{name + '.' if name else ''}{k}"] = v
+    return {"saturated": sum(bufs.values()), "buffers": bufs}
