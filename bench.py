@@ -224,6 +224,8 @@ def _alg_mrf_fused(x32, pm, out32, **kw):
     taps = sum(k * 2 * len(pm.dil1[j]) for j, k in enumerate(pm.ksize))
     flops = 2.0 * B * L * pm.C * pm.C * taps
     byts = 8.0 * B * L * pm.C + 2.0 * taps * pm.C * pm.C + (2.0 * B * L * pm.C if kw.get("out16") is not None else 0.0)
+    if kw.get("accumulate"):
+        byts += 4.0 * B * L * pm.C   # the partial mean read back
     return flops, byts
 
 
@@ -384,6 +386,10 @@ def run_workload(name, args, dev, rank, world, barrier, all_max, *, full: bool):
             m.micro_batch = args.micro_batch
         if args.no_fuse_mrf and hasattr(m, "fuse_mrf"):
             m.fuse_mrf = False
+        if args.no_fuse_pairs and hasattr(m, "fuse_mrf_pairs"):
+            m.fuse_mrf_pairs = False
+        if args.mrf_silu_h2 and hasattr(m, "mrf_silu_h2"):
+            m.mrf_silu_h2 = True
         if args.no_fuse_snake and hasattr(m, "fuse_snake"):
             m.fuse_snake = False
         if args.mrf_silu_exact and hasattr(m, "mrf_silu_tanh"):
@@ -593,6 +599,8 @@ def main():
     ap.add_argument("--no-sustained", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-fuse-mrf", action="store_true", help="layer-wise fv_conv1d launches instead of fv_mrf_fused")
+    ap.add_argument("--no-fuse-pairs", action="store_true", help="layer-wise C = 128 stage instead of pair-wise fv_mrf_fused")
+    ap.add_argument("--mrf-silu-h2", action="store_true", help="packed fp16x2 SiLU inside fv_mrf_fused (FV_ACT_SILU_H2)")
     ap.add_argument("--no-fuse-snake", action="store_true", help="standalone fv_snake_aa launches instead of fv_snake_conv")
     ap.add_argument("--tc-tuning", default="", help="block_n,m_sub,epilogue,mainloop overrides for fv_conv1d (0 = auto)")
     ap.add_argument("--mrf-silu-exact", action="store_true", help="ex2+rcp SiLU inside fv_mrf_fused instead of tanh.approx")

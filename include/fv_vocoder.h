@@ -48,8 +48,11 @@ enum fv_act {
   FV_ACT_TANH = 4,  /* torch.tanh: hifigan.py:247                                                  */
   FV_ACT_POLAR = 5, /* column pairs (2k,2k+1) = (log-mag, phase) -> (min(exp(m),100)cos p, ..sin p):
                        generators/vocos.py:57-67                                                  */
-  FV_ACT_SILU_TANH = 6 /* F.silu as x/2 + x/2 tanh(x/2) with tanh.approx (one SFU op, |err| <= 2.4e-4 |x|):
-                          opt-in inner activation of fv_mrf_fused only                             */
+  FV_ACT_SILU_TANH = 6, /* F.silu as x/2 + x/2 tanh(x/2) with tanh.approx (one SFU op, |err| <= 2.4e-4 |x|):
+                          inner activation of fv_mrf_fused and the SiLU epilogues of fv_conv1d     */
+  FV_ACT_SILU_H2 = 7    /* the same formula on packed fp16 pairs (cvt.f16x2, tanh.approx.f16x2, fma.f16x2: one SFU op per
+                          TWO channels, the operand word carries ~3 fp16 roundings instead of 1): opt-in inner activation
+                          of fv_mrf_fused only; as an out_act / in fv_conv1d it is evaluated like FV_ACT_SILU_TANH */
 };
 
 /* how the two anti-alias filters of fv_snake_aa pad their inputs (the BigVGAN-flavoured Activation1d
@@ -211,7 +214,9 @@ FV_API int fv_log_mel_out(const float* x32, float* out, int B, int C, int T, int
  *     out32[b, t, c] = (1/n_blocks) * sum_j block_j(x)[b, t, c]        (also the running-sum scratch: required)
  *     out16          = fp16(out_act(out32))                            (optional)
  * Replaces ParralelBlock.forward / ResBlock1.forward (hifigan.py:101-108,117-133): the stack([...]).mean(0) over
- * kernel sizes (3,7,11) of 3 x {silu, conv(k,d), silu, conv(k,1), +x}.  C in {16, 32, 64}; tap reach (k-1)/2*dil <= 32.
+ * kernel sizes (3,7,11) of 3 x {silu, conv(k,d), silu, conv(k,1), +x}.  C in {16, 32, 64}: whole stages on 512-row
+ * tiles; C = 128: 256-row tiles and at most ONE pair per launch (n_blocks = n_pairs = 1; x -> x + pair(x), chained by the
+ * host with `accumulate` / `out_scale` building the mean).  Tap reach (k-1)/2*dil <= 32.
  */
 #define FV_MRF_MAX_BLOCKS 4
 #define FV_MRF_MAX_PAIRS 4
@@ -234,6 +239,9 @@ typedef struct fv_mrf_desc {
   int32_t out16_pitch;
   int32_t out_act;
   float out_act_param;
+  /* pair-wise evaluation of a stage (C = 128: one launch per (conv, conv) pair, the host chains them): */
+  int32_t accumulate; /* 1: the result is ADDED to what out32 already holds (out32 += out_scale * block(x)) */
+  float out_scale;    /* 0 = 1 / n_blocks (the MRF mean of a whole-stage launch) */
 } fv_mrf_desc;
 FV_API int fv_mrf_fused(const fv_mrf_desc* d, void* stream);
 

@@ -293,7 +293,68 @@ def test_mrf_fused_kernel(C, L, B, ks):
     assert e16 <= 2e-3 * scale, f"out16 err {e16:.3e}"
 
 
-@pytest.mark.parametrize("variant", ["layerwise", "fused", "fused_silu_tanh"])
+@pytest.mark.parametrize("k,d,L,B", [(3, 1, 300, 2), (7, 3, 777, 1), (11, 5, 256, 3), (11, 1, 1000, 2), (3, 5, 6016, 4)])
+def test_mrf_fused_pair_kernel_c128(k, d, L, B):
+    """C = 128: one (dilated conv, conv) pair per launch on 256-row tiles with two K halves per operand row; plain,
+    scaled and accumulating exits (what the host chains into the MRF mean), against the fp64 contract."""
+    C = 128
+    torch.manual_seed(k * 100 + d)
+    mk = lambda dd: torch.nn.Conv1d(C, C, k, dilation=dd, padding=(k * dd - dd) // 2)
+    c1, c2 = mk(d), mk(1)
+    for c in (c1, c2):
+        c.weight.data.normal_(0, 0.5 / math.sqrt(C * k))
+        c.bias.data.normal_(0, 0.05)
+    blocks = [([c1], [c2])]
+    assert cabi.mrf_fusable(C, blocks, pairwise=True) and not cabi.mrf_fusable(C, blocks)
+    x = torch.randn(B, L, C)
+    with torch.no_grad():
+        want32, want16 = _mrf_reference(x, blocks, cabi.ACT_SILU)
+        pm = cabi.pack_mrf(C, blocks)
+        pm.w, pm.bias = pm.w.cuda(), pm.bias.cuda()
+        xg = x.cuda()
+        out32 = torch.full((B, L, C), float("nan"), device="cuda")
+        out16 = torch.full((B, L, C), float("nan"), device="cuda", dtype=torch.float16)
+        cabi.mrf_fused(xg, pm, out32, out16=out16, act=cabi.ACT_SILU, out_act=cabi.ACT_SILU, out_scale=1.0)
+        acc = torch.randn(B, L, C, device="cuda")
+        acc0 = acc.clone()
+        cabi.mrf_fused(xg, pm, acc, act=cabi.ACT_SILU, accumulate=True, out_scale=1.0 / 3.0)
+        torch.cuda.synchronize()
+    scale = max(1.0, float(want32.abs().max()))
+    e32 = float((out32.cpu().double() - want32).abs().max())
+    e16 = float((out16.cpu().double() - want16).abs().max())
+    eacc = float((acc.cpu().double() - (acc0.cpu().double() + want32 / 3.0)).abs().max())
+    print(f"mrf_fused pair C=128 k={k} d={d} L={L} B={B}: out32 err {e32:.3e}, out16 err {e16:.3e}, accumulate err {eacc:.3e}")
+    assert e32 <= 3e-4 * scale and e16 <= 2e-3 * scale and eacc <= 3e-4 * scale
+
+
+@pytest.mark.parametrize("act", ["tanh", "h2"])
+def test_mrf_fused_inner_activation_variants(act):
+    """FV_ACT_SILU_TANH (tanh.approx.f32) and FV_ACT_SILU_H2 (packed tanh.approx.f16x2 + fma.f16x2) against the exact SiLU
+    contract: stage outputs within 1e-3 of the fp64 evaluation (3 kernel sizes x 3 pairs = 18 activations deep)."""
+    C, L, B = 64, 1500, 2
+    torch.manual_seed(5)
+    blocks = []
+    for k in (3, 7, 11):
+        mk = lambda d: torch.nn.Conv1d(C, C, k, dilation=d, padding=(k * d - d) // 2)
+        c1s, c2s = [mk(d) for d in (1, 3, 5)], [mk(1) for _ in range(3)]
+        for c in c1s + c2s:
+            c.weight.data.normal_(0, 0.5 / math.sqrt(C * k))
+            c.bias.data.normal_(0, 0.05)
+        blocks.append((c1s, c2s))
+    x = torch.randn(B, L, C)
+    with torch.no_grad():
+        want32, _ = _mrf_reference(x, blocks, cabi.ACT_SILU)
+        pm = cabi.pack_mrf(C, blocks)
+        pm.w, pm.bias = pm.w.cuda(), pm.bias.cuda()
+        out32 = torch.empty(B, L, C, device="cuda")
+        cabi.mrf_fused(x.cuda(), pm, out32, act=cabi.ACT_SILU_TANH if act == "tanh" else cabi.ACT_SILU_H2)
+    scale = max(1.0, float(want32.abs().max()))
+    err = float((out32.cpu().double() - want32).abs().max())
+    print(f"mrf_fused inner activation {act}: stage error {err:.3e} (scale {scale:.2f})")
+    assert err <= 1e-3 * scale
+
+
+@pytest.mark.parametrize("variant", ["layerwise", "fused", "fused_silu_tanh", "fused_silu_h2", "no_pair_fusion"])
 def test_full_width_stress_hifigan_vs_oracle(variant):
     """Full-width HiFiGAN (cfg A/B channels) with SURVEY-8d stress weights, so the residual branches of the C = 64 / 32
     stages (the ones fv_mrf_fused evaluates on chip) carry signal: every MRF variant within 1e-3 of the fp32 oracle."""
@@ -306,7 +367,9 @@ def test_full_width_stress_hifigan_vs_oracle(variant):
     want = _oracle_full("hifigan", m, mel)
     m = m.cuda()
     m.fuse_mrf = variant != "layerwise"
-    m.mrf_silu_tanh = variant == "fused_silu_tanh"
+    m.fuse_mrf_pairs = variant != "no_pair_fusion"
+    m.mrf_silu_tanh = variant in ("fused_silu_tanh", "fused_silu_h2", "no_pair_fusion")
+    m.mrf_silu_h2 = variant == "fused_silu_h2"
     with torch.no_grad():
         y = m(mel.cuda()).cpu()
     peak = max(1.0, float(want.abs().max()))
@@ -340,7 +403,8 @@ def test_five_stage_hifigan_fused_c16_vs_oracle_and_layerwise():
         layer = m(mel.cuda()).cpu()
         n_layer = cabi.launch_count()
     assert fused.shape == want.shape == (2, 1, 11 * 512)
-    assert n_layer - n_fused == 3 * (18 - 1)          # three stages collapse from 18 conv launches to one each
+    # three stages (C = 64, 32, 16) collapse from 18 conv launches to one each, the C = 128 stage to one per conv pair
+    assert n_layer - n_fused == 3 * (18 - 1) + (18 - 9)
     peak = max(1.0, float(want.abs().max()))
     e_f, e_l = float((fused - want).abs().max()), float((layer - want).abs().max())
     print(f"5-stage stress hifigan: fused {e_f:.3e}, layer-wise {e_l:.3e} vs fp32 oracle (peak {peak:.3f})")

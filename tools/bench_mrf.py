@@ -14,12 +14,12 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from vocoder_b200 import cabi  # noqa: E402
 
 
-def make_blocks(C, ks=(3, 7, 11), seed=0):
+def make_blocks(C, ks=(3, 7, 11), seed=0, dils=(1, 3, 5)):
     torch.manual_seed(seed)
     blocks = []
     for k in ks:
         mk = lambda d: torch.nn.Conv1d(C, C, k, dilation=d, padding=(k * d - d) // 2)
-        c1s, c2s = [mk(d) for d in (1, 3, 5)], [mk(1) for _ in range(3)]
+        c1s, c2s = [mk(d) for d in dils], [mk(1) for _ in dils]
         for c in c1s + c2s:
             c.weight.data.normal_(0, 0.5 / math.sqrt(C * k))
             c.bias.data.normal_(0, 0.05)
@@ -45,11 +45,11 @@ def reference(x, blocks):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--acts", default="silu,tanh")
+    ap.add_argument("--acts", default="silu,tanh,h2")
     ap.add_argument("--shapes", default="64x12032x64,32x24064x64,16x44544x32")
     ap.add_argument("--iters", type=int, default=10)
     args = ap.parse_args()
-    acts = {"silu": cabi.ACT_SILU, "tanh": cabi.ACT_SILU_TANH, "leaky": cabi.ACT_LEAKY}
+    acts = {"silu": cabi.ACT_SILU, "tanh": cabi.ACT_SILU_TANH, "leaky": cabi.ACT_LEAKY, "h2": cabi.ACT_SILU_H2}
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     for shp in args.shapes.split(","):
         C, L, B = (int(v) for v in shp.split("x"))
@@ -85,5 +85,39 @@ def main():
                   f"max|err| vs fp64 contract {err:.2e} (scale {float(want.abs().max()):.2f})", flush=True)
 
 
+def main_pairs(iters=10):
+    """C = 128 stage of HiFiGAN cfg B (L = 6016, B = 64), pair by pair: time per (k, d) launch and for the whole stage."""
+    C, L, B = 128, 6016, 64
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    x = torch.randn(B, L, C, device="cuda")
+    out32 = torch.empty(B, L, C, device="cuda")
+    total = 0.0
+    for k in (3, 7, 11):
+        for d in (1, 3, 5):
+            blocks = make_blocks(C, ks=(k,), dils=(d,))
+            pm = cabi.pack_mrf(C, blocks)
+            pm.w, pm.bias = pm.w.cuda(), pm.bias.cuda()
+            for _ in range(2):
+                cabi.mrf_fused(x, pm, out32, act=cabi.ACT_SILU_TANH, out_scale=1.0)
+            ts = []
+            for _ in range(iters):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                cabi.mrf_fused(x, pm, out32, act=cabi.ACT_SILU_TANH, out_scale=1.0)
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            ms = sorted(ts)[len(ts) // 2]
+            total += ms
+            flops = 2.0 * B * L * C * C * 2 * k
+            print(f"mrf_fused pair C=128 k={k} d={d}: {ms * 1e3:.1f} us  {flops / ms / 1e9:.1f} TFLOP/s  "
+                  f"{8.0 * B * L * C / ms / 1e6:.0f} GB/s algorithmic", flush=True)
+    print(f"C=128 stage, 9 pair launches: {total:.3f} ms (layer-wise conv_tc: ~2.0 ms)")
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "pairs":
+        main_pairs()
+    else:
+        main()

@@ -13,10 +13,10 @@ from vocoder_b200 import cabi  # noqa: E402
 def main():
     L = cabi.lib()
     out = torch.zeros(256, dtype=torch.int32, device="cuda")
-    names = {0: "SS cta_group::1", 1: "SS cta_group::2 (pair)", 2: "A in TMEM"}
+    names = {0: "SS cta_group::1", 1: "SS cta_group::2 (pair)", 2: "A in TMEM", 3: "SS weight-stationary (.ws)"}
     print("| operands | N | background smem traffic | cycles / UMMA (median over CTAs) | floor N/2 | ratio |")
     print("|---|---:|---|---:|---:|---:|")
-    for mode in (0, 1, 2):
+    for mode in (0, 1, 2, 3):
         for n in (32, 64, 128, 256):
             for bg in (0, 1, 2):
                 out.zero_()

@@ -18,7 +18,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libfv_b200.so")
 
-ACT_NONE, ACT_SILU, ACT_LEAKY, ACT_GELU, ACT_TANH, ACT_POLAR, ACT_SILU_TANH = range(7)
+ACT_NONE, ACT_SILU, ACT_LEAKY, ACT_GELU, ACT_TANH, ACT_POLAR, ACT_SILU_TANH, ACT_SILU_H2 = range(8)
 ENGINE_TC, ENGINE_SIMT = 0, 1
 EDGE_MODES = {"replicate": 0, "reflect": 1, "zero": 2}  # enum fv_edge_mode
 MAX_TAPS = 64
@@ -71,6 +71,7 @@ class MrfDesc(ctypes.Structure):
         ("out32", ctypes.c_void_p), ("out32_pitch", ctypes.c_int32),
         ("out16", ctypes.c_void_p), ("out16_pitch", ctypes.c_int32),
         ("out_act", ctypes.c_int32), ("out_act_param", ctypes.c_float),
+        ("accumulate", ctypes.c_int32), ("out_scale", ctypes.c_float),
     ]
 
 
@@ -594,9 +595,17 @@ class PackedMrf:
     w_row0: Sequence[Sequence[Sequence[int]]]
 
 
-def mrf_fusable(C: int, blocks) -> bool:
-    """blocks: [(convs1, convs2)] of nn.Conv1d-like modules.  True when fv_mrf_fused covers the stage."""
-    if is_strict() or C not in (16, 32, 64) or not 1 <= len(blocks) <= MRF_MAX_BLOCKS:
+def mrf_fusable(C: int, blocks, pairwise: bool = False) -> bool:
+    """blocks: [(convs1, convs2)] of nn.Conv1d-like modules.  True when fv_mrf_fused covers the stage: as one launch for
+    C in {16, 32, 64}; pairwise=True asks whether every (conv, conv) pair can be its own launch (C = 128)."""
+    if pairwise:
+        return C == 128 and all(_mrf_fusable(C, [([c1], [c2])], _tile=256, _chans=(128,))
+                                for c1s, c2s in blocks for c1, c2 in zip(c1s, c2s)) and len(blocks) >= 1
+    return _mrf_fusable(C, blocks)
+
+
+def _mrf_fusable(C: int, blocks, _tile: int = 512, _chans=(16, 32, 64)) -> bool:
+    if is_strict() or C not in _chans or not 1 <= len(blocks) <= MRF_MAX_BLOCKS:
         return False
     n_pairs = len(blocks[0][0])
     halo = 0
@@ -615,7 +624,7 @@ def mrf_fusable(C: int, blocks) -> bool:
                 return False
             h += reach
         halo = max(halo, h)
-    return 512 - round_up(halo, 32) - halo >= 32
+    return _tile - round_up(halo, 32) - halo >= 32
 
 
 def pack_mrf(C: int, blocks) -> PackedMrf:
@@ -643,8 +652,13 @@ def pack_mrf(C: int, blocks) -> PackedMrf:
 
 
 def mrf_fused(x32: torch.Tensor, pm: PackedMrf, out32: torch.Tensor, *, out16: Optional[torch.Tensor] = None,
-              act: int = ACT_SILU, act_param: float = 0.0, out_act: int = ACT_NONE, out_act_param: float = 0.0) -> None:
-    """x32 [B, L, pitch] fp32 -> out32 = mean over residual blocks (and out16 = fp16(out_act(out32)))."""
+              act: int = ACT_SILU, act_param: float = 0.0, out_act: int = ACT_NONE, out_act_param: float = 0.0,
+              accumulate: bool = False, out_scale: float = 0.0) -> None:
+    """x32 [B, L, pitch] fp32 -> out32 = mean over residual blocks (and out16 = fp16(out_act(out32))).
+    accumulate / out_scale: out32 += out_scale * block(x) (pair-wise evaluation of a C = 128 stage; out_scale 0 = 1/n_blocks).
+    out32 must not alias x32: tiles read their neighbours' rows of x as halo."""
+    if out32.data_ptr() == x32.data_ptr():
+        raise FvError("fv_mrf_fused: out32 must not alias x (tiles read their neighbours' rows as halo)")
     B, L, pitch = x32.shape
     d = MrfDesc()
     d.x, d.B, d.L, d.C, d.x_pitch = _ptr(x32, torch.float32), B, L, pm.C, pitch
@@ -662,6 +676,7 @@ def mrf_fused(x32: torch.Tensor, pm: PackedMrf, out32: torch.Tensor, *, out16: O
     d.out32, d.out32_pitch = _ptr(out32, torch.float32), out32.shape[2]
     d.out16, d.out16_pitch = _ptr(out16, torch.float16), (0 if out16 is None else out16.shape[2])
     d.out_act, d.out_act_param = int(out_act), float(out_act_param)
+    d.accumulate, d.out_scale = int(bool(accumulate)), float(out_scale)
     _check(lib().fv_mrf_fused(ctypes.byref(d), _stream()), "fv_mrf_fused")
 
 

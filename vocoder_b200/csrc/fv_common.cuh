@@ -364,6 +364,31 @@ __device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t desc_a, ui
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// weight-stationary form: B is latched in one of four collector buffers by `fill` and re-used by `use` / `lastuse` with
+// different A operands (COL = collector index, OP: 0 fill, 1 use, 2 lastuse)
+template <int COL, int OP>
+__device__ __forceinline__ void umma_f16_ws(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+#define FV_WS(colname, opname)                                                                                     \
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"                                                \
+               "tcgen05.mma.ws.cta_group::1.kind::f16.collector::" colname "::" opname " [%0], %1, %2, %3, p;\n\t}" \
+               ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)                                \
+               : "memory")
+  if constexpr (COL == 0 && OP == 0) FV_WS("b0", "fill");
+  else if constexpr (COL == 0 && OP == 1) FV_WS("b0", "use");
+  else if constexpr (COL == 0 && OP == 2) FV_WS("b0", "lastuse");
+  else if constexpr (COL == 1 && OP == 0) FV_WS("b1", "fill");
+  else if constexpr (COL == 1 && OP == 1) FV_WS("b1", "use");
+  else if constexpr (COL == 1 && OP == 2) FV_WS("b1", "lastuse");
+  else if constexpr (COL == 2 && OP == 0) FV_WS("b2", "fill");
+  else if constexpr (COL == 2 && OP == 1) FV_WS("b2", "use");
+  else if constexpr (COL == 2 && OP == 2) FV_WS("b2", "lastuse");
+  else if constexpr (COL == 3 && OP == 0) FV_WS("b3", "fill");
+  else if constexpr (COL == 3 && OP == 1) FV_WS("b3", "use");
+  else FV_WS("b3", "lastuse");
+#undef FV_WS
+}
+
 // mbarrier arrives when every previously issued tcgen05.mma of this thread has completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))

@@ -85,7 +85,8 @@ __global__ void __launch_bounds__(128, 1) rowshift_probe_kernel(const __grid_con
 // (4 accumulator blocks x 4 K steps, cycling through 4 A tiles and 2 B tiles so the shared-memory reads are real) and
 // times the span from the first issue to the completion of the last one with clock64.
 //   mode 0: SS, cta_group::1                      mode 1: SS, cta_group::2 (M = 256 over a CTA pair, B split)
-//   mode 2: A from TMEM (TS), cta_group::1
+//   mode 2: A from TMEM (TS), cta_group::1        mode 3: SS weight-stationary (tcgen05.mma.ws, B latched in a collector
+//                                                         buffer per K step and reused by the 4 accumulator blocks)
 //   bg    : 0 = idle epilogue warps; 1 = 8 warps stream st.shared.v4 into a scratch slab (an epilogue writing its
 //           operand rows); 2 = 8 warps stream ld.shared.v4
 // out[cta] = cycles per UMMA * 1000 (int).
@@ -150,6 +151,25 @@ __global__ void __launch_bounds__(320, 1) umma_rate_kernel(const RateParams p) {
     if ((!PAIR || rank == 0) && elect_one()) {
       const uint32_t idesc = make_idesc_f16(PAIR ? 256 : 128, N);
       const long long t0 = clock64();
+      if (p.mode == 3 && !PAIR) {
+        // weight-stationary: K step outermost, the B chunk of a K step is filled once and used by all accumulator blocks
+        for (int rep = 0; rep < p.reps; ++rep) {
+          const uint64_t db0 = make_kmajor_desc(smem_u32(sB) + (rep & 1) * 32768, 128);
+#define FV_WS_STEP(KK)                                                                                               \
+  {                                                                                                                  \
+    const uint64_t db = desc_advance(db0, KK * 32);                                                                  \
+    for (int m = 0; m < blocks; ++m) {                                                                               \
+      const uint64_t da = desc_advance(make_kmajor_desc(smem_u32(sA) + ((m + rep) & 3) * 16384, 128), KK * 32);      \
+      const uint32_t d = tmem_base + m * N;                                                                          \
+      if (m == 0) umma_f16_ws<KK, 0>(d, da, db, idesc, 1u);                                                          \
+      else if (m == blocks - 1) umma_f16_ws<KK, 2>(d, da, db, idesc, 1u);                                            \
+      else umma_f16_ws<KK, 1>(d, da, db, idesc, 1u);                                                                 \
+    }                                                                                                                \
+  }
+          FV_WS_STEP(0) FV_WS_STEP(1) FV_WS_STEP(2) FV_WS_STEP(3)
+#undef FV_WS_STEP
+        }
+      } else
       for (int rep = 0; rep < p.reps; ++rep) {
 #pragma unroll 1
         for (int m = 0; m < blocks; ++m) {
@@ -241,7 +261,7 @@ extern "C" int fv_debug_rowshift_probe(const void* a16, const void* w16, float* 
 }
 
 extern "C" int fv_debug_umma_rate(int mode, int n, int reps, int bg, int* out, void* stream) {
-  FV_REQUIRE(out && (mode >= 0 && mode <= 2) && n >= 16 && n <= 256 && n % 16 == 0 && reps > 0 && bg >= 0 && bg <= 2,
+  FV_REQUIRE(out && (mode >= 0 && mode <= 3) && n >= 16 && n <= 256 && n % 16 == 0 && reps > 0 && bg >= 0 && bg <= 2,
              FV_E_BADARG, "fv_debug_umma_rate: bad arguments");
   RateParams p = {out, n, reps, mode, bg};
   const int smem = 4 * 16384 + 2 * 32768 + 32768 + 64;

@@ -25,8 +25,6 @@
 
 namespace fv {
 
-constexpr int kFrTile = 512;     // rows per tile = 4 UMMA M blocks of 128
-constexpr int kFrMBlocks = 4;
 constexpr int kFrGuard = 32;     // guard rows either side of an operand slab = largest tap reach supported
 constexpr int kFrSmemSm = 233472;  // shared memory of one SM; every resident CTA also pays 1 KB of driver reservation
 constexpr int kFrMaxConvs = FV_MRF_MAX_BLOCKS * FV_MRF_MAX_PAIRS * 2;
@@ -44,22 +42,32 @@ struct MrfParams {
   int w_row0[FV_MRF_MAX_BLOCKS][FV_MRF_MAX_PAIRS][2];
   const float* bias;
   int act, out_act, has_o16;
+  int accumulate;  // the first block's exit adds onto what out32 already holds (pair-wise launches building the MRF mean)
+  int use_ws;  // weight-stationary MMAs (tcgen05.mma.ws): the tap tile's K chunk is latched once per four 128-row blocks
   float act_param, out_act_param, out_scale;
 };
 
-// EW epilogue warps (a multiple of 4, at most 16: warp w owns TMEM lane quarter w % 4 and walks 16 / EW row groups),
-// NCTA co-resident CTAs per SM: with C = 32 two CTAs fit (256 TMEM columns and < 113 KB each), so the tensor pipe
-// works on one CTA's conv while the other CTA's epilogue warps turn accumulators into the next operand.
-template <int C, int EW, int NCTA>
+// EW epilogue warps (a multiple of 4, at most 16: warp w owns TMEM lane quarter w % 4), NCTA co-resident CTAs per SM (with
+// C = 32 two CTAs fit - 256 TMEM columns and < 113 KB each - so the tensor pipe works on one CTA's conv while the other
+// CTA's epilogue warps turn accumulators into the next operand), MB 128-row blocks per tile (4 = 512 rows; 2 for C = 128,
+// whose residual stream + conv1 accumulator fill TMEM with 256 rows), MAXCONV convs whose biases are staged.
+// C = 128: an operand row (256 B) spans two 128-byte swizzle atoms, so every operand slab is KH = 2 sub-slabs of
+// [rows x 64 channels] and every tap tile streams through the ring as KH K-halves [C_out x 64].
+template <int C, int EW, int NCTA, int MB = 4, int MAXCONV = kFrMaxConvs>
 struct FrCfg {
   static constexpr int THREADS = 64 + EW * 32;                // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
   static constexpr int SMEM_LIMIT = kFrSmemSm / NCTA - 1024;
-  static constexpr int ROWB = C * 2;                          // bytes per operand row = swizzle span
-  static constexpr int SLAB_ROWS = kFrTile + 2 * kFrGuard;
-  static constexpr int SLAB = SLAB_ROWS * ROWB;               // multiple of 1024
-  static constexpr int W_BYTES = C * ROWB;                    // one [C_out x C_in] tap tile
+  static constexpr int KH = C > 64 ? C / 64 : 1;              // K halves per operand row / tap tile
+  static constexpr int KC = C / KH;                           // channels per K half
+  static constexpr int ROWB = KC * 2;                         // bytes per sub-slab row = swizzle span
+  static constexpr int TILE = MB * 128;                       // rows per tile
+  static constexpr int SLAB_ROWS = TILE + 2 * kFrGuard;
+  static constexpr int SUB = SLAB_ROWS * ROWB;                // one sub-slab (multiple of 1024)
+  static constexpr int SLAB = KH * SUB;
+  static constexpr int W_BYTES = C * ROWB;                    // one [C_out x KC] K-half of a tap tile
   static constexpr int W_TILE = W_BYTES < 1024 ? 1024 : W_BYTES;  // ring slot (swizzled tiles stay 1024-byte aligned)
   static constexpr int CW = C < 32 ? C : 32;                  // columns per epilogue patch (one TMEM load / TMA box)
+  static constexpr int NCH = C / CW;                          // patches per row
   static constexpr int P32 = 32 * CW * 4;                     // per-warp 32 x CW fp32 patch, swizzle span = CW * 4 bytes
   static constexpr int P16 = 32 * CW * 2;                     // per-warp 32 x CW fp16 patch, swizzle span = CW * 2 bytes
   static constexpr int STG32 = EW * P32;
@@ -71,21 +79,22 @@ struct FrCfg {
   static constexpr int STG32_OFF = ALIAS ? TA_OFF : 2 * SLAB;
   static constexpr int STG16_OFF = ALIAS ? XA_OFF : 2 * SLAB + STG32;
   static constexpr int RING_OFF = ALIAS ? 2 * SLAB : 2 * SLAB + STG32 + STG16;
-  static constexpr int BIAS_BYTES = kFrMaxConvs * C * 4;
+  static constexpr int BIAS_BYTES = MAXCONV * C * 4;
   static constexpr int TAIL = 1024 + BIAS_BYTES;
   static constexpr int NS_RAW = (SMEM_LIMIT - RING_OFF - TAIL) / W_TILE;
   static constexpr int NS = NS_RAW > 16 ? 16 : NS_RAW;
   static constexpr int SMEM = RING_OFF + NS * W_TILE + TAIL;
-  static constexpr int TMEM_COLS = 2 * kFrMBlocks * C;        // 512 (C = 64) / 256 (C = 32)
+  static constexpr int TMEM_COLS = 2 * MB * C;                // 512 (C = 64, 128) / 256 (C = 32) / 128 (C = 16)
   static constexpr int GROUPS = EW / 4;                       // epilogue warps per TMEM lane quarter
-  static constexpr int RR = kFrMBlocks / GROUPS;              // 128-row blocks each epilogue warp walks
-  static_assert(EW % 4 == 0 && EW >= 4 && EW <= 16 && kFrMBlocks % GROUPS == 0, "bad epilogue warp count");
+  static constexpr int ITEMS = MB * NCH;                      // (128-row block, column patch) items per lane quarter
+  static constexpr int IPW = ITEMS / GROUPS;                  // items each epilogue warp walks
+  static_assert(EW % 4 == 0 && EW >= 4 && EW <= 16 && ITEMS % GROUPS == 0, "bad epilogue warp count");
   static_assert(TMEM_COLS * NCTA <= 512, "co-resident CTAs exceed TMEM");
   static_assert(!ALIAS || (STG32 <= SLAB && STG16 <= SLAB), "staging does not fit in the slabs it aliases");
-  static_assert(NS >= 4, "weight ring too shallow");
-  static_assert(SLAB % 1024 == 0 && W_TILE % 1024 == 0 && (STG32 % 1024 == 0) && (STG16 % 1024 == 0),
+  static_assert(NS >= 3, "weight ring too shallow");
+  static_assert(SUB % 1024 == 0 && W_TILE % 1024 == 0 && (STG32 % 1024 == 0) && (STG16 % 1024 == 0),
                 "swizzled tiles must stay 1024-byte aligned");
-  static_assert(C == 16 || C == 32 || C == 64, "supported channel counts");
+  static_assert(C == 16 || C == 32 || C == 64 || C == 128, "supported channel counts");
 };
 
 // byte offset of 16-byte chunk `chunk` of row `row` inside a swizzled tile whose rows are ROWB bytes = the swizzle span
@@ -122,28 +131,42 @@ __device__ __forceinline__ void tmem_st_cw(uint32_t taddr, const uint32_t (&r)[3
 //   kActSilu     x / (1 + 2^(-x log2 e)): ex2.approx.ftz + rcp.approx.ftz (2 SFU ops, ~1e-7 relative)
 //   kActSiluTanh x/2 + x/2 * tanh(x/2):   tanh.approx (1 SFU op, |error| <= 2.4e-4 |x|) - opt-in, see fv_set_mrf_tuning
 //   kActLeaky    x > 0 ? x : slope * x
-constexpr int kActSilu = 0, kActSiluTanh = 1, kActLeaky = 2;
+//   kActSiluH2   the same formula evaluated on packed fp16 pairs: cvt.rn.f16x2 of (x0/2, x1/2), ONE tanh.approx.f16x2 and
+//                one fma.rn.f16x2 produce the operand word of two channels (5 instructions / 1 SFU op per pair instead of
+//                9 / 2); the result carries ~3 fp16 roundings instead of 1 - opt-in (FV_ACT_SILU_H2)
+constexpr int kActSilu = 0, kActSiluTanh = 1, kActLeaky = 2, kActSiluH2 = 3;
 template <int ACT>
 __device__ __forceinline__ float fr_act(float v, float param) {
   if constexpr (ACT == kActSilu) {
     return silu_fast(v);
-  } else if constexpr (ACT == kActSiluTanh) {
+  } else if constexpr (ACT == kActSiluTanh || ACT == kActSiluH2) {
     return silu_tanh(v);
   } else {
     return v > 0.f ? v : v * param;
   }
 }
+// packed operand word of two channels: fp16x2(act(a), act(b)), a in the low half
+template <int ACT>
+__device__ __forceinline__ uint32_t fr_act_pack(float a, float b, float param) {
+  if constexpr (ACT == kActSiluH2) {
+    const uint32_t h = pack_half2_sat(0.5f * a, 0.5f * b);
+    uint32_t t, r;
+    asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(h));
+    asm("fma.rn.f16x2 %0, %1, %2, %1;" : "=r"(r) : "r"(h), "r"(t));
+    return r;
+  } else {
+    return pack_half2_sat(fr_act<ACT>(a, param), fr_act<ACT>(b, param));
+  }
+}
 
-// PIPE = true (needs EW = C / 4): every conv is issued as two half-tile passes (128-row blocks {0,1}, then {2,3}; the tap
-// tiles are streamed twice) with their own "accumulator complete" barriers, so the epilogue of the first half runs
-// under the MMAs of the second, and the next conv's first half starts as soon as blocks 0-2 of its operand exist.
-template <int C, int ACT, int EW, int NCTA, bool PIPE>
-__global__ void __launch_bounds__(FrCfg<C, EW, NCTA>::THREADS, NCTA) mrf_fused_kernel(const __grid_constant__ MrfParams p) {
-  using Cfg = FrCfg<C, EW, NCTA>;
-  static_assert(!PIPE || EW * 4 == C, "the half-tile pipeline maps one 32x32 / 32x16 accumulator patch to each warp");
+template <int C, int ACT, int EW, int NCTA, int MB, int MAXCONV>
+__global__ void __launch_bounds__(FrCfg<C, EW, NCTA, MB, MAXCONV>::THREADS, NCTA)
+    mrf_fused_kernel(const __grid_constant__ MrfParams p) {
+  using Cfg = FrCfg<C, EW, NCTA, MB, MAXCONV>;
   constexpr int ROWB = Cfg::ROWB;
+  constexpr int KH = Cfg::KH, KC = Cfg::KC;
   constexpr int CW = Cfg::CW;      // columns per epilogue patch
-  constexpr int NCH = C / CW;      // patches per row
+  constexpr int NCH = Cfg::NCH;    // patches per row
   constexpr int R32 = CW * 4, R16 = CW * 2;  // row bytes of the fp32 / fp16 staging patches
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) {
@@ -156,7 +179,6 @@ __global__ void __launch_bounds__(FrCfg<C, EW, NCTA>::THREADS, NCTA) mrf_fused_k
   uint64_t* a_ready = w_empty + Cfg::NS;   // [2] epilogue warps -> MMA: operand of the next conv is in smem / X is in TMEM
   uint64_t* acc_full = a_ready + 2;        // [2] MMA -> epilogue: accumulators of the current conv are complete
   uint64_t* stg_bar = acc_full + 2;        // one per epilogue warp: TMA loads into its staging patch
-  // (PIPE: index = tile half; a_ready[0] also covers 128-row block 2, whose first rows the first half's taps reach)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stg_bar + EW);
   float* s_bias = reinterpret_cast<float*>(tail + 1024);  // [block][pair][2][C]: b1, cumulative b2
 
@@ -194,11 +216,12 @@ __global__ void __launch_bounds__(FrCfg<C, EW, NCTA>::THREADS, NCTA) mrf_fused_k
       s_bias[((j * p.n_pairs + pi) * 2 + 1) * C + c] = cum;
     }
   }
-  // guard rows of both slabs: never written afterwards, only ever feed rows outside a tile's valid window
-  for (int i = threadIdx.x; i < 2 * 2 * kFrGuard * ROWB / 16; i += blockDim.x) {
+  // guard rows of every sub-slab of both slabs: never written afterwards, only ever feed rows outside a tile's valid window
+  for (int i = threadIdx.x; i < 2 * KH * 2 * kFrGuard * ROWB / 16; i += blockDim.x) {
     const int per = kFrGuard * ROWB / 16;
-    const int which = i / per, o = i % per;
-    uint8_t* base = smem + ((which & 1) ? Cfg::TA_OFF : Cfg::XA_OFF) + ((which & 2) ? (kFrGuard + kFrTile) * ROWB : 0);
+    const int which = i / per, o = i % per;   // which = ((slab * KH + sub) * 2 + end)
+    const int end = which & 1, sub = (which >> 1) % KH, slab = (which >> 1) / KH;
+    uint8_t* base = smem + (slab ? Cfg::TA_OFF : Cfg::XA_OFF) + sub * Cfg::SUB + (end ? (kFrGuard + Cfg::TILE) * ROWB : 0);
     reinterpret_cast<uint4*>(base)[o] = make_uint4(0, 0, 0, 0);
   }
   fence_proxy_async_smem();
@@ -206,7 +229,7 @@ __global__ void __launch_bounds__(FrCfg<C, EW, NCTA>::THREADS, NCTA) mrf_fused_k
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  constexpr uint32_t X_COL = 0, T_COL = kFrMBlocks * C;
+  constexpr uint32_t X_COL = 0, T_COL = MB * C;
 
   if (warp == 0) {
     // ---------------------------------------------------------------- weight-tile producer
@@ -217,13 +240,13 @@ __global__ void __launch_bounds__(FrCfg<C, EW, NCTA>::THREADS, NCTA) mrf_fused_k
         for (int pi = 0; pi < p.n_pairs; ++pi)
           for (int cv = 0; cv < 2; ++cv) {
             const int row0 = p.w_row0[j][pi][cv];
-            for (int h = 0; h < (PIPE ? 2 : 1); ++h)
-              for (int tap = 0; tap < p.ksize[j]; ++tap, ++it) {
+            for (int tap = 0; tap < p.ksize[j]; ++tap)
+              for (int kh = 0; kh < KH; ++kh, ++it) {   // ring item = one K-half [C_out x KC] of a tap tile
                 const int s = it % Cfg::NS;
                 mbar_wait(&w_empty[s], ((it / Cfg::NS) & 1) ^ 1);
                 if (leader) {
                   mbar_arrive_expect_tx(&w_full[s], Cfg::W_BYTES);
-                  tma_load_2d(smem + Cfg::RING_OFF + s * Cfg::W_TILE, &p.tmW, &w_full[s], 0, row0 + tap * C);
+                  tma_load_2d(smem + Cfg::RING_OFF + s * Cfg::W_TILE, &p.tmW, &w_full[s], kh * KC, row0 + tap * C);
                 }
               }
           }
@@ -241,38 +264,60 @@ __global__ void __launch_bounds__(FrCfg<C, EW, NCTA>::THREADS, NCTA) mrf_fused_k
             const uint32_t slab = smem_u32(smem + (cv == 0 ? Cfg::XA_OFF : Cfg::TA_OFF)) + kFrGuard * ROWB;
             const uint32_t d_col = tmem_base + (cv == 0 ? T_COL : X_COL);
             const int dil = p.dil[j][pi][cv];
-            constexpr int MB = PIPE ? kFrMBlocks / 2 : kFrMBlocks;  // 128-row blocks per pass
-            for (int h = 0; h < (PIPE ? 2 : 1); ++h) {
-              mbar_wait(&a_ready[h], n & 1);
-              tc_fence_after();
-              for (int tap = 0; tap < k; ++tap, ++it) {
+            mbar_wait(&a_ready[0], n & 1);
+            tc_fence_after();
+            for (int tap = 0; tap < k; ++tap)
+              for (int kh = 0; kh < KH; ++kh, ++it) {
                 const int s = it % Cfg::NS;
                 mbar_wait(&w_full[s], (it / Cfg::NS) & 1);
                 tc_fence_after();
                 if (leader) {
-                  const uint64_t da0 = make_kmajor_desc(slab + ((tap - half_k) * dil + h * MB * 128) * ROWB, ROWB);
+                  // a tap / dilation shift = a descriptor that starts `off` rows into the (sub-)slab
+                  const uint64_t da0 = make_kmajor_desc(slab + kh * Cfg::SUB + ((tap - half_k) * dil) * ROWB, ROWB);
                   const uint64_t db0 = make_kmajor_desc(smem_u32(smem + Cfg::RING_OFF + s * Cfg::W_TILE), ROWB);
+                  const uint32_t acc0 = (cv == 1 || tap > 0 || kh > 0) ? 1u : 0u;
+                  bool done = false;
+                  if constexpr (C == 64 && MB == 4) {
+                    if (p.use_ws) {
+                      // K step outermost: B chunk kk is read from shared memory ONCE (collector fill) for the four blocks
+                      // instead of four times: 4 x 4 KB (A) + 2 KB (B) per four UMMAs instead of 4 x 6 KB
+#define FV_WS_STEP(KK)                                                                                                   \
+  {                                                                                                                      \
+    const uint64_t db = desc_advance(db0, KK * 32);                                                                      \
+    const uint32_t acc = (acc0 || KK > 0) ? 1u : 0u;                                                                     \
+    umma_f16_ws<KK, 0>(d_col + 0 * C, desc_advance(da0, 0 * 128 * ROWB + KK * 32), db, idesc, acc);                     \
+    umma_f16_ws<KK, 1>(d_col + 1 * C, desc_advance(da0, 1 * 128 * ROWB + KK * 32), db, idesc, acc);                     \
+    umma_f16_ws<KK, 1>(d_col + 2 * C, desc_advance(da0, 2 * 128 * ROWB + KK * 32), db, idesc, acc);                     \
+    umma_f16_ws<KK, 2>(d_col + 3 * C, desc_advance(da0, 3 * 128 * ROWB + KK * 32), db, idesc, acc);                     \
+  }
+                      FV_WS_STEP(0) FV_WS_STEP(1) FV_WS_STEP(2) FV_WS_STEP(3)
+#undef FV_WS_STEP
+                      done = true;
+                    }
+                  }
+                  if (!done) {
 #pragma unroll
-                  for (int m = 0; m < MB; ++m) {
+                    for (int m = 0; m < MB; ++m) {
 #pragma unroll
-                    for (int kk = 0; kk < C / 16; ++kk)
-                      umma_f16_ss(d_col + (h * MB + m) * C, desc_advance(da0, m * 128 * ROWB + kk * 32),
-                                  desc_advance(db0, kk * 32), idesc, (cv == 1 || tap > 0 || kk > 0) ? 1u : 0u);
+                      for (int kk = 0; kk < KC / 16; ++kk)
+                        umma_f16_ss(d_col + m * C, desc_advance(da0, m * 128 * ROWB + kk * 32), desc_advance(db0, kk * 32),
+                                    idesc, (acc0 || kk > 0) ? 1u : 0u);
+                    }
                   }
                   umma_commit(&w_empty[s]);
                 }
                 __syncwarp();
               }
-              if (leader) umma_commit(&acc_full[h]);
-              __syncwarp();
-            }
+            if (leader) umma_commit(&acc_full[0]);
+            __syncwarp();
           }
       }
     }
   } else {
-    // ---------------------------------------------------------------- epilogue: thread = tile row (RR rows in turn)
-    // warp w may only touch TMEM lanes 32 (w % 4) .. +31: it owns that lane quarter of the 128-row blocks
-    // m = g, g + GROUPS, ... (g = its index among the warps of the quarter); local row = 128 m + 32 q + lane
+    // ---------------------------------------------------------------- epilogue: thread = tile row
+    // warp w may only touch TMEM lanes 32 (w % 4) .. +31: it owns that lane quarter; the (128-row block m, column patch cc)
+    // items of a quarter are dealt to its GROUPS warps: item = g + i * GROUPS, m = item / NCH, cc = item % NCH
+    // (g = the warp's index among the warps of the quarter); local row = 128 m + 32 q + lane
     const int e = warp - 2;
     const int q = warp & 3;
     const int g = e >> 2;
@@ -284,16 +329,22 @@ __global__ void __launch_bounds__(FrCfg<C, EW, NCTA>::THREADS, NCTA) mrf_fused_k
     uint64_t* my_bar = &stg_bar[e];
     uint32_t stg_phase = 0, n = 0;
 
-    // activation -> fp16 -> this thread's CW columns (CW / 8 16-byte chunks) of operand row `srow`
-    auto put_operand = [&](uint32_t slab_base, int srow, int cc, const float (&v)[32]) {
+    // activation -> fp16 -> this thread's CW columns (CW / 8 16-byte chunks) of operand row `srow`; rows outside the
+    // sequence (live == false) are written as zeros = the reference's zero padding
+    auto put_operand = [&](uint32_t slab_base, int srow, int cc, const float (&v)[32], bool live) {
 #pragma unroll
       for (int qq = 0; qq < CW / 8; ++qq) {
-        const uint32_t w0 = pack_half2_sat(v[8 * qq + 0], v[8 * qq + 1]);
-        const uint32_t w1 = pack_half2_sat(v[8 * qq + 2], v[8 * qq + 3]);
-        const uint32_t w2 = pack_half2_sat(v[8 * qq + 4], v[8 * qq + 5]);
-        const uint32_t w3 = pack_half2_sat(v[8 * qq + 6], v[8 * qq + 7]);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(slab_base + swz_off<ROWB>(srow, cc * (CW / 8) + qq)),
-                     "r"(w0), "r"(w1), "r"(w2), "r"(w3)
+        uint32_t w[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t pk = fr_act_pack<ACT>(v[8 * qq + 2 * u], v[8 * qq + 2 * u + 1], p.act_param);
+          w[u] = live ? pk : 0u;
+        }
+        // channel cc * CW + 8 qq lives in sub-slab (K half) ch / KC, 16-byte chunk (ch % KC) / 8 of its row
+        const int ch = cc * CW + 8 * qq;
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(slab_base + (ch / KC) * Cfg::SUB +
+                                                                     swz_off<ROWB>(srow, (ch % KC) / 8)),
+                     "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
                      : "memory");
       }
     };
@@ -319,41 +370,7 @@ __global__ void __launch_bounds__(FrCfg<C, EW, NCTA>::THREADS, NCTA) mrf_fused_k
       tmem_ld_wait();
       float v[32];
       add_bias(v, r, bias + cc * CW);
-#pragma unroll
-      for (int i = 0; i < CW; ++i) v[i] = in_seq ? fr_act<ACT>(v[i], p.act_param) : 0.f;
-      put_operand(slab_base, kFrGuard + row_l, cc, v);
-    };
-    // the same for a 32-row x 16-column patch (column group c16): the half-tile pipeline's unit for blocks 2 and 3
-    auto acc_item16 = [&](uint32_t col, int m, int c16, const float* bias, uint32_t slab_base, int g0) {
-      const int row_l = m * 128 + q * 32 + lane;
-      const int gr = g0 + row_l;
-      const bool in_seq = gr >= 0 && gr < p.L;
-      uint32_t r[32];
-      tmem_ld_32x32b_x16(t_lane + col + m * C + c16 * 16, r);
-      tmem_ld_wait();
-      const float4* b4 = reinterpret_cast<const float4*>(bias + c16 * 16);
-      float v[16];
-#pragma unroll
-      for (int qq = 0; qq < 4; ++qq) {
-        const float4 bb = b4[qq];
-        v[4 * qq] = __uint_as_float(r[4 * qq]) + bb.x;
-        v[4 * qq + 1] = __uint_as_float(r[4 * qq + 1]) + bb.y;
-        v[4 * qq + 2] = __uint_as_float(r[4 * qq + 2]) + bb.z;
-        v[4 * qq + 3] = __uint_as_float(r[4 * qq + 3]) + bb.w;
-      }
-#pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = in_seq ? fr_act<ACT>(v[i], p.act_param) : 0.f;
-#pragma unroll
-      for (int qq = 0; qq < 2; ++qq) {
-        const uint32_t w0 = pack_half2_sat(v[8 * qq + 0], v[8 * qq + 1]);
-        const uint32_t w1 = pack_half2_sat(v[8 * qq + 2], v[8 * qq + 3]);
-        const uint32_t w2 = pack_half2_sat(v[8 * qq + 4], v[8 * qq + 5]);
-        const uint32_t w3 = pack_half2_sat(v[8 * qq + 6], v[8 * qq + 7]);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(
-                         slab_base + swz_off<ROWB>(kFrGuard + row_l, c16 * 2 + qq)),
-                     "r"(w0), "r"(w1), "r"(w2), "r"(w3)
-                     : "memory");
-      }
+      put_operand(slab_base, kFrGuard + row_l, cc, v, in_seq);
     };
     // tile entry of one patch: x -> X (TMEM, fp32) and act(x) -> XA (fp16); rows outside the sequence arrive as zeros
     auto entry_item = [&](int m, int cc, int b, int g0) {
@@ -376,18 +393,19 @@ __global__ void __launch_bounds__(FrCfg<C, EW, NCTA>::THREADS, NCTA) mrf_fused_k
       tmem_st_cw<CW>(t_lane + X_COL + m * C + cc * CW, r);
       float v[32];
 #pragma unroll
-      for (int i = 0; i < CW; ++i) v[i] = fr_act<ACT>(__uint_as_float(r[i]), p.act_param);
-      put_operand(xa_base, kFrGuard + blk0 + lane, cc, v);
+      for (int i = 0; i < CW; ++i) v[i] = __uint_as_float(r[i]);
+      put_operand(xa_base, kFrGuard + blk0 + lane, cc, v, true);   // act(0) == 0: out-of-sequence rows stay zero
     };
     // tile exit of one patch: block output -> running mean in out32 (-> activated fp16 after the last block)
     auto exit_item = [&](int m, int cc, int b, int g0, int j, const float* b2c) {
       const bool last = j == p.n_blocks - 1;
+      const bool add_old = j > 0 || p.accumulate;   // out32 already holds a partial mean (earlier block / earlier launch)
       const int blk0 = m * 128 + q * 32;
       const int grow = g0 + blk0;
       if (!(blk0 >= p.h0 && blk0 < p.h0 + p.V && grow < p.L)) return;  // halo rows / past the sequence
       __syncwarp();
       if (lane == 0) {
-        if (j > 0) {
+        if (add_old) {
           tma_store_wait_all();  // the partial sums this warp stored for block j-1 are visible
           mbar_arrive_expect_tx(my_bar, Cfg::P32);
           tma_load_3d(patch32, &p.tmO32, my_bar, cc * CW, grow, b);
@@ -403,7 +421,7 @@ __global__ void __launch_bounds__(FrCfg<C, EW, NCTA>::THREADS, NCTA) mrf_fused_k
       add_bias(v, r, b2c + cc * CW);
 #pragma unroll
       for (int i = 0; i < CW; ++i) v[i] *= p.out_scale;
-      if (j > 0) {
+      if (add_old) {
         mbar_wait(my_bar, stg_phase);
         stg_phase ^= 1;
 #pragma unroll
@@ -427,7 +445,7 @@ __global__ void __launch_bounds__(FrCfg<C, EW, NCTA>::THREADS, NCTA) mrf_fused_k
         if (p.out_act == FV_ACT_SILU) {
 #pragma unroll
           for (int i = 0; i < CW; ++i) v[i] = fr_act<kActSilu>(v[i], 0.f);
-        } else if (p.out_act == FV_ACT_SILU_TANH) {
+        } else if (p.out_act == FV_ACT_SILU_TANH || p.out_act == FV_ACT_SILU_H2) {
 #pragma unroll
           for (int i = 0; i < CW; ++i) v[i] = fr_act<kActSiluTanh>(v[i], 0.f);
         } else if (p.out_act == FV_ACT_LEAKY) {
@@ -464,25 +482,17 @@ __global__ void __launch_bounds__(FrCfg<C, EW, NCTA>::THREADS, NCTA) mrf_fused_k
       __syncwarp();
       if (lane == 0) mbar_arrive(bar);
     };
-    // PIPE: this warp's patch inside a tile half (blocks {0,1} / {2,3}) and its 16-column group inside one block
-    const int pm = g / NCH, pcc = g % NCH;
-
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int b = tile / p.tiles_per_b;
       const int g0 = (tile % p.tiles_per_b) * p.V - p.h0;  // global row of tile row 0
       for (int j = 0; j < p.n_blocks; ++j) {
-        if constexpr (PIPE) {
-          entry_item(pm, pcc, b, g0);
-          entry_item(pm + 2, pcc, b, g0);
-        } else {
 #pragma unroll 1
-          for (int rr = 0; rr < Cfg::RR; ++rr)
-#pragma unroll 1
-            for (int cc = 0; cc < NCH; ++cc) entry_item(g + rr * Cfg::GROUPS, cc, b, g0);
+        for (int i = 0; i < Cfg::IPW; ++i) {
+          const int item = g + i * Cfg::GROUPS;
+          entry_item(item / NCH, item % NCH, b, g0);
         }
         tmem_st_wait();
         publish(&a_ready[0]);
-        if constexpr (PIPE) publish(&a_ready[1]);
         for (int pi = 0; pi < p.n_pairs; ++pi) {
           const float* b1 = s_bias + ((j * p.n_pairs + pi) * 2) * C;
           const float* b2c = b1 + C;
@@ -495,34 +505,18 @@ __global__ void __launch_bounds__(FrCfg<C, EW, NCTA>::THREADS, NCTA) mrf_fused_k
             const bool is_exit = cv == 1 && pi + 1 == p.n_pairs;
             mbar_wait(&acc_full[0], n & 1);
             tc_fence_after();
-            if constexpr (PIPE) {
-              if (!is_exit) {
-                acc_item32(col, pm, pcc, bias, dst, g0);       // first half under the MMAs of the second
-                mbar_wait(&acc_full[1], n & 1);
-                tc_fence_after();
-                acc_item16(col, 2, g, bias, dst, g0);
-                publish(&a_ready[0]);                          // blocks 0-2 written: next conv's first half may go
-                acc_item16(col, 3, g, bias, dst, g0);
-                publish(&a_ready[1]);
-              } else {
-                // the staging patches alias the slabs the second half's MMAs still read: exit after both halves
-                mbar_wait(&acc_full[1], n & 1);
-                tc_fence_after();
-                exit_item(pm, pcc, b, g0, j, b2c);
-                exit_item(pm + 2, pcc, b, g0, j, b2c);
+            if (!is_exit) {
+#pragma unroll 1
+              for (int i = 0; i < Cfg::IPW; ++i) {
+                const int item = g + i * Cfg::GROUPS;
+                acc_item32(col, item / NCH, item % NCH, bias, dst, g0);
               }
+              publish(&a_ready[0]);
             } else {
-              if (!is_exit) {
 #pragma unroll 1
-                for (int rr = 0; rr < Cfg::RR; ++rr)
-#pragma unroll 1
-                  for (int cc = 0; cc < NCH; ++cc) acc_item32(col, g + rr * Cfg::GROUPS, cc, bias, dst, g0);
-                publish(&a_ready[0]);
-              } else {
-#pragma unroll 1
-                for (int rr = 0; rr < Cfg::RR; ++rr)
-#pragma unroll 1
-                  for (int cc = 0; cc < NCH; ++cc) exit_item(g + rr * Cfg::GROUPS, cc, b, g0, j, b2c);
+              for (int i = 0; i < Cfg::IPW; ++i) {
+                const int item = g + i * Cfg::GROUPS;
+                exit_item(item / NCH, item % NCH, b, g0, j, b2c);
               }
             }
             if (is_exit && Cfg::ALIAS && j == p.n_blocks - 1 && p.has_o16) {
@@ -571,19 +565,21 @@ static const int g_mrf_c32_ctas = [] {
   return (e && e[0] == '1') ? 1 : 2;
 }();
 
-// FV_MRF_PIPE=1 selects the half-tile pipelined schedule.  Measured on B200 (HiFiGAN cfg B stages): it helps the
-// ex2+rcp SiLU by 5% (C=64: 1.79 -> 1.71 ms) and costs 2% with the tanh SiLU (1.54 -> 1.57 ms): the MMA phase of an
-// N <= 64 tile is bound by the shared-memory reads of the A operand (4 KB + 32 N bytes per 128xNx16 UMMA against 128 B/clk),
-// so the concurrent epilogue competes for the same port and every conv pays two barrier round trips instead of one.
-// Default: serial schedule.
-static const bool g_mrf_pipe = [] {
-  const char* e = getenv("FV_MRF_PIPE");
+// FV_MRF_WS=1: weight-stationary MMAs for the C = 64 stage (see MrfParams::use_ws); A/B measurement switch
+static const bool g_mrf_ws = [] {
+  const char* e = getenv("FV_MRF_WS");
   return e && e[0] == '1';
 }();
 
-template <int C, int ACT, int EW, int NCTA, bool PIPE>
+// rows per tile for a channel count (what FrCfg<C, ..., MB> is instantiated with below)
+static int tile_rows_for(int C) { return C == 128 ? 256 : 512; }
+
+template <int C, int ACT, int EW, int NCTA, int MB, int MAXCONV>
 static int launch_mrf(const fv_mrf_desc* d, MrfParams& p, cudaStream_t stream) {
-  using Cfg = FrCfg<C, EW, NCTA>;
+  using Cfg = FrCfg<C, EW, NCTA, MB, MAXCONV>;
+  FV_REQUIRE(d->n_blocks * d->n_pairs * 2 <= MAXCONV, FV_E_UNSUPPORTED,
+             "fv_mrf_fused: C = %d supports at most %d convs per launch (got %d blocks x %d pairs)", C, MAXCONV, d->n_blocks,
+             d->n_pairs);
   EncodeTiledFn enc = get_encode_fn();
   FV_REQUIRE(enc != nullptr, FV_E_DRIVER, "cuTensorMapEncodeTiled not available from the driver");
   int rc = encode_rows_map(enc, &p.tmX, d->x, false, C, d->x_pitch, d->L, d->B, Cfg::CW);
@@ -591,9 +587,10 @@ static int launch_mrf(const fv_mrf_desc* d, MrfParams& p, cudaStream_t stream) {
   if (!rc && d->out16) rc = encode_rows_map(enc, &p.tmO16, d->out16, true, C, d->out16_pitch, d->L, d->B, Cfg::CW);
   if (rc) return rc;
   {
+    // tap tiles [C_out x C_in] row-major; one ring item = a [C_out x KC] K-half (the whole tile for C <= 64)
     cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)d->w_rows};
     cuuint64_t strides[1] = {(cuuint64_t)C * 2};
-    cuuint32_t box[2] = {(cuuint32_t)C, (cuuint32_t)C};
+    cuuint32_t box[2] = {(cuuint32_t)Cfg::KC, (cuuint32_t)C};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(&p.tmW, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(d->w), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -603,13 +600,13 @@ static int launch_mrf(const fv_mrf_desc* d, MrfParams& p, cudaStream_t stream) {
     FV_REQUIRE(r == CUDA_SUCCESS, FV_E_DRIVER, "cuTensorMapEncodeTiled(mrf W) failed: %d", (int)r);
   }
   static std::atomic<unsigned long long> attr_done{0};
-  rc = check_cuda(ensure_dyn_smem(mrf_fused_kernel<C, ACT, EW, NCTA, PIPE>, Cfg::SMEM, attr_done),
+  rc = check_cuda(ensure_dyn_smem(mrf_fused_kernel<C, ACT, EW, NCTA, MB, MAXCONV>, Cfg::SMEM, attr_done),
                   "cudaFuncSetAttribute(mrf_fused_kernel)");
   if (rc) return rc;
   const int slots = num_sms() * NCTA;
   const int grid = p.total_tiles < slots ? p.total_tiles : slots;
-  rc = check_cuda(launch_kernel(mrf_fused_kernel<C, ACT, EW, NCTA, PIPE>, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM, stream,
-                                1, p),
+  rc = check_cuda(launch_kernel(mrf_fused_kernel<C, ACT, EW, NCTA, MB, MAXCONV>, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM,
+                                stream, 1, p),
                   "cudaLaunchKernelEx(mrf_fused_kernel)");
   if (rc) return rc;
   FV_CHECK_LAUNCH("mrf_fused_kernel");
@@ -624,13 +621,15 @@ extern "C" int fv_mrf_fused(const fv_mrf_desc* d, void* stream) {
   FV_REQUIRE(d != nullptr, FV_E_BADARG, "fv_mrf_fused: null descriptor");
   FV_REQUIRE(d->x && d->w && d->bias && d->out32, FV_E_BADARG, "fv_mrf_fused: null pointer (x, w, bias, out32 required)");
   FV_REQUIRE(d->B > 0 && d->L > 0, FV_E_BADARG, "fv_mrf_fused: bad sizes B=%d L=%d", d->B, d->L);
-  FV_REQUIRE(d->C == 16 || d->C == 32 || d->C == 64, FV_E_UNSUPPORTED, "fv_mrf_fused: C must be 16, 32 or 64 (got %d)", d->C);
+  FV_REQUIRE(d->C == 16 || d->C == 32 || d->C == 64 || d->C == 128, FV_E_UNSUPPORTED,
+             "fv_mrf_fused: C must be 16, 32, 64 or 128 (got %d)", d->C);
   FV_REQUIRE(d->n_blocks >= 1 && d->n_blocks <= FV_MRF_MAX_BLOCKS && d->n_pairs >= 1 && d->n_pairs <= FV_MRF_MAX_PAIRS,
              FV_E_BADARG, "fv_mrf_fused: n_blocks=%d n_pairs=%d out of range", d->n_blocks, d->n_pairs);
-  FV_REQUIRE(d->act == FV_ACT_SILU || d->act == FV_ACT_LEAKY || d->act == FV_ACT_SILU_TANH, FV_E_UNSUPPORTED,
-             "fv_mrf_fused: inner activation must be SiLU or leaky ReLU");
-  FV_REQUIRE((d->out_act >= FV_ACT_NONE && d->out_act <= FV_ACT_TANH) || d->out_act == FV_ACT_SILU_TANH, FV_E_BADARG,
-             "fv_mrf_fused: bad out_act");
+  FV_REQUIRE(d->act == FV_ACT_SILU || d->act == FV_ACT_LEAKY || d->act == FV_ACT_SILU_TANH || d->act == FV_ACT_SILU_H2,
+             FV_E_UNSUPPORTED, "fv_mrf_fused: inner activation must be SiLU or leaky ReLU");
+  FV_REQUIRE((d->out_act >= FV_ACT_NONE && d->out_act <= FV_ACT_TANH) || d->out_act == FV_ACT_SILU_TANH ||
+                 d->out_act == FV_ACT_SILU_H2,
+             FV_E_BADARG, "fv_mrf_fused: bad out_act");
   FV_REQUIRE(d->x_pitch >= d->C && d->x_pitch % 4 == 0 && d->out32_pitch >= d->C && d->out32_pitch % 4 == 0 &&
                  (!d->out16 || (d->out16_pitch >= d->C && d->out16_pitch % 8 == 0)),
              FV_E_ALIGN, "fv_mrf_fused: bad pitches");
@@ -660,10 +659,11 @@ extern "C" int fv_mrf_fused(const fv_mrf_desc* d, void* stream) {
     halo = h > halo ? h : halo;
     p.ksize[j] = k;
   }
+  const int tile_rows = tile_rows_for(d->C);
   p.h0 = round_up(halo, 32);
-  p.V = (kFrTile - p.h0 - halo) / 32 * 32;
+  p.V = (tile_rows - p.h0 - halo) / 32 * 32;
   FV_REQUIRE(p.V >= 32, FV_E_UNSUPPORTED, "fv_mrf_fused: receptive field (%d rows per side) too large for a %d-row tile",
-             halo, kFrTile);
+             halo, tile_rows);
   p.B = d->B;
   p.L = d->L;
   p.tiles_per_b = ceil_div(d->L, p.V);
@@ -678,23 +678,25 @@ extern "C" int fv_mrf_fused(const fv_mrf_desc* d, void* stream) {
   p.out_act = d->out_act;
   p.out_act_param = d->out_act_param;
   p.has_o16 = d->out16 != nullptr;
-  p.out_scale = 1.0f / (float)d->n_blocks;
+  p.out_scale = d->out_scale != 0.f ? d->out_scale : 1.0f / (float)d->n_blocks;
+  p.accumulate = d->accumulate ? 1 : 0;
+  p.use_ws = g_mrf_ws ? 1 : 0;
   cudaStream_t st = (cudaStream_t)stream;
   // C = 64: the residual stream + conv1 accumulator of a 512-row tile fill TMEM -> one CTA per SM, 16 epilogue warps;
-  // C = 32: two co-resident CTAs with 8 epilogue warps each (MMA of one overlaps the epilogue of the other)
-#define FV_MRF_DISPATCH(CC, EW, NCTA, PIPE)                                                          \
-  do {                                                                                                \
-    if (d->act == FV_ACT_SILU) return launch_mrf<CC, kActSilu, EW, NCTA, PIPE>(d, p, st);            \
-    if (d->act == FV_ACT_SILU_TANH) return launch_mrf<CC, kActSiluTanh, EW, NCTA, PIPE>(d, p, st);   \
-    return launch_mrf<CC, kActLeaky, EW, NCTA, PIPE>(d, p, st);                                      \
+  // C = 32 / 16: two co-resident CTAs with 8 epilogue warps each (MMA of one overlaps the epilogue of the other);
+  // C = 128: 256-row tiles (X + T = 512 TMEM columns), operand rows in two K halves, at most one pair (2 convs) per launch:
+  //          the host runs the stage pair by pair (halo <= 30 rows instead of 60 for the whole chain)
+#define FV_MRF_DISPATCH(CC, EW, NCTA, MB, MAXCONV)                                                            \
+  do {                                                                                                         \
+    if (d->act == FV_ACT_SILU) return launch_mrf<CC, kActSilu, EW, NCTA, MB, MAXCONV>(d, p, st);              \
+    if (d->act == FV_ACT_SILU_TANH) return launch_mrf<CC, kActSiluTanh, EW, NCTA, MB, MAXCONV>(d, p, st);     \
+    if (d->act == FV_ACT_SILU_H2) return launch_mrf<CC, kActSiluH2, EW, NCTA, MB, MAXCONV>(d, p, st);         \
+    return launch_mrf<CC, kActLeaky, EW, NCTA, MB, MAXCONV>(d, p, st);                                        \
   } while (0)
-  if (d->C == 64) {
-    if (g_mrf_pipe) FV_MRF_DISPATCH(64, 16, 1, true);
-    FV_MRF_DISPATCH(64, 16, 1, false);
-  }
-  if (d->C == 16) FV_MRF_DISPATCH(16, 8, 2, false);  // 32-byte operand rows, 16-column patches, two CTAs per SM
-  if (g_mrf_c32_ctas == 1) FV_MRF_DISPATCH(32, 16, 1, false);
-  if (g_mrf_pipe) FV_MRF_DISPATCH(32, 8, 2, true);
-  FV_MRF_DISPATCH(32, 8, 2, false);
+  if (d->C == 128) FV_MRF_DISPATCH(128, 16, 1, 2, 2);
+  if (d->C == 64) FV_MRF_DISPATCH(64, 16, 1, 4, kFrMaxConvs);
+  if (d->C == 16) FV_MRF_DISPATCH(16, 8, 2, 4, kFrMaxConvs);  // 32-byte operand rows, 16-column patches, two CTAs per SM
+  if (g_mrf_c32_ctas == 1) FV_MRF_DISPATCH(32, 16, 1, 4, kFrMaxConvs);
+  FV_MRF_DISPATCH(32, 8, 2, 4, kFrMaxConvs);
 #undef FV_MRF_DISPATCH
 }

@@ -318,14 +318,30 @@ __device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
   asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
   return d;
 }
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  unsigned long long ra, rb, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
 __device__ __forceinline__ float2 bc2(float f) { return make_float2(f, f); }
+// sin.approx.ftz: the non-ftz form pays an FSEL + ISETP pair per sine for subnormal arguments, whose sine is the argument
+// itself to 2^-126 either way
+__device__ __forceinline__ float sin_fast(float t) {
+  float r;
+  asm("sin.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t));
+  return r;
+}
 
 // x + sin^2(a x) / b for two channels.  sin.approx = one multiply by 1/(2 pi) + MUFU.SIN, which reduces the argument
 // itself: absolute error ~2^-21 inside [-2 pi, 2 pi] and ~1.2e-7 |t| beyond (rounding of the product), i.e. <= 2.5e-5 for
 // the |alpha * u| <= 200 a Snake sees - two orders below the parity budget and below the fp16 rounding of the output.
 __device__ __forceinline__ float2 snake_fn2(float2 u, float2 a, float2 inv_b) {
   const float2 t = fmul2(u, a);
-  const float2 sn = make_float2(__sinf(t.x), __sinf(t.y));
+  const float2 sn = make_float2(sin_fast(t.x), sin_fast(t.y));
   return ffma2(fmul2(inv_b, sn), sn, u);
 }
 
@@ -415,9 +431,14 @@ __device__ __forceinline__ void snake_segment(const float* __restrict__ xc, __ha
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
       const int t = tb + k;
-      float2 o = zero2;
+      // two independent partial sums (even / odd taps): dependent FFMA2 chains of 6 instead of 12
+      float2 oe = fmul2(V[(2 * k) % 12], bc2(f.dn[0])), oo = fmul2(V[(2 * k + 1) % 12], bc2(f.dn[1]));
 #pragma unroll
-      for (int j = 0; j < 12; ++j) o = ffma2(V[(2 * k + j) % 12], bc2(f.dn[j]), o);
+      for (int j = 2; j < 12; j += 2) {
+        oe = ffma2(V[(2 * k + j) % 12], bc2(f.dn[j]), oe);
+        oo = ffma2(V[(2 * k + j + 1) % 12], bc2(f.dn[j + 1]), oo);
+      }
+      const float2 o = fadd2(oe, oo);
       if (!EDGE || t < t_end) store_half2_split(po + (size_t)k * opitch, o, SPLIT ? split : 0);
       X[k] = xw[k];
       float2 uo = zero2, ue = zero2;

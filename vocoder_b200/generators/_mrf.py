@@ -167,23 +167,27 @@ class MRFGeneratorBase(nn.Module):
         raise NotImplementedError
 
     def _ensure_packed(self, device):
-        key = params_key(list(self.parameters()) + list(self.buffers())) + (self.fuse_mrf, self.engine)
+        key = params_key(list(self.parameters()) + list(self.buffers())) + (self.fuse_mrf, self.fuse_mrf_pairs, self.engine)
         if self._packed is not None and self._packed_key == key:
             return self._packed
         with torch.no_grad():
             with self._trunk_ctx():
                 P = {"pre": cabi.pack_conv(self.conv_pre.weight, self.conv_pre.bias), "ups": [], "blocks": [],
-                     "noise": [], "fused": []}
+                     "noise": [], "fused": [], "pairs": []}
             for i, up in enumerate(self.ups):
                 with self._trunk_ctx():
                     P["ups"].append(cabi.pack_conv_transpose(up.weight, up.bias, self.upsample_rates[i]))
                 blocks = []
                 mods = self._block_modules(i)
                 pairs = [(list(blk.convs1), list(blk.convs2)) for blk in mods]
-                fused = None
-                if (self.fuse_mrf and not self.snake_blocks and self.engine == cabi.ENGINE_TC
-                        and cabi.mrf_fusable(self.stage_channels[i], pairs)):
+                fused, fused_pairs = None, None
+                can_fuse = self.fuse_mrf and not self.snake_blocks and self.engine == cabi.ENGINE_TC
+                if can_fuse and cabi.mrf_fusable(self.stage_channels[i], pairs):
                     fused = cabi.pack_mrf(self.stage_channels[i], pairs)   # whole stage = one fv_mrf_fused launch
+                elif can_fuse and self.fuse_mrf_pairs and cabi.mrf_fusable(self.stage_channels[i], pairs, pairwise=True):
+                    # C = 128: one fv_mrf_fused launch per (conv, conv) pair (256-row tiles, pair halo <= 30 rows)
+                    fused_pairs = [[cabi.pack_mrf(self.stage_channels[i], [([c1], [c2])]) for c1, c2 in zip(c1s, c2s)]
+                                   for c1s, c2s in pairs]
                 else:
                     for blk in mods:
                         c1 = [cabi.pack_conv(c.weight, c.bias, c.dilation[0]) for c in blk.convs1]
@@ -191,6 +195,7 @@ class MRFGeneratorBase(nn.Module):
                         blocks.append((c1, c2, blk))
                 P["blocks"].append(blocks)
                 P["fused"].append(fused)
+                P["pairs"].append(fused_pairs)
             for nc in self.noise_convs:
                 P["noise"].append((nc.weight.detach().float().reshape(nc.out_channels, -1).contiguous(),
                                    nc.bias.detach().float().contiguous(), nc.kernel_size[0], nc.stride[0],
@@ -254,8 +259,36 @@ class MRFGeneratorBase(nn.Module):
                 h_next = ws.f16(f"h_{i}", B, Lo, C, dev)
                 out_act, out_act_p = self._stage_out_act(last_stage)
                 cabi.mrf_fused(x0, fused, acc, out16=h_next if out_act is not None else None,
-                               act=self._silu(),
+                               act=cabi.ACT_SILU_H2 if (self.mrf_silu_h2 and self.mrf_silu_tanh) else self._silu(),
                                out_act=out_act or cabi.ACT_NONE, out_act_param=out_act_p)
+                if last_stage:
+                    self._final_activation(acc, h_next, C, 0)
+                h16, L = h_next, Lo
+                continue
+            fpairs = P["pairs"][i]
+            if fpairs is not None:
+                # C = 128 SiLU stage, pair by pair on chip: x -> x + conv2(silu(conv1(silu(x)))) per launch, fp32 in / out;
+                # the last pair of every chain adds its chain's share of the MRF mean onto acc
+                cabi.conv1d(h16, up, Lo, residual=nz, out32=x0, engine=eng)
+                acc = ws.f32(f"acc_{i}", B, Lo, C, dev)
+                h_next = ws.f16(f"h_{i}", B, Lo, C, dev)
+                xp = (ws.f32(f"xp0_{i}", B, Lo, C, dev), ws.f32(f"xp1_{i}", B, Lo, C, dev))
+                out_act, out_act_p = self._stage_out_act(last_stage)
+                inner = cabi.ACT_SILU_H2 if (self.mrf_silu_h2 and self.mrf_silu_tanh) else self._silu()
+                nk = len(fpairs)
+                for j, chain in enumerate(fpairs):
+                    src = x0
+                    for p_i, pm in enumerate(chain):
+                        if p_i + 1 < len(chain):
+                            dst = xp[0] if src is not xp[0] else xp[1]
+                            cabi.mrf_fused(src, pm, dst, act=inner, out_scale=1.0)
+                            src = dst
+                        else:
+                            final = j == nk - 1
+                            cabi.mrf_fused(src, pm, acc, act=inner, accumulate=j > 0, out_scale=1.0 / nk,
+                                           out16=h_next if (final and out_act is not None) else None,
+                                           out_act=(out_act or cabi.ACT_NONE) if final else cabi.ACT_NONE,
+                                           out_act_param=out_act_p)
                 if last_stage:
                     self._final_activation(acc, h_next, C, 0)
                 h16, L = h_next, Lo
@@ -321,6 +354,8 @@ class MRFGeneratorBase(nn.Module):
 
     #: C <= 64 SiLU stages as one on-chip kernel per stage (fv_mrf_fused); False = layer-wise fv_conv1d launches
     fuse_mrf = True
+    #: C = 128 SiLU stages as one on-chip kernel per (conv, conv) pair (needs fuse_mrf); False = layer-wise launches
+    fuse_mrf_pairs = True
     def _silu(self) -> int:
         return cabi.ACT_SILU_TANH if self.mrf_silu_tanh else cabi.ACT_SILU
 
@@ -329,6 +364,9 @@ class MRFGeneratorBase(nn.Module):
     #: 5.8e-5 vs 4.3e-5 (ex2 + rcp) against the fp64 contract, waveform error of the full-width stress model unchanged
     #: (8.1e-5 both); False selects the ex2 + rcp form.
     mrf_silu_tanh = True
+    #: inner SiLU of the fused stages on packed fp16 pairs (FV_ACT_SILU_H2: one SFU op per two channels, ~3 fp16 roundings in
+    #: the operand instead of 1).  Opt-in until measured: see DESIGN.md section 4.2.
+    mrf_silu_h2 = False
 
     #: utterances per residual-block pass; None = whole batch; 0 = size the block working set for L2 (_micro_batch)
     micro_batch = None
