@@ -77,23 +77,23 @@ def test_snake_edge_modes(mode, kind, logscale):
 
 def test_bigvgan_edge_mode_generator_level():
     """BigVGANGenerator.aa_edge_mode reaches every anti-aliased activation: the waveform follows the oracle evaluated with
-    the same mode and differs from the default mode only near the two ends of the sequence."""
+    the same mode and differs from the default mode only within the receptive field of the two sequence ends."""
     kwargs, sd, ins, out, extra = load_golden("bigvgan_small_stress")
     m = build_module("bigvgan_small_stress", kwargs)
     m.load_state_dict(sd)
     m = m.eval().cuda()
     _set_precision(m, "strict")
+    mel = torch.empty(1, kwargs["num_mels"], 160).uniform_(-11.5129, 2.0, generator=torch.Generator().manual_seed(9))
     with torch.no_grad():
-        base = m(ins["mel"].cuda()).cpu()
+        base = m(mel.cuda()).cpu()
         for mode in ("reflect", "zero"):
             m.aa_edge_mode = mode
-            y = m(ins["mel"].cuda()).cpu()
-            want = G.bigvgan_forward(sd, ins["mel"], kwargs["upsample_rates"], kwargs["resblock_dilation_sizes"],
-                                     edge_mode=mode)
+            y = m(mel.cuda()).cpu()
+            want = G.bigvgan_forward(sd, mel, kwargs["upsample_rates"], kwargs["resblock_dilation_sizes"], edge_mode=mode)
             assert float((y - want).abs().max()) <= 2e-4, mode
             assert float((y - base).abs().max()) > 1e-4          # the mode matters at the edges ...
             mid = y.shape[-1] // 2
-            assert float((y - base)[..., mid - 8:mid + 8].abs().max()) <= 1e-4   # ... and only there
+            assert float((y - base)[..., mid - 256:mid + 256].abs().max()) <= 1e-5   # ... and only there
 
 
 # ------------------------------------------------------------------------------------------------

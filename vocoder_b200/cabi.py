@@ -599,8 +599,8 @@ def mrf_fusable(C: int, blocks, pairwise: bool = False) -> bool:
     """blocks: [(convs1, convs2)] of nn.Conv1d-like modules.  True when fv_mrf_fused covers the stage: as one launch for
     C in {16, 32, 64}; pairwise=True asks whether every (conv, conv) pair can be its own launch (C = 128)."""
     if pairwise:
-        return C == 128 and all(_mrf_fusable(C, [([c1], [c2])], _tile=256, _chans=(128,))
-                                for c1s, c2s in blocks for c1, c2 in zip(c1s, c2s)) and len(blocks) >= 1
+        return C in (64, 128) and len(blocks) >= 1 and all(
+            _mrf_fusable(C, [([c1], [c2])], _tile=256, _chans=(64, 128)) for c1s, c2s in blocks for c1, c2 in zip(c1s, c2s))
     return _mrf_fusable(C, blocks)
 
 

@@ -1102,7 +1102,20 @@ int conv1d_tc(const fv_conv_desc* d, cudaStream_t stream, int block_n_override, 
     p.use_pair = (d->a_split == 0 && !p.use_slab) ? pair_mask : 0;
   }
 
-  const int bn = block_n_override ? block_n_override : pick_block_n(d->C_out, d->C_out_pad);
+  int bn = block_n_override ? block_n_override : pick_block_n(d->C_out, d->C_out_pad);
+  if (!block_n_override && bn >= 128 && d->a_split == 0) {
+    // short sequences at small batch (test.py runs B = 1-2): a 256-wide tile leaves most SMs idle (C = 256, L = 752, B = 1:
+    // 3 pair tiles on 148 SMs).  Narrow the N tile until the launch has at least a quarter wave of tiles.
+    static const bool split_n = [] {
+      const char* e = getenv("FV_TC_SPLITN");  // FV_TC_SPLITN=0 disables (A/B measurements)
+      return !(e && e[0] == '0');
+    }();
+    auto tiles_for = [&](int n) {
+      const long long rows = (n == 256) ? 256 : (p.q_rows > 128 ? 256 : 128);
+      return (long long)ceil_div(p.q_rows, (int)rows) * ceil_div(d->C_out, n) * d->B * d->n_phase;
+    };
+    while (split_n && bn > 64 && tiles_for(bn) * 4 < num_sms() && (d->C_out % (bn / 2)) == 0) bn /= 2;
+  }
   // two 128-row accumulators per CTA share every weight tile; a single one when the sequence is short
   int m_sub = m_sub_override ? m_sub_override : ((p.q_rows > 128 && bn < 256) ? 2 : 1);
   if (bn == 256) m_sub = 1;  // two 256-column accumulators do not leave room for a pipelined smem ring

@@ -565,14 +565,27 @@ static const int g_mrf_c32_ctas = [] {
   return (e && e[0] == '1') ? 1 : 2;
 }();
 
-// FV_MRF_WS=1: weight-stationary MMAs for the C = 64 stage (see MrfParams::use_ws); A/B measurement switch
+// Weight-stationary MMAs for the C = 64 whole-stage configuration (see MrfParams::use_ws): measured on B200 (HiFiGAN cfg B,
+// C = 64, L = 12032, B = 64) 1.640 -> 1.556 ms with bit-identical results.  FV_MRF_WS=0 disables (A/B measurements).
 static const bool g_mrf_ws = [] {
   const char* e = getenv("FV_MRF_WS");
-  return e && e[0] == '1';
+  return !(e && e[0] == '0');
 }();
 
-// rows per tile for a channel count (what FrCfg<C, ..., MB> is instantiated with below)
-static int tile_rows_for(int C) { return C == 128 ? 256 : 512; }
+// FV_MRF_C64_PAIR=0: single-pair C = 64 launches use the whole-stage configuration (512-row tiles, one CTA per SM) instead
+// of the pair configuration (256-row tiles, two co-resident CTAs); A/B measurement switch
+static const bool g_mrf_c64_pair = [] {
+  const char* e = getenv("FV_MRF_C64_PAIR");
+  return !(e && e[0] == '0');
+}();
+
+// pair configuration: 256-row tiles (MB = 2), at most one (conv, conv) pair per launch.  Always for C = 128 (X + T fill
+// TMEM with 256 rows); for C = 64 when the launch IS a single pair: 256 TMEM columns and < 113 KB per CTA, so two CTAs
+// share an SM and the MMAs of one overlap the epilogue / entry / exit of the other.
+static bool pair_config(const fv_mrf_desc* d) {
+  return d->C == 128 || (d->C == 64 && d->n_blocks == 1 && d->n_pairs == 1 && g_mrf_c64_pair);
+}
+static int tile_rows_for(const fv_mrf_desc* d) { return pair_config(d) ? 256 : 512; }
 
 template <int C, int ACT, int EW, int NCTA, int MB, int MAXCONV>
 static int launch_mrf(const fv_mrf_desc* d, MrfParams& p, cudaStream_t stream) {
@@ -659,7 +672,7 @@ extern "C" int fv_mrf_fused(const fv_mrf_desc* d, void* stream) {
     halo = h > halo ? h : halo;
     p.ksize[j] = k;
   }
-  const int tile_rows = tile_rows_for(d->C);
+  const int tile_rows = tile_rows_for(d);
   p.h0 = round_up(halo, 32);
   p.V = (tile_rows - p.h0 - halo) / 32 * 32;
   FV_REQUIRE(p.V >= 32, FV_E_UNSUPPORTED, "fv_mrf_fused: receptive field (%d rows per side) too large for a %d-row tile",
@@ -694,6 +707,7 @@ extern "C" int fv_mrf_fused(const fv_mrf_desc* d, void* stream) {
     return launch_mrf<CC, kActLeaky, EW, NCTA, MB, MAXCONV>(d, p, st);                                        \
   } while (0)
   if (d->C == 128) FV_MRF_DISPATCH(128, 16, 1, 2, 2);
+  if (d->C == 64 && pair_config(d)) FV_MRF_DISPATCH(64, 8, 2, 2, 2);
   if (d->C == 64) FV_MRF_DISPATCH(64, 16, 1, 4, kFrMaxConvs);
   if (d->C == 16) FV_MRF_DISPATCH(16, 8, 2, 4, kFrMaxConvs);  // 32-byte operand rows, 16-column patches, two CTAs per SM
   if (g_mrf_c32_ctas == 1) FV_MRF_DISPATCH(32, 16, 1, 4, kFrMaxConvs);

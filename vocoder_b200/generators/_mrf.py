@@ -167,7 +167,8 @@ class MRFGeneratorBase(nn.Module):
         raise NotImplementedError
 
     def _ensure_packed(self, device):
-        key = params_key(list(self.parameters()) + list(self.buffers())) + (self.fuse_mrf, self.fuse_mrf_pairs, self.engine)
+        key = params_key(list(self.parameters()) + list(self.buffers())) + (
+            self.fuse_mrf, self.fuse_mrf_pairs, tuple(self.mrf_pairwise_channels), self.engine)
         if self._packed is not None and self._packed_key == key:
             return self._packed
         with torch.no_grad():
@@ -182,7 +183,12 @@ class MRFGeneratorBase(nn.Module):
                 pairs = [(list(blk.convs1), list(blk.convs2)) for blk in mods]
                 fused, fused_pairs = None, None
                 can_fuse = self.fuse_mrf and not self.snake_blocks and self.engine == cabi.ENGINE_TC
-                if can_fuse and cabi.mrf_fusable(self.stage_channels[i], pairs):
+                Ci = self.stage_channels[i]
+                if (can_fuse and Ci in self.mrf_pairwise_channels and Ci != 128
+                        and cabi.mrf_fusable(Ci, pairs, pairwise=True)):
+                    # opt-in: a C = 64 stage pair by pair as well (two co-resident CTAs per SM overlap MMA and epilogue)
+                    fused_pairs = [[cabi.pack_mrf(Ci, [([c1], [c2])]) for c1, c2 in zip(c1s, c2s)] for c1s, c2s in pairs]
+                elif can_fuse and cabi.mrf_fusable(self.stage_channels[i], pairs):
                     fused = cabi.pack_mrf(self.stage_channels[i], pairs)   # whole stage = one fv_mrf_fused launch
                 elif can_fuse and self.fuse_mrf_pairs and cabi.mrf_fusable(self.stage_channels[i], pairs, pairwise=True):
                     # C = 128: one fv_mrf_fused launch per (conv, conv) pair (256-row tiles, pair halo <= 30 rows)
@@ -354,8 +360,15 @@ class MRFGeneratorBase(nn.Module):
 
     #: C <= 64 SiLU stages as one on-chip kernel per stage (fv_mrf_fused); False = layer-wise fv_conv1d launches
     fuse_mrf = True
-    #: C = 128 SiLU stages as one on-chip kernel per (conv, conv) pair (needs fuse_mrf); False = layer-wise launches
-    fuse_mrf_pairs = True
+    #: C = 128 SiLU stages as one on-chip kernel per (conv, conv) pair (needs fuse_mrf); False = layer-wise launches.
+    #: Measured on B200 (HiFiGAN cfg B, C = 128, L = 6016, B = 64): 2.42 ms pair-wise against 2.0 ms layer-wise - an N = 128
+    #: UMMA costs ~97 cycles whatever feeds it, the 256-row tiles recompute 25% halo, and with TMEM full (X + T) one CTA per
+    #: SM cannot overlap its epilogue / entry / exit with MMAs the way the layer-wise kernel's double-buffered
+    #: accumulators do.  Off by default; kept for sequences too short to fill the layer-wise kernels.
+    fuse_mrf_pairs = False
+    #: channel counts (besides 128) whose stage runs pair by pair instead of as one whole-stage launch; (64,) trades ~7x the
+    #: stage's HBM traffic for MMA / epilogue overlap between two co-resident CTAs.  Measured: see DESIGN.md section 4.2.
+    mrf_pairwise_channels = ()
     def _silu(self) -> int:
         return cabi.ACT_SILU_TANH if self.mrf_silu_tanh else cabi.ACT_SILU
 

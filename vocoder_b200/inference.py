@@ -211,7 +211,7 @@ def main(argv=None) -> int:
                     help="directory of <name>.pt/.npy templates [1, T*hop] for generators built with use_template=True")
     args = ap.parse_args(argv)
     dev = torch.device(args.device)
-    if dev.type == "cuda":
+    if dev.type == "cuda" and dev.index is not None:
         torch.cuda.set_device(dev)  # kernels launch on the current device's stream
     with open(args.config) as f:
         cfg = yaml.safe_load(f)
