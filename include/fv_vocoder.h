@@ -250,9 +250,14 @@ FV_API int fv_mrf_fused(const fv_mrf_desc* d, void* stream);
 FV_API int fv_debug_rowshift_probe(const void* a16, const void* w16, float* out, void* stream);
 
 /* bring-up probe (not on the product path): SM cycles per tcgen05.mma (M = 128 per CTA, K = 16, fp16) with resident
- * operands.  mode 0 = SS cta_group::1, 1 = SS cta_group::2 (CTA pair, M = 256), 2 = A from TMEM; n = UMMA N; bg = background
+ * operands.  mode 0 = SS cta_group::1, 1 = SS cta_group::2 (CTA pair, M = 256), 2 = A from TMEM, 3 = SS weight-stationary
+ * (tcgen05.mma.ws); n = UMMA N; bg = background
  * shared-memory traffic of 8 other warps (0 none, 1 stores, 2 loads).  out[cta] = cycles per UMMA x 1000. */
 FV_API int fv_debug_umma_rate(int mode, int n, int reps, int bg, int* out, void* stream);
+/* bring-up probe: fp32 FMA throughput of the CUDA cores (the roofline of fv_snake_aa).  variant 0 = scalar fma, three register
+ * operands; 1 = scalar fma with a kernel-constant multiplier; 2 = packed fma.rn.f32x2.  Every thread of num_sms x 8 x 256
+ * runs `iters` x 16 dependent-chain FMAs over 8 independent chains; out[1] = elapsed SM cycles of block 0. */
+FV_API int fv_debug_fma_rate(int variant, int iters, float* sink, long long* out, void* stream);
 
 #ifdef __cplusplus
 }

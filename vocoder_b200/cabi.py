@@ -29,7 +29,7 @@ EXPORTS = [
     "fv_set_tc_tuning", "fv_pack_input", "fv_unpack_output", "fv_conv_post_tanh", "fv_snake_aa",
     "fv_dwconv_layernorm", "fv_istft_ola", "fv_noise_conv", "fv_act_cast", "fv_resample_linear",
     "fv_mrf_fused", "fv_frame_audio", "fv_spec_mag", "fv_log_mel_out", "fv_debug_rowshift_probe",
-    "fv_debug_umma_rate",
+    "fv_debug_umma_rate", "fv_debug_fma_rate",
 ]
 MRF_MAX_BLOCKS, MRF_MAX_PAIRS, MRF_MAX_REACH = 4, 4, 32
 
@@ -111,6 +111,7 @@ def lib() -> ctypes.CDLL:
     L.fv_log_mel_out.argtypes = [vp, vp, ci, ci, ci, ci, cf, vp]
     L.fv_debug_rowshift_probe.argtypes = [vp, vp, vp, vp]
     L.fv_debug_umma_rate.argtypes = [ci, ci, ci, ci, vp, vp]
+    L.fv_debug_fma_rate.argtypes = [ci, ci, vp, vp, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("fv_last_error", "fv_launch_count", "fv_reset_launch_count", "fv_set_tc_tuning"):

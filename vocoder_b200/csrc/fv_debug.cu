@@ -191,6 +191,11 @@ __global__ void __launch_bounds__(320, 1) umma_rate_kernel(const RateParams p) {
       const long long t1 = clock64();
       p.out[blockIdx.x] = (int)((t1 - t0) * 1000 / ((long long)p.reps * blocks * 4));
       *stop = 1;
+    } else if (PAIR && rank != 0 && lane == 0) {
+      // the leader's commit is multicast to this CTA's barrier as well: release this CTA's background warps
+      while (!mbar_try_wait(&bar[0], 0)) {
+      }
+      *stop = 1;
     }
     __syncwarp();
   } else if (warp >= 2 && p.bg != 0) {
@@ -218,6 +223,50 @@ __global__ void __launch_bounds__(320, 1) umma_rate_kernel(const RateParams p) {
     if constexpr (PAIR) tmem_dealloc_pair(tmem_base, 512);
     else tmem_dealloc(tmem_base, 512);
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fv_debug_fma_rate: fp32 FMA throughput of the CUDA cores, the roofline of the anti-aliased Snake kernel (26 filter FMAs +
+// 4 activation FMAs per sample, no tensor-core form: SURVEY B4).  Every thread runs 8 independent accumulator chains:
+//   variant 0: scalar fma.rn.f32, all three operands in registers        variant 1: scalar, multiplier a kernel constant
+//   variant 2: packed fma.rn.f32x2 (two fp32 lanes per instruction), multiplier a broadcast kernel constant
+// out[0] = FMAs executed (lanes x 2 for the packed form), out[1] = elapsed SM cycles of block 0.
+// ------------------------------------------------------------------------------------------------
+template <int VARIANT>
+__global__ void __launch_bounds__(256) fma_rate_kernel(float* sink, long long* out, int iters, float m0, float m1) {
+  float a[8], b[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    a[i] = threadIdx.x * 1e-3f + i;
+    b[i] = 1.0f + i * 1e-3f;
+  }
+  float mv = m0 + threadIdx.x * 0.f;  // a register copy of the multiplier for the 3-register form
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if constexpr (VARIANT == 0) {
+        a[i] = fmaf(a[i], mv, b[i]);
+        b[i] = fmaf(b[i], mv, a[i]);
+      } else if constexpr (VARIANT == 1) {
+        a[i] = fmaf(a[i], m0, b[i]);
+        b[i] = fmaf(b[i], m1, a[i]);
+      } else {
+        unsigned long long ra, rb, rm;
+        asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a[i]), "f"(b[i]));
+        asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b[i]), "f"(a[i]));
+        asm("mov.b64 %0, {%1, %1};" : "=l"(rm) : "f"(m0));
+        asm("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(ra) : "l"(rm), "l"(rb));
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(a[i]), "=f"(b[i]) : "l"(ra));
+      }
+    }
+  }
+  const long long t1 = clock64();
+  float acc = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc += a[i] + b[i];
+  if (acc == 1.2345e-30f) sink[0] = acc;
+  if (blockIdx.x == 0 && threadIdx.x == 0) out[1] = t1 - t0;
 }
 
 }  // namespace fv
@@ -281,5 +330,16 @@ extern "C" int fv_debug_umma_rate(int mode, int n, int reps, int bg, int* out, v
   int rc = check_cuda(e, "umma_rate_kernel");
   if (rc) return rc;
   FV_CHECK_LAUNCH("umma_rate_kernel");
+  return 0;
+}
+
+extern "C" int fv_debug_fma_rate(int variant, int iters, float* sink, long long* out, void* stream) {
+  FV_REQUIRE(sink && out && variant >= 0 && variant <= 2 && iters > 0, FV_E_BADARG, "fv_debug_fma_rate: bad arguments");
+  const int blocks = num_sms() * 8;  // 8 x 256 threads per SM = full occupancy at <= 32 registers
+  const float m0 = 0.999f, m1 = 1.001f;
+  if (variant == 0) fma_rate_kernel<0><<<blocks, 256, 0, (cudaStream_t)stream>>>(sink, out, iters, m0, m1);
+  else if (variant == 1) fma_rate_kernel<1><<<blocks, 256, 0, (cudaStream_t)stream>>>(sink, out, iters, m0, m1);
+  else fma_rate_kernel<2><<<blocks, 256, 0, (cudaStream_t)stream>>>(sink, out, iters, m0, m1);
+  FV_CHECK_LAUNCH("fma_rate_kernel");
   return 0;
 }
