@@ -1105,10 +1105,12 @@ int conv1d_tc(const fv_conv_desc* d, cudaStream_t stream, int block_n_override, 
   int bn = block_n_override ? block_n_override : pick_block_n(d->C_out, d->C_out_pad);
   if (!block_n_override && bn >= 128 && d->a_split == 0) {
     // short sequences at small batch (test.py runs B = 1-2): a 256-wide tile leaves most SMs idle (C = 256, L = 752, B = 1:
-    // 3 pair tiles on 148 SMs).  Narrow the N tile until the launch has at least a quarter wave of tiles.
+    // 3 pair tiles on 148 SMs).  FV_TC_SPLITN=1 narrows the N tile until the launch has at least a quarter wave of tiles.
+    // Measured on B200 (hifigan_b1, CUDA-graph replay): 0.832 ms without, 0.890 ms with - every narrower tile re-reads the
+    // operand and a 64-wide UMMA costs 69 cycles against 161 for four times the columns - so it stays opt-in.
     static const bool split_n = [] {
-      const char* e = getenv("FV_TC_SPLITN");  // FV_TC_SPLITN=0 disables (A/B measurements)
-      return !(e && e[0] == '0');
+      const char* e = getenv("FV_TC_SPLITN");
+      return e && e[0] == '1';
     }();
     auto tiles_for = [&](int n) {
       const long long rows = (n == 256) ? 256 : (p.q_rows > 128 ? 256 : 128);

@@ -363,14 +363,34 @@ __device__ __forceinline__ void store_half2_split(__half* dst, float2 v, int spl
 // compile-time registers): per sample pair one 8-byte load, 24 FFMA2, 4 SFU sines and one 4-byte store; six "pre-roll"
 // steps fill the rings.  Loads run one 6-step window ahead of the math (software pipeline).
 // EDGE = false is the interior fast path (no index clamps, no replicate logic, pointer increments only).
-template <bool EDGE, bool SPLIT>
+// RING = true: the look-ahead loads go through a per-thread shared-memory ring filled by cp.async (18 slots of 8 bytes, two
+// 6-step windows in flight) instead of 12 prefetch registers: deeper latency cover with fewer registers, so three blocks
+// fit an SM.  `ring` = this thread's slot 0 (slot stride = blockDim.x float2, i.e. every warp access is 256 contiguous bytes).
+template <bool EDGE, bool SPLIT, bool RING = false>
 __device__ __forceinline__ void snake_segment(const float* __restrict__ xc, __half* __restrict__ orow,
                                               const SnakeFilt& f, float2 a, float2 inv_b, int t0, int t_end, int L,
-                                              int pitch, int opitch, int split) {
+                                              int pitch, int opitch, int split, float2* ring = nullptr,
+                                              int ring_stride = 0) {
   const int nl = 2 * L - 1;
   auto ldx = [&](int t) {
     if (EDGE) t = t < 0 ? 0 : (t > L - 1 ? L - 1 : t);  // replicate edge of the INPUT (first filter pads its own input)
     return *reinterpret_cast<const float2*>(xc + (size_t)t * pitch);
+  };
+  // ring: window w (steps t0 + 6 w + 6 .. + 11) lives in slots (w % 3) * 6 + k
+  auto ring_issue = [&](int w) {
+    if constexpr (RING) {
+      const int tw = t0 + 6 * w + 6;
+      if (tw < t_end + 6) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          int t = tw + k;
+          if (EDGE) t = t < 0 ? 0 : (t > L - 1 ? L - 1 : t);  // (interior segments: only needed windows are issued)
+          const uint32_t dst = smem_u32(ring + (size_t)((w % 3) * 6 + k) * ring_stride);
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(xc + (size_t)t * pitch) : "memory");
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
   };
   const float2 zero2 = make_float2(0.f, 0.f);
   float2 X[6];   // ring: x~[t+6-q] lives in X[(k - q) mod 6] at unrolled position k
@@ -386,12 +406,17 @@ __device__ __forceinline__ void snake_segment(const float* __restrict__ xc, __ha
   // ... and so is the first main-loop window x~[t0+6 .. t0+11]
   float2 xn[6];
   const float* px = xc + (size_t)(t0 + 6) * pitch;  // interior path: running pointers instead of index math
+  if constexpr (RING) {
+    ring_issue(0);
+    ring_issue(1);
+  } else {
 #pragma unroll
-  for (int k = 0; k < 6; ++k) {
-    if (EDGE) xn[k] = ldx(t0 + k + 6);
-    else xn[k] = *reinterpret_cast<const float2*>(px + (size_t)k * pitch);
+    for (int k = 0; k < 6; ++k) {
+      if (EDGE) xn[k] = ldx(t0 + k + 6);
+      else xn[k] = *reinterpret_cast<const float2*>(px + (size_t)k * pitch);
+    }
+    px += (size_t)6 * pitch;
   }
-  px += (size_t)6 * pitch;
 #pragma unroll
   for (int k = 0; k < 6; ++k) {  // pre-roll: t = t0 - 6 + k produces v[2t0-5+2k], v[2t0-4+2k]
     const int t = t0 - 6 + k;
@@ -416,17 +441,25 @@ __device__ __forceinline__ void snake_segment(const float* __restrict__ xc, __ha
     for (int j = 0; j < 5; ++j) V[j] = V[5];
   }
   __half* po = orow + (size_t)t0 * opitch;
-  for (int tb = t0; tb < t_end; tb += 6) {
+  int w = 0;
+  for (int tb = t0; tb < t_end; tb += 6, ++w) {
     float2 xw[6];
+    if constexpr (RING) {
+      asm volatile("cp.async.wait_group 1;" ::: "memory");  // window w has landed (window w + 1 may still be in flight)
 #pragma unroll
-    for (int k = 0; k < 6; ++k) xw[k] = xn[k];
-    if (tb + 6 < t_end) {  // next window: six independent loads in flight under this window's math
+      for (int k = 0; k < 6; ++k) xw[k] = ring[(size_t)((w % 3) * 6 + k) * ring_stride];
+      ring_issue(w + 2);  // into the slots window w - 1 was read from in the previous iteration
+    } else {
 #pragma unroll
-      for (int k = 0; k < 6; ++k) {
-        if (EDGE) xn[k] = ldx(tb + k + 12);
-        else xn[k] = *reinterpret_cast<const float2*>(px + (size_t)k * pitch);
+      for (int k = 0; k < 6; ++k) xw[k] = xn[k];
+      if (tb + 6 < t_end) {  // next window: six independent loads in flight under this window's math
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          if (EDGE) xn[k] = ldx(tb + k + 12);
+          else xn[k] = *reinterpret_cast<const float2*>(px + (size_t)k * pitch);
+        }
+        px += (size_t)6 * pitch;
       }
-      px += (size_t)6 * pitch;
     }
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
@@ -498,6 +531,45 @@ __global__ void __launch_bounds__(256, SN_BLOCKS) snake_aa_kernel(const float* _
   const bool interior = (t0 >= 6) && (t0 + seg_len + 6 <= L - 1);
   if (interior) snake_segment<false, SPLIT>(xc, orow, f, a, inv_b, t0, t_end, L, pitch, opitch, split);
   else snake_segment<true, SPLIT>(xc, orow, f, a, inv_b, t0, t_end, L, pitch, opitch, split);
+}
+
+// The same kernel with the look-ahead in a shared-memory ring (see snake_segment<..., RING = true>): three blocks per SM.
+constexpr int SN_RING_BLOCKS = 3;
+constexpr int SN_RING_SLOTS = 18;
+__global__ void __launch_bounds__(256, SN_RING_BLOCKS)
+    snake_aa_ring_kernel(const float* __restrict__ x, __half* __restrict__ out, const float* __restrict__ alpha,
+                         const float* __restrict__ beta, const SnakeFilt f, int logscale, int B, int L, int C, int pitch,
+                         int n_seg, int seg_len) {
+  pdl_launch_dependents();
+  pdl_wait();
+  extern __shared__ float2 s_ring[];  // [SN_RING_SLOTS][256]
+  const int hp = pitch >> 1;
+  const long long total = (long long)B * n_seg * hp;
+  const long long item = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (item >= total) return;
+  const int c = 2 * (int)(item % hp);
+  const int seg = (int)((item / hp) % n_seg);
+  const int b = (int)(item / ((long long)hp * n_seg));
+  const int t0 = seg * seg_len;
+  const int t_end = min(t0 + seg_len, L);
+  __half* orow = out + ((size_t)b * L) * pitch + c;
+  if (c >= C) {  // padded channels stay zero
+    for (int t = t0; t < t_end; ++t) store_half2_split(orow + (size_t)t * pitch, make_float2(0.f, 0.f), 0);
+    return;
+  }
+  const int c1 = c + 1 < C ? c + 1 : c;
+  float2 a = make_float2(alpha[c], alpha[c1]);
+  float2 bb = beta ? make_float2(beta[c], beta[c1]) : a;
+  if (logscale) {
+    a = make_float2(expf(a.x), expf(a.y));
+    bb = make_float2(expf(bb.x), expf(bb.y));
+  }
+  const float2 inv_b = make_float2(1.0f / (bb.x + 1e-9f), 1.0f / (bb.y + 1e-9f));
+  const float* xc = x + ((size_t)b * L) * pitch + c;
+  float2* ring = s_ring + threadIdx.x;
+  const bool interior = (t0 >= 6) && (t0 + seg_len + 6 <= L - 1);
+  if (interior) snake_segment<false, false, true>(xc, orow, f, a, inv_b, t0, t_end, L, pitch, pitch, 0, ring, 256);
+  else snake_segment<true, false, true>(xc, orow, f, a, inv_b, t0, t_end, L, pitch, pitch, 0, ring, 256);
 }
 
 // Edge modes other than `replicate` (FV_EDGE_REFLECT / FV_EDGE_ZERO: what another release of alias_free_torch may pad
@@ -1066,9 +1138,15 @@ extern "C" int fv_snake_aa(const float* x32, void* out16, const float* alpha, co
   // Segment length: every thread does the same amount of work, so the grid runs in whole waves of SN_BLOCKS x 256 threads per
   // SM and a launch of 3.1 waves costs 4.  Pick the multiple of 6 in [36, 96] with the best (work / waves) ratio,
   // counting the 6 pre-roll steps every segment pays.
+  // FV_SNAKE_RING=1: the shared-memory-ring variant (three blocks per SM); A/B measurement switch
+  static const bool ring_on = [] {
+    const char* e = getenv("FV_SNAKE_RING");
+    return e && e[0] == '1';
+  }();
+  const bool use_ring = ring_on && split == 0;
   int seg_len = 48;
   {
-    const long long per_wave = (long long)num_sms() * SN_BLOCKS * 256;
+    const long long per_wave = (long long)num_sms() * (use_ring ? SN_RING_BLOCKS : SN_BLOCKS) * 256;
     double best = -1.0;
     for (int sl = SN_SEG_MIN; sl <= SN_SEG_MAX; sl += 6) {
       const long long thr = (long long)B * ceil_div(L, sl) * (pitch / 2);
@@ -1082,6 +1160,14 @@ extern "C" int fv_snake_aa(const float* x32, void* out16, const float* alpha, co
   }
   const int n_seg = ceil_div(L, seg_len);
   const long long total = (long long)B * n_seg * (pitch / 2);
+  if (use_ring) {
+    const int smem = SN_RING_SLOTS * 256 * (int)sizeof(float2);
+    FV_REQUIRE(launch_kernel(snake_aa_ring_kernel, dim3(grid1d(total, 256)), dim3(256), smem, (cudaStream_t)stream, 1, x32,
+                             (__half*)out16, alpha, beta, f, logscale, B, L, C, pitch, n_seg, seg_len) == cudaSuccess,
+               FV_E_DRIVER, "launch of snake_aa_ring_kernel failed");
+    FV_CHECK_LAUNCH("snake_aa_ring_kernel");
+    return 0;
+  }
   if (split)  // strict precision: [hi | lo] fp16 pairs (the extra stores stay out of the default instantiation)
     FV_REQUIRE(launch_kernel(snake_aa_kernel<true>, dim3(grid1d(total, 256)), dim3(256), 0, (cudaStream_t)stream, 1, x32,
                              (__half*)out16, alpha, beta, f, logscale, B, L, C, pitch, n_seg, seg_len,
