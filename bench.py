@@ -389,6 +389,8 @@ def run_workload(name, args, dev, rank, world, barrier, all_max, *, full: bool):
             m.fuse_mrf = False
         if args.no_fuse_pairs and hasattr(m, "fuse_mrf_pairs"):
             m.fuse_mrf_pairs = False
+        if args.fuse_pairs and hasattr(m, "fuse_mrf_pairs"):
+            m.fuse_mrf_pairs = True
         if args.pairwise_c64 and hasattr(m, "mrf_pairwise_channels"):
             m.mrf_pairwise_channels = (64,)
         if args.mrf_silu_h2 and hasattr(m, "mrf_silu_h2"):
@@ -602,7 +604,8 @@ def main():
     ap.add_argument("--no-sustained", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-fuse-mrf", action="store_true", help="layer-wise fv_conv1d launches instead of fv_mrf_fused")
-    ap.add_argument("--no-fuse-pairs", action="store_true", help="layer-wise C = 128 stage instead of pair-wise fv_mrf_fused")
+    ap.add_argument("--no-fuse-pairs", action="store_true", help="always layer-wise C = 128 stage (default: auto by rows)")
+    ap.add_argument("--fuse-pairs", action="store_true", help="always pair-wise fv_mrf_fused for the C = 128 stage")
     ap.add_argument("--pairwise-c64", action="store_true", help="C = 64 stage pair by pair (two co-resident CTAs per SM)")
     ap.add_argument("--mrf-silu-h2", action="store_true", help="packed fp16x2 SiLU inside fv_mrf_fused (FV_ACT_SILU_H2)")
     ap.add_argument("--no-fuse-snake", action="store_true", help="standalone fv_snake_aa launches instead of fv_snake_conv")

@@ -380,7 +380,7 @@ def test_full_width_stress_hifigan_vs_oracle(variant):
     want = _oracle_full("hifigan", m, mel)
     m = m.cuda()
     m.fuse_mrf = variant != "layerwise"
-    m.fuse_mrf_pairs = variant != "no_pair_fusion"
+    m.fuse_mrf_pairs = variant != "no_pair_fusion"   # True forces the pair-wise C = 128 stage, False the layer-wise one
     m.mrf_silu_tanh = variant in ("fused_silu_tanh", "fused_silu_h2", "no_pair_fusion")
     m.mrf_silu_h2 = variant == "fused_silu_h2"
     with torch.no_grad():
@@ -418,7 +418,7 @@ def test_five_stage_hifigan_fused_c16_vs_oracle_and_layerwise():
     assert fused.shape == want.shape == (2, 1, 11 * 512)
     # three stages (C = 64, 32, 16) collapse from 18 conv launches to one each (+ the C = 128 stage to one launch per conv
     # pair when fuse_mrf_pairs is on)
-    assert n_layer - n_fused == 3 * (18 - 1) + ((18 - 9) if m.fuse_mrf_pairs else 0)
+    assert n_layer - n_fused == 3 * (18 - 1) + (18 - 9)   # "auto": 2 x 704 rows -> the pair-wise path
     peak = max(1.0, float(want.abs().max()))
     e_f, e_l = float((fused - want).abs().max()), float((layer - want).abs().max())
     print(f"5-stage stress hifigan: fused {e_f:.3e}, layer-wise {e_l:.3e} vs fp32 oracle (peak {peak:.3f})")

@@ -8,12 +8,12 @@ set -uo pipefail
 OUT="${1:-gpurun_out/sanitizer}"
 mkdir -p "$OUT"
 SAN=/usr/local/cuda/bin/compute-sanitizer
-K='(test_mrf_fused_kernel and (16-45 or 32-52 or 64-384)) or test_conv1d_kernels or test_cuda_core_kernels or (test_generator_matches_reference_golden and (hifigan_small_stress or bigvgan_small_stress or vocos_small_stress)) or test_snake_edge_modes or test_fused_snake_conv'
+K='(test_mrf_fused_kernel and (16-45 or 32-52 or 64-384)) or test_conv1d_kernels or test_cuda_core_kernels or (test_generator_matches_reference_golden and (hifigan_small_stress or bigvgan_small_stress or vocos_small_stress)) or (test_snake_edge_modes and replicate-snakebeta-True) or (test_mrf_fused_pair_kernel_c128 and 3-1-300) or test_tiny_weights'
 for tool in memcheck racecheck; do
   echo "== $tool"
   timeout 1700 "$SAN" --tool "$tool" --print-limit 20 --error-exitcode 9 \
-    python -m pytest tests/test_parity_gpu.py -x -q -m gpu -k "$K" -p no:cacheprovider \
+    python -m pytest tests/test_parity_gpu.py tests/test_round2_gpu.py -x -q -m gpu -k "$K" -p no:cacheprovider \
     > "$OUT/$tool.log" 2>&1
   echo "exit $? ($tool)" | tee -a "$OUT/$tool.log"
-  grep -E "ERROR SUMMARY|RACECHECK SUMMARY|passed|failed" "$OUT/$tool.log" | tail -8
+  grep -E "ERROR SUMMARY|RACECHECK SUMMARY|passed|failed" "$OUT/$tool.log" | tail -n 8
 done

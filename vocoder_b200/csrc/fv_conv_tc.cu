@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(64 + (FAT ? 16 : kEpiWarps) * 32, 1)
   }
   tc_fence_before();
   if constexpr (PAIR) cluster_sync_all();  // barrier inits of BOTH CTAs are visible before any remote arrive / TMA
-  else __syncthreads();
+  __syncthreads();                         // (pair: the cluster barrier already orders this; the CTA barrier is what tools see)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();  // everything above touched only this CTA's smem / TMEM; global memory of the previous kernel from here on

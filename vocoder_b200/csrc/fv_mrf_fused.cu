@@ -491,6 +491,9 @@ __global__ void __launch_bounds__(FrCfg<C, EW, NCTA, MB, MAXCONV>::THREADS, NCTA
           const int item = g + i * Cfg::GROUPS;
           entry_item(item / NCH, item % NCH, b, g0);
         }
+        // the staging patches alias operand-slab rows that OTHER warps write in the conv epilogues that follow: make "every
+        // warp is done with its entry patches" an explicit barrier, not only a consequence of the mbarrier chain
+        if constexpr (Cfg::ALIAS) named_bar_sync(1, EW * 32);
         tmem_st_wait();
         publish(&a_ready[0]);
         for (int pi = 0; pi < p.n_pairs; ++pi) {
@@ -513,6 +516,9 @@ __global__ void __launch_bounds__(FrCfg<C, EW, NCTA, MB, MAXCONV>::THREADS, NCTA
               }
               publish(&a_ready[0]);
             } else {
+              // same on the way out: no warp touches its (aliased) exit patches before every warp has finished writing
+              // operand rows of the previous conv epilogue
+              if constexpr (Cfg::ALIAS) named_bar_sync(1, EW * 32);
 #pragma unroll 1
               for (int i = 0; i < Cfg::IPW; ++i) {
                 const int item = g + i * Cfg::GROUPS;

@@ -190,15 +190,16 @@ class MRFGeneratorBase(nn.Module):
                     fused_pairs = [[cabi.pack_mrf(Ci, [([c1], [c2])]) for c1, c2 in zip(c1s, c2s)] for c1s, c2s in pairs]
                 elif can_fuse and cabi.mrf_fusable(self.stage_channels[i], pairs):
                     fused = cabi.pack_mrf(self.stage_channels[i], pairs)   # whole stage = one fv_mrf_fused launch
-                elif can_fuse and self.fuse_mrf_pairs and cabi.mrf_fusable(self.stage_channels[i], pairs, pairwise=True):
-                    # C = 128: one fv_mrf_fused launch per (conv, conv) pair (256-row tiles, pair halo <= 30 rows)
-                    fused_pairs = [[cabi.pack_mrf(self.stage_channels[i], [([c1], [c2])]) for c1, c2 in zip(c1s, c2s)]
-                                   for c1s, c2s in pairs]
                 else:
-                    for blk in mods:
-                        c1 = [cabi.pack_conv(c.weight, c.bias, c.dilation[0]) for c in blk.convs1]
-                        c2 = [cabi.pack_conv(c.weight, c.bias, c.dilation[0]) for c in blk.convs2]
-                        blocks.append((c1, c2, blk))
+                    if can_fuse and self.fuse_mrf_pairs and cabi.mrf_fusable(Ci, pairs, pairwise=True):
+                        # C = 128: one fv_mrf_fused launch per (conv, conv) pair (256-row tiles, pair halo <= 30 rows);
+                        # "auto" keeps the layer-wise weights as well and chooses per forward by the number of rows
+                        fused_pairs = [[cabi.pack_mrf(Ci, [([c1], [c2])]) for c1, c2 in zip(c1s, c2s)] for c1s, c2s in pairs]
+                    if fused_pairs is None or self.fuse_mrf_pairs == "auto":
+                        for blk in mods:
+                            c1 = [cabi.pack_conv(c.weight, c.bias, c.dilation[0]) for c in blk.convs1]
+                            c2 = [cabi.pack_conv(c.weight, c.bias, c.dilation[0]) for c in blk.convs2]
+                            blocks.append((c1, c2, blk))
                 P["blocks"].append(blocks)
                 P["fused"].append(fused)
                 P["pairs"].append(fused_pairs)
@@ -272,6 +273,8 @@ class MRFGeneratorBase(nn.Module):
                 h16, L = h_next, Lo
                 continue
             fpairs = P["pairs"][i]
+            if fpairs is not None and self.fuse_mrf_pairs == "auto" and B * Lo > self.mrf_pairs_max_rows:
+                fpairs = None   # enough rows to fill the layer-wise kernels: they are faster there (see fuse_mrf_pairs)
             if fpairs is not None:
                 # C = 128 SiLU stage, pair by pair on chip: x -> x + conv2(silu(conv1(silu(x)))) per launch, fp32 in / out;
                 # the last pair of every chain adds its chain's share of the MRF mean onto acc
@@ -364,8 +367,11 @@ class MRFGeneratorBase(nn.Module):
     #: Measured on B200 (HiFiGAN cfg B, C = 128, L = 6016, B = 64): 2.42 ms pair-wise against 2.0 ms layer-wise - an N = 128
     #: UMMA costs ~97 cycles whatever feeds it, the 256-row tiles recompute 25% halo, and with TMEM full (X + T) one CTA per
     #: SM cannot overlap its epilogue / entry / exit with MMAs the way the layer-wise kernel's double-buffered
-    #: accumulators do.  Off by default; kept for sequences too short to fill the layer-wise kernels.
-    fuse_mrf_pairs = False
+    #: accumulators do.  At B = 1 (6016 rows: 32 tiles on 148 SMs either way) the pair-wise stage saves nine launches and
+    #: measured 0.776 against 0.832 ms per forward.  "auto" (default) = pair-wise when the stage has at most
+    #: `mrf_pairs_max_rows` rows (batch x length), layer-wise above; True / False force one path.
+    fuse_mrf_pairs = "auto"
+    mrf_pairs_max_rows = 148 * 256
     #: channel counts (besides 128) whose stage runs pair by pair instead of as one whole-stage launch; (64,) trades ~7x the
     #: stage's HBM traffic for MMA / epilogue overlap between two co-resident CTAs.  Measured: see DESIGN.md section 4.2.
     mrf_pairwise_channels = ()
