@@ -294,11 +294,13 @@ W_SCALE_LO, W_SCALE_HI = 2.0 ** -9, 2.0 ** 13
 
 def weight_row_scale(amax: torch.Tensor) -> Optional[torch.Tensor]:
     """amax [C_out] = max |w| of every output channel.  None when every (non-zero) row is inside the comfortable fp16
-    range; otherwise the power-of-two scale s[o] that brings the row maximum into [0.5, 1)."""
+    range; otherwise the power-of-two scale s[o] that brings the row maximum into [0.5, 1).  One device sync per call."""
     amax = amax.detach().float()
-    nz = amax > 0
-    if not bool(nz.any()) or not bool(((amax[nz] < W_SCALE_LO) | (amax[nz] > W_SCALE_HI)).any()):
+    inf = torch.full_like(amax, float("inf"))
+    lo, hi = torch.stack([torch.where(amax > 0, amax, inf).min(), amax.max()]).tolist()
+    if hi <= 0.0 or (lo >= W_SCALE_LO and hi <= W_SCALE_HI):
         return None
+    nz = amax > 0
     e = torch.ceil(torch.log2(torch.where(nz, amax, torch.ones_like(amax))))
     return torch.where(nz, torch.exp2(-e), torch.ones_like(amax))
 
