@@ -395,6 +395,10 @@ def run_workload(name, args, dev, rank, world, barrier, all_max, *, full: bool):
             m.mrf_pairwise_channels = (64,)
         if args.mrf_silu_h2 and hasattr(m, "mrf_silu_h2"):
             m.mrf_silu_h2 = True
+        if args.no_row_pairs and hasattr(m, "conv_row_pairs"):
+            m.conv_row_pairs = False
+        if args.chain_streams != "auto" and hasattr(m, "chain_streams"):
+            m.chain_streams = args.chain_streams == "on"
         if args.no_fuse_snake and hasattr(m, "fuse_snake"):
             m.fuse_snake = False
         if args.mrf_silu_exact and hasattr(m, "mrf_silu_tanh"):
@@ -606,6 +610,10 @@ def main():
     ap.add_argument("--no-fuse-mrf", action="store_true", help="layer-wise fv_conv1d launches instead of fv_mrf_fused")
     ap.add_argument("--no-fuse-pairs", action="store_true", help="always layer-wise C = 128 stage (default: auto by rows)")
     ap.add_argument("--fuse-pairs", action="store_true", help="always pair-wise fv_mrf_fused for the C = 128 stage")
+    ap.add_argument("--chain-streams", choices=("auto", "on", "off"), default="auto",
+                    help="kernel-size chains of a stage on two streams (auto: short sequences only)")
+    ap.add_argument("--no-row-pairs", action="store_true",
+                    help="C <= 16 Snake stages one row per GEMM row instead of the [L/2, 2C] row-pair view (A/B switch)")
     ap.add_argument("--pairwise-c64", action="store_true", help="C = 64 stage pair by pair (two co-resident CTAs per SM)")
     ap.add_argument("--mrf-silu-h2", action="store_true", help="packed fp16x2 SiLU inside fv_mrf_fused (FV_ACT_SILU_H2)")
     ap.add_argument("--no-fuse-snake", action="store_true", help="standalone fv_snake_aa launches instead of fv_snake_conv")

@@ -416,9 +416,9 @@ def test_five_stage_hifigan_fused_c16_vs_oracle_and_layerwise():
         layer = m(mel.cuda()).cpu()
         n_layer = cabi.launch_count()
     assert fused.shape == want.shape == (2, 1, 11 * 512)
-    # three stages (C = 64, 32, 16) collapse from 18 conv launches to one each (+ the C = 128 stage to one launch per conv
-    # pair when fuse_mrf_pairs is on)
-    assert n_layer - n_fused == 3 * (18 - 1) + (18 - 9)   # "auto": 2 x 704 rows -> the pair-wise path
+    # three stages (C = 64, 32, 16) collapse from 18 conv launches to three each at this size (chain_streams "auto": two
+    # concurrent fv_mrf_fused launches + the sum; one launch for long sequences), the C = 128 stage to one launch per conv pair
+    assert n_layer - n_fused == 3 * (18 - 3) + (18 - 9)   # "auto": 2 x 704 rows -> the pair-wise path
     peak = max(1.0, float(want.abs().max()))
     e_f, e_l = float((fused - want).abs().max()), float((layer - want).abs().max())
     print(f"5-stage stress hifigan: fused {e_f:.3e}, layer-wise {e_l:.3e} vs fp32 oracle (peak {peak:.3f})")

@@ -159,7 +159,7 @@ def test_mixed_mode_packs_only_the_sensitive_layers_strict():
     with cabi.precision("mixed"):
         P = BigVGANGenerator(**kw)._ensure_packed("cpu")
         assert P["pre"].split > 0 and all(u.split > 0 for u in P["ups"])
-        assert all(c.split == 0 for blocks in P["blocks"] for c1, c2, _ in blocks for c in c1 + c2)
+        assert all(c.split == 0 for blocks in P["blocks"] for c1, c2, _, _ in blocks for c in c1 + c2)
         H = HiFiGANGenerator(**kw)
         H.fuse_mrf = False
         PH = H._ensure_packed("cpu")
@@ -239,3 +239,56 @@ def test_abi_header_declares_version_3_and_edge_modes():
     # every FV_API declaration is in EXPORTS and vice versa
     declared = set(re.findall(r"FV_API\s+[\w\s\*]+?\b(fv_\w+)\s*\(", hdr))
     assert declared == set(cabi.EXPORTS)
+
+
+@pytest.mark.parametrize("k,d", [(3, 1), (3, 3), (3, 5), (7, 1), (7, 3), (7, 5), (11, 1), (11, 3), (11, 5)])
+def test_row_pair_packing_is_the_same_conv(k, d):
+    """cabi.pack_conv_row_pairs: the [B, L/2, 2C] view of a channels-last buffer convolved with the 2C x 2C pair taps equals
+    the original "same"-padded Conv1d (hifigan.py:21-22 padding rule), for every (kernel, dilation) of an AMP block."""
+    torch.manual_seed(k * 10 + d)
+    C, L, B = 16, 46, 2
+    w = torch.randn(C, C, k) * 0.2
+    b = torch.randn(C)
+    x = torch.randn(B, C, L)
+    with cabi.precision("fp16"):
+        pc = cabi.pack_conv_row_pairs(w, b, d)
+    assert pc.c_in == 2 * C and pc.c_out == 2 * C and pc.n_phase == 1 and pc.n_taps <= cabi.MAX_TAPS
+    assert pc.n_taps == len(set((p + (j - (k - 1) // 2) * d) // 2 for p in (0, 1) for j in range(k)))
+    ref = F.conv1d(x, w.half().float(), b, padding=(k * d - d) // 2, dilation=d)           # [B, C, L]
+    a2 = x.permute(0, 2, 1).reshape(B, L // 2, 2 * C)                                          # the row-pair view
+    out2 = torch.zeros(B, L // 2, 2 * C)
+    W = pc.w.float()                                                                           # [1, taps, C_out_pad, w_pitch]
+    for i, off in enumerate(pc.tap_off):
+        sh = torch.zeros_like(a2)
+        lo, hi = max(0, -off), min(L // 2, L // 2 - off)
+        if hi > lo:
+            sh[:, lo:hi] = a2[:, lo + off:hi + off]                                            # rows outside [0, L/2) are zero
+        out2 += sh @ W[0, i, :2 * C, :2 * C].t()
+    scale = 1.0 if pc.w_scale is None else pc.w_scale
+    out2 = (out2 + pc.bias) * scale
+    got = out2.reshape(B, L, C).permute(0, 2, 1)
+    assert torch.allclose(got, ref, atol=2e-5, rtol=1e-5), float((got - ref).abs().max())
+
+
+def test_snake_stage_packs_row_pairs_only_for_narrow_unpadded_channels():
+    from vocoder_b200.generators import BigVGANGenerator
+    kw = dict(hop_length=8, upsample_rates=[4, 2], upsample_kernel_sizes=[8, 4], num_mels=12, upsample_initial_channel=64,
+              use_template=False)
+    with cabi.precision("mixed"):
+        g = BigVGANGenerator(**kw)                       # stages of 32 and 16 channels
+        P = g._ensure_packed("cpu")
+        assert all(bp is None for _, _, _, bp in P["blocks"][0])
+        assert all(bp is not None and bp[0][0].c_out == 32 for _, _, _, bp in P["blocks"][1])
+        g.conv_row_pairs = False
+        assert all(bp is None for blocks in g._ensure_packed("cpu")["blocks"] for _, _, _, bp in blocks)
+    with cabi.precision("strict"):
+        assert all(bp is None for blocks in BigVGANGenerator(**kw)._ensure_packed("cpu")["blocks"] for _, _, _, bp in blocks)
+    assert cabi.row_pairs_ok(16, 10) and not cabi.row_pairs_ok(16, 11) and not cabi.row_pairs_ok(12, 10)
+
+
+def test_chain_streams_auto_threshold():
+    from vocoder_b200.generators import HiFiGANGenerator
+    m = HiFiGANGenerator()
+    assert m._chains_concurrent(1, 24064) and m._chains_concurrent(2, 12032) and not m._chains_concurrent(64, 752 * 8)
+    m.chain_streams = False
+    assert not m._chains_concurrent(1, 10)

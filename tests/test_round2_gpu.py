@@ -284,3 +284,94 @@ def test_pointer_of_another_device_is_refused():
     with torch.no_grad():
         y = m(torch.randn(1, 20, 9, device="cuda:1"))           # forward enters the tensor's device itself
     assert y.device.index == 1 and bool(torch.isfinite(y).all())
+
+
+# ------------------------------------------------------------------------------------------------
+# row-pair convs of the narrow Snake stages (cabi.pack_conv_row_pairs)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("C", [16, 8])
+@pytest.mark.parametrize("k,d", [(3, 1), (3, 5), (7, 3), (11, 1), (11, 5)])
+def test_row_pair_conv_matches_the_plain_conv(C, k, d):
+    """Same weights, same buffers: fv_conv1d on the [B, L/2, 2C] view with pair taps == fv_conv1d on [B, L, C] (residual,
+    running-sum accumulate and out_scale included), and both match an fp32 torch conv on the fp16-rounded operands."""
+    import torch.nn.functional as F
+    torch.manual_seed(100 * C + 10 * k + d)
+    B, L = 3, 2 * 1187                      # ragged against every tile size
+    w = (torch.randn(C, C, k) * 0.3).cuda()
+    bias = torch.randn(C).cuda()
+    a16 = torch.randn(B, L, C, device="cuda").half()
+    res = torch.randn(B, L, C, device="cuda")
+    acc0 = torch.randn(B, L, C, device="cuda")
+    with cabi.precision("fp16"):
+        plain, pairs = cabi.pack_conv(w, bias, d), cabi.pack_conv_row_pairs(w, bias, d)
+        o_plain, o_pairs = acc0.clone(), acc0.clone()
+        cabi.conv1d(a16, plain, residual=res, out32=o_plain, accumulate=True, out_scale=0.5)
+        cabi.conv1d_row_pairs(a16, pairs, residual=res, out32=o_pairs, accumulate=True, out_scale=0.5)
+        t_plain, t_pairs = torch.empty_like(acc0), torch.empty_like(acc0)
+        cabi.conv1d(a16, plain, out32=t_plain)
+        cabi.conv1d_row_pairs(a16, pairs, out32=t_pairs)
+    torch.cuda.synchronize()
+    ref = F.conv1d(a16.float().permute(0, 2, 1), w.half().float(), bias, padding=(k * d - d) // 2, dilation=d).permute(0, 2, 1)
+    scale = float(ref.abs().max())
+    assert float((t_pairs - ref).abs().max()) <= 2e-5 * scale + 1e-5
+    assert float((t_pairs - t_plain).abs().max()) <= 2e-5 * scale + 1e-5      # fp32 sums in a different order
+    want = (ref + res) * 0.5 + acc0
+    assert float((o_pairs - want).abs().max()) <= 2e-5 * scale + 1e-5
+    assert float((o_pairs - o_plain).abs().max()) <= 2e-5 * scale + 1e-5
+
+
+def test_bigvgan_row_pair_stage_equals_plain_stage():
+    """Generator level: BigVGAN with a 16-channel last stage, conv_row_pairs on / off, same weights: identical up to fp32
+    summation order, and within tolerance of the oracle."""
+    from vocoder_b200.generators import BigVGANGenerator
+    torch.manual_seed(5)
+    kw = dict(hop_length=16, upsample_rates=[4, 2, 2], upsample_kernel_sizes=[8, 4, 4], num_mels=20,
+              upsample_initial_channel=128, use_template=False)
+    m = BigVGANGenerator(**kw).eval()
+    stress_init(m, seed=3)
+    mel = torch.randn(2, 20, 37)
+    sd = {k_: v.detach().cpu().float() for k_, v in m.state_dict().items()}
+    with torch.no_grad():
+        want = G.bigvgan_forward(sd, mel, kw["upsample_rates"])
+        m = m.cuda()
+        launches0 = cabi.launch_count()
+        y_pairs = m(mel.cuda()).cpu()
+        n_pairs = cabi.launch_count() - launches0
+        m.conv_row_pairs = False
+        y_plain = m(mel.cuda()).cpu()
+    assert m._packed["blocks"][-1][0][3] is None        # repacked without the pair taps
+    peak = max(1.0, float(want.abs().max()))
+    assert float((y_pairs - want).abs().max()) <= TOL * peak
+    assert float((y_pairs - y_plain).abs().max()) <= 1e-4 * peak
+    assert n_pairs > 0
+
+
+# ------------------------------------------------------------------------------------------------
+# short sequences: kernel-size chains on two streams (MRFGeneratorBase.chain_streams)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["hifigan", "bigvgan"])
+@pytest.mark.parametrize("graph", [False, True])
+def test_chain_streams_are_bit_identical_to_the_serial_order(kind, graph):
+    """B = 1, T = 94 (test.py's shape): every stage type (layer-wise C = 256, pair-wise C = 128, whole-stage fused C = 64 / 32;
+    BigVGAN: Snake stages incl. row-pair convs) with the largest kernel-size chain on the side stream == the serial schedule,
+    eagerly and under CUDA-graph replay (fork / join captured), repeated to catch ordering races."""
+    import bench
+    model = bench.build_model(kind).eval()
+    stress_init(model, seed=2)
+    n_mels = model.num_mels
+    mel = bench.synthetic_mel(1, n_mels, 94, 77).cuda()
+    model = model.cuda()
+    with torch.no_grad():
+        model.chain_streams, model.use_cuda_graph = False, False
+        serial = model(mel).clone()
+        model.chain_streams, model.use_cuda_graph = True, graph
+        n0 = cabi.launch_count()
+        outs = [model(mel).clone() for _ in range(5)]
+        assert cabi.launch_count() > n0 or graph
+    torch.cuda.synchronize()
+    for y in outs:
+        assert torch.equal(y, serial), float((y - serial).abs().max())
+    sd = {k: v.detach().cpu().float() for k, v in model.state_dict().items()}
+    with torch.no_grad():
+        want = bench.oracle_forward(kind, sd, mel.cpu(), model)
+    assert float((outs[-1].cpu() - want).abs().max()) <= TOL * max(1.0, float(want.abs().max()))

@@ -360,6 +360,51 @@ def pack_taps(mats: Sequence[torch.Tensor], offsets: Sequence[int], bias: Option
                       w.shape[-1], split, None if s is None else (1.0 / s).contiguous())
 
 
+def pack_conv_row_pairs(weight: torch.Tensor, bias: Optional[torch.Tensor], dilation: int = 1) -> PackedConv:
+    """The "same"-padded Conv1d of `pack_conv`, evaluated on PAIRS of time steps.  A channels-last buffer [B, L, C] whose rows
+    are exactly C values apart (pitch == C) and whose L is even is also [B, L/2, 2C]; on that view the conv is a conv with
+    2C x 2C tap matrices: out[2m + p] = sum_j W_j a[2m + p + o_j] with p + o_j = 2q + r puts W_j into block (p, r) of the
+    tap at pair offset q.  For C = 16 this turns half-empty 32-column tiles (16 real channels) into full ones and halves
+    the rows every epilogue touches (BigVGAN's last stage: 48 / 67 -> ~30 / 42 us per launch); a dilated tap list gets
+    longer (k = 11, d = 5: 17 pair taps) but stays far below the launch's memory time.  Call through `conv1d_row_pairs`."""
+    c_out, c_in, k = weight.shape
+    assert k % 2 == 1, "same-padded convs on this path have odd kernels"
+    wf = weight.detach().float()
+    half = (k - 1) // 2
+    mats = {}
+    for p in (0, 1):
+        for j in range(k):
+            q, r = divmod(p + (j - half) * dilation, 2)
+            m = mats.get(q)
+            if m is None:
+                m = mats[q] = torch.zeros(2 * c_out, 2 * c_in, dtype=torch.float32, device=weight.device)
+            m[p * c_out:(p + 1) * c_out, r * c_in:(r + 1) * c_in] += wf[:, :, j]
+    offs = sorted(mats)
+    b2 = None if bias is None else torch.cat([bias.detach().float(), bias.detach().float()])
+    return pack_taps([mats[q] for q in offs], offs, b2)
+
+
+def row_pairs_ok(channels: int, L: int) -> bool:
+    """True when [B, L, C] buffers of this layer can be viewed as [B, L/2, 2C] (no channel padding, even length)."""
+    return L % 2 == 0 and pitch_of(channels) == channels and f16_width(channels) == channels
+
+
+def _pair_view(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    B, L, P = t.shape
+    if L % 2 or not t.is_contiguous():
+        raise FvError(f"row-pair view needs a contiguous [B, even L, C] buffer, got {tuple(t.shape)} / strides {t.stride()}")
+    return t.view(B, L // 2, 2 * P)
+
+
+def conv1d_row_pairs(a16: torch.Tensor, pc: PackedConv, *, residual=None, out32=None, accumulate=False, out_scale=1.0,
+                     out16=None, act=ACT_NONE, act_param=0.0, engine=ENGINE_TC) -> None:
+    """`conv1d` for weights packed by `pack_conv_row_pairs`: every [B, L, C] buffer is passed as its [B, L/2, 2C] view."""
+    conv1d(_pair_view(a16), pc, residual=_pair_view(residual), out32=_pair_view(out32), accumulate=accumulate,
+           out_scale=out_scale, out16=_pair_view(out16), act=act, act_param=act_param, engine=engine, out16_split=0)
+
+
 def pack_linear(weight: torch.Tensor, bias: Optional[torch.Tensor]) -> PackedConv:
     """nn.Linear / 1x1 conv weight [C_out, C_in]."""
     return pack_conv(weight.reshape(weight.shape[0], weight.shape[1], 1), bias)

@@ -99,6 +99,7 @@ class MRFGeneratorBase(nn.Module):
         self._packed = None
         self._packed_key = None
         self._pack_gen = 0  # bumped by every re-pack: part of the key of every CUDA graph that replays packed pointers
+        self._side_streams, self._ones_cache = {}, {}
         self._graphed: Optional[GraphedForward] = None
         self._ws.add_listener(self._drop_graphs)
         self.use_cuda_graph = False
@@ -168,20 +169,20 @@ class MRFGeneratorBase(nn.Module):
 
     def _ensure_packed(self, device):
         key = params_key(list(self.parameters()) + list(self.buffers())) + (
-            self.fuse_mrf, self.fuse_mrf_pairs, tuple(self.mrf_pairwise_channels), self.engine)
+            self.fuse_mrf, self.fuse_mrf_pairs, tuple(self.mrf_pairwise_channels), self.engine, self.conv_row_pairs, self.row_pairs_max_taps, self.chain_streams, self.chain_streams_max_rows)
         if self._packed is not None and self._packed_key == key:
             return self._packed
         with torch.no_grad():
             with self._trunk_ctx():
                 P = {"pre": cabi.pack_conv(self.conv_pre.weight, self.conv_pre.bias), "ups": [], "blocks": [],
-                     "noise": [], "fused": [], "pairs": []}
+                     "noise": [], "fused": [], "fused_split": [], "pairs": []}
             for i, up in enumerate(self.ups):
                 with self._trunk_ctx():
                     P["ups"].append(cabi.pack_conv_transpose(up.weight, up.bias, self.upsample_rates[i]))
                 blocks = []
                 mods = self._block_modules(i)
                 pairs = [(list(blk.convs1), list(blk.convs2)) for blk in mods]
-                fused, fused_pairs = None, None
+                fused, fused_pairs, fused_split = None, None, None
                 can_fuse = self.fuse_mrf and not self.snake_blocks and self.engine == cabi.ENGINE_TC
                 Ci = self.stage_channels[i]
                 if (can_fuse and Ci in self.mrf_pairwise_channels and Ci != 128
@@ -190,18 +191,35 @@ class MRFGeneratorBase(nn.Module):
                     fused_pairs = [[cabi.pack_mrf(Ci, [([c1], [c2])]) for c1, c2 in zip(c1s, c2s)] for c1s, c2s in pairs]
                 elif can_fuse and cabi.mrf_fusable(self.stage_channels[i], pairs):
                     fused = cabi.pack_mrf(self.stage_channels[i], pairs)   # whole stage = one fv_mrf_fused launch
+                    if len(pairs) > 1:   # short sequences: the last (largest) kernel size as its own concurrent launch
+                        fused_split = (cabi.pack_mrf(Ci, pairs[:-1]), cabi.pack_mrf(Ci, pairs[-1:]))
                 else:
                     if can_fuse and self.fuse_mrf_pairs and cabi.mrf_fusable(Ci, pairs, pairwise=True):
                         # C = 128: one fv_mrf_fused launch per (conv, conv) pair (256-row tiles, pair halo <= 30 rows);
                         # "auto" keeps the layer-wise weights as well and chooses per forward by the number of rows
                         fused_pairs = [[cabi.pack_mrf(Ci, [([c1], [c2])]) for c1, c2 in zip(c1s, c2s)] for c1s, c2s in pairs]
                     if fused_pairs is None or self.fuse_mrf_pairs == "auto":
+                        # Snake stages with C <= 16 (BigVGAN's last): the same convs on pairs of time steps, see
+                        # cabi.pack_conv_row_pairs; chosen per forward (even length, plain fp16 operands)
+                        pair_rows = (self.conv_row_pairs and self.snake_blocks and Ci <= 16 and not cabi.is_strict()
+                                     and cabi.pitch_of(Ci) == Ci)
                         for blk in mods:
                             c1 = [cabi.pack_conv(c.weight, c.bias, c.dilation[0]) for c in blk.convs1]
                             c2 = [cabi.pack_conv(c.weight, c.bias, c.dilation[0]) for c in blk.convs2]
-                            blocks.append((c1, c2, blk))
+                            if pair_rows:
+                                # measured on B200 (C = 16, L = 44544, B = 32; us per launch, plain -> pairs): k=3 48 -> 30,
+                                # k=7 d=3,5 (11 pair taps) 48 -> 45, k=11 d=1 (7) 59 -> 35, k=11 d=3,5 (17) 58 -> 61: beyond
+                                # `row_pairs_max_taps` pair taps the MMA issue time of the longer tap list outweighs the epilogue
+                                def rp_pack(c):
+                                    pc = cabi.pack_conv_row_pairs(c.weight, c.bias, c.dilation[0])
+                                    return pc if pc.n_taps <= self.row_pairs_max_taps else None
+                                blk_pairs = ([rp_pack(c) for c in blk.convs1], [rp_pack(c) for c in blk.convs2])
+                            else:
+                                blk_pairs = None
+                            blocks.append((c1, c2, blk, blk_pairs))
                 P["blocks"].append(blocks)
                 P["fused"].append(fused)
+                P["fused_split"].append(fused_split)
                 P["pairs"].append(fused_pairs)
             for nc in self.noise_convs:
                 P["noise"].append((nc.weight.detach().float().reshape(nc.out_channels, -1).contiguous(),
@@ -265,9 +283,26 @@ class MRFGeneratorBase(nn.Module):
                 acc = ws.f32(f"acc_{i}", B, Lo, C, dev)
                 h_next = ws.f16(f"h_{i}", B, Lo, C, dev)
                 out_act, out_act_p = self._stage_out_act(last_stage)
-                cabi.mrf_fused(x0, fused, acc, out16=h_next if out_act is not None else None,
-                               act=cabi.ACT_SILU_H2 if (self.mrf_silu_h2 and self.mrf_silu_tanh) else self._silu(),
-                               out_act=out_act or cabi.ACT_NONE, out_act_param=out_act_p)
+                inner = cabi.ACT_SILU_H2 if (self.mrf_silu_h2 and self.mrf_silu_tanh) else self._silu()
+                split_packs = P["fused_split"][i]
+                if split_packs is not None and self._chains_concurrent(B, Lo):
+                    # few tiles (B = 1 ... 2): the largest kernel size (more taps than the others together) runs as its own
+                    # launch on the side stream next to the launch of the other chains; the same three scaled terms are
+                    # summed in the same order as in the single launch
+                    nk = len(fused.ksize)
+                    a_side = ws.f32(f"acc_side_{i}", B, Lo, C, dev)
+                    side, cur = self._side_stream(dev), torch.cuda.current_stream()
+                    side.wait_stream(cur)
+                    with torch.cuda.stream(side):
+                        cabi.mrf_fused(x0, split_packs[1], a_side, act=inner, out_scale=1.0 / nk)
+                    cabi.mrf_fused(x0, split_packs[0], acc, act=inner, out_scale=1.0 / nk)
+                    cur.wait_stream(side)
+                    cabi.act_cast(acc, C, cabi.ACT_NONE, noise=a_side, noise_w=self._ones(C, dev), out32=acc,
+                                  out16=h_next if out_act is not None else None, act16=out_act or cabi.ACT_NONE,
+                                  act16_param=out_act_p)
+                else:
+                    cabi.mrf_fused(x0, fused, acc, out16=h_next if out_act is not None else None, act=inner,
+                                   out_act=out_act or cabi.ACT_NONE, out_act_param=out_act_p)
                 if last_stage:
                     self._final_activation(acc, h_next, C, 0)
                 h16, L = h_next, Lo
@@ -281,23 +316,28 @@ class MRFGeneratorBase(nn.Module):
                 cabi.conv1d(h16, up, Lo, residual=nz, out32=x0, engine=eng)
                 acc = ws.f32(f"acc_{i}", B, Lo, C, dev)
                 h_next = ws.f16(f"h_{i}", B, Lo, C, dev)
-                xp = (ws.f32(f"xp0_{i}", B, Lo, C, dev), ws.f32(f"xp1_{i}", B, Lo, C, dev))
                 out_act, out_act_p = self._stage_out_act(last_stage)
                 inner = cabi.ACT_SILU_H2 if (self.mrf_silu_h2 and self.mrf_silu_tanh) else self._silu()
                 nk = len(fpairs)
-                for j, chain in enumerate(fpairs):
-                    src = x0
+
+                def pair_chain(j, tag, before_final=None):
+                    xp = (ws.f32(f"xp0{tag}_{i}", B, Lo, C, dev), ws.f32(f"xp1{tag}_{i}", B, Lo, C, dev))
+                    src, chain = x0, fpairs[j]
                     for p_i, pm in enumerate(chain):
                         if p_i + 1 < len(chain):
                             dst = xp[0] if src is not xp[0] else xp[1]
                             cabi.mrf_fused(src, pm, dst, act=inner, out_scale=1.0)
                             src = dst
                         else:
+                            if before_final is not None:
+                                before_final()
                             final = j == nk - 1
                             cabi.mrf_fused(src, pm, acc, act=inner, accumulate=j > 0, out_scale=1.0 / nk,
                                            out16=h_next if (final and out_act is not None) else None,
                                            out_act=(out_act or cabi.ACT_NONE) if final else cabi.ACT_NONE,
                                            out_act_param=out_act_p)
+
+                self._run_chains(nk, pair_chain, B, Lo, dev)
                 if last_stage:
                     self._final_activation(acc, h_next, C, 0)
                 h16, L = h_next, Lo
@@ -328,14 +368,44 @@ class MRFGeneratorBase(nn.Module):
                 n = b1 - b0
                 x0_m, acc_m, h_m = x0[b0:b1], acc[b0:b1], h_next[b0:b1]
                 xa0_m = None if xa0 is None else xa0[b0:b1]
-                xr_m, xa_m, ta_m = xr_w[:n], xa_w[:n], ta[:n]
-                t32_m = None if t32 is None else t32[:n]
-                for j, (c1s, c2s, blk) in enumerate(blocks):
+
+                def layer_chain(j, tag, before_final=None):
+                    if tag:   # a chain on the side stream works in its own buffers
+                        xr_m = ws.f32(f"xr{tag}_{i}", mb, Lo, C, dev)[:n]
+                        xa_m = ws.f16(f"xa{tag}_{i}", mb, Lo, C, dev)[:n]
+                        ta_m = ws.f16(f"ta{tag}_{i}", mb, Lo, C, dev)[:n]
+                        t32_m = ws.f32(f"t32{tag}_{i}", mb, Lo, C, dev)[:n] if self.snake_blocks else None
+                    else:
+                        xr_m, xa_m, ta_m = xr_w[:n], xa_w[:n], ta[:n]
+                        t32_m = None if t32 is None else t32[:n]
+                    c1s, c2s, blk, blk_pairs = blocks[j]
                     xr, xa = x0_m, xa0_m
                     n_pairs = len(c1s)
+                    rp = (blk_pairs is not None and cabi.row_pairs_ok(C, Lo)
+                          and all(t.shape[-1] == C for t in (x0_m, xr_m, xa_m, ta_m, t32_m, acc_m)))
                     for p_i in range(n_pairs):
                         last_pair = p_i == n_pairs - 1
-                        if self.snake_blocks:
+                        if rp:   # snake stage on [n, Lo / 2, 2 C] views: full 32-column tiles for C = 16
+                            self._snake(blk.activations[2 * p_i], xr, xa_m, C)
+                            if blk_pairs[0][p_i] is not None:
+                                cabi.conv1d_row_pairs(xa_m, blk_pairs[0][p_i], out32=t32_m, engine=eng)
+                            else:
+                                cabi.conv1d(xa_m, c1s[p_i], out32=t32_m, engine=eng)
+                            self._snake(blk.activations[2 * p_i + 1], t32_m, ta_m, C)
+                            if blk_pairs[1][p_i] is None:
+                                pass   # plain view below
+                            elif not last_pair:
+                                cabi.conv1d_row_pairs(ta_m, blk_pairs[1][p_i], residual=xr, out32=xr_m, engine=eng)
+                                xr = xr_m
+                                continue
+                            elif not ((j == nk - 1) and out_act is not None):
+                                if before_final is not None:
+                                    before_final()
+                                cabi.conv1d_row_pairs(ta_m, blk_pairs[1][p_i], residual=xr, out32=acc_m, accumulate=j > 0,
+                                                      out_scale=1.0 / nk, engine=eng)
+                                continue
+                            # the stage's very last conv also writes the next ups operand ([hi | lo] rows in "mixed"): plain view
+                        elif self.snake_blocks:
                             self._snake(blk.activations[2 * p_i], xr, xa_m, C)
                             cabi.conv1d(xa_m, c1s[p_i], out32=t32_m, engine=eng)
                             self._snake(blk.activations[2 * p_i + 1], t32_m, ta_m, C)
@@ -346,11 +416,15 @@ class MRFGeneratorBase(nn.Module):
                                         out16=None if self.snake_blocks else xa_m, act=self._silu(), engine=eng)
                             xr, xa = xr_m, xa_m
                         else:
+                            if before_final is not None:
+                                before_final()
                             want16 = (j == nk - 1) and out_act is not None
                             cabi.conv1d(ta_m, c2s[p_i], residual=xr, out32=acc_m, accumulate=j > 0,
                                         out_scale=1.0 / nk, out16=h_m if want16 else None,
                                         act=out_act if want16 else cabi.ACT_NONE, act_param=out_act_p, engine=eng,
                                         out16_split=h_split if want16 else None)
+
+                self._run_chains(nk, layer_chain, n, Lo, dev, allow=(mb == B))
             if last_stage:
                 self._final_activation(acc, h_next, C, h_split)
             h16, L = h_next, Lo
@@ -360,6 +434,52 @@ class MRFGeneratorBase(nn.Module):
 
     def _snake(self, act_module, x32, out16, C, split=None):
         raise NotImplementedError
+
+    # ---- short sequences: the kernel-size chains of a stage are independent until the MRF mean -------------------------
+    #: Run the last (largest) kernel-size chain of every stage on a side stream next to the others when the stage is too
+    #: small to fill the GPU (test.py runs B = 1 ... 2: a 752-row C = 256 stage is 3 tiles on 148 SMs, and every launch
+    #: is a serial chain of MMAs on one tile).  With kernel sizes (3, 7, 11) the k = 11 chain has more taps than the other two
+    #: together, so two streams already halve the critical path.  The chains meet at their final conv (running-mean
+    #: accumulate, ordered by an event), i.e. results are bit-identical to the serial order.  "auto" = stages with at most
+    #: `chain_streams_max_rows` rows (batch x length); True / False force it.  Works under CUDA-graph capture (fork / join).
+    chain_streams = "auto"
+    chain_streams_max_rows = 148 * 256
+
+    def _chains_concurrent(self, B: int, L: int) -> bool:
+        if self.chain_streams == "auto":
+            return B * L <= self.chain_streams_max_rows
+        return bool(self.chain_streams)
+
+    def _side_stream(self, device) -> "torch.cuda.Stream":
+        key = str(device)
+        st = self._side_streams.get(key)
+        if st is None:
+            st = self._side_streams[key] = torch.cuda.Stream(device=device)
+        return st
+
+    def _ones(self, C: int, device) -> torch.Tensor:
+        key = (C, str(device))
+        t = self._ones_cache.get(key)
+        if t is None:
+            t = self._ones_cache[key] = torch.ones(C, dtype=torch.float32, device=device)
+        return t
+
+    def _run_chains(self, nk: int, chain_fn, B: int, L: int, device, allow: bool = True) -> None:
+        """chain_fn(j, tag, before_final): issue chain j; `tag` names its private work buffers; `before_final` must be called
+        right before the chain's final launch (the one that accumulates onto the stage's running mean)."""
+        if not (allow and nk > 1 and self._chains_concurrent(B, L)):
+            for j in range(nk):
+                chain_fn(j, "")
+            return
+        side, cur = self._side_stream(device), torch.cuda.current_stream()
+        side.wait_stream(cur)                       # fork: the stage input is complete
+        for j in range(nk - 1):
+            chain_fn(j, "")
+        done = torch.cuda.Event()
+        done.record(cur)                            # running mean holds chains 0 .. nk-2
+        with torch.cuda.stream(side):
+            chain_fn(nk - 1, "s", before_final=lambda: side.wait_event(done))
+        cur.wait_stream(side)                       # join
 
     #: C <= 64 SiLU stages as one on-chip kernel per stage (fv_mrf_fused); False = layer-wise fv_conv1d launches
     fuse_mrf = True
@@ -371,6 +491,10 @@ class MRFGeneratorBase(nn.Module):
     #: measured 0.776 against 0.832 ms per forward.  "auto" (default) = pair-wise when the stage has at most
     #: `mrf_pairs_max_rows` rows (batch x length), layer-wise above; True / False force one path.
     fuse_mrf_pairs = "auto"
+    #: C <= 16 Snake stages: convs on the [B, L/2, 2C] view of the channels-last buffers (cabi.pack_conv_row_pairs);
+    #: False = one 16-channel row per GEMM row (half-empty 32-column tiles)
+    conv_row_pairs = True
+    row_pairs_max_taps = 12
     mrf_pairs_max_rows = 148 * 256
     #: channel counts (besides 128) whose stage runs pair by pair instead of as one whole-stage launch; (64,) trades ~7x the
     #: stage's HBM traffic for MMA / epilogue overlap between two co-resident CTAs.  Measured: see DESIGN.md section 4.2.
