@@ -37,6 +37,7 @@ WORKLOADS = {
     "hifigan_b1": ("hifigan", 1, 80, 94, 256, 24000, "hifigan baseline generator, batch 1 x 1 s @ 24 kHz"),
     "bigvgan_b32": ("bigvgan", 32, 100, 87, 512, 44100,
                     "bigvgan generator with anti-aliased Snake (100 mel, hop 512), batch 32 x 1 s @ 44.1 kHz"),
+    "bigvgan_b1": ("bigvgan", 1, 100, 87, 512, 44100, "bigvgan generator, batch 1 x 1 s @ 44.1 kHz (latency case)"),
     "hifigan_yaml_b32": ("hifigan5", 32, 128, 87, 512, 44100,
                          "hifigan.yaml as written (128 mel, hop 512, rates 8-8-2-2-2, ch 512), batch 32 x 1 s @ 44.1 kHz"),
     "firefly_b32": ("firefly", 32, 128, 87, 512, 44100,

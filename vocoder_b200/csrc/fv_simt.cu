@@ -940,6 +940,183 @@ __global__ void __launch_bounds__(256, 2) dwconv_ln_vec_kernel(const float* __re
   }
 }
 
+// Persistent bulk-copy variant (round 2): the vectorised kernel above moves 1.8 TB/s - every CTA loads, reduces and stores in
+// sequence and two or three resident CTAs per SM do not keep enough bytes in flight.  Here one CTA per SM walks over tiles of
+// DW8_R time steps; the 14 input rows of a tile are ONE contiguous range of the channels-last tensor, fetched by a single
+// 1-D bulk copy (cp.async.bulk, completion on an mbarrier) into one of two shared-memory stages, so the loads of the next
+// two tiles are always in flight while this tile is filtered, normalised and stored.  A thread owns one group of four
+// channels for the whole launch: depthwise taps, bias and LayerNorm affine live in registers across tiles, the conv results
+// stay in registers for both LayerNorm passes (no shared-memory parking).  Rows outside [0, T) (the conv's zero padding) are
+// zero-filled by the thread that later reads them (its own four columns), so no extra barrier orders them.
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+constexpr int DWT_MAX_THREADS = 512;
+
+template <int K>
+__global__ void __launch_bounds__(DWT_MAX_THREADS, 1)
+    dwconv_ln_bulk_kernel(const float* __restrict__ x, __half* __restrict__ out16, float* __restrict__ out32,
+                          const float* __restrict__ dw_wT, const float* __restrict__ dw_b,
+                          const float* __restrict__ ln_w, const float* __restrict__ ln_b, float eps, int T, int C,
+                          int pitch, int tiles_per_b, int total_tiles, int split) {
+  pdl_launch_dependents();
+  constexpr int R = DW8_R;
+  constexpr int HALF = K > 0 ? (K - 1) / 2 : 0;
+  constexpr int WIN = R + (K > 0 ? K - 1 : 0);
+  extern __shared__ __align__(128) float s_in[];  // [2][WIN][pitch]
+  __shared__ __align__(8) uint64_t full_bar[2];
+  __shared__ float s_red[DWT_MAX_THREADS / 32][R], s_red2[DWT_MAX_THREADS / 32][R];
+  __shared__ float s_mean[R], s_rstd[R];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarp = blockDim.x >> 5;
+  const int c = tid * 4;                 // this thread's channel group (c >= pitch: idle, only joins the barriers)
+  const bool live = c < C, padcol = c >= C && c < pitch;
+  const size_t stage_elems = (size_t)WIN * pitch;
+  if (tid == 0) {
+    mbar_init(&full_bar[0], 1);
+    mbar_init(&full_bar[1], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  pdl_wait();
+
+  // stage fill: zero rows outside the sequence (own columns), then one bulk copy of the rows inside it
+  auto issue = [&](int tile, int s) {
+    const int b = tile / tiles_per_b, t_first = (tile % tiles_per_b) * R - HALF;
+    const int lo = t_first < 0 ? 0 : t_first;
+    const int hi = t_first + WIN > T ? T : t_first + WIN;
+    float* st = s_in + s * stage_elems;
+    if (live) {
+      for (int i = 0; i < lo - t_first; ++i) *reinterpret_cast<float4*>(st + (size_t)i * pitch + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = hi - t_first; i < WIN; ++i) *reinterpret_cast<float4*>(st + (size_t)i * pitch + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (tid == 0) {
+      fence_proxy_async_smem();  // the stage's previous readers (ordered by the CTA barrier) before the async-proxy writes
+      const uint32_t bytes = (uint32_t)(hi - lo) * (uint32_t)pitch * 4u;
+      mbar_arrive_expect_tx(&full_bar[s], bytes);
+      bulk_load_1d(st + (size_t)(lo - t_first) * pitch, x + ((size_t)b * T + lo) * pitch, bytes, &full_bar[s]);
+    }
+  };
+
+  float4 w[K > 0 ? K : 1], bias = make_float4(0.f, 0.f, 0.f, 0.f), gw = bias, gb = bias;
+  if (live) {
+    if constexpr (K > 0) {
+      bias = *reinterpret_cast<const float4*>(dw_b + c);
+#pragma unroll
+      for (int j = 0; j < K; ++j) w[j] = *reinterpret_cast<const float4*>(dw_wT + (size_t)j * C + c);
+    }
+    gw = *reinterpret_cast<const float4*>(ln_w + c);
+    gb = *reinterpret_cast<const float4*>(ln_b + c);
+  }
+  const int stride = (int)gridDim.x;
+  if ((int)blockIdx.x < total_tiles) issue((int)blockIdx.x, 0);
+  if ((int)blockIdx.x + stride < total_tiles) issue((int)blockIdx.x + stride, 1);
+  const float inv_c = 1.0f / (float)C;
+  uint32_t it = 0;
+  for (int tile = (int)blockIdx.x; tile < total_tiles; tile += stride, ++it) {
+    const int s = (int)(it & 1u);
+    const int b = tile / tiles_per_b, t0 = (tile % tiles_per_b) * R;
+    const float* st = s_in + s * stage_elems;
+    mbar_wait(&full_bar[s], (it >> 1) & 1u);
+    float4 acc[R];
+    float sum[R];
+    if (live) {
+      if constexpr (K > 0) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = bias;
+#pragma unroll
+        for (int i = 0; i < WIN; ++i) {
+          const float4 xv = *reinterpret_cast<const float4*>(st + (size_t)i * pitch + c);
+#pragma unroll
+          for (int j = 0; j < K; ++j) {  // input row i is tap j of output row r = i - j
+            const int r = i - j;
+            if (r >= 0 && r < R) {
+              acc[r].x = fmaf(w[j].x, xv.x, acc[r].x);
+              acc[r].y = fmaf(w[j].y, xv.y, acc[r].y);
+              acc[r].z = fmaf(w[j].z, xv.z, acc[r].z);
+              acc[r].w = fmaf(w[j].w, xv.w, acc[r].w);
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = *reinterpret_cast<const float4*>(st + (size_t)r * pitch + c);
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) sum[r] = (acc[r].x + acc[r].y) + (acc[r].z + acc[r].w);
+    } else {
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+        sum[r] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], off);
+      if (lane == 0) s_red[warp][r] = sum[r];
+    }
+    __syncthreads();  // every thread has read its columns of stage s: refill it with the tile after next
+    if (tile + 2 * stride < total_tiles) issue(tile + 2 * stride, s);
+    if (tid < R) {
+      float m = 0.f;
+      for (int wv = 0; wv < nwarp; ++wv) m += s_red[wv][tid];
+      s_mean[tid] = m * inv_c;
+    }
+    __syncthreads();
+    float var[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const float m = s_mean[r];
+      const float d0 = acc[r].x - m, d1 = acc[r].y - m, d2 = acc[r].z - m, d3 = acc[r].w - m;
+      var[r] = live ? fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, d3 * d3))) : 0.f;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) var[r] += __shfl_xor_sync(0xffffffffu, var[r], off);
+      if (lane == 0) s_red2[warp][r] = var[r];
+    }
+    __syncthreads();
+    if (tid < R) {
+      float v = 0.f;
+      for (int wv = 0; wv < nwarp; ++wv) v += s_red2[wv][tid];
+      s_rstd[tid] = 1.0f / sqrtf(v * inv_c + eps);
+    }
+    __syncthreads();
+    if (live || padcol) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int t = t0 + r;
+        if (t < T) {
+          float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (live) {
+            const float m = s_mean[r], rs = s_rstd[r];
+            y.x = fmaf((acc[r].x - m) * rs, gw.x, gb.x);
+            y.y = fmaf((acc[r].y - m) * rs, gw.y, gb.y);
+            y.z = fmaf((acc[r].z - m) * rs, gw.z, gb.z);
+            y.w = fmaf((acc[r].w - m) * rs, gw.w, gb.w);
+          }
+          const size_t row = (size_t)b * T + t;
+          if (out16) {
+            __half* dst = out16 + row * (pitch + split) + c;
+            const uint32_t h0 = pack_half2_sat(y.x, y.y), h1 = pack_half2_sat(y.z, y.w);
+            *reinterpret_cast<uint2*>(dst) = make_uint2(h0, h1);
+            if (split > 0) {
+              const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&h0));
+              const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&h1));
+              *reinterpret_cast<uint2*>(dst + split) =
+                  make_uint2(pack_half2_sat(y.x - f0.x, y.y - f0.y), pack_half2_sat(y.z - f1.x, y.w - f1.y));
+            }
+          }
+          if (out32) *reinterpret_cast<float4*>(out32 + row * pitch + c) = y;
+        }
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // ISTFT("same") overlap-add + envelope normalisation
 // ------------------------------------------------------------------------------------------------
@@ -1198,6 +1375,44 @@ extern "C" int fv_dwconv_layernorm(const float* x32, void* out16, float* out32, 
     const char* e = getenv("FV_DWLN_VEC");  // FV_DWLN_VEC=0: the scalar 4-row kernel (A/B measurements)
     return !(e && e[0] == '0');
   }();
+  static const bool bulk_on = [] {
+    const char* e = getenv("FV_DWLN_BULK");  // FV_DWLN_BULK=0: the per-tile CTA kernels (A/B measurements)
+    return !(e && e[0] == '0');
+  }();
+  {
+    const int win = DW8_R + (k > 0 ? k - 1 : 0);
+    const int bulk_smem = 2 * win * pitch * (int)sizeof(float);
+    const int threads = round_up(pitch / 4, 32);
+    if (bulk_on && (k <= 0 || k == 7) && C % 4 == 0 && pitch % 4 == 0 && aligned16 && threads <= DWT_MAX_THREADS &&
+        bulk_smem <= 200 * 1024) {
+      static std::atomic<unsigned long long> bulk_done7{0}, bulk_done0{0};
+      int rc = check_cuda(ensure_dyn_smem(dwconv_ln_bulk_kernel<7>, 200 * 1024, bulk_done7),
+                          "cudaFuncSetAttribute(dwconv_ln_bulk_kernel)");
+      if (!rc) rc = check_cuda(ensure_dyn_smem(dwconv_ln_bulk_kernel<0>, 200 * 1024, bulk_done0),
+                               "cudaFuncSetAttribute(dwconv_ln_bulk_kernel)");
+      if (rc) return rc;
+      const int tiles_per_b = ceil_div(T, DW8_R);
+      const int total_tiles = B * tiles_per_b;
+      // narrow layers leave room for several resident CTAs per SM (each with its own two stages in flight)
+      int per_sm = (200 * 1024) / (bulk_smem + 4096);
+      per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
+      if (per_sm * threads > 2048) per_sm = 2048 / threads;
+      const int slots = num_sms() * per_sm;
+      const int grid = total_tiles < slots ? total_tiles : slots;
+      cudaError_t le;
+      if (k == 7)
+        le = launch_kernel(dwconv_ln_bulk_kernel<7>, dim3(grid), dim3(threads), bulk_smem, (cudaStream_t)stream, 1, x32,
+                           (__half*)out16, out32, dw_w, dw_b, ln_w, ln_b, eps, T, C, pitch, tiles_per_b, total_tiles,
+                           split);
+      else
+        le = launch_kernel(dwconv_ln_bulk_kernel<0>, dim3(grid), dim3(threads), bulk_smem, (cudaStream_t)stream, 1, x32,
+                           (__half*)out16, out32, dw_w, dw_b, ln_w, ln_b, eps, T, C, pitch, tiles_per_b, total_tiles,
+                           split);
+      FV_REQUIRE(le == cudaSuccess, FV_E_DRIVER, "launch of dwconv_ln_bulk_kernel failed: %s", cudaGetErrorString(le));
+      FV_CHECK_LAUNCH("dwconv_ln_bulk_kernel");
+      return 0;
+    }
+  }
   if (vec_on && (k <= 0 || k == 7) && C % 4 == 0 && pitch % 4 == 0 && aligned16 && vec_smem <= 200 * 1024) {
     static std::atomic<unsigned long long> attr_done7{0}, attr_done0{0};
     int rc = check_cuda(ensure_dyn_smem(dwconv_ln_vec_kernel<7>, 200 * 1024, attr_done7),
