@@ -210,15 +210,20 @@ __global__ void conv_post_kernel(const __half* __restrict__ a, const float* __re
   }
 }
 
-// Sliding-window variant for the common shapes (k <= 7 taps, plain fp16 rows): a group of G lanes (one 16-byte chunk of 8
-// channels each) produces PT consecutive samples from PT + K - 1 rows read ONCE (the per-sample kernel above re-reads every
-// row K times through L1), with the lane's K x 8 weights held in registers.
+// Sliding-window variant for the common shapes (k = 7 taps): a group of G lanes (one 16-byte chunk of 8 channels each)
+// produces PT consecutive samples from PT + K - 1 rows read ONCE (the per-sample kernel above re-reads every row K times
+// through L1), with the lane's K x 8 weights held in registers.  Interior segments load their 14 rows in two batches of
+// seven unconditional 16-byte loads (all in flight before the first use: the per-row bounds test of the edge path kept the
+// loads behind their branches, one latency per row: 76 us for 98 MB); SPLIT: rows hold [hi | lo] and the operand is hi + lo.
 constexpr int POST_T = 8;
-template <int G, int K>
+template <int G, int K, bool SPLIT>
 __global__ void __launch_bounds__(256) conv_post_sliding_kernel(const __half* __restrict__ a, const float* __restrict__ w,
                                                                 const float* bias, float* __restrict__ wav, int B, int L,
                                                                 int C, int pitch, int apply_tanh) {
   constexpr int HALF = (K - 1) / 2;
+  constexpr int WIN = POST_T + K - 1;
+  constexpr int BATCH = (WIN + 1) / 2;
+  const int rpitch = SPLIT ? 2 * pitch : pitch;
   const int g = threadIdx.x % G;
   float wr[K][8];
 #pragma unroll
@@ -241,30 +246,59 @@ __global__ void __launch_bounds__(256) conv_post_sliding_kernel(const __half* __
 #pragma unroll
     for (int i = 0; i < POST_T; ++i) acc[i] = 0.f;
     int b = 0, t0 = 0;
+    auto consume = [&](int i, const uint4& pk, const uint4& pl) {  // window row i is tap j of local output i - j
+      const __half2* h2 = reinterpret_cast<const __half2*>(&pk);
+      const __half2* l2 = reinterpret_cast<const __half2*>(&pl);
+      float x[8];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float2 f = __half22float2(h2[e]);
+        if (SPLIT) {
+          const float2 fl = __half22float2(l2[e]);
+          f.x += fl.x;
+          f.y += fl.y;
+        }
+        x[2 * e] = f.x;
+        x[2 * e + 1] = f.y;
+      }
+#pragma unroll
+      for (int j = 0; j < K; ++j) {
+        const int o = i - j;
+        if (o >= 0 && o < POST_T) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[o] = fmaf(x[e], wr[j][e], acc[o]);
+        }
+      }
+    };
     if (live) {
       b = (int)(sidx / segs_per_b);
       t0 = (int)(sidx % segs_per_b) * POST_T;
-      const __half* base = a + (size_t)b * L * pitch + g * 8;
+      const __half* base = a + (size_t)b * L * rpitch + g * 8;
+      if (t0 - HALF >= 0 && t0 - HALF + WIN <= L) {
+        const __half* row0 = base + (size_t)(t0 - HALF) * rpitch;
 #pragma unroll
-      for (int i = 0; i < POST_T + K - 1; ++i) {
-        const int r = t0 - HALF + i;
-        if (r < 0 || r >= L) continue;
-        const uint4 pk = *reinterpret_cast<const uint4*>(base + (size_t)r * pitch);
-        const __half2* h2 = reinterpret_cast<const __half2*>(&pk);
-        float x[8];
+        for (int i0 = 0; i0 < WIN; i0 += BATCH) {
+          uint4 pk[BATCH], pl[SPLIT ? BATCH : 1];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 f = __half22float2(h2[e]);
-          x[2 * e] = f.x;
-          x[2 * e + 1] = f.y;
-        }
-#pragma unroll
-        for (int j = 0; j < K; ++j) {   // row r is tap j of output t = r - j + HALF, i.e. local output i - j
-          const int o = i - j;
-          if (o >= 0 && o < POST_T) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) acc[o] = fmaf(x[e], wr[j][e], acc[o]);
+          for (int u = 0; u < BATCH; ++u) {
+            if (i0 + u < WIN) {
+              pk[u] = *reinterpret_cast<const uint4*>(row0 + (size_t)(i0 + u) * rpitch);
+              if (SPLIT) pl[u] = *reinterpret_cast<const uint4*>(row0 + (size_t)(i0 + u) * rpitch + pitch);
+            }
           }
+#pragma unroll
+          for (int u = 0; u < BATCH; ++u)
+            if (i0 + u < WIN) consume(i0 + u, pk[u], pl[SPLIT ? u : 0]);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < WIN; ++i) {
+          const int r = t0 - HALF + i;
+          if (r < 0 || r >= L) continue;
+          const uint4 pk = *reinterpret_cast<const uint4*>(base + (size_t)r * rpitch);
+          uint4 pl = make_uint4(0u, 0u, 0u, 0u);
+          if (SPLIT) pl = *reinterpret_cast<const uint4*>(base + (size_t)r * rpitch + pitch);
+          consume(i, pk, pl);
         }
       }
     }
@@ -835,13 +869,9 @@ __global__ void __launch_bounds__(256, 2) dwconv_ln_vec_kernel(const float* __re
       float4 w[K];
 #pragma unroll
       for (int j = 0; j < K; ++j) w[j] = *reinterpret_cast<const float4*>(dw_wT + (size_t)j * C + c);
+      auto tap_row = [&](int i, const float4& xv) {  // input row i is tap j of output row r = i - j
 #pragma unroll
-      for (int i = 0; i < WIN; ++i) {
-        const int t = t0 - HALF + i;
-        float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (t >= 0 && t < T) xv = *reinterpret_cast<const float4*>(xb + (size_t)t * pitch + c);
-#pragma unroll
-        for (int j = 0; j < K; ++j) {  // input row i is tap j of output row r = i - j
+        for (int j = 0; j < K; ++j) {
           const int r = i - j;
           if (r >= 0 && r < DW8_R) {
             acc[r].x = fmaf(w[j].x, xv.x, acc[r].x);
@@ -849,6 +879,30 @@ __global__ void __launch_bounds__(256, 2) dwconv_ln_vec_kernel(const float* __re
             acc[r].z = fmaf(w[j].z, xv.z, acc[r].z);
             acc[r].w = fmaf(w[j].w, xv.w, acc[r].w);
           }
+        }
+      };
+      if (t0 - HALF >= 0 && t0 - HALF + WIN <= T) {
+        // interior tile: two batches of seven unconditional loads, all in flight before their first use (behind the
+        // per-row bounds test of the edge path every load waits for its own branch: one DRAM latency per row)
+        constexpr int BATCH = (WIN + 1) / 2;
+        const float* x0 = xb + (size_t)(t0 - HALF) * pitch + c;
+#pragma unroll
+        for (int i0 = 0; i0 < WIN; i0 += BATCH) {
+          float4 xin[BATCH];
+#pragma unroll
+          for (int u = 0; u < BATCH; ++u)
+            if (i0 + u < WIN) xin[u] = *reinterpret_cast<const float4*>(x0 + (size_t)(i0 + u) * pitch);
+#pragma unroll
+          for (int u = 0; u < BATCH; ++u)
+            if (i0 + u < WIN) tap_row(i0 + u, xin[u]);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < WIN; ++i) {
+          const int t = t0 - HALF + i;
+          float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (t >= 0 && t < T) xv = *reinterpret_cast<const float4*>(xb + (size_t)t * pitch + c);
+          tap_row(i, xv);
         }
       }
     } else {
@@ -1252,14 +1306,18 @@ extern "C" int fv_conv_post_tanh(const void* a16, const float* w32, const float*
   const int chunks = pitch / 8;
   const int threads = 256;
   const long long total = (long long)B * L;
-  if (split == 0 && k == 7 && (chunks == 1 || chunks == 2 || chunks == 4 || chunks == 8)) {
+  if (k == 7 && (chunks == 1 || chunks == 2 || chunks == 4 || chunks == 8)) {
     const long long groups_total = (long long)B * ceil_div(L, POST_T);
 #define FV_POST_S(G)                                                                                        \
   {                                                                                                         \
     long long blocks = (groups_total + (threads / G) - 1) / (threads / G);                                  \
     if (blocks > 148 * 8) blocks = 148 * 8;                                                                 \
-    conv_post_sliding_kernel<G, 7><<<(int)blocks, threads, 0, (cudaStream_t)stream>>>(                      \
-        (const __half*)a16, w32, bias, wav, B, L, C, pitch, apply_tanh);                                    \
+    if (split)                                                                                              \
+      conv_post_sliding_kernel<G, 7, true><<<(int)blocks, threads, 0, (cudaStream_t)stream>>>(              \
+          (const __half*)a16, w32, bias, wav, B, L, C, pitch, apply_tanh);                                  \
+    else                                                                                                    \
+      conv_post_sliding_kernel<G, 7, false><<<(int)blocks, threads, 0, (cudaStream_t)stream>>>(             \
+          (const __half*)a16, w32, bias, wav, B, L, C, pitch, apply_tanh);                                  \
   }
     if (chunks == 1) FV_POST_S(1)
     else if (chunks == 2) FV_POST_S(2)
