@@ -1009,10 +1009,35 @@ __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, u
                : "memory");
 }
 
-constexpr int DWT_MAX_THREADS = 512;
+// warp-wide sums of eight per-thread values in 12 shuffles instead of 40: every step halves the number of values a lane
+// still carries (lanes keep the half selected by one of their lane-id bits and send the other half to their partner);
+// returns the sum of v[row] over the warp with row = 4*bit4 + 2*bit3 + bit2 of the lane id
+__device__ __forceinline__ float warp_reduce8(const float (&v)[8], int lane) {
+  const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0, b2 = (lane & 4) != 0;
+  float a[4], b[2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float keep = b4 ? v[4 + i] : v[i], send = b4 ? v[i] : v[4 + i];
+    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float keep = b3 ? a[2 + i] : a[i], send = b3 ? a[i] : a[2 + i];
+    b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  const float keep = b2 ? b[1] : b[0], send = b2 ? b[0] : b[1];
+  float c = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  c += __shfl_xor_sync(0xffffffffu, c, 2);
+  c += __shfl_xor_sync(0xffffffffu, c, 1);
+  return c;
+}
 
-template <int K>
-__global__ void __launch_bounds__(DWT_MAX_THREADS, 1)
+// A thread owns one PAIR of channels (packed fp32x2 math, 704 threads = 22 warps for C = 1408) for the whole launch.
+// MAXT = block-size bound of the instantiation (register budget).  ncu of the first version of this kernel (4 channels per
+// thread, scalar math, 11 warps): 1250 instructions per thread and tile, a quarter of them integer address / bounds work,
+// 0.39 IPC per scheduler - issue-bound with too few warps, not memory-bound (long-scoreboard 0.18 per issue).
+template <int K, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1)
     dwconv_ln_bulk_kernel(const float* __restrict__ x, __half* __restrict__ out16, float* __restrict__ out32,
                           const float* __restrict__ dw_wT, const float* __restrict__ dw_b,
                           const float* __restrict__ ln_w, const float* __restrict__ ln_b, float eps, int T, int C,
@@ -1023,12 +1048,13 @@ __global__ void __launch_bounds__(DWT_MAX_THREADS, 1)
   constexpr int WIN = R + (K > 0 ? K - 1 : 0);
   extern __shared__ __align__(128) float s_in[];  // [2][WIN][pitch]
   __shared__ __align__(8) uint64_t full_bar[2];
-  __shared__ float s_red[DWT_MAX_THREADS / 32][R], s_red2[DWT_MAX_THREADS / 32][R];
+  __shared__ float s_red[MAXT / 32][R], s_red2[MAXT / 32][R];
   __shared__ float s_mean[R], s_rstd[R];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarp = blockDim.x >> 5;
-  const int c = tid * 4;                 // this thread's channel group (c >= pitch: idle, only joins the barriers)
+  const int c = tid * 2;                 // this thread's channel pair (c >= pitch: idle, only joins the barriers)
   const bool live = c < C, padcol = c >= C && c < pitch;
   const size_t stage_elems = (size_t)WIN * pitch;
+  const int red_row = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
   if (tid == 0) {
     mbar_init(&full_bar[0], 1);
     mbar_init(&full_bar[1], 1);
@@ -1044,8 +1070,8 @@ __global__ void __launch_bounds__(DWT_MAX_THREADS, 1)
     const int hi = t_first + WIN > T ? T : t_first + WIN;
     float* st = s_in + s * stage_elems;
     if (live) {
-      for (int i = 0; i < lo - t_first; ++i) *reinterpret_cast<float4*>(st + (size_t)i * pitch + c) = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int i = hi - t_first; i < WIN; ++i) *reinterpret_cast<float4*>(st + (size_t)i * pitch + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = 0; i < lo - t_first; ++i) *reinterpret_cast<float2*>(st + (size_t)i * pitch + c) = make_float2(0.f, 0.f);
+      for (int i = hi - t_first; i < WIN; ++i) *reinterpret_cast<float2*>(st + (size_t)i * pitch + c) = make_float2(0.f, 0.f);
     }
     if (tid == 0) {
       fence_proxy_async_smem();  // the stage's previous readers (ordered by the CTA barrier) before the async-proxy writes
@@ -1055,116 +1081,110 @@ __global__ void __launch_bounds__(DWT_MAX_THREADS, 1)
     }
   };
 
-  float4 w[K > 0 ? K : 1], bias = make_float4(0.f, 0.f, 0.f, 0.f), gw = bias, gb = bias;
+  float2 w[K > 0 ? K : 1], bias = make_float2(0.f, 0.f), gw = bias, gb = bias;
   if (live) {
     if constexpr (K > 0) {
-      bias = *reinterpret_cast<const float4*>(dw_b + c);
+      bias = *reinterpret_cast<const float2*>(dw_b + c);
 #pragma unroll
-      for (int j = 0; j < K; ++j) w[j] = *reinterpret_cast<const float4*>(dw_wT + (size_t)j * C + c);
+      for (int j = 0; j < K; ++j) w[j] = *reinterpret_cast<const float2*>(dw_wT + (size_t)j * C + c);
     }
-    gw = *reinterpret_cast<const float4*>(ln_w + c);
-    gb = *reinterpret_cast<const float4*>(ln_b + c);
+    gw = *reinterpret_cast<const float2*>(ln_w + c);
+    gb = *reinterpret_cast<const float2*>(ln_b + c);
   }
   const int stride = (int)gridDim.x;
   if ((int)blockIdx.x < total_tiles) issue((int)blockIdx.x, 0);
   if ((int)blockIdx.x + stride < total_tiles) issue((int)blockIdx.x + stride, 1);
   const float inv_c = 1.0f / (float)C;
+  const int opitch = pitch + split;
   uint32_t it = 0;
   for (int tile = (int)blockIdx.x; tile < total_tiles; tile += stride, ++it) {
     const int s = (int)(it & 1u);
     const int b = tile / tiles_per_b, t0 = (tile % tiles_per_b) * R;
-    const float* st = s_in + s * stage_elems;
+    const float* st = s_in + s * stage_elems + c;
     mbar_wait(&full_bar[s], (it >> 1) & 1u);
-    float4 acc[R];
-    float sum[R];
+    float2 acc[R];
+    float red[R];
     if (live) {
       if constexpr (K > 0) {
 #pragma unroll
         for (int r = 0; r < R; ++r) acc[r] = bias;
 #pragma unroll
         for (int i = 0; i < WIN; ++i) {
-          const float4 xv = *reinterpret_cast<const float4*>(st + (size_t)i * pitch + c);
+          const float2 xv = *reinterpret_cast<const float2*>(st + (size_t)i * pitch);
 #pragma unroll
           for (int j = 0; j < K; ++j) {  // input row i is tap j of output row r = i - j
             const int r = i - j;
-            if (r >= 0 && r < R) {
-              acc[r].x = fmaf(w[j].x, xv.x, acc[r].x);
-              acc[r].y = fmaf(w[j].y, xv.y, acc[r].y);
-              acc[r].z = fmaf(w[j].z, xv.z, acc[r].z);
-              acc[r].w = fmaf(w[j].w, xv.w, acc[r].w);
-            }
+            if (r >= 0 && r < R) acc[r] = ffma2(w[j], xv, acc[r]);
           }
         }
       } else {
 #pragma unroll
-        for (int r = 0; r < R; ++r) acc[r] = *reinterpret_cast<const float4*>(st + (size_t)r * pitch + c);
+        for (int r = 0; r < R; ++r) acc[r] = *reinterpret_cast<const float2*>(st + (size_t)r * pitch);
       }
 #pragma unroll
-      for (int r = 0; r < R; ++r) sum[r] = (acc[r].x + acc[r].y) + (acc[r].z + acc[r].w);
+      for (int r = 0; r < R; ++r) red[r] = acc[r].x + acc[r].y;
     } else {
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-        sum[r] = 0.f;
+        acc[r] = make_float2(0.f, 0.f);
+        red[r] = 0.f;
       }
     }
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], off);
-      if (lane == 0) s_red[warp][r] = sum[r];
+    {
+      const float v = warp_reduce8(red, lane);
+      if ((lane & 3) == 0) s_red[warp][red_row] = v;
     }
     __syncthreads();  // every thread has read its columns of stage s: refill it with the tile after next
     if (tile + 2 * stride < total_tiles) issue(tile + 2 * stride, s);
-    if (tid < R) {
+    if (warp == 0) {  // lane = (part, row): four partial sums over the warps per row, combined by two shuffles
       float m = 0.f;
-      for (int wv = 0; wv < nwarp; ++wv) m += s_red[wv][tid];
-      s_mean[tid] = m * inv_c;
+      for (int wv = lane >> 3; wv < nwarp; wv += 4) m += s_red[wv][lane & 7];
+      m += __shfl_xor_sync(0xffffffffu, m, 8);
+      m += __shfl_xor_sync(0xffffffffu, m, 16);
+      if (lane < R) s_mean[lane] = m * inv_c;
     }
     __syncthreads();
-    float var[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       const float m = s_mean[r];
-      const float d0 = acc[r].x - m, d1 = acc[r].y - m, d2 = acc[r].z - m, d3 = acc[r].w - m;
-      var[r] = live ? fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, d3 * d3))) : 0.f;
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) var[r] += __shfl_xor_sync(0xffffffffu, var[r], off);
-      if (lane == 0) s_red2[warp][r] = var[r];
+      const float d0 = acc[r].x - m, d1 = acc[r].y - m;
+      red[r] = live ? fmaf(d0, d0, d1 * d1) : 0.f;
+    }
+    {
+      const float v = warp_reduce8(red, lane);
+      if ((lane & 3) == 0) s_red2[warp][red_row] = v;
     }
     __syncthreads();
-    if (tid < R) {
+    if (warp == 0) {
       float v = 0.f;
-      for (int wv = 0; wv < nwarp; ++wv) v += s_red2[wv][tid];
-      s_rstd[tid] = 1.0f / sqrtf(v * inv_c + eps);
+      for (int wv = lane >> 3; wv < nwarp; wv += 4) v += s_red2[wv][lane & 7];
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if (lane < R) s_rstd[lane] = 1.0f / sqrtf(v * inv_c + eps);
     }
     __syncthreads();
     if (live || padcol) {
+      const int rows = T - t0 < R ? T - t0 : R;
+      const size_t row0 = (size_t)b * T + t0;
+      __half* o16 = out16 ? out16 + row0 * opitch + c : nullptr;
+      float* o32 = out32 ? out32 + row0 * pitch + c : nullptr;
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        const int t = t0 + r;
-        if (t < T) {
-          float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < rows) {
+          float2 y = make_float2(0.f, 0.f);
           if (live) {
-            const float m = s_mean[r], rs = s_rstd[r];
-            y.x = fmaf((acc[r].x - m) * rs, gw.x, gb.x);
-            y.y = fmaf((acc[r].y - m) * rs, gw.y, gb.y);
-            y.z = fmaf((acc[r].z - m) * rs, gw.z, gb.z);
-            y.w = fmaf((acc[r].w - m) * rs, gw.w, gb.w);
+            const float rs = s_rstd[r], off = -s_mean[r] * rs;
+            y = ffma2(ffma2(acc[r], bc2(rs), bc2(off)), gw, gb);
           }
-          const size_t row = (size_t)b * T + t;
-          if (out16) {
-            __half* dst = out16 + row * (pitch + split) + c;
-            const uint32_t h0 = pack_half2_sat(y.x, y.y), h1 = pack_half2_sat(y.z, y.w);
-            *reinterpret_cast<uint2*>(dst) = make_uint2(h0, h1);
+          if (o16) {
+            const uint32_t h = pack_half2_sat(y.x, y.y);
+            *reinterpret_cast<uint32_t*>(o16 + (size_t)r * opitch) = h;
             if (split > 0) {
-              const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&h0));
-              const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&h1));
-              *reinterpret_cast<uint2*>(dst + split) =
-                  make_uint2(pack_half2_sat(y.x - f0.x, y.y - f0.y), pack_half2_sat(y.z - f1.x, y.w - f1.y));
+              const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h));
+              *reinterpret_cast<uint32_t*>(o16 + (size_t)r * opitch + split) = pack_half2_sat(y.x - f.x, y.y - f.y);
             }
           }
-          if (out32) *reinterpret_cast<float4*>(out32 + row * pitch + c) = y;
+          if (o32) *reinterpret_cast<float2*>(o32 + (size_t)r * pitch) = y;
         }
       }
     }
@@ -1440,33 +1460,43 @@ extern "C" int fv_dwconv_layernorm(const float* x32, void* out16, float* out32, 
   {
     const int win = DW8_R + (k > 0 ? k - 1 : 0);
     const int bulk_smem = 2 * win * pitch * (int)sizeof(float);
-    const int threads = round_up(pitch / 4, 32);
-    if (bulk_on && (k <= 0 || k == 7) && C % 4 == 0 && pitch % 4 == 0 && aligned16 && threads <= DWT_MAX_THREADS &&
+    const int threads = round_up(pitch / 2, 32);
+    if (bulk_on && (k <= 0 || k == 7) && C % 2 == 0 && pitch % 4 == 0 && aligned16 && threads <= 1024 &&
         bulk_smem <= 200 * 1024) {
-      static std::atomic<unsigned long long> bulk_done7{0}, bulk_done0{0};
-      int rc = check_cuda(ensure_dyn_smem(dwconv_ln_bulk_kernel<7>, 200 * 1024, bulk_done7),
-                          "cudaFuncSetAttribute(dwconv_ln_bulk_kernel)");
-      if (!rc) rc = check_cuda(ensure_dyn_smem(dwconv_ln_bulk_kernel<0>, 200 * 1024, bulk_done0),
-                               "cudaFuncSetAttribute(dwconv_ln_bulk_kernel)");
-      if (rc) return rc;
       const int tiles_per_b = ceil_div(T, DW8_R);
       const int total_tiles = B * tiles_per_b;
       // narrow layers leave room for several resident CTAs per SM (each with its own two stages in flight)
       int per_sm = (200 * 1024) / (bulk_smem + 4096);
       per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
-      if (per_sm * threads > 2048) per_sm = 2048 / threads;
+      {  // ... and the register file: ~112 / 80 / 64 registers per thread in the 384 / 768 / 1024-thread instantiations
+        const int regs = threads <= 384 ? 112 : (threads <= 768 ? 80 : 64);
+        const int by_regs = 65536 / (threads * regs);
+        per_sm = per_sm > by_regs ? (by_regs > 0 ? by_regs : 1) : per_sm;
+      }
       const int slots = num_sms() * per_sm;
       const int grid = total_tiles < slots ? total_tiles : slots;
-      cudaError_t le;
-      if (k == 7)
-        le = launch_kernel(dwconv_ln_bulk_kernel<7>, dim3(grid), dim3(threads), bulk_smem, (cudaStream_t)stream, 1, x32,
-                           (__half*)out16, out32, dw_w, dw_b, ln_w, ln_b, eps, T, C, pitch, tiles_per_b, total_tiles,
-                           split);
-      else
-        le = launch_kernel(dwconv_ln_bulk_kernel<0>, dim3(grid), dim3(threads), bulk_smem, (cudaStream_t)stream, 1, x32,
-                           (__half*)out16, out32, dw_w, dw_b, ln_w, ln_b, eps, T, C, pitch, tiles_per_b, total_tiles,
-                           split);
-      FV_REQUIRE(le == cudaSuccess, FV_E_DRIVER, "launch of dwconv_ln_bulk_kernel failed: %s", cudaGetErrorString(le));
+#define FV_DWLN_BULK_LAUNCH(KK, MAXT)                                                                              \
+  do {                                                                                                             \
+    static std::atomic<unsigned long long> done{0};                                                                \
+    int rc = check_cuda(ensure_dyn_smem(dwconv_ln_bulk_kernel<KK, MAXT>, 200 * 1024, done),                        \
+                        "cudaFuncSetAttribute(dwconv_ln_bulk_kernel)");                                            \
+    if (rc) return rc;                                                                                             \
+    cudaError_t le = launch_kernel(dwconv_ln_bulk_kernel<KK, MAXT>, dim3(grid), dim3(threads), bulk_smem,          \
+                                   (cudaStream_t)stream, 1, x32, (__half*)out16, out32, dw_w, dw_b, ln_w, ln_b,    \
+                                   eps, T, C, pitch, tiles_per_b, total_tiles, split);                             \
+    FV_REQUIRE(le == cudaSuccess, FV_E_DRIVER, "launch of dwconv_ln_bulk_kernel failed: %s",                       \
+               cudaGetErrorString(le));                                                                            \
+  } while (0)
+      if (k == 7) {
+        if (threads <= 384) FV_DWLN_BULK_LAUNCH(7, 384);
+        else if (threads <= 768) FV_DWLN_BULK_LAUNCH(7, 768);
+        else FV_DWLN_BULK_LAUNCH(7, 1024);
+      } else {
+        if (threads <= 384) FV_DWLN_BULK_LAUNCH(0, 384);
+        else if (threads <= 768) FV_DWLN_BULK_LAUNCH(0, 768);
+        else FV_DWLN_BULK_LAUNCH(0, 1024);
+      }
+#undef FV_DWLN_BULK_LAUNCH
       FV_CHECK_LAUNCH("dwconv_ln_bulk_kernel");
       return 0;
     }
