@@ -1049,12 +1049,12 @@ __global__ void __launch_bounds__(MAXT, 1)
   extern __shared__ __align__(128) float s_in[];  // [2][WIN][pitch]
   __shared__ __align__(8) uint64_t full_bar[2];
   __shared__ float s_red[MAXT / 32][R], s_red2[MAXT / 32][R];
-  __shared__ float s_mean[R], s_rstd[R];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarp = blockDim.x >> 5;
   const int c = tid * 2;                 // this thread's channel pair (c >= pitch: idle, only joins the barriers)
   const bool live = c < C, padcol = c >= C && c < pitch;
   const size_t stage_elems = (size_t)WIN * pitch;
   const int red_row = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+  const bool issuer = tid == (int)blockDim.x - 32;   // lane 0 of the last warp issues the bulk copies
   if (tid == 0) {
     mbar_init(&full_bar[0], 1);
     mbar_init(&full_bar[1], 1);
@@ -1065,20 +1065,29 @@ __global__ void __launch_bounds__(MAXT, 1)
 
   // stage fill: zero rows outside the sequence (own columns), then one bulk copy of the rows inside it
   auto issue = [&](int tile, int s) {
-    const int b = tile / tiles_per_b, t_first = (tile % tiles_per_b) * R - HALF;
+    const int b = tile / tiles_per_b, t_first = (tile - b * tiles_per_b) * R - HALF;
     const int lo = t_first < 0 ? 0 : t_first;
     const int hi = t_first + WIN > T ? T : t_first + WIN;
     float* st = s_in + s * stage_elems;
-    if (live) {
+    if (live && (lo != t_first || hi != t_first + WIN)) {
       for (int i = 0; i < lo - t_first; ++i) *reinterpret_cast<float2*>(st + (size_t)i * pitch + c) = make_float2(0.f, 0.f);
       for (int i = hi - t_first; i < WIN; ++i) *reinterpret_cast<float2*>(st + (size_t)i * pitch + c) = make_float2(0.f, 0.f);
     }
-    if (tid == 0) {
+    if (issuer) {
       fence_proxy_async_smem();  // the stage's previous readers (ordered by the CTA barrier) before the async-proxy writes
       const uint32_t bytes = (uint32_t)(hi - lo) * (uint32_t)pitch * 4u;
       mbar_arrive_expect_tx(&full_bar[s], bytes);
       bulk_load_1d(st + (size_t)(lo - t_first) * pitch, x + ((size_t)b * T + lo) * pitch, bytes, &full_bar[s]);
     }
+  };
+  // every warp sums the per-warp partials itself (lane = (part, row): four strided partial sums per row, two shuffles), so
+  // no single warp computes while the others wait at a barrier; returns the total of row (lane & 7) in every lane
+  auto cross_warp = [&](const float (*part)[R]) {
+    float m = 0.f;
+    for (int wv = lane >> 3; wv < nwarp; wv += 4) m += part[wv][lane & 7];
+    m += __shfl_xor_sync(0xffffffffu, m, 8);
+    m += __shfl_xor_sync(0xffffffffu, m, 16);
+    return m;
   };
 
   float2 w[K > 0 ? K : 1], bias = make_float2(0.f, 0.f), gw = bias, gb = bias;
@@ -1096,21 +1105,27 @@ __global__ void __launch_bounds__(MAXT, 1)
   if ((int)blockIdx.x + stride < total_tiles) issue((int)blockIdx.x + stride, 1);
   const float inv_c = 1.0f / (float)C;
   const int opitch = pitch + split;
+  const uint32_t row_bytes = (uint32_t)pitch * 4u;
   uint32_t it = 0;
   for (int tile = (int)blockIdx.x; tile < total_tiles; tile += stride, ++it) {
     const int s = (int)(it & 1u);
-    const int b = tile / tiles_per_b, t0 = (tile % tiles_per_b) * R;
-    const float* st = s_in + s * stage_elems + c;
+    const int b = tile / tiles_per_b, t0 = (tile - b * tiles_per_b) * R;
+    const uint32_t st = smem_u32(s_in + s * stage_elems + c);
     mbar_wait(&full_bar[s], (it >> 1) & 1u);
     float2 acc[R];
     float red[R];
     if (live) {
+      auto lds2 = [&](int i) {
+        float2 v;
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(st + (uint32_t)i * row_bytes));
+        return v;
+      };
       if constexpr (K > 0) {
 #pragma unroll
         for (int r = 0; r < R; ++r) acc[r] = bias;
 #pragma unroll
         for (int i = 0; i < WIN; ++i) {
-          const float2 xv = *reinterpret_cast<const float2*>(st + (size_t)i * pitch);
+          const float2 xv = lds2(i);
 #pragma unroll
           for (int j = 0; j < K; ++j) {  // input row i is tap j of output row r = i - j
             const int r = i - j;
@@ -1119,7 +1134,7 @@ __global__ void __launch_bounds__(MAXT, 1)
         }
       } else {
 #pragma unroll
-        for (int r = 0; r < R; ++r) acc[r] = *reinterpret_cast<const float2*>(st + (size_t)r * pitch);
+        for (int r = 0; r < R; ++r) acc[r] = lds2(r);
       }
 #pragma unroll
       for (int r = 0; r < R; ++r) red[r] = acc[r].x + acc[r].y;
@@ -1136,18 +1151,12 @@ __global__ void __launch_bounds__(MAXT, 1)
     }
     __syncthreads();  // every thread has read its columns of stage s: refill it with the tile after next
     if (tile + 2 * stride < total_tiles) issue(tile + 2 * stride, s);
-    if (warp == 0) {  // lane = (part, row): four partial sums over the warps per row, combined by two shuffles
-      float m = 0.f;
-      for (int wv = lane >> 3; wv < nwarp; wv += 4) m += s_red[wv][lane & 7];
-      m += __shfl_xor_sync(0xffffffffu, m, 8);
-      m += __shfl_xor_sync(0xffffffffu, m, 16);
-      if (lane < R) s_mean[lane] = m * inv_c;
-    }
-    __syncthreads();
+    const float mean_l = cross_warp(s_red) * inv_c;      // of row (lane & 7)
+    float mean[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      const float m = s_mean[r];
-      const float d0 = acc[r].x - m, d1 = acc[r].y - m;
+      mean[r] = __shfl_sync(0xffffffffu, mean_l, r);
+      const float d0 = acc[r].x - mean[r], d1 = acc[r].y - mean[r];
       red[r] = live ? fmaf(d0, d0, d1 * d1) : 0.f;
     }
     {
@@ -1155,14 +1164,7 @@ __global__ void __launch_bounds__(MAXT, 1)
       if ((lane & 3) == 0) s_red2[warp][red_row] = v;
     }
     __syncthreads();
-    if (warp == 0) {
-      float v = 0.f;
-      for (int wv = lane >> 3; wv < nwarp; wv += 4) v += s_red2[wv][lane & 7];
-      v += __shfl_xor_sync(0xffffffffu, v, 8);
-      v += __shfl_xor_sync(0xffffffffu, v, 16);
-      if (lane < R) s_rstd[lane] = 1.0f / sqrtf(v * inv_c + eps);
-    }
-    __syncthreads();
+    const float rstd_l = rsqrtf(cross_warp(s_red2) * inv_c + eps);
     if (live || padcol) {
       const int rows = T - t0 < R ? T - t0 : R;
       const size_t row0 = (size_t)b * T + t0;
@@ -1170,21 +1172,23 @@ __global__ void __launch_bounds__(MAXT, 1)
       float* o32 = out32 ? out32 + row0 * pitch + c : nullptr;
 #pragma unroll
       for (int r = 0; r < R; ++r) {
+        const float rs = __shfl_sync(0xffffffffu, rstd_l, r);
         if (r < rows) {
           float2 y = make_float2(0.f, 0.f);
-          if (live) {
-            const float rs = s_rstd[r], off = -s_mean[r] * rs;
-            y = ffma2(ffma2(acc[r], bc2(rs), bc2(off)), gw, gb);
-          }
+          if (live) y = ffma2(ffma2(acc[r], bc2(rs), bc2(-mean[r] * rs)), gw, gb);
           if (o16) {
             const uint32_t h = pack_half2_sat(y.x, y.y);
-            *reinterpret_cast<uint32_t*>(o16 + (size_t)r * opitch) = h;
+            *reinterpret_cast<uint32_t*>(o16) = h;
             if (split > 0) {
               const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h));
-              *reinterpret_cast<uint32_t*>(o16 + (size_t)r * opitch + split) = pack_half2_sat(y.x - f.x, y.y - f.y);
+              *reinterpret_cast<uint32_t*>(o16 + split) = pack_half2_sat(y.x - f.x, y.y - f.y);
             }
+            o16 += opitch;
           }
-          if (o32) *reinterpret_cast<float2*>(o32 + (size_t)r * pitch) = y;
+          if (o32) {
+            *reinterpret_cast<float2*>(o32) = y;
+            o32 += pitch;
+          }
         }
       }
     }
