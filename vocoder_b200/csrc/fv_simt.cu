@@ -1077,14 +1077,26 @@ __global__ void __launch_bounds__(MAXT, 1)
       fence_proxy_async_smem();  // the stage's previous readers (ordered by the CTA barrier) before the async-proxy writes
       const uint32_t bytes = (uint32_t)(hi - lo) * (uint32_t)pitch * 4u;
       mbar_arrive_expect_tx(&full_bar[s], bytes);
-      bulk_load_1d(st + (size_t)(lo - t_first) * pitch, x + ((size_t)b * T + lo) * pitch, bytes, &full_bar[s]);
+      // one copy per pair of rows: the copies of a tile proceed concurrently (a single 79 KB copy arrived later than
+      // two tiles' worth of compute: the mbarrier wait of the first version spun ~11 times per tile)
+      const float* src = x + ((size_t)b * T + lo) * pitch;
+      float* dst = st + (size_t)(lo - t_first) * pitch;
+      for (int r = lo; r < hi; r += 2) {
+        const uint32_t nb = (uint32_t)(hi - r < 2 ? hi - r : 2) * (uint32_t)pitch * 4u;
+        bulk_load_1d(dst, src, nb, &full_bar[s]);
+        src += 2 * (size_t)pitch;
+        dst += 2 * (size_t)pitch;
+      }
     }
   };
   // every warp sums the per-warp partials itself (lane = (part, row): four strided partial sums per row, two shuffles), so
   // no single warp computes while the others wait at a barrier; returns the total of row (lane & 7) in every lane
   auto cross_warp = [&](const float (*part)[R]) {
     float m = 0.f;
-    for (int wv = lane >> 3; wv < nwarp; wv += 4) m += part[wv][lane & 7];
+    const float* pl = &part[lane >> 3][lane & 7];
+#pragma unroll
+    for (int u = 0; u < MAXT / 128; ++u)
+      if ((lane >> 3) + 4 * u < nwarp) m += pl[4 * u * R];
     m += __shfl_xor_sync(0xffffffffu, m, 8);
     m += __shfl_xor_sync(0xffffffffu, m, 16);
     return m;
