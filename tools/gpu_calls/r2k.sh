@@ -4,10 +4,10 @@ O=gpurun_out/r2k; mkdir -p $O
 timeout 900 python -m pytest tests -m gpu -q --maxfail=30 -p no:cacheprovider -s > $O/pytest.log 2>&1; echo "pytest exit $?" >> $O/pytest.log
 tail -n 4 $O/pytest.log
 BA="--extra none --no-cpu-baseline --no-sustained --no-stress-parity"
-FV_DWLN_BULK=1 timeout 300 python bench.py $BA --steps 20 --warmup 3 --workload vocos_huge_b128 > $O/bench_vocos_bulk.json 2> $O/bench_vocos_bulk.err
-FV_DWLN_BULK=0 timeout 300 python bench.py $BA --steps 20 --warmup 3 --workload vocos_huge_b128 > $O/bench_vocos_vec.json 2> $O/bench_vocos_vec.err
+FV_DWLN_PIPE=1 timeout 300 python bench.py $BA --steps 20 --warmup 3 --workload vocos_huge_b128 > $O/bench_vocos_pipe.json 2> $O/bench_vocos_pipe.err
+FV_DWLN_PIPE=0 timeout 300 python bench.py $BA --steps 20 --warmup 3 --workload vocos_huge_b128 > $O/bench_vocos_vec.json 2> $O/bench_vocos_vec.err
 timeout 300 python bench.py $BA --steps 20 --warmup 3 --workload firefly_b32 > $O/bench_firefly.json 2> $O/bench_firefly.err
-FV_DWLN_BULK=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:dwconv_ln -s 190 -c 2 -f -o $O/prof_dwln \
+FV_DWLN_PIPE=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:dwconv_ln -s 190 -c 2 -f -o $O/prof_dwln \
     python bench.py $BA --no-graph --steps 1 --warmup 3 --workload vocos_huge_b128 > $O/ncu_dwln.log 2>&1
 ncu -i $O/prof_dwln.ncu-rep --page raw --csv > $O/prof_dwln_raw.csv 2>/dev/null
 ncu -i $O/prof_dwln.ncu-rep --page source --csv > $O/prof_dwln_source.csv 2>/dev/null

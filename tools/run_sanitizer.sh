@@ -3,7 +3,7 @@
 # memcheck (out-of-bounds / misaligned shared and global accesses) and racecheck (shared-memory hazards between the
 # generic-proxy writes of the epilogue warps and everything else).  Usage (GPU box): bash tools/run_sanitizer.sh [outdir]
 # The selection covers fv_mrf_fused C = 16 / 32 / 64 (incl. the ALIAS staging configurations), conv_tc (single CTA,
-# CTA pair, slab mainloop, 16-warp epilogue, strict operands), snake_aa (streaming + edge modes), dwconv_ln (bulk-copy pipeline), ISTFT, row-pair convs.
+# CTA pair, slab mainloop, 16-warp epilogue, strict operands), snake_aa (streaming + edge modes), dwconv_ln (cp.async pipeline), ISTFT, row-pair convs.
 set -uo pipefail
 OUT="${1:-gpurun_out/sanitizer}"
 mkdir -p "$OUT"

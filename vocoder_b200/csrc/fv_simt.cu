@@ -994,19 +994,16 @@ __global__ void __launch_bounds__(256, 2) dwconv_ln_vec_kernel(const float* __re
   }
 }
 
-// Persistent bulk-copy variant (round 2): the vectorised kernel above moves 1.8 TB/s - every CTA loads, reduces and stores in
-// sequence and two or three resident CTAs per SM do not keep enough bytes in flight.  Here one CTA per SM walks over tiles of
-// DW8_R time steps; the 14 input rows of a tile are ONE contiguous range of the channels-last tensor, fetched by a single
-// 1-D bulk copy (cp.async.bulk, completion on an mbarrier) into one of two shared-memory stages, so the loads of the next
-// two tiles are always in flight while this tile is filtered, normalised and stored.  A thread owns one group of four
-// channels for the whole launch: depthwise taps, bias and LayerNorm affine live in registers across tiles, the conv results
-// stay in registers for both LayerNorm passes (no shared-memory parking).  Rows outside [0, T) (the conv's zero padding) are
-// zero-filled by the thread that later reads them (its own four columns), so no extra barrier orders them.
-__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(smem_dst)),
-               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
+// Persistent pipelined variant (round 2): one CTA per SM walks over tiles of DW8_R time steps with the input rows of the next
+// two tiles always in flight.  A thread owns one PAIR of channels for the whole launch and copies exactly the columns it later
+// reads - 14 rows x 8 bytes per tile with cp.async into one of two shared-memory stages, no registers held, completion by
+// the thread's own cp.async group - so no barrier or mbarrier orders the stages.  (First version: ONE 79 KB cp.async.bulk per
+// tile, then one per row pair: the data arrived later than two tiles of compute, ~11 spins of the mbarrier wait per tile at
+// 18% DRAM utilisation - the bulk-copy engine keeps too few bytes in flight per SM for DRAM-latency streams.)
+// Depthwise taps, bias and LayerNorm affine live in registers across tiles, the conv results stay in registers for both
+// LayerNorm passes, all math is packed fp32x2.  Rows outside [0, T) (the conv's zero padding) are zero-filled in place.
+__device__ __forceinline__ void cp_async8(uint32_t smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_dst), "l"(gsrc) : "memory");
 }
 
 // warp-wide sums of eight per-thread values in 12 shuffles instead of 40: every step halves the number of values a lane
@@ -1038,7 +1035,7 @@ __device__ __forceinline__ float warp_reduce8(const float (&v)[8], int lane) {
 // 0.39 IPC per scheduler - issue-bound with too few warps, not memory-bound (long-scoreboard 0.18 per issue).
 template <int K, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1)
-    dwconv_ln_bulk_kernel(const float* __restrict__ x, __half* __restrict__ out16, float* __restrict__ out32,
+    dwconv_ln_pipe_kernel(const float* __restrict__ x, __half* __restrict__ out16, float* __restrict__ out32,
                           const float* __restrict__ dw_wT, const float* __restrict__ dw_b,
                           const float* __restrict__ ln_w, const float* __restrict__ ln_b, float eps, int T, int C,
                           int pitch, int tiles_per_b, int total_tiles, int split) {
@@ -1047,47 +1044,30 @@ __global__ void __launch_bounds__(MAXT, 1)
   constexpr int HALF = K > 0 ? (K - 1) / 2 : 0;
   constexpr int WIN = R + (K > 0 ? K - 1 : 0);
   extern __shared__ __align__(128) float s_in[];  // [2][WIN][pitch]
-  __shared__ __align__(8) uint64_t full_bar[2];
   __shared__ float s_red[MAXT / 32][R], s_red2[MAXT / 32][R];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarp = blockDim.x >> 5;
   const int c = tid * 2;                 // this thread's channel pair (c >= pitch: idle, only joins the barriers)
   const bool live = c < C, padcol = c >= C && c < pitch;
   const size_t stage_elems = (size_t)WIN * pitch;
+  const uint32_t row_bytes = (uint32_t)pitch * 4u;
   const int red_row = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-  const bool issuer = tid == (int)blockDim.x - 32;   // lane 0 of the last warp issues the bulk copies
-  if (tid == 0) {
-    mbar_init(&full_bar[0], 1);
-    mbar_init(&full_bar[1], 1);
-    fence_barrier_init();
-  }
-  __syncthreads();
   pdl_wait();
 
-  // stage fill: zero rows outside the sequence (own columns), then one bulk copy of the rows inside it
+  // stage fill (this thread's two columns of the tile's WIN input rows): async copies of the rows inside the sequence,
+  // zeros for the rows outside it; always commits a group so that "all but the newest group" is the tile being waited for
   auto issue = [&](int tile, int s) {
-    const int b = tile / tiles_per_b, t_first = (tile - b * tiles_per_b) * R - HALF;
-    const int lo = t_first < 0 ? 0 : t_first;
-    const int hi = t_first + WIN > T ? T : t_first + WIN;
-    float* st = s_in + s * stage_elems;
-    if (live && (lo != t_first || hi != t_first + WIN)) {
-      for (int i = 0; i < lo - t_first; ++i) *reinterpret_cast<float2*>(st + (size_t)i * pitch + c) = make_float2(0.f, 0.f);
-      for (int i = hi - t_first; i < WIN; ++i) *reinterpret_cast<float2*>(st + (size_t)i * pitch + c) = make_float2(0.f, 0.f);
-    }
-    if (issuer) {
-      fence_proxy_async_smem();  // the stage's previous readers (ordered by the CTA barrier) before the async-proxy writes
-      const uint32_t bytes = (uint32_t)(hi - lo) * (uint32_t)pitch * 4u;
-      mbar_arrive_expect_tx(&full_bar[s], bytes);
-      // one copy per pair of rows: the copies of a tile proceed concurrently (a single 79 KB copy arrived later than
-      // two tiles' worth of compute: the mbarrier wait of the first version spun ~11 times per tile)
-      const float* src = x + ((size_t)b * T + lo) * pitch;
-      float* dst = st + (size_t)(lo - t_first) * pitch;
-      for (int r = lo; r < hi; r += 2) {
-        const uint32_t nb = (uint32_t)(hi - r < 2 ? hi - r : 2) * (uint32_t)pitch * 4u;
-        bulk_load_1d(dst, src, nb, &full_bar[s]);
-        src += 2 * (size_t)pitch;
-        dst += 2 * (size_t)pitch;
+    if (live && tile < total_tiles) {
+      const int b = tile / tiles_per_b, t_first = (tile - b * tiles_per_b) * R - HALF;
+      const uint32_t st = smem_u32(s_in + s * stage_elems + c);
+      const float* src = x + ((size_t)b * T + t_first) * pitch + c;   // (row t_first may lie outside: never dereferenced)
+#pragma unroll
+      for (int i = 0; i < WIN; ++i) {
+        const int t = t_first + i;
+        if (t >= 0 && t < T) cp_async8(st + (uint32_t)i * row_bytes, src + (size_t)i * pitch);
+        else asm volatile("st.shared.v2.f32 [%0], {%1, %1};" ::"r"(st + (uint32_t)i * row_bytes), "f"(0.f) : "memory");
       }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   };
   // every warp sums the per-warp partials itself (lane = (part, row): four strided partial sums per row, two shuffles), so
   // no single warp computes while the others wait at a barrier; returns the total of row (lane & 7) in every lane
@@ -1113,17 +1093,16 @@ __global__ void __launch_bounds__(MAXT, 1)
     gb = *reinterpret_cast<const float2*>(ln_b + c);
   }
   const int stride = (int)gridDim.x;
-  if ((int)blockIdx.x < total_tiles) issue((int)blockIdx.x, 0);
-  if ((int)blockIdx.x + stride < total_tiles) issue((int)blockIdx.x + stride, 1);
+  issue((int)blockIdx.x, 0);
+  issue((int)blockIdx.x + stride, 1);
   const float inv_c = 1.0f / (float)C;
   const int opitch = pitch + split;
-  const uint32_t row_bytes = (uint32_t)pitch * 4u;
   uint32_t it = 0;
   for (int tile = (int)blockIdx.x; tile < total_tiles; tile += stride, ++it) {
     const int s = (int)(it & 1u);
     const int b = tile / tiles_per_b, t0 = (tile - b * tiles_per_b) * R;
     const uint32_t st = smem_u32(s_in + s * stage_elems + c);
-    mbar_wait(&full_bar[s], (it >> 1) & 1u);
+    asm volatile("cp.async.wait_group 1;" ::: "memory");  // this tile's copies (own columns) have landed
     float2 acc[R];
     float red[R];
     if (live) {
@@ -1161,8 +1140,8 @@ __global__ void __launch_bounds__(MAXT, 1)
       const float v = warp_reduce8(red, lane);
       if ((lane & 3) == 0) s_red[warp][red_row] = v;
     }
-    __syncthreads();  // every thread has read its columns of stage s: refill it with the tile after next
-    if (tile + 2 * stride < total_tiles) issue(tile + 2 * stride, s);
+    issue(tile + 2 * stride, s);  // this thread's columns of stage s are in registers: refill them with the tile after next
+    __syncthreads();
     const float mean_l = cross_warp(s_red) * inv_c;      // of row (lane & 7)
     float mean[R];
 #pragma unroll
@@ -1469,20 +1448,20 @@ extern "C" int fv_dwconv_layernorm(const float* x32, void* out16, float* out32, 
     const char* e = getenv("FV_DWLN_VEC");  // FV_DWLN_VEC=0: the scalar 4-row kernel (A/B measurements)
     return !(e && e[0] == '0');
   }();
-  static const bool bulk_on = [] {
-    const char* e = getenv("FV_DWLN_BULK");  // FV_DWLN_BULK=0: the per-tile CTA kernels (A/B measurements)
+  static const bool pipe_on = [] {
+    const char* e = getenv("FV_DWLN_PIPE");  // FV_DWLN_PIPE=0: the per-tile CTA kernels (A/B measurements)
     return !(e && e[0] == '0');
   }();
   {
     const int win = DW8_R + (k > 0 ? k - 1 : 0);
-    const int bulk_smem = 2 * win * pitch * (int)sizeof(float);
+    const int pipe_smem = 2 * win * pitch * (int)sizeof(float);
     const int threads = round_up(pitch / 2, 32);
-    if (bulk_on && (k <= 0 || k == 7) && C % 2 == 0 && pitch % 4 == 0 && aligned16 && threads <= 1024 &&
-        bulk_smem <= 200 * 1024) {
+    if (pipe_on && (k <= 0 || k == 7) && C % 2 == 0 && pitch % 4 == 0 && aligned16 && threads <= 1024 &&
+        pipe_smem <= 200 * 1024) {
       const int tiles_per_b = ceil_div(T, DW8_R);
       const int total_tiles = B * tiles_per_b;
       // narrow layers leave room for several resident CTAs per SM (each with its own two stages in flight)
-      int per_sm = (200 * 1024) / (bulk_smem + 4096);
+      int per_sm = (200 * 1024) / (pipe_smem + 4096);
       per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
       {  // ... and the register file: ~112 / 80 / 64 registers per thread in the 384 / 768 / 1024-thread instantiations
         const int regs = threads <= 384 ? 112 : (threads <= 768 ? 80 : 64);
@@ -1491,29 +1470,29 @@ extern "C" int fv_dwconv_layernorm(const float* x32, void* out16, float* out32, 
       }
       const int slots = num_sms() * per_sm;
       const int grid = total_tiles < slots ? total_tiles : slots;
-#define FV_DWLN_BULK_LAUNCH(KK, MAXT)                                                                              \
+#define FV_DWLN_PIPE_LAUNCH(KK, MAXT)                                                                              \
   do {                                                                                                             \
     static std::atomic<unsigned long long> done{0};                                                                \
-    int rc = check_cuda(ensure_dyn_smem(dwconv_ln_bulk_kernel<KK, MAXT>, 200 * 1024, done),                        \
-                        "cudaFuncSetAttribute(dwconv_ln_bulk_kernel)");                                            \
+    int rc = check_cuda(ensure_dyn_smem(dwconv_ln_pipe_kernel<KK, MAXT>, 200 * 1024, done),                        \
+                        "cudaFuncSetAttribute(dwconv_ln_pipe_kernel)");                                            \
     if (rc) return rc;                                                                                             \
-    cudaError_t le = launch_kernel(dwconv_ln_bulk_kernel<KK, MAXT>, dim3(grid), dim3(threads), bulk_smem,          \
+    cudaError_t le = launch_kernel(dwconv_ln_pipe_kernel<KK, MAXT>, dim3(grid), dim3(threads), pipe_smem,          \
                                    (cudaStream_t)stream, 1, x32, (__half*)out16, out32, dw_w, dw_b, ln_w, ln_b,    \
                                    eps, T, C, pitch, tiles_per_b, total_tiles, split);                             \
-    FV_REQUIRE(le == cudaSuccess, FV_E_DRIVER, "launch of dwconv_ln_bulk_kernel failed: %s",                       \
+    FV_REQUIRE(le == cudaSuccess, FV_E_DRIVER, "launch of dwconv_ln_pipe_kernel failed: %s",                       \
                cudaGetErrorString(le));                                                                            \
   } while (0)
       if (k == 7) {
-        if (threads <= 384) FV_DWLN_BULK_LAUNCH(7, 384);
-        else if (threads <= 768) FV_DWLN_BULK_LAUNCH(7, 768);
-        else FV_DWLN_BULK_LAUNCH(7, 1024);
+        if (threads <= 384) FV_DWLN_PIPE_LAUNCH(7, 384);
+        else if (threads <= 768) FV_DWLN_PIPE_LAUNCH(7, 768);
+        else FV_DWLN_PIPE_LAUNCH(7, 1024);
       } else {
-        if (threads <= 384) FV_DWLN_BULK_LAUNCH(0, 384);
-        else if (threads <= 768) FV_DWLN_BULK_LAUNCH(0, 768);
-        else FV_DWLN_BULK_LAUNCH(0, 1024);
+        if (threads <= 384) FV_DWLN_PIPE_LAUNCH(0, 384);
+        else if (threads <= 768) FV_DWLN_PIPE_LAUNCH(0, 768);
+        else FV_DWLN_PIPE_LAUNCH(0, 1024);
       }
-#undef FV_DWLN_BULK_LAUNCH
-      FV_CHECK_LAUNCH("dwconv_ln_bulk_kernel");
+#undef FV_DWLN_PIPE_LAUNCH
+      FV_CHECK_LAUNCH("dwconv_ln_pipe_kernel");
       return 0;
     }
   }
