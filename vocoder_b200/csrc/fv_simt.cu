@@ -1054,17 +1054,30 @@ __global__ void __launch_bounds__(MAXT, 1)
   pdl_wait();
 
   // stage fill (this thread's two columns of the tile's WIN input rows): async copies of the rows inside the sequence,
-  // zeros for the rows outside it; always commits a group so that "all but the newest group" is the tile being waited for
-  auto issue = [&](int tile, int s) {
-    if (live && tile < total_tiles) {
-      const int b = tile / tiles_per_b, t_first = (tile - b * tiles_per_b) * R - HALF;
-      const uint32_t st = smem_u32(s_in + s * stage_elems + c);
+  // zeros for the rows outside it; always commits a group so that "all but the newest group" is the tile being waited for.
+  // (b, tb) = batch item and tile-in-item of the tile to fetch; `ok` = that tile exists.
+  const uint32_t st_base0 = smem_u32(s_in + c), st_stage = (uint32_t)(stage_elems * sizeof(float));
+  auto issue = [&](bool ok, int b, int tb, int s) {
+    if (live && ok) {
+      const int t_first = tb * R - HALF;
+      uint32_t dst = st_base0 + (uint32_t)s * st_stage;
       const float* src = x + ((size_t)b * T + t_first) * pitch + c;   // (row t_first may lie outside: never dereferenced)
+      if (t_first >= 0 && t_first + WIN <= T) {
 #pragma unroll
-      for (int i = 0; i < WIN; ++i) {
-        const int t = t_first + i;
-        if (t >= 0 && t < T) cp_async8(st + (uint32_t)i * row_bytes, src + (size_t)i * pitch);
-        else asm volatile("st.shared.v2.f32 [%0], {%1, %1};" ::"r"(st + (uint32_t)i * row_bytes), "f"(0.f) : "memory");
+        for (int i = 0; i < WIN; ++i) {
+          cp_async8(dst, src);
+          dst += row_bytes;
+          src += pitch;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < WIN; ++i) {
+          const int t = t_first + i;
+          if (t >= 0 && t < T) cp_async8(dst, src);
+          else asm volatile("st.shared.v2.f32 [%0], {%1, %1};" ::"r"(dst), "f"(0.f) : "memory");
+          dst += row_bytes;
+          src += pitch;
+        }
       }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -1092,23 +1105,39 @@ __global__ void __launch_bounds__(MAXT, 1)
     gw = *reinterpret_cast<const float2*>(ln_w + c);
     gb = *reinterpret_cast<const float2*>(ln_b + c);
   }
+  // tiles of this CTA: blockIdx.x + k * gridDim.x; (b, tb) advance by (q, rem) with a carry instead of a division per tile
   const int stride = (int)gridDim.x;
-  issue((int)blockIdx.x, 0);
-  issue((int)blockIdx.x + stride, 1);
+  const int q = stride / tiles_per_b, rem = stride - q * tiles_per_b;
+  int b = (int)blockIdx.x / tiles_per_b, tb = (int)blockIdx.x - b * tiles_per_b;   // the tile being computed
+  int bi = b, tbi = tb, tile_i = (int)blockIdx.x;                                   // the tile being fetched
+  auto advance = [&](int& bb, int& tt) {
+    bb += q;
+    tt += rem;
+    if (tt >= tiles_per_b) {
+      tt -= tiles_per_b;
+      ++bb;
+    }
+  };
+  issue(tile_i < total_tiles, bi, tbi, 0);
+  advance(bi, tbi);
+  tile_i += stride;
+  issue(tile_i < total_tiles, bi, tbi, 1);
   const float inv_c = 1.0f / (float)C;
   const int opitch = pitch + split;
   uint32_t it = 0;
   for (int tile = (int)blockIdx.x; tile < total_tiles; tile += stride, ++it) {
     const int s = (int)(it & 1u);
-    const int b = tile / tiles_per_b, t0 = (tile - b * tiles_per_b) * R;
-    const uint32_t st = smem_u32(s_in + s * stage_elems + c);
+    const int t0 = tb * R;
+    const uint32_t st = st_base0 + (uint32_t)s * st_stage;
     asm volatile("cp.async.wait_group 1;" ::: "memory");  // this tile's copies (own columns) have landed
     float2 acc[R];
     float red[R];
     if (live) {
-      auto lds2 = [&](int i) {
+      uint32_t la = st;
+      auto lds2 = [&]() {   // next input row of this thread's columns
         float2 v;
-        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(st + (uint32_t)i * row_bytes));
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(la));
+        la += row_bytes;
         return v;
       };
       if constexpr (K > 0) {
@@ -1116,7 +1145,7 @@ __global__ void __launch_bounds__(MAXT, 1)
         for (int r = 0; r < R; ++r) acc[r] = bias;
 #pragma unroll
         for (int i = 0; i < WIN; ++i) {
-          const float2 xv = lds2(i);
+          const float2 xv = lds2();
 #pragma unroll
           for (int j = 0; j < K; ++j) {  // input row i is tap j of output row r = i - j
             const int r = i - j;
@@ -1125,7 +1154,7 @@ __global__ void __launch_bounds__(MAXT, 1)
         }
       } else {
 #pragma unroll
-        for (int r = 0; r < R; ++r) acc[r] = lds2(r);
+        for (int r = 0; r < R; ++r) acc[r] = lds2();
       }
 #pragma unroll
       for (int r = 0; r < R; ++r) red[r] = acc[r].x + acc[r].y;
@@ -1140,7 +1169,9 @@ __global__ void __launch_bounds__(MAXT, 1)
       const float v = warp_reduce8(red, lane);
       if ((lane & 3) == 0) s_red[warp][red_row] = v;
     }
-    issue(tile + 2 * stride, s);  // this thread's columns of stage s are in registers: refill them with the tile after next
+    advance(bi, tbi);
+    tile_i += stride;
+    issue(tile_i < total_tiles, bi, tbi, s);  // stage s is in registers: refill this thread's columns with the tile after next
     __syncthreads();
     const float mean_l = cross_warp(s_red) * inv_c;      // of row (lane & 7)
     float mean[R];
@@ -1156,6 +1187,9 @@ __global__ void __launch_bounds__(MAXT, 1)
     }
     __syncthreads();
     const float rstd_l = rsqrtf(cross_warp(s_red2) * inv_c + eps);
+    float rstd[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) rstd[r] = __shfl_sync(0xffffffffu, rstd_l, r);   // (whole warp: before any lane drops out)
     if (live || padcol) {
       const int rows = T - t0 < R ? T - t0 : R;
       const size_t row0 = (size_t)b * T + t0;
@@ -1163,10 +1197,9 @@ __global__ void __launch_bounds__(MAXT, 1)
       float* o32 = out32 ? out32 + row0 * pitch + c : nullptr;
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        const float rs = __shfl_sync(0xffffffffu, rstd_l, r);
         if (r < rows) {
           float2 y = make_float2(0.f, 0.f);
-          if (live) y = ffma2(ffma2(acc[r], bc2(rs), bc2(-mean[r] * rs)), gw, gb);
+          if (live) y = ffma2(ffma2(acc[r], bc2(rstd[r]), bc2(-mean[r] * rstd[r])), gw, gb);
           if (o16) {
             const uint32_t h = pack_half2_sat(y.x, y.y);
             *reinterpret_cast<uint32_t*>(o16) = h;
@@ -1183,6 +1216,7 @@ __global__ void __launch_bounds__(MAXT, 1)
         }
       }
     }
+    advance(b, tb);
   }
 }
 
