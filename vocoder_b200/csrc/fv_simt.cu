@@ -1006,6 +1006,18 @@ __device__ __forceinline__ void cp_async8(uint32_t smem_dst, const void* gsrc) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_dst), "l"(gsrc) : "memory");
 }
 
+// edge tiles of the pipelined kernel: rows outside [0, T) are the conv's zero padding (kept out of line: two tiles in twelve)
+__device__ __noinline__ void dwln_fill_edge(uint32_t dst, const float* src, int t_first, int T, int win, uint32_t row_bytes,
+                                            int pitch) {
+  for (int i = 0; i < win; ++i) {
+    const int t = t_first + i;
+    if (t >= 0 && t < T) cp_async8(dst, src);
+    else asm volatile("st.shared.v2.f32 [%0], {%1, %1};" ::"r"(dst), "f"(0.f) : "memory");
+    dst += row_bytes;
+    src += pitch;
+  }
+}
+
 // warp-wide sums of eight per-thread values in 12 shuffles instead of 40: every step halves the number of values a lane
 // still carries (lanes keep the half selected by one of their lane-id bits and send the other half to their partner);
 // returns the sum of v[row] over the warp with row = 4*bit4 + 2*bit3 + bit2 of the lane id
@@ -1051,6 +1063,11 @@ __global__ void __launch_bounds__(MAXT, 1)
   const size_t stage_elems = (size_t)WIN * pitch;
   const uint32_t row_bytes = (uint32_t)pitch * 4u;
   const int red_row = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+  for (int i = tid; i < (MAXT / 32) * R; i += (int)blockDim.x) {
+    (&s_red[0][0])[i] = 0.f;
+    (&s_red2[0][0])[i] = 0.f;
+  }
+  __syncthreads();
   pdl_wait();
 
   // stage fill (this thread's two columns of the tile's WIN input rows): async copies of the rows inside the sequence,
@@ -1070,14 +1087,7 @@ __global__ void __launch_bounds__(MAXT, 1)
           src += pitch;
         }
       } else {
-#pragma unroll
-        for (int i = 0; i < WIN; ++i) {
-          const int t = t_first + i;
-          if (t >= 0 && t < T) cp_async8(dst, src);
-          else asm volatile("st.shared.v2.f32 [%0], {%1, %1};" ::"r"(dst), "f"(0.f) : "memory");
-          dst += row_bytes;
-          src += pitch;
-        }
+        dwln_fill_edge(dst, src, t_first, T, WIN, row_bytes, pitch);   // first / last tile of an utterance (out of line)
       }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -1088,8 +1098,7 @@ __global__ void __launch_bounds__(MAXT, 1)
     float m = 0.f;
     const float* pl = &part[lane >> 3][lane & 7];
 #pragma unroll
-    for (int u = 0; u < MAXT / 128; ++u)
-      if ((lane >> 3) + 4 * u < nwarp) m += pl[4 * u * R];
+    for (int u = 0; u < MAXT / 128; ++u) m += pl[4 * u * R];   // rows of warps that do not exist stay zero
     m += __shfl_xor_sync(0xffffffffu, m, 8);
     m += __shfl_xor_sync(0xffffffffu, m, 16);
     return m;
@@ -1195,25 +1204,30 @@ __global__ void __launch_bounds__(MAXT, 1)
       const size_t row0 = (size_t)b * T + t0;
       __half* o16 = out16 ? out16 + row0 * opitch + c : nullptr;
       float* o32 = out32 ? out32 + row0 * pitch + c : nullptr;
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        if (r < rows) {
-          float2 y = make_float2(0.f, 0.f);
-          if (live) y = ffma2(ffma2(acc[r], bc2(rstd[r]), bc2(-mean[r] * rstd[r])), gw, gb);
-          if (o16) {
-            const uint32_t h = pack_half2_sat(y.x, y.y);
-            *reinterpret_cast<uint32_t*>(o16) = h;
-            if (split > 0) {
-              const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h));
-              *reinterpret_cast<uint32_t*>(o16 + split) = pack_half2_sat(y.x - f.x, y.y - f.y);
-            }
-            o16 += opitch;
+      auto put_row = [&](int r) {
+        float2 y = make_float2(0.f, 0.f);
+        if (live) y = ffma2(ffma2(acc[r], bc2(rstd[r]), bc2(-mean[r] * rstd[r])), gw, gb);
+        if (o16) {
+          const uint32_t h = pack_half2_sat(y.x, y.y);
+          *reinterpret_cast<uint32_t*>(o16) = h;
+          if (split > 0) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h));
+            *reinterpret_cast<uint32_t*>(o16 + split) = pack_half2_sat(y.x - f.x, y.y - f.y);
           }
-          if (o32) {
-            *reinterpret_cast<float2*>(o32) = y;
-            o32 += pitch;
-          }
+          o16 += opitch;
         }
+        if (o32) {
+          *reinterpret_cast<float2*>(o32) = y;
+          o32 += pitch;
+        }
+      };
+      if (rows == R) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) put_row(r);
+      } else {
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+          if (r < rows) put_row(r);
       }
     }
     advance(b, tb);
