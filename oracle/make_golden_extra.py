@@ -9,6 +9,8 @@
                             whose first-stage AMPBlocks are rebuilt as AMPBlock(activation=Snake, snake_logscale=False) and
                             whose second-stage blocks as AMPBlock(activation=SnakeBeta, snake_logscale=False)
                             (bigvgan.py:139-146,60-71,122-135): plain Snake and the non-logscale parameterisation.
+* bigvgan_template_stress   reference BigVGANGenerator(use_template=True): the noise_convs / template path of BigVGAN
+                            (bigvgan.py:300-317,357-359), three kernel sizes, stages of 32 and 16 channels.
 TEST INFRASTRUCTURE ONLY.
 """
 import os
@@ -64,6 +66,20 @@ def main():
     m.load_state_dict(sd)
     x = mel_input(2, 20, 12)
     save("bigvgan_snake_mix_stress", bk, m, {"mel": x}, m(x))
+
+    # BigVGAN with the template path (use_template=True is the constructor DEFAULT, bigvgan.py:262,300-317,357-359:
+    # x = ups[i](x) + noise_convs[i](template) before every AMP stage); the last stage has 16 channels (row-pair convs)
+    tk = dict(hop_length=8, upsample_rates=[4, 2], upsample_kernel_sizes=[8, 4],
+              resblock_kernel_sizes=[3, 7, 11], resblock_dilation_sizes=[[1, 3, 5]] * 3,
+              num_mels=20, upsample_initial_channel=64, use_template=True,
+              pre_conv_kernel_size=7, post_conv_kernel_size=7)
+    torch.manual_seed(0)
+    m = BigVGANGenerator(**tk).eval()
+    stress_init(m)
+    x = mel_input(2, 20, 13)
+    torch.manual_seed(9)
+    tpl = torch.randn(2, 1, 13 * 8) * 0.3
+    save("bigvgan_template_stress", tk, m, {"mel": x, "template": tpl}, m(x, tpl))
 
 
 if __name__ == "__main__":

@@ -49,7 +49,7 @@ def oracle_forward(name, kwargs, sd, ins, extra=None):
 
 ALL_GOLDEN = ["hifigan_small_ref", "hifigan_small_stress", "hifigan_template_stress", "bigvgan_small_ref",
               "bigvgan_small_stress", "vocos_small_ref", "vocos_small_stress", "refinegan_small_stress", "firefly_small_stress",
-              "vocos_center_stress", "bigvgan_snake_mix_stress"]
+              "vocos_center_stress", "bigvgan_snake_mix_stress", "bigvgan_template_stress"]
 
 
 def build_module(name, kwargs):
