@@ -277,7 +277,8 @@ def _mrf_reference(x, blocks, out_act):
 
 @pytest.mark.parametrize("C,L,B,ks", [(16, 45, 2, (3, 7, 11)), (16, 3000, 3, (3, 7, 11)), (16, 777, 1, (5,)),
                                         (32, 52, 2, (3, 7, 11)), (64, 1000, 2, (3, 7, 11)), (32, 1537, 3, (3, 7, 11)),
-                                        (64, 384, 1, (11,)), (64, 4000, 5, (3, 5)), (32, 6016, 40, (3, 7, 11))])
+                                        (64, 384, 1, (11,)), (64, 4000, 5, (3, 5)), (32, 6016, 40, (3, 7, 11)),
+                                        (64, 3000, 12, (3, 7, 11))])   # short launches take the 256-row configurations
 def test_mrf_fused_kernel(C, L, B, ks):
     torch.manual_seed(C + L)
     blocks = []

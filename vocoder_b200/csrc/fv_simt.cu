@@ -1057,7 +1057,7 @@ __global__ void __launch_bounds__(MAXT, 1)
   constexpr int WIN = R + (K > 0 ? K - 1 : 0);
   extern __shared__ __align__(128) float s_in[];  // [2][WIN][pitch]
   __shared__ float s_red[MAXT / 32][R], s_red2[MAXT / 32][R];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarp = blockDim.x >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int c = tid * 2;                 // this thread's channel pair (c >= pitch: idle, only joins the barriers)
   const bool live = c < C, padcol = c >= C && c < pitch;
   const size_t stage_elems = (size_t)WIN * pitch;
