@@ -488,3 +488,51 @@ class MRFGeneratorBase(nn.Module):
                 prev.record(st)                     # ... and chains 0 .. j
         for st in sides:
             cur.wait_stream(st)                     # join
+
+    #: C <= 64 SiLU stages as one on-chip kernel per stage (fv_mrf_fused); False = layer-wise fv_conv1d launches
+    fuse_mrf = True
+    #: C = 128 SiLU stages as one on-chip kernel per (conv, conv) pair (needs fuse_mrf); False = layer-wise launches.
+    #: Measured on B200 (HiFiGAN cfg B, C = 128, L = 6016, B = 64): 2.42 ms pair-wise against 2.0 ms layer-wise - an N = 128
+    #: UMMA costs ~97 cycles whatever feeds it, the 256-row tiles recompute 25% halo, and with TMEM full (X + T) one CTA per
+    #: SM cannot overlap its epilogue / entry / exit with MMAs the way the layer-wise kernel's double-buffered
+    #: accumulators do.  At B = 1 (6016 rows: 32 tiles on 148 SMs either way) the pair-wise stage saves nine launches and
+    #: measured 0.776 against 0.832 ms per forward.  "auto" (default) = pair-wise when the stage has at most
+    #: `mrf_pairs_max_rows` rows (batch x length), layer-wise above; True / False force one path.
+    fuse_mrf_pairs = "auto"
+    #: C <= 16 Snake stages: convs on the [B, L/2, 2C] view of the channels-last buffers (cabi.pack_conv_row_pairs);
+    #: False = one 16-channel row per GEMM row (half-empty 32-column tiles)
+    conv_row_pairs = True
+    row_pairs_max_taps = 12
+    mrf_pairs_max_rows = 148 * 256
+    #: channel counts (besides 128) whose stage runs pair by pair instead of as one whole-stage launch; (64,) trades ~7x the
+    #: stage's HBM traffic for MMA / epilogue overlap between two co-resident CTAs.  Measured: see DESIGN.md section 4.2.
+    mrf_pairwise_channels = ()
+    def _silu(self) -> int:
+        return cabi.ACT_SILU_TANH if self.mrf_silu_tanh else cabi.ACT_SILU
+
+    #: SiLU epilogues (fused stages and layer-wise convs) as x/2 + x/2 tanh(x/2) with tanh.approx (one SFU op instead of two; |error| <=
+    #: 2.4e-4 |x| before the fp16 rounding of the operand, see FV_ACT_SILU_TANH).  Measured on B200: stage-level error
+    #: 5.8e-5 vs 4.3e-5 (ex2 + rcp) against the fp64 contract, waveform error of the full-width stress model unchanged
+    #: (8.1e-5 both); False selects the ex2 + rcp form.
+    mrf_silu_tanh = True
+    #: inner SiLU of the fused stages on packed fp16 pairs (FV_ACT_SILU_H2: one SFU op per two channels, ~3 fp16 roundings in
+    #: the operand instead of 1).  Opt-in until measured: see DESIGN.md section 4.2.
+    mrf_silu_h2 = False
+
+    #: utterances per residual-block pass; None = whole batch; 0 = size the block working set for L2 (_micro_batch)
+    micro_batch = None
+    l2_budget_bytes = 96 * 1024 * 1024
+
+    def _micro_batch(self, B: int, L: int, C: int) -> int:
+        if self.micro_batch is None:
+            return B
+        if self.micro_batch > 0:
+            return max(1, min(B, int(self.micro_batch)))
+        # live set of one (c1, c2) pair per utterance: xr fp32 (read + written in place), xa + ta fp16 (+ t32 fp32)
+        per_utt = L * cabi.pitch_of(C) * (4 + 2 + 2 + (4 if self.snake_blocks else 0))
+        mb = max(1, self.l2_budget_bytes // max(1, per_utt))
+        # keep at least ~2 waves of 256-row tiles on 148 SMs when the batch allows it
+        tiles_per_utt = -(-L // 256)
+        mb = min(B, max(mb, -(-296 // tiles_per_utt)))
+        n_chunks = -(-B // mb)
+        return int(-(-B // n_chunks))  # equal-sized chunks
