@@ -45,13 +45,15 @@ def _run(name, m, ins, extra):
 
 
 GOLDEN_GPU = list(ALL_GOLDEN)
-# The one fixture the default ("mixed") precision of its generator does not bring under 1e-3: 1.13e-3 measured (fp16
+# The fixtures the default ("mixed") precision of their generator does not bring under 1e-3.  bigvgan_small_stress: 1.13e-3 measured (fp16
 # everywhere: 3.7e-3; the reference's own TF32 GPU arithmetic: 3.4e-3).  Its residual-block convs sit at C = 32 ... 4 with
 # stress weights; the error is the fp16 rounding of THEIR operands (tools/precision_probe.py), which only precision="strict"
 # removes.  The golden test therefore runs it in "strict" (1.1e-5) and bounds the default mode at 1.5e-3; bench.py reports the
 # strict-mode throughput of BigVGAN beside the default one (workloads.bigvgan_b32_strict).  At the benched width
 # (test_benched_shape_parity_vs_oracle) the default mode is at 4.8e-4.
-NEEDS_STRICT = {"bigvgan_small_stress": 1.5e-3}
+# Round 2 added bigvgan_template_stress (reference BigVGAN with use_template=True, stages of 32 / 16 channels): the same
+# picture - 1.58e-3 in "mixed" (fp16: 4.9e-3, the TF32-grade gap of the fixture: 5.5e-3), 1.1e-5 in "strict".
+NEEDS_STRICT = {"bigvgan_small_stress": 1.5e-3, "bigvgan_template_stress": 2.0e-3}
 
 
 def _set_precision(m, mode):
@@ -278,7 +280,7 @@ def _mrf_reference(x, blocks, out_act):
 @pytest.mark.parametrize("C,L,B,ks", [(16, 45, 2, (3, 7, 11)), (16, 3000, 3, (3, 7, 11)), (16, 777, 1, (5,)),
                                         (32, 52, 2, (3, 7, 11)), (64, 1000, 2, (3, 7, 11)), (32, 1537, 3, (3, 7, 11)),
                                         (64, 384, 1, (11,)), (64, 4000, 5, (3, 5)), (32, 6016, 40, (3, 7, 11)),
-                                        (64, 3000, 12, (3, 7, 11))])   # short launches take the 256-row configurations
+                                        (64, 3000, 12, (3, 7, 11))])
 def test_mrf_fused_kernel(C, L, B, ks):
     torch.manual_seed(C + L)
     blocks = []

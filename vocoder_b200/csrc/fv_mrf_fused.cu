@@ -591,26 +591,9 @@ static const bool g_mrf_c64_pair = [] {
 static bool pair_config(const fv_mrf_desc* d) {
   return d->C == 128 || (d->C == 64 && d->n_blocks == 1 && d->n_pairs == 1 && g_mrf_c64_pair);
 }
-// short launches (test.py's B = 1 ... 2): when 512-row tiles would occupy fewer than half the SMs, the whole-stage kernel
-// runs on 256-row tiles with two co-resident CTAs per SM instead - twice the halo recompute, but every CTA's serial chain of
-// convs is half as long and more SMs work (C = 64, L = 12032, B = 1: 94 tiles instead of 32).  FV_MRF_SMALL=0 disables.
-static const bool g_mrf_small = [] {
-  const char* e = getenv("FV_MRF_SMALL");
-  return !(e && e[0] == '0');
-}();
-static bool small_config(const fv_mrf_desc* d) {
-  if (!g_mrf_small || pair_config(d) || !(d->C == 64 || d->C == 32)) return false;
-  int halo = 0;
-  for (int j = 0; j < d->n_blocks; ++j) {
-    int h = 0;
-    for (int i = 0; i < d->n_pairs; ++i) h += (d->ksize[j] - 1) / 2 * (d->dil1[j][i] + d->dil2[j][i]);
-    halo = h > halo ? h : halo;
-  }
-  const int v512 = (512 - round_up(halo, 32) - halo) / 32 * 32, v256 = (256 - round_up(halo, 32) - halo) / 32 * 32;
-  if (v512 < 32 || v256 < 32) return false;
-  return (long long)d->B * ceil_div(d->L, v512) * 2 <= num_sms();
-}
-static int tile_rows_for(const fv_mrf_desc* d) { return (pair_config(d) || small_config(d)) ? 256 : 512; }
+// (Measured and dropped, round 2: 256-row whole-stage tiles with two co-resident CTAs for short launches - C = 64, L = 12032,
+// B = 1: 94 tiles instead of 32 - hifigan_b1 0.546 ms against 0.537 ms without: twice the halo recompute eats the shorter chains.)
+static int tile_rows_for(const fv_mrf_desc* d) { return pair_config(d) ? 256 : 512; }
 
 template <int C, int ACT, int EW, int NCTA, int MB, int MAXCONV>
 static int launch_mrf(const fv_mrf_desc* d, MrfParams& p, cudaStream_t stream) {
@@ -733,10 +716,8 @@ extern "C" int fv_mrf_fused(const fv_mrf_desc* d, void* stream) {
   } while (0)
   if (d->C == 128) FV_MRF_DISPATCH(128, 16, 1, 2, 2);
   if (d->C == 64 && pair_config(d)) FV_MRF_DISPATCH(64, 8, 2, 2, 2);
-  if (d->C == 64 && small_config(d)) FV_MRF_DISPATCH(64, 8, 2, 2, kFrMaxConvs);
   if (d->C == 64) FV_MRF_DISPATCH(64, 16, 1, 4, kFrMaxConvs);
   if (d->C == 16) FV_MRF_DISPATCH(16, 8, 2, 4, kFrMaxConvs);  // 32-byte operand rows, 16-column patches, two CTAs per SM
-  if (d->C == 32 && small_config(d)) FV_MRF_DISPATCH(32, 4, 2, 2, kFrMaxConvs);  // (8 warps: staging would not fit)
   if (g_mrf_c32_ctas == 1) FV_MRF_DISPATCH(32, 16, 1, 4, kFrMaxConvs);
   FV_MRF_DISPATCH(32, 8, 2, 4, kFrMaxConvs);
 #undef FV_MRF_DISPATCH
