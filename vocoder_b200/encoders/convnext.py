@@ -15,7 +15,7 @@ import torch
 from torch import nn
 
 from .. import cabi
-from ..runtime import (GraphedForward, Workspace, forward_signature, params_key, require_channels, require_cuda,
+from ..runtime import (GraphedForward, Workspace, forward_signature, module_params_key, params_key, require_channels, require_cuda,
                        with_precision)
 
 
@@ -120,7 +120,7 @@ class ConvNeXtEncoder(nn.Module):
 
     # ---- packing ----------------------------------------------------------------------------------
     def _ensure_packed(self, device):
-        key = params_key(self.parameters())
+        key = module_params_key(self, buffers=False)
         if self._packed is not None and self._packed_key == key:
             return self._packed
         f32 = lambda t: t.detach().float().contiguous()

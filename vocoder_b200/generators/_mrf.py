@@ -25,7 +25,7 @@ from torch.nn.utils.parametrize import remove_parametrizations as _torch_remove_
 from .. import cabi
 import contextlib
 
-from ..runtime import (GraphedForward, Workspace, forward_signature, params_key, require_channels, require_cuda,
+from ..runtime import (GraphedForward, Workspace, forward_signature, module_params_key, params_key, require_channels, require_cuda,
                        with_precision)
 
 
@@ -168,7 +168,7 @@ class MRFGeneratorBase(nn.Module):
         raise NotImplementedError
 
     def _ensure_packed(self, device):
-        key = params_key(list(self.parameters()) + list(self.buffers())) + (
+        key = module_params_key(self) + (
             self.fuse_mrf, self.fuse_mrf_pairs, tuple(self.mrf_pairwise_channels), self.engine, self.conv_row_pairs, self.row_pairs_max_taps, self.chain_streams, self.chain_streams_max_rows)
         if self._packed is not None and self._packed_key == key:
             return self._packed

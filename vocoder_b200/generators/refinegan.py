@@ -22,7 +22,7 @@ from torch import nn
 from torch.nn.utils.parametrizations import weight_norm
 
 from .. import cabi
-from ..runtime import (GraphedForward, Workspace, forward_signature, params_key, require_channels, require_cuda,
+from ..runtime import (GraphedForward, Workspace, forward_signature, module_params_key, params_key, require_channels, require_cuda,
                        with_precision)
 from ._mrf import same_padding, strip_weight_norm
 
@@ -138,7 +138,7 @@ class RefineGANGenerator(nn.Module):
         return c1, c2
 
     def _ensure_packed(self, device):
-        key = params_key(self.parameters())
+        key = module_params_key(self, buffers=False)
         if self._packed is not None and self._packed_key == key:
             return self._packed
         f32 = lambda t: t.detach().float().contiguous()

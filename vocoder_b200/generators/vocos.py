@@ -20,7 +20,7 @@ import torch
 from torch import nn
 
 from .. import cabi
-from ..runtime import (GraphedForward, Workspace, forward_signature, params_key, require_channels, require_cuda,
+from ..runtime import (GraphedForward, Workspace, forward_signature, module_params_key, params_key, require_channels, require_cuda,
                        with_precision)
 
 
@@ -80,7 +80,7 @@ class ISTFTHead(nn.Module):
         return cabi.strict_layer(cabi.is_mixed())
 
     def _ensure_packed(self, device):
-        key = params_key(list(self.parameters()) + list(self.buffers()))
+        key = module_params_key(self)
         if self._packed is not None and self._packed_key == key:
             return self._packed
         center = self.istft.padding == "center"

@@ -8,6 +8,8 @@ import functools
 from collections import OrderedDict
 from typing import Callable, Dict, Iterable, List, Tuple
 
+import operator
+
 import torch
 
 from . import cabi
@@ -97,6 +99,46 @@ def forward_signature(*tensors) -> Tuple:
 def params_key(tensors: Iterable[torch.Tensor]) -> Tuple:
     """Cheap fingerprint of a parameter set: changes when any tensor is updated in place, replaced or moved."""
     return (cabi.mode(), cabi.is_strict()) + tuple((t.data_ptr(), t._version, t.device.index) for t in tensors)
+
+
+class _ModuleSlots:
+    """Where a module tree keeps its parameters and buffers: [(dict, name)] slots + per-module structure counts.
+
+    `module.parameters()` walks ~150 sub-modules of a weight-normed generator on every call (1.1 ms for HiFiGAN, 2.7 ms for
+    BigVGAN on the build host) - more than a whole B = 1 forward takes on the GPU.  The slots are collected once; every
+    forward only reads them (dict lookups), so tensors that are updated in place, moved (`.to()` swaps `.data`) or replaced
+    in their slot (`load_state_dict(assign=True)`, optimizers that re-assign) still change the fingerprint, and a change of
+    the tree itself (parametrizations removed, parameters / sub-modules added or deleted) changes the per-module counts and
+    rebuilds the slot list."""
+
+    def __init__(self, module: torch.nn.Module, buffers: bool):
+        mods = list(module.modules())
+        self.dicts = [d for m in mods for d in (m._parameters, m._buffers, m._modules)]
+        self.counts = tuple(map(len, self.dicts))
+        self.slots = [(m._parameters, n) for m in mods for n in m._parameters]
+        if buffers:
+            self.slots += [(m._buffers, n) for m in mods for n in m._buffers]
+
+    def valid(self) -> bool:
+        return tuple(map(len, self.dicts)) == self.counts
+
+    def tensors(self):
+        return [t for t in (d.get(n) for d, n in self.slots) if t is not None]
+
+
+_data_ptr = operator.methodcaller("data_ptr")
+_version = operator.attrgetter("_version")
+
+
+def module_params_key(module: torch.nn.Module, buffers: bool = True) -> Tuple:
+    """`params_key` over the parameters (and buffers) of `module`, without walking the module tree on every call."""
+    st = module.__dict__.get("_fv_slots")
+    if st is None or not st.valid():
+        st = _ModuleSlots(module, buffers)
+        module.__dict__["_fv_slots"] = st
+    ts = st.tensors()
+    return (cabi.mode(), cabi.is_strict(), ts[0].device if ts else None,
+            tuple(map(_data_ptr, ts)), tuple(map(_version, ts)))
 
 
 def require_cuda(x: torch.Tensor, who: str) -> None:
