@@ -435,6 +435,14 @@ def run_workload(name, args, dev, rank, world, barrier, all_max, *, full: bool):
             model(mel)
         torch.cuda.synchronize()
 
+        # host cost of one forward call (python + graph launch, nothing waited for): what bounds B = 1 once the GPU is faster
+        n_host = 100
+        t0 = time.perf_counter()
+        for _ in range(n_host):
+            model(mel)
+        host_us = (time.perf_counter() - t0) / n_host * 1e6
+        torch.cuda.synchronize()
+
         flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
         sampler = ClockSampler(dev.index).start() if rank == 0 else None
         # ---- device-resident timing: K steps, L2 flushed between steps, device time summed per step
@@ -490,6 +498,7 @@ def run_workload(name, args, dev, rank, world, barrier, all_max, *, full: bool):
                    "h2d_bytes_per_step": mel_host.numel() * 4, "d2h_bytes_per_step": wav_host.numel() * 4,
                    "ms_per_step": e2e_ms / steps},
            "gpu_launches": launches_per_step * steps, "launches_per_step": launches_per_step,
+           "host_us_per_forward_call": host_us,
            "pack_ms": pack_ms, "wall_s_timed_region": wall, "clocks": clocks}
     if sustained is not None:
         sus_ms, n_sus = all_max([sustained[0]])[0], sustained[1]

@@ -118,12 +118,15 @@ class _ModuleSlots:
         self.slots = [(m._parameters, n) for m in mods for n in m._parameters]
         if buffers:
             self.slots += [(m._buffers, n) for m in mods for n in m._buffers]
+        # empty slots (bias=None) stay in the list: one that is filled later must change the fingerprint
+        self.has_none = any(d[n] is None for d, n in self.slots)
 
     def valid(self) -> bool:
         return tuple(map(len, self.dicts)) == self.counts
 
     def tensors(self):
-        return [t for t in (d.get(n) for d, n in self.slots) if t is not None]
+        ts = [d[n] for d, n in self.slots]          # (a slot that disappeared changes the counts first: valid() is called before)
+        return [t for t in ts if t is not None] if self.has_none else ts
 
 
 _data_ptr = operator.methodcaller("data_ptr")
