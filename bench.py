@@ -704,7 +704,8 @@ def main():
                          "f32 accumulate / residual stream",
                 "data": "synthetic", "config": config, "rtf_per_gpu": head["rtf_per_gpu"], "e2e": head["e2e"],
                 "gpu_launches": head["gpu_launches"], "launches_per_step": head["launches_per_step"],
-                "pack_ms": head["pack_ms"], "wall_s_timed_region": head["wall_s_timed_region"],
+                "pack_ms": head["pack_ms"], "host_us_per_forward_call": head.get("host_us_per_forward_call"),
+                "wall_s_timed_region": head["wall_s_timed_region"],
                 "sustained": head.get("sustained"), "parity": head.get("parity"), "roofline": head.get("roofline"),
                 "cpu_baseline": head.get("cpu_baseline"), "clocks": head["clocks"], "workloads": others}
         if not args.no_cpu_baseline and world == 1:
