@@ -292,3 +292,33 @@ def test_chain_streams_auto_threshold():
     assert m._chains_concurrent(1, 24064) and m._chains_concurrent(2, 12032) and not m._chains_concurrent(64, 752 * 8)
     m.chain_streams = False
     assert not m._chains_concurrent(1, 10)
+
+
+def test_module_params_key_sees_every_kind_of_weight_change():
+    """runtime.module_params_key (the per-forward fingerprint that keeps packed weights and CUDA graphs valid) reads cached
+    parameter slots instead of walking the module tree: it must still change on in-place updates, dtype / device style
+    `.data` swaps, slot replacement (load_state_dict(assign=True)), removed parametrizations and added parameters."""
+    from vocoder_b200.generators import HiFiGANGenerator
+    from vocoder_b200.runtime import module_params_key
+    m = HiFiGANGenerator(hop_length=8, upsample_rates=[4, 2], upsample_kernel_sizes=[8, 4], num_mels=12,
+                         upsample_initial_channel=32, use_template=False).eval()
+    k0 = module_params_key(m)
+    assert module_params_key(m) == k0                                   # stable while nothing changes
+    with torch.no_grad():
+        m.conv_pre.bias.add_(1.0)
+    k1 = module_params_key(m)
+    assert k1 != k0                                                     # in-place update (_version)
+    m.conv_post.bias.data = m.conv_post.bias.data.clone()
+    k2 = module_params_key(m)
+    assert k2 != k1                                                     # .data swapped (what .to() / .half() do)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    m.load_state_dict(sd, assign=True)
+    k3 = module_params_key(m)
+    assert k3 != k2                                                     # tensors replaced in their slots
+    torch.nn.utils.parametrize.remove_parametrizations(m.ups[0], "weight")   # directly on a sub-module, not our method
+    k4 = module_params_key(m)
+    assert k4 != k3 and len(k4[3]) == len(k3[3]) - 1                    # tree changed: slots rebuilt (g, v -> weight)
+    m.register_buffer("extra", torch.zeros(1))
+    assert len(module_params_key(m)[3]) == len(k4[3]) + 1               # new slot
+    with cabi.precision("strict"):
+        assert module_params_key(m)[:2] != k4[:2]                       # precision mode is part of the key
