@@ -435,14 +435,6 @@ def run_workload(name, args, dev, rank, world, barrier, all_max, *, full: bool):
             model(mel)
         torch.cuda.synchronize()
 
-        # host cost of one forward call (python + graph launch, nothing waited for): what bounds B = 1 once the GPU is faster
-        n_host = 100
-        t0 = time.perf_counter()
-        for _ in range(n_host):
-            model(mel)
-        host_us = (time.perf_counter() - t0) / n_host * 1e6
-        torch.cuda.synchronize()
-
         flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
         sampler = ClockSampler(dev.index).start() if rank == 0 else None
         # ---- device-resident timing: K steps, L2 flushed between steps, device time summed per step
@@ -487,6 +479,16 @@ def run_workload(name, args, dev, rank, world, barrier, all_max, *, full: bool):
             sus_ms = s0.elapsed_time(s1)
             sus_clocks = sampler2.stop() if sampler2 else None
             sustained = (sus_ms, n_sus, sus_clocks)
+
+        # host cost of one forward call (python + graph launch, nothing waited for): what bounds B = 1 once the GPU is faster.
+        # Measured LAST: 100 back-to-back forwards before the timed region would push the GPU into its power cap.
+        torch.cuda.synchronize()
+        n_host = 100
+        t0 = time.perf_counter()
+        for _ in range(n_host):
+            model(mel)
+        host_us = (time.perf_counter() - t0) / n_host * 1e6
+        torch.cuda.synchronize()
 
     dev_ms, e2e_ms = all_max([dev_ms, e2e_ms])
     total_samples = samples_per_step * steps * world
