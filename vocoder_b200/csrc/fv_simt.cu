@@ -567,10 +567,11 @@ __global__ void __launch_bounds__(256, SN_BLOCKS) snake_aa_kernel(const float* _
   else snake_segment<true, SPLIT>(xc, orow, f, a, inv_b, t0, t_end, L, pitch, opitch, split);
 }
 
-// The same kernel with the look-ahead in a shared-memory ring (see snake_segment<..., RING = true>): three blocks per SM.
-constexpr int SN_RING_BLOCKS = 3;
+// The same kernel with the look-ahead in a shared-memory ring (see snake_segment<..., RING = true>): RB = 3 blocks per SM
+// (80 registers) or RB = 2 (the register budget of the default kernel, only the deeper look-ahead differs).
 constexpr int SN_RING_SLOTS = 18;
-__global__ void __launch_bounds__(256, SN_RING_BLOCKS)
+template <int RB>
+__global__ void __launch_bounds__(256, RB)
     snake_aa_ring_kernel(const float* __restrict__ x, __half* __restrict__ out, const float* __restrict__ alpha,
                          const float* __restrict__ beta, const SnakeFilt f, int logscale, int B, int L, int C, int pitch,
                          int n_seg, int seg_len) {
@@ -1436,15 +1437,15 @@ extern "C" int fv_snake_aa(const float* x32, void* out16, const float* alpha, co
   // Segment length: every thread does the same amount of work, so the grid runs in whole waves of SN_BLOCKS x 256 threads per
   // SM and a launch of 3.1 waves costs 4.  Pick the multiple of 6 in [36, 96] with the best (work / waves) ratio,
   // counting the 6 pre-roll steps every segment pays.
-  // FV_SNAKE_RING=1: the shared-memory-ring variant (three blocks per SM); A/B measurement switch
-  static const bool ring_on = [] {
+  // FV_SNAKE_RING=1 / 2: the shared-memory-ring variant with three / two blocks per SM; A/B measurement switch
+  static const int ring_blocks = [] {
     const char* e = getenv("FV_SNAKE_RING");
-    return e && e[0] == '1';
+    return (e && e[0] == '1') ? 3 : ((e && e[0] == '2') ? 2 : 0);
   }();
-  const bool use_ring = ring_on && split == 0;
+  const bool use_ring = ring_blocks != 0 && split == 0;
   int seg_len = 48;
   {
-    const long long per_wave = (long long)num_sms() * (use_ring ? SN_RING_BLOCKS : SN_BLOCKS) * 256;
+    const long long per_wave = (long long)num_sms() * (use_ring ? ring_blocks : SN_BLOCKS) * 256;
     double best = -1.0;
     for (int sl = SN_SEG_MIN; sl <= SN_SEG_MAX; sl += 6) {
       const long long thr = (long long)B * ceil_div(L, sl) * (pitch / 2);
@@ -1460,9 +1461,14 @@ extern "C" int fv_snake_aa(const float* x32, void* out16, const float* alpha, co
   const long long total = (long long)B * n_seg * (pitch / 2);
   if (use_ring) {
     const int smem = SN_RING_SLOTS * 256 * (int)sizeof(float2);
-    FV_REQUIRE(launch_kernel(snake_aa_ring_kernel, dim3(grid1d(total, 256)), dim3(256), smem, (cudaStream_t)stream, 1, x32,
-                             (__half*)out16, alpha, beta, f, logscale, B, L, C, pitch, n_seg, seg_len) == cudaSuccess,
-               FV_E_DRIVER, "launch of snake_aa_ring_kernel failed");
+    cudaError_t le;
+    if (ring_blocks == 3)
+      le = launch_kernel(snake_aa_ring_kernel<3>, dim3(grid1d(total, 256)), dim3(256), smem, (cudaStream_t)stream, 1, x32,
+                         (__half*)out16, alpha, beta, f, logscale, B, L, C, pitch, n_seg, seg_len);
+    else
+      le = launch_kernel(snake_aa_ring_kernel<2>, dim3(grid1d(total, 256)), dim3(256), smem, (cudaStream_t)stream, 1, x32,
+                         (__half*)out16, alpha, beta, f, logscale, B, L, C, pitch, n_seg, seg_len);
+    FV_REQUIRE(le == cudaSuccess, FV_E_DRIVER, "launch of snake_aa_ring_kernel failed");
     FV_CHECK_LAUNCH("snake_aa_ring_kernel");
     return 0;
   }
