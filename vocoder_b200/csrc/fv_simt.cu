@@ -1437,10 +1437,13 @@ extern "C" int fv_snake_aa(const float* x32, void* out16, const float* alpha, co
   // Segment length: every thread does the same amount of work, so the grid runs in whole waves of SN_BLOCKS x 256 threads per
   // SM and a launch of 3.1 waves costs 4.  Pick the multiple of 6 in [36, 96] with the best (work / waves) ratio,
   // counting the 6 pre-roll steps every segment pays.
-  // FV_SNAKE_RING=1 / 2: the shared-memory-ring variant with three / two blocks per SM; A/B measurement switch
+  // Look-ahead of the plain (non-split) launches: a shared-memory ring with two 6-step windows in flight and two blocks per SM
+  // (default; measured on B200, BigVGAN cfg C: 4.12 -> 3.96 ms of Snake time per forward against the one-window register
+  // look-ahead at the same occupancy; three blocks per SM at 80 registers: 4.27 ms).  FV_SNAKE_RING=0 / 1 / 2: register
+  // look-ahead / ring with three blocks / ring with two blocks.
   static const int ring_blocks = [] {
     const char* e = getenv("FV_SNAKE_RING");
-    return (e && e[0] == '1') ? 3 : ((e && e[0] == '2') ? 2 : 0);
+    return (e && e[0] == '0') ? 0 : ((e && e[0] == '1') ? 3 : 2);
   }();
   const bool use_ring = ring_blocks != 0 && split == 0;
   int seg_len = 48;
