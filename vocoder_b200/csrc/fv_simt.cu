@@ -400,7 +400,7 @@ __device__ __forceinline__ void store_half2_split(__half* dst, float2 v, int spl
 // RING = true: the look-ahead loads go through a per-thread shared-memory ring filled by cp.async (18 slots of 8 bytes, two
 // 6-step windows in flight) instead of 12 prefetch registers: deeper latency cover with fewer registers, so three blocks
 // fit an SM.  `ring` = this thread's slot 0 (slot stride = blockDim.x float2, i.e. every warp access is 256 contiguous bytes).
-template <bool EDGE, bool SPLIT, bool RING = false>
+template <bool EDGE, bool SPLIT, int RING = 0>
 __device__ __forceinline__ void snake_segment(const float* __restrict__ xc, __half* __restrict__ orow,
                                               const SnakeFilt& f, float2 a, float2 inv_b, int t0, int t_end, int L,
                                               int pitch, int opitch, int split, float2* ring = nullptr,
@@ -410,16 +410,17 @@ __device__ __forceinline__ void snake_segment(const float* __restrict__ xc, __ha
     if (EDGE) t = t < 0 ? 0 : (t > L - 1 ? L - 1 : t);  // replicate edge of the INPUT (first filter pads its own input)
     return *reinterpret_cast<const float2*>(xc + (size_t)t * pitch);
   };
-  // ring: window w (steps t0 + 6 w + 6 .. + 11) lives in slots (w % 3) * 6 + k
+  // ring: window w (steps t0 + 6 w + 6 .. + 11) lives in slots (w % (RING + 1)) * 6 + k; RING windows are in flight
+  constexpr int RW = RING > 0 ? RING + 1 : 1;
   auto ring_issue = [&](int w) {
-    if constexpr (RING) {
+    if constexpr (RING > 0) {
       const int tw = t0 + 6 * w + 6;
       if (tw < t_end + 6) {
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
           int t = tw + k;
           if (EDGE) t = t < 0 ? 0 : (t > L - 1 ? L - 1 : t);  // (interior segments: only needed windows are issued)
-          const uint32_t dst = smem_u32(ring + (size_t)((w % 3) * 6 + k) * ring_stride);
+          const uint32_t dst = smem_u32(ring + (size_t)((w % RW) * 6 + k) * ring_stride);
           asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(xc + (size_t)t * pitch) : "memory");
         }
       }
@@ -440,9 +441,9 @@ __device__ __forceinline__ void snake_segment(const float* __restrict__ xc, __ha
   // ... and so is the first main-loop window x~[t0+6 .. t0+11]
   float2 xn[6];
   const float* px = xc + (size_t)(t0 + 6) * pitch;  // interior path: running pointers instead of index math
-  if constexpr (RING) {
-    ring_issue(0);
-    ring_issue(1);
+  if constexpr (RING > 0) {
+#pragma unroll
+    for (int w0 = 0; w0 < RING; ++w0) ring_issue(w0);
   } else {
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
@@ -478,11 +479,11 @@ __device__ __forceinline__ void snake_segment(const float* __restrict__ xc, __ha
   int w = 0;
   for (int tb = t0; tb < t_end; tb += 6, ++w) {
     float2 xw[6];
-    if constexpr (RING) {
-      asm volatile("cp.async.wait_group 1;" ::: "memory");  // window w has landed (window w + 1 may still be in flight)
+    if constexpr (RING > 0) {
+      asm volatile("cp.async.wait_group %0;" ::"n"(RING - 1) : "memory");  // window w has landed (later ones may be in flight)
 #pragma unroll
-      for (int k = 0; k < 6; ++k) xw[k] = ring[(size_t)((w % 3) * 6 + k) * ring_stride];
-      ring_issue(w + 2);  // into the slots window w - 1 was read from in the previous iteration
+      for (int k = 0; k < 6; ++k) xw[k] = ring[(size_t)((w % RW) * 6 + k) * ring_stride];
+      ring_issue(w + RING);  // into the slots window w - 1 was read from in the previous iteration
     } else {
 #pragma unroll
       for (int k = 0; k < 6; ++k) xw[k] = xn[k];
@@ -569,15 +570,14 @@ __global__ void __launch_bounds__(256, SN_BLOCKS) snake_aa_kernel(const float* _
 
 // The same kernel with the look-ahead in a shared-memory ring (see snake_segment<..., RING = true>): RB = 3 blocks per SM
 // (80 registers) or RB = 2 (the register budget of the default kernel, only the deeper look-ahead differs).
-constexpr int SN_RING_SLOTS = 18;
-template <int RB>
+template <int RB, int RW>   // RW = windows in flight: (RW + 1) x 6 ring slots of 8 bytes per thread
 __global__ void __launch_bounds__(256, RB)
     snake_aa_ring_kernel(const float* __restrict__ x, __half* __restrict__ out, const float* __restrict__ alpha,
                          const float* __restrict__ beta, const SnakeFilt f, int logscale, int B, int L, int C, int pitch,
                          int n_seg, int seg_len) {
   pdl_launch_dependents();
   pdl_wait();
-  extern __shared__ float2 s_ring[];  // [SN_RING_SLOTS][256]
+  extern __shared__ float2 s_ring[];  // [(RW + 1) * 6][256]
   const int hp = pitch >> 1;
   const long long total = (long long)B * n_seg * hp;
   const long long item = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -603,8 +603,8 @@ __global__ void __launch_bounds__(256, RB)
   const float* xc = x + ((size_t)b * L) * pitch + c;
   float2* ring = s_ring + threadIdx.x;
   const bool interior = (t0 >= 6) && (t0 + seg_len + 6 <= L - 1);
-  if (interior) snake_segment<false, false, true>(xc, orow, f, a, inv_b, t0, t_end, L, pitch, pitch, 0, ring, 256);
-  else snake_segment<true, false, true>(xc, orow, f, a, inv_b, t0, t_end, L, pitch, pitch, 0, ring, 256);
+  if (interior) snake_segment<false, false, RW>(xc, orow, f, a, inv_b, t0, t_end, L, pitch, pitch, 0, ring, 256);
+  else snake_segment<true, false, RW>(xc, orow, f, a, inv_b, t0, t_end, L, pitch, pitch, 0, ring, 256);
 }
 
 // Edge modes other than `replicate` (FV_EDGE_REFLECT / FV_EDGE_ZERO: what another release of alias_free_torch may pad
@@ -1445,6 +1445,10 @@ extern "C" int fv_snake_aa(const float* x32, void* out16, const float* alpha, co
     const char* e = getenv("FV_SNAKE_RING");
     return (e && e[0] == '0') ? 0 : ((e && e[0] == '1') ? 3 : 2);
   }();
+  static const int ring_windows = [] {   // FV_SNAKE_RING=3: two blocks per SM, three windows in flight
+    const char* e = getenv("FV_SNAKE_RING");
+    return (e && e[0] == '3') ? 3 : 2;
+  }();
   const bool use_ring = ring_blocks != 0 && split == 0;
   int seg_len = 48;
   {
@@ -1463,13 +1467,16 @@ extern "C" int fv_snake_aa(const float* x32, void* out16, const float* alpha, co
   const int n_seg = ceil_div(L, seg_len);
   const long long total = (long long)B * n_seg * (pitch / 2);
   if (use_ring) {
-    const int smem = SN_RING_SLOTS * 256 * (int)sizeof(float2);
+    const int smem = (ring_windows + 1) * 6 * 256 * (int)sizeof(float2);
     cudaError_t le;
     if (ring_blocks == 3)
-      le = launch_kernel(snake_aa_ring_kernel<3>, dim3(grid1d(total, 256)), dim3(256), smem, (cudaStream_t)stream, 1, x32,
+      le = launch_kernel(snake_aa_ring_kernel<3, 2>, dim3(grid1d(total, 256)), dim3(256), smem, (cudaStream_t)stream, 1, x32,
+                         (__half*)out16, alpha, beta, f, logscale, B, L, C, pitch, n_seg, seg_len);
+    else if (ring_windows == 3)
+      le = launch_kernel(snake_aa_ring_kernel<2, 3>, dim3(grid1d(total, 256)), dim3(256), smem, (cudaStream_t)stream, 1, x32,
                          (__half*)out16, alpha, beta, f, logscale, B, L, C, pitch, n_seg, seg_len);
     else
-      le = launch_kernel(snake_aa_ring_kernel<2>, dim3(grid1d(total, 256)), dim3(256), smem, (cudaStream_t)stream, 1, x32,
+      le = launch_kernel(snake_aa_ring_kernel<2, 2>, dim3(grid1d(total, 256)), dim3(256), smem, (cudaStream_t)stream, 1, x32,
                          (__half*)out16, alpha, beta, f, logscale, B, L, C, pitch, n_seg, seg_len);
     FV_REQUIRE(le == cudaSuccess, FV_E_DRIVER, "launch of snake_aa_ring_kernel failed");
     FV_CHECK_LAUNCH("snake_aa_ring_kernel");
