@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Throughput of the mel front-end (audio -> log-mel) on the GPU path next to the oracle (torch.stft + matmul) on the host
-cores: python tools/bench_frontend.py [--batch 64] [--seconds 1.0]"""
+cores: python tests/diag/bench_frontend.py [--batch 64] [--seconds 1.0]"""
 import argparse
 import json
 import os
@@ -9,7 +9,7 @@ import time
 
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import frontend as O  # noqa: E402  (checker / CPU baseline only)
 from vocoder_b200 import cabi  # noqa: E402
 from vocoder_b200.transforms import LogMelSpectrogram  # noqa: E402

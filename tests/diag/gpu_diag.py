@@ -1,4 +1,4 @@
-"""Kernel bring-up diagnostics (run on the B200 box):  python tools/gpu_diag.py [--group NAME]
+"""Kernel bring-up diagnostics (run on the B200 box):  python tests/diag/gpu_diag.py [--group NAME]
 
 Without --group, every group runs in its own subprocess (a trapped kernel poisons the CUDA context) under a
 timeout; results are merged into gpurun_out/diag.json.  References are computed on the CPU with torch.
@@ -10,7 +10,7 @@ import subprocess
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402

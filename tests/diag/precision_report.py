@@ -7,7 +7,7 @@ import time
 
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from tests.util import ALL_GOLDEN, build_module, channels_last_noise, load_golden, stress_init  # noqa: E402
 

@@ -47,7 +47,7 @@ def _run(name, m, ins, extra):
 GOLDEN_GPU = list(ALL_GOLDEN)
 # The fixtures the default ("mixed") precision of their generator does not bring under 1e-3.  bigvgan_small_stress: 1.13e-3 measured (fp16
 # everywhere: 3.7e-3; the reference's own TF32 GPU arithmetic: 3.4e-3).  Its residual-block convs sit at C = 32 ... 4 with
-# stress weights; the error is the fp16 rounding of THEIR operands (tools/precision_probe.py), which only precision="strict"
+# stress weights; the error is the fp16 rounding of THEIR operands (tests/diag/precision_report.py), which only precision="strict"
 # removes.  The golden test therefore runs it in "strict" (1.1e-5) and bounds the default mode at 1.5e-3; bench.py reports the
 # strict-mode throughput of BigVGAN beside the default one (workloads.bigvgan_b32_strict).  At the benched width
 # (test_benched_shape_parity_vs_oracle) the default mode is at 4.8e-4.
@@ -452,7 +452,7 @@ def test_mrf_fused_generator_matches_layerwise():
 def _diag():
     import os
     import sys
-    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "diag"))
     import gpu_diag
     return gpu_diag
 

@@ -6,7 +6,7 @@ timeout 1000 python -m pytest tests -m gpu -q --maxfail=60 -p no:cacheprovider -
 timeout 200 python tools/bench_mrf.py > $O/bench_mrf.log 2>&1
 FV_MRF_WS=1 timeout 200 python tools/bench_mrf.py --shapes 64x12032x64 > $O/bench_mrf_ws.log 2>&1
 timeout 200 python tools/bench_mrf.py pairs > $O/bench_mrf_pairs.log 2>&1
-timeout 400 python tools/precision_report.py > $O/precision_report.md 2>&1
+timeout 400 python tests/diag/precision_report.py > $O/precision_report.md 2>&1
 timeout 600 python bench.py --steps 20 --warmup 3 > $O/bench.json 2> $O/bench.err
 timeout 200 python bench.py --extra none --no-cpu-baseline --no-sustained --no-fuse-pairs > $O/bench_nopairs.json 2>> $O/bench.err
 timeout 200 python bench.py --extra none --no-cpu-baseline --no-sustained --mrf-silu-h2 > $O/bench_h2.json 2>> $O/bench.err

@@ -162,7 +162,7 @@ def round_up(x: int, m: int) -> int:
 # The mode is thread-local state entered by the module's forward (``module.precision``).
 # ----------------------------------------------------------------------------------------------
 #   "mixed"  fp16 operands, except on the few contractions that dominate the waveform error (measured per layer on the
-#            reference goldens, tools/precision_probe.py): the trunk of BigVGAN (conv_pre, ups, conv_post) and the stem /
+#            reference goldens, tests/diag/precision_report.py): the trunk of BigVGAN (conv_pre, ups, conv_post) and the stem /
 #            downsample / head / inverse-DFT contractions of the Vocos path, which run strict.  The residual-block convs
 #            and the ConvNeXt pointwise GEMMs (>= 95% of the tensor work) stay single fp16.
 PRECISIONS = ("fp16", "mixed", "strict")

@@ -151,7 +151,7 @@ class MRFGeneratorBase(nn.Module):
 
     def _trunk_strict(self) -> bool:
         """ "mixed" precision: conv_pre / ups / conv_post of the Snake generators carry [hi | lo] operands.  Measured on the
-        reference goldens (tools/precision_probe.py): the trunk alone is ~90% of the fp16-operand waveform error, at
+        reference goldens (tests/diag/precision_report.py): the trunk alone is ~90% of the fp16-operand waveform error, at
         < 5% of the tensor work."""
         return cabi.is_mixed() and self.snake_blocks
 
