@@ -274,8 +274,9 @@ def group_simt():
         res.append({"name": f"snake_B{B}_L{L}_C{C}", "err": float((got[..., :C] - ref).abs().max()),
                     "pad_ok": bool((got[..., C:] == 0).all()), "absmax": float(ref.abs().max())})
     # dwconv + LN, plain LN
+    # (C = 20 / 36: padded channel columns; T = 21 / 9 / 30: ragged last tiles; 1408: the 704-thread pipelined configuration)
     for (B, T, C, k) in ((2, 94, 352, 7), (1, 10, 32, 7), (2, 50, 2816, 7), (2, 50, 704, 0), (2, 13, 20, 5), (1, 7, 48, 7),
-                         (3, 5, 2816, 0)):
+                         (3, 5, 2816, 0), (2, 21, 20, 7), (1, 30, 1408, 7), (4, 9, 36, 0), (150, 17, 64, 7)):
         pitch = cabi.pitch_of(C)
         xx = torch.zeros(B, T, pitch)
         xx[..., :C] = torch.randn(B, T, C, generator=g)
@@ -287,12 +288,13 @@ def group_simt():
             dw = db = None
             h = xx[..., :C]
         ref = F.layer_norm(h, (C,), lw, lb, 1e-6)
-        o16 = torch.empty(B, T, pitch, dtype=torch.float16, device=dev)
-        o32 = torch.empty(B, T, pitch, device=dev)
+        o16 = torch.full((B, T, pitch), float("nan"), dtype=torch.float16, device=dev)
+        o32 = torch.full((B, T, pitch), float("nan"), device=dev)
         cabi.dwconv_layernorm(xx.to(dev), C, None if dw is None else dw.reshape(C, k).t().contiguous().to(dev),
                               None if db is None else db.to(dev), lw.to(dev), lb.to(dev), 1e-6, k, out16=o16, out32=o32)
-        res.append({"name": f"dwconv_ln_C{C}_k{k}", "err32": float((o32.cpu()[..., :C] - ref).abs().max()),
-                    "err16": float((o16.float().cpu()[..., :C] - ref).abs().max())})
+        res.append({"name": f"dwconv_ln_B{B}_T{T}_C{C}_k{k}", "err32": float((o32.cpu()[..., :C] - ref).abs().max()),
+                    "err16": float((o16.float().cpu()[..., :C] - ref).abs().max()),
+                    "pad_ok": bool((o16.float().cpu()[..., C:] == 0).all()) and bool((o32.cpu()[..., C:] == 0).all())})
     # istft ola
     for (n_fft, hop, T) in ((64, 16, 9), (1024, 256, 20)):
         K = n_fft // 2 + 1
