@@ -592,7 +592,8 @@ static bool pair_config(const fv_mrf_desc* d) {
   return d->C == 128 || (d->C == 64 && d->n_blocks == 1 && d->n_pairs == 1 && g_mrf_c64_pair);
 }
 // (Measured and dropped, round 2: 256-row whole-stage tiles with two co-resident CTAs for short launches - C = 64, L = 12032,
-// B = 1: 94 tiles instead of 32 - hifigan_b1 0.546 ms against 0.537 ms without: twice the halo recompute eats the shorter chains.)
+// B = 1: 94 tiles instead of 32 - hifigan_b1 0.546 ms against 0.537 ms without while the forward was still host-bound, 0.429 against
+// 0.426 ms after that was fixed: the fused stages' launches are shorter (0.47 against 0.50 ms summed) but not on the critical path.)
 static int tile_rows_for(const fv_mrf_desc* d) { return pair_config(d) ? 256 : 512; }
 
 template <int C, int ACT, int EW, int NCTA, int MB, int MAXCONV>
