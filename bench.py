@@ -400,6 +400,8 @@ def run_workload(name, args, dev, rank, world, barrier, all_max, *, full: bool):
             m.conv_row_pairs = False
         if args.chain_streams != "auto" and hasattr(m, "chain_streams"):
             m.chain_streams = args.chain_streams == "on"
+        if args.chain_rows > 0 and hasattr(m, "chain_streams_max_rows"):
+            m.chain_streams_max_rows = args.chain_rows
         if args.no_fuse_snake and hasattr(m, "fuse_snake"):
             m.fuse_snake = False
         if args.mrf_silu_exact and hasattr(m, "mrf_silu_tanh"):
@@ -624,6 +626,8 @@ def main():
     ap.add_argument("--fuse-pairs", action="store_true", help="always pair-wise fv_mrf_fused for the C = 128 stage")
     ap.add_argument("--chain-streams", choices=("auto", "on", "off"), default="auto",
                     help="kernel-size chains of a stage on two streams (auto: short sequences only)")
+    ap.add_argument("--chain-rows", type=int, default=0,
+                    help="row threshold (batch x length) below which a stage's chains run concurrently (default: the module's)")
     ap.add_argument("--no-row-pairs", action="store_true",
                     help="C <= 16 Snake stages one row per GEMM row instead of the [L/2, 2C] row-pair view (A/B switch)")
     ap.add_argument("--pairwise-c64", action="store_true", help="C = 64 stage pair by pair (two co-resident CTAs per SM)")
