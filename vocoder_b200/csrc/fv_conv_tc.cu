@@ -189,11 +189,11 @@ __global__ void __launch_bounds__(64 + (FAT ? 16 : kEpiWarps) * 32, 1)
         return (p.a_split > 0 && col >= 2 * p.a_split) ? col - 2 * p.a_split : col;
       };
       for (int tile = worker; tile < p.total_tiles; tile += n_workers) {
-        int r = tile;
+        int r = tile;   // phase fastest: the phases of a polyphase ConvTranspose share their input rows and interleave their
+        const int phase = r % p.n_phase; r /= p.n_phase;   // output rows, so they run side by side (L2 hits, merged lines)
         const int n_t = r % p.n_tiles; r /= p.n_tiles;
         const int m_t = r % p.m_tiles; r /= p.m_tiles;
-        const int b = r % p.B;
-        const int phase = r / p.B;
+        const int b = r;
         const int q0 = m_t * TILE_ROWS + (int)cta_rank * (M_SUB * 128);
         const int n0 = n_t * BLOCK_N;
         if constexpr (SLAB) {
@@ -265,10 +265,7 @@ __global__ void __launch_bounds__(64 + (FAT ? 16 : kEpiWarps) * 32, 1)
         mbar_wait(&tempty_bar[buf], ((tile_i / Cfg::ACC_BUFS) & 1) ^ 1);
         tc_fence_after();
         if constexpr (SLAB) {
-          int r = tile;
-          r /= p.n_tiles;
-          r /= p.m_tiles;
-          const int phase = r / p.B;
+          const int phase = tile % p.n_phase;
           const uint32_t b_ring = smem_u32(smem + 2 * Cfg::A_SLAB);
           for (int kc = 0; kc < p.k_chunks; ++kc, ++ita) {
             const int sa = ita & 1;
@@ -362,11 +359,11 @@ __global__ void __launch_bounds__(64 + (FAT ? 16 : kEpiWarps) * 32, 1)
       const uint32_t h_xor = static_cast<uint32_t>((lane >> 1) & 3);
       uint32_t tile_i = 0;
       for (int tile = worker; tile < p.total_tiles; tile += n_workers, ++tile_i) {
-        int r = tile;
+        int r = tile;   // phase fastest: the phases of a polyphase ConvTranspose share their input rows and interleave their
+        const int phase = r % p.n_phase; r /= p.n_phase;   // output rows, so they run side by side (L2 hits, merged lines)
         const int n_t = r % p.n_tiles; r /= p.n_tiles;
         const int m_t = r % p.m_tiles; r /= p.m_tiles;
-        const int b = r % p.B;
-        const int phase = r / p.B;
+        const int b = r;
         const int q0 = m_t * TILE_ROWS + (int)cta_rank * (M_SUB * 128);
         const int n0 = n_t * BLOCK_N;
         const uint32_t buf = tile_i % Cfg::ACC_BUFS;
@@ -468,11 +465,11 @@ __global__ void __launch_bounds__(64 + (FAT ? 16 : kEpiWarps) * 32, 1)
       const bool has_res = p.residual != nullptr, has_o32 = p.out32 != nullptr, has_o16 = p.out16 != nullptr;
       uint32_t tile_i = 0;
       for (int tile = worker; tile < p.total_tiles; tile += n_workers, ++tile_i) {
-        int r = tile;
+        int r = tile;   // phase fastest: the phases of a polyphase ConvTranspose share their input rows and interleave their
+        const int phase = r % p.n_phase; r /= p.n_phase;   // output rows, so they run side by side (L2 hits, merged lines)
         const int n_t = r % p.n_tiles; r /= p.n_tiles;
         const int m_t = r % p.m_tiles; r /= p.m_tiles;
-        const int b = r % p.B;
-        const int phase = r / p.B;
+        const int b = r;
         const int q0 = m_t * TILE_ROWS + (int)cta_rank * (M_SUB * 128);
         const int n0 = n_t * BLOCK_N;
         const uint32_t buf = tile_i % Cfg::ACC_BUFS;
@@ -679,11 +676,11 @@ __global__ void __launch_bounds__(64 + (FAT ? 16 : kEpiWarps) * 32, 1)
     constexpr int N_ITEMS = M_SUB * Cfg::NCH;
     uint32_t tile_i = 0;
     for (int tile = worker; tile < p.total_tiles; tile += n_workers, ++tile_i) {
-      int r = tile;
+      int r = tile;   // phase fastest: the phases of a polyphase ConvTranspose share their input rows and interleave their
+      const int phase = r % p.n_phase; r /= p.n_phase;   // output rows, so they run side by side (L2 hits, merged lines)
       const int n_t = r % p.n_tiles; r /= p.n_tiles;
       const int m_t = r % p.m_tiles; r /= p.m_tiles;
-      const int b = r % p.B;
-      const int phase = r / p.B;
+      const int b = r;
       const int q0 = m_t * TILE_ROWS + (int)cta_rank * (M_SUB * 128);
       const int n0 = n_t * BLOCK_N;
       const uint32_t buf = tile_i % Cfg::ACC_BUFS;
