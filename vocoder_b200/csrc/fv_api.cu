@@ -33,6 +33,18 @@ int check_cuda(cudaError_t e, const char* what) {
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// Tile-order direction of the streaming kernels (fv_conv1d on tensor cores, fv_snake_aa): it alternates launch by launch, so a
+// consumer starts with the tiles its producer wrote LAST - the part of a 90-200 MB intermediate that is still in the 126 MB L2
+// - instead of the tiles written first, which have already been evicted.  FV_SERPENTINE=0 disables (A/B measurements).
+static std::atomic<unsigned> g_direction{0};
+int next_tile_direction() {
+  static const bool on = [] {
+    const char* e = getenv("FV_SERPENTINE");
+    return !(e && e[0] == '0');
+  }();
+  return on ? (int)(g_direction.fetch_add(1, std::memory_order_relaxed) & 1u) : 0;
+}
+
 int conv1d_tc(const fv_conv_desc* d, cudaStream_t stream, int block_n_override, int m_sub_override, int epilogue,
               int mainloop);
 int conv1d_simt(const fv_conv_desc* d, cudaStream_t stream);

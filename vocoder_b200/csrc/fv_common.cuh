@@ -21,6 +21,7 @@ namespace fv {
 int set_error(int code, const char* fmt, ...);
 int check_cuda(cudaError_t e, const char* what);
 void count_launch(int n = 1);
+int next_tile_direction();  // 0 / 1 alternating per launch of a streaming kernel (fv_api.cu)
 
 #define FV_REQUIRE(cond, code, ...)                      \
   do {                                                   \

@@ -40,6 +40,7 @@ struct ConvTcParams {
   int B, n_phase, n_taps, k_chunks, C_out, C_out_r8, C_out_pad, q_rows, L_out;
   int m_tiles, n_tiles, total_tiles;
   int a_split, out16_split;  // strict precision: [hi | lo] operand / output layout (0 = plain fp16), see fv_conv_desc
+  int reverse;   // walk the tiles from the last to the first (see next_tile_direction)
   int use_pair;  // host only: launch the cta_group::2 variant when the tile shape has one
   int use_slab, off_min, slab_boxes, w_resident;  // slab mainloop: smallest tap offset, 64-row boxes per slab, weights stay in smem
   const float* bias;
@@ -189,7 +190,7 @@ __global__ void __launch_bounds__(64 + (FAT ? 16 : kEpiWarps) * 32, 1)
         return (p.a_split > 0 && col >= 2 * p.a_split) ? col - 2 * p.a_split : col;
       };
       for (int tile = worker; tile < p.total_tiles; tile += n_workers) {
-        int r = tile;   // phase fastest: the phases of a polyphase ConvTranspose share their input rows and interleave their
+        int r = p.reverse ? p.total_tiles - 1 - tile : tile;   // phase fastest: the phases of a polyphase ConvTranspose share their input rows and interleave their
         const int phase = r % p.n_phase; r /= p.n_phase;   // output rows, so they run side by side (L2 hits, merged lines)
         const int n_t = r % p.n_tiles; r /= p.n_tiles;
         const int m_t = r % p.m_tiles; r /= p.m_tiles;
@@ -265,7 +266,7 @@ __global__ void __launch_bounds__(64 + (FAT ? 16 : kEpiWarps) * 32, 1)
         mbar_wait(&tempty_bar[buf], ((tile_i / Cfg::ACC_BUFS) & 1) ^ 1);
         tc_fence_after();
         if constexpr (SLAB) {
-          const int phase = tile % p.n_phase;
+          const int phase = (p.reverse ? p.total_tiles - 1 - tile : tile) % p.n_phase;
           const uint32_t b_ring = smem_u32(smem + 2 * Cfg::A_SLAB);
           for (int kc = 0; kc < p.k_chunks; ++kc, ++ita) {
             const int sa = ita & 1;
@@ -359,7 +360,7 @@ __global__ void __launch_bounds__(64 + (FAT ? 16 : kEpiWarps) * 32, 1)
       const uint32_t h_xor = static_cast<uint32_t>((lane >> 1) & 3);
       uint32_t tile_i = 0;
       for (int tile = worker; tile < p.total_tiles; tile += n_workers, ++tile_i) {
-        int r = tile;   // phase fastest: the phases of a polyphase ConvTranspose share their input rows and interleave their
+        int r = p.reverse ? p.total_tiles - 1 - tile : tile;   // phase fastest: the phases of a polyphase ConvTranspose share their input rows and interleave their
         const int phase = r % p.n_phase; r /= p.n_phase;   // output rows, so they run side by side (L2 hits, merged lines)
         const int n_t = r % p.n_tiles; r /= p.n_tiles;
         const int m_t = r % p.m_tiles; r /= p.m_tiles;
@@ -465,7 +466,7 @@ __global__ void __launch_bounds__(64 + (FAT ? 16 : kEpiWarps) * 32, 1)
       const bool has_res = p.residual != nullptr, has_o32 = p.out32 != nullptr, has_o16 = p.out16 != nullptr;
       uint32_t tile_i = 0;
       for (int tile = worker; tile < p.total_tiles; tile += n_workers, ++tile_i) {
-        int r = tile;   // phase fastest: the phases of a polyphase ConvTranspose share their input rows and interleave their
+        int r = p.reverse ? p.total_tiles - 1 - tile : tile;   // phase fastest: the phases of a polyphase ConvTranspose share their input rows and interleave their
         const int phase = r % p.n_phase; r /= p.n_phase;   // output rows, so they run side by side (L2 hits, merged lines)
         const int n_t = r % p.n_tiles; r /= p.n_tiles;
         const int m_t = r % p.m_tiles; r /= p.m_tiles;
@@ -676,7 +677,7 @@ __global__ void __launch_bounds__(64 + (FAT ? 16 : kEpiWarps) * 32, 1)
     constexpr int N_ITEMS = M_SUB * Cfg::NCH;
     uint32_t tile_i = 0;
     for (int tile = worker; tile < p.total_tiles; tile += n_workers, ++tile_i) {
-      int r = tile;   // phase fastest: the phases of a polyphase ConvTranspose share their input rows and interleave their
+      int r = p.reverse ? p.total_tiles - 1 - tile : tile;   // phase fastest: the phases of a polyphase ConvTranspose share their input rows and interleave their
       const int phase = r % p.n_phase; r /= p.n_phase;   // output rows, so they run side by side (L2 hits, merged lines)
       const int n_t = r % p.n_tiles; r /= p.n_tiles;
       const int m_t = r % p.m_tiles; r /= p.m_tiles;
@@ -1086,6 +1087,7 @@ int conv1d_tc(const fv_conv_desc* d, cudaStream_t stream, int block_n_override, 
   p.act_param = d->act_param;
   p.a_split = d->a_split;
   p.out16_split = d->out16_split;
+  p.reverse = next_tile_direction();
   // mainloop: 0 = auto, 1 = per-tap stages, 2 = slab.  Measured on B200 (BigVGAN cfg C, per launch): for C_in >= 64 the two
   // are within 3% (C = 256: slab up to 20% slower), for C_in <= 32 with k >= 7 the slab saves 8-25% (one operand load
   // per tile instead of one small TMA stage per tap: 96.7 -> 76.2 us for C = 16, k = 11).  Auto picks accordingly.

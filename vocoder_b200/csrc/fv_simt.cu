@@ -534,13 +534,14 @@ __global__ void __launch_bounds__(256, SN_BLOCKS) snake_aa_kernel(const float* _
                                                           const float* __restrict__ alpha,
                                                           const float* __restrict__ beta, const SnakeFilt f,
                                                           int logscale, int B, int L, int C, int pitch, int n_seg,
-                                                          int seg_len, int split) {
+                                                          int seg_len, int split, int reverse) {
   pdl_launch_dependents();
   pdl_wait();
   const int hp = pitch >> 1;
   const long long total = (long long)B * n_seg * hp;
-  const long long item = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  long long item = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (item >= total) return;
+  if (reverse) item = total - 1 - item;   // start with what the producer wrote last (next_tile_direction)
   const int c = 2 * (int)(item % hp);
   const int seg = (int)((item / hp) % n_seg);
   const int b = (int)(item / ((long long)hp * n_seg));
@@ -574,14 +575,15 @@ template <int RB, int RW>   // RW = windows in flight: (RW + 1) x 6 ring slots o
 __global__ void __launch_bounds__(256, RB)
     snake_aa_ring_kernel(const float* __restrict__ x, __half* __restrict__ out, const float* __restrict__ alpha,
                          const float* __restrict__ beta, const SnakeFilt f, int logscale, int B, int L, int C, int pitch,
-                         int n_seg, int seg_len) {
+                         int n_seg, int seg_len, int reverse) {
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ float2 s_ring[];  // [(RW + 1) * 6][256]
   const int hp = pitch >> 1;
   const long long total = (long long)B * n_seg * hp;
-  const long long item = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  long long item = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (item >= total) return;
+  if (reverse) item = total - 1 - item;   // start with what the producer wrote last (next_tile_direction)
   const int c = 2 * (int)(item % hp);
   const int seg = (int)((item / hp) % n_seg);
   const int b = (int)(item / ((long long)hp * n_seg));
@@ -1466,18 +1468,19 @@ extern "C" int fv_snake_aa(const float* x32, void* out16, const float* alpha, co
   }
   const int n_seg = ceil_div(L, seg_len);
   const long long total = (long long)B * n_seg * (pitch / 2);
+  const int reverse = next_tile_direction();
   if (use_ring) {
     const int smem = (ring_windows + 1) * 6 * 256 * (int)sizeof(float2);
     cudaError_t le;
     if (ring_blocks == 3)
       le = launch_kernel(snake_aa_ring_kernel<3, 2>, dim3(grid1d(total, 256)), dim3(256), smem, (cudaStream_t)stream, 1, x32,
-                         (__half*)out16, alpha, beta, f, logscale, B, L, C, pitch, n_seg, seg_len);
+                         (__half*)out16, alpha, beta, f, logscale, B, L, C, pitch, n_seg, seg_len, reverse);
     else if (ring_windows == 3)
       le = launch_kernel(snake_aa_ring_kernel<2, 3>, dim3(grid1d(total, 256)), dim3(256), smem, (cudaStream_t)stream, 1, x32,
-                         (__half*)out16, alpha, beta, f, logscale, B, L, C, pitch, n_seg, seg_len);
+                         (__half*)out16, alpha, beta, f, logscale, B, L, C, pitch, n_seg, seg_len, reverse);
     else
       le = launch_kernel(snake_aa_ring_kernel<2, 2>, dim3(grid1d(total, 256)), dim3(256), smem, (cudaStream_t)stream, 1, x32,
-                         (__half*)out16, alpha, beta, f, logscale, B, L, C, pitch, n_seg, seg_len);
+                         (__half*)out16, alpha, beta, f, logscale, B, L, C, pitch, n_seg, seg_len, reverse);
     FV_REQUIRE(le == cudaSuccess, FV_E_DRIVER, "launch of snake_aa_ring_kernel failed");
     FV_CHECK_LAUNCH("snake_aa_ring_kernel");
     return 0;
@@ -1485,12 +1488,12 @@ extern "C" int fv_snake_aa(const float* x32, void* out16, const float* alpha, co
   if (split)  // strict precision: [hi | lo] fp16 pairs (the extra stores stay out of the default instantiation)
     FV_REQUIRE(launch_kernel(snake_aa_kernel<true>, dim3(grid1d(total, 256)), dim3(256), 0, (cudaStream_t)stream, 1, x32,
                              (__half*)out16, alpha, beta, f, logscale, B, L, C, pitch, n_seg, seg_len,
-                             split) == cudaSuccess,
+                             split, reverse) == cudaSuccess,
                FV_E_DRIVER, "launch of snake_aa_kernel failed");
   else
     FV_REQUIRE(launch_kernel(snake_aa_kernel<false>, dim3(grid1d(total, 256)), dim3(256), 0, (cudaStream_t)stream, 1, x32,
                              (__half*)out16, alpha, beta, f, logscale, B, L, C, pitch, n_seg, seg_len,
-                             split) == cudaSuccess,
+                             split, reverse) == cudaSuccess,
                FV_E_DRIVER, "launch of snake_aa_kernel failed");
   FV_CHECK_LAUNCH("snake_aa_kernel");
   return 0;
